@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- ROI-crops/s through iDispNet (cost volume + 28-layer 3-D stack + soft-argmin) on B200.
+
+Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]`; under torchrun one rank
+per GPU.  A step = one pass of the hot path over one batch of synthetic ROI feature pairs
+(BASELINE.json configs[1]: 32 ROI pairs of 112x112x32-ch features, D=48 -> 448x448 disparity, per
+GPU; weak scaling).  Prints ONE JSON line on rank 0.
+
+  value ....... whole-job ROIs/s with the inputs already resident in HBM (device-timed, max over ranks)
+  e2e ......... same metric through the C-ABI call with HOST (pinned) buffers, H2D + D2H inside the timed region
+  roofline .... the 3-D conv launches: algorithmic FLOPs (644544*V - (64-2C)*1728*V per ROI)
+                / their summed device time (CUDA events between launches on the launching stream),
+                against MEASURED_PEAKS.json's sustained bf16 tensor peak
+  cpu_baseline  the oracle (CPU port of the reference's PyTorch path) on the host cores, bounded sample
+`--impl reference` times that CPU path alone with the same metric/config keys.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C, HF, WF, MIND, MAXD, B_PER_GPU = 32, 112, 112, -96, 96, 32
+D = (MAXD - MIND) // 4
+V = D * HF * WF
+H, W = 4 * HF, 4 * WF
+FLOP_PER_ROI = 644544 * V - (64 - 2 * C) * 1728 * V  # 388.09 GFLOP
+WORKLOAD = (f'configs[1]: batch={B_PER_GPU} ROI pairs/GPU, {HF}x{WF}x{C}ch features, D={D} '
+            f'(mindisp {MIND}, maxdisp {MAXD}) -> {H}x{W} disparity')
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return j.get('bf16_tflops_sustained', 1400.0), j.get('bf16_tflops', 1590.0), j.get('hbm_gbs', 6650.0), 'measured'
+    return 1400.0, 1590.0, 6650.0, 'fallback'
+
+
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.idx}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_port_rois_per_s(model_sd, n_steps, n_warm, budget_s=150.0):
+    """Time the oracle (CPU restatement of stackhourglass.py:115-174 on torch CPU ops, all host threads).
+
+    Each step = a bounded sample of the config-2 workload: one ROI pair at full depth/width and `rows`
+    feature rows (work is linear in V, so ROIs/s = (rows/HF) / t); rows shrinks until K+W steps fit the budget.
+    """
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import idispnet_oracle as O  # the checker, used here ONLY as the reported CPU baseline
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: v.detach().cpu().float() for k, v in model_sd.items()}
+    g = torch.Generator().manual_seed(0)
+
+    def run(rows):
+        L = torch.randn(1, C, rows, WF, generator=g).relu()
+        R = torch.randn(1, C, rows, WF, generator=g).relu()
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            O.idispnet_from_features(L, R, sd, MIND, MAXD)
+        return time.perf_counter() - t0
+
+    t_probe = run(8)  # 1/14 of an ROI
+    rows = HF
+    while rows > 8 and t_probe * (rows / 8.0) * (n_steps + n_warm) > budget_s:
+        rows //= 2
+        rows -= rows % 4
+    for _ in range(n_warm):
+        run(rows)
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        run(rows)
+    dt = (time.perf_counter() - t0) / max(n_steps, 1)
+    return (rows / HF) / dt, dt, cores, f'{n_steps} step(s) of 1 ROI pair x {rows}/{HF} feature rows (D={D}, W={WF}, C={C}), {n_warm} warm-up'
+
+
+def make_model(precision, device):
+    import torch
+    import torch.nn as nn
+    from disprcnn_b200.modeling.psmnet.stackhourglass import PSMNet
+    torch.manual_seed(0)
+    m = PSMNet(MAXD, MIND, precision=precision)  # random init of the reference architecture
+    m.feature_extraction = nn.Identity()
+    # benign BN statistics + damped classifier so logits stay finite through 28 random layers
+    with torch.no_grad():
+        for c in (m.classif1, m.classif2, m.classif3):
+            c[2].weight.mul_(0.1)
+    return m.to(device).eval()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--precision', default=os.environ.get('IDISP_BENCH_PRECISION', 'fp32'), choices=['fp32', 'bf16'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    warm = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    tens_sus, tens_burst, hbm, peak_src = peaks()
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        import torch
+        import torch.nn as nn
+        from disprcnn_b200.modeling.psmnet.stackhourglass import PSMNet
+        torch.manual_seed(0)
+        m = PSMNet(MAXD, MIND)
+        with torch.no_grad():
+            for c in (m.classif1, m.classif2, m.classif3):
+                c[2].weight.mul_(0.1)
+        sd = {k: v for k, v in m.state_dict().items() if not k.startswith('feature_extraction')}
+        val, dt, cores, sample = cpu_port_rois_per_s(sd, args.steps, args.warmup)
+        print(json.dumps({
+            'impl': 'reference', 'metric': 'idispnet_roi_crops_per_s', 'value': val, 'unit': 'ROIs/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'global_batch': B_PER_GPU * args.gpus, 'parallelism': f'dp{args.gpus}'},
+            'cpu_baseline': {'value': val, 'unit': 'ROIs/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': 'ROIs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0,
+        }))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from disprcnn_b200 import _lib
+    from disprcnn_b200.parallel import gather_disparity
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    lib = _lib.load()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    Bg = B_PER_GPU * world
+    m = make_model(args.precision, dev)
+    g = torch.Generator().manual_seed(1234 + rank)
+    L_host = torch.randn(B_PER_GPU, C, HF, WF, generator=g).relu().pin_memory()
+    R_host = torch.randn(B_PER_GPU, C, HF, WF, generator=g).relu().pin_memory()
+    out_host = torch.empty(B_PER_GPU, H, W).pin_memory()
+    L, R = L_host.to(dev), R_host.to(dev)
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        local = m.forward_features(L, R)
+        return gather_disparity(local, Bg) if world > 1 else local
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(n):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return ms.item()
+
+    with torch.no_grad():
+        for _ in range(warm):
+            out = step_device()
+        assert torch.isfinite(out).all(), 'non-finite disparity in warm-up'
+        plan = m._plan
+        # ---- value: device-resident inputs, per-launch events on (roofline leg) ----
+        _lib.check(lib.idisp_plan_enable_timing(plan, 1))
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        layer_ms = {}
+        ms_total = 0.0
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        per_step = []
+        for _ in range(args.steps):
+            step_device()
+            n = lib.idisp_plan_launches_per_forward(plan)
+            ms = (ctypes.c_float * n)()
+            ly = (ctypes.c_int * n)()
+            # reading the events waits for this step only; the next step is enqueued right after
+            _lib.check(lib.idisp_plan_get_timing(plan, ms, ly, n))
+            per_step.append((list(ms), list(ly)))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = t.item()
+        clocks = sampler.stop() if rank == 0 else None
+        _lib.check(lib.idisp_plan_enable_timing(plan, 0))
+        launches_per_step = lib.idisp_plan_launches_per_forward(plan) + (1 if world > 1 else 0)
+        conv_ms = sum(v for msl, lyl in per_step for v, l in zip(msl, lyl) if 0 <= l <= 27)
+        other_ms = sum(v for msl, lyl in per_step for v, l in zip(msl, lyl) if l < 0)
+        by_layer = {}
+        for msl, lyl in per_step:
+            for v, l in zip(msl, lyl):
+                by_layer[l] = by_layer.get(l, 0.0) + v / args.steps
+
+        # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----
+        def step_host():
+            _lib.check(lib.idisp_plan_forward_host(plan, _lib.ptr(L_host), _lib.ptr(R_host), B_PER_GPU, HF, WF, H, W,
+                                                   _lib.ptr(out_host), _lib.stream_ptr()))
+            if world > 1:
+                # the gathered result is what a multi-GPU user reads; gather from the device copy of the output
+                gather_disparity(out_host.to(dev, non_blocking=True), Bg)
+            torch.cuda.current_stream().synchronize()  # the user reads out_host now
+        step_host()
+        ms_e2e = timed(step_host, args.steps)
+
+    value = Bg * args.steps / (ms_total / 1e3)
+    e2e = Bg * args.steps / (ms_e2e / 1e3)
+    conv_flops = FLOP_PER_ROI * B_PER_GPU * args.steps  # this rank's conv launches
+    achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+
+    if rank == 0:
+        result = {
+            'metric': 'idispnet_roi_crops_per_s', 'value': value, 'unit': 'ROIs/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': warm, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32' if args.precision == 'fp32' else 'bf16 (fp32 accumulate)', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'global_batch': Bg, 'parallelism': f'dp{world} (ROI shards, one all-gather of disparity maps)',
+                       'precision_mode': args.precision,
+                       'l2': 'no explicit flush: each step streams >10 GB of activations per GPU, far beyond the 126 MB L2'},
+            'e2e': {'value': e2e, 'unit': 'ROIs/s', 'h2d_bytes_per_step': 2 * B_PER_GPU * C * HF * WF * 4 * world,
+                    'd2h_bytes_per_step': B_PER_GPU * H * W * 4 * world, 'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': launches_per_step * args.steps,
+            'roofline': {'bound': 'tensor', 'kernel': '3-D conv launches (28 layers/step)', 'achieved': achieved,
+                         'peak': tens_sus, 'unit': 'TFLOP/s', 'frac': achieved / tens_sus, 'traffic': None,
+                         'peak_source': f'{peak_src} bf16 sustained (burst {tens_burst})',
+                         'flop_per_roi': FLOP_PER_ROI, 'conv_ms_per_step': conv_ms / args.steps,
+                         'other_ms_per_step': other_ms / args.steps,
+                         'whole_step_frac': value / world * FLOP_PER_ROI / 1e12 / tens_sus},
+            'ms_by_layer': {str(k): round(v, 4) for k, v in sorted(by_layer.items())},
+            'clocks': clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            sd = {k: v for k, v in m.state_dict().items() if not k.startswith('feature_extraction')}
+            val, dt, cores, sample = cpu_port_rois_per_s(sd, 1, 0, budget_s=40.0)
+            result['cpu_baseline'] = {'value': val, 'unit': 'ROIs/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+        print(json.dumps(result))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,22 @@
+// conv3d_tc.cuh -- interface of the tcgen05 (5th-gen tensor core) 3x3x3 convolution path.
+#pragma once
+#include "common.cuh"
+
+namespace idisp {
+
+// bf16 weights re-laid for the UMMA B operand (see conv3d_tc.cu), device memory
+struct TcWeights {
+  void *dev = nullptr;
+  size_t bytes = 0;
+  int kind = -1, cin = 0, cout = 0;
+};
+
+// w_tap: HOST pointer, [27][cin][cout] f32 with the BN scale already folded in
+int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, TcWeights &out, cudaStream_t s);
+void tc_weights_free(TcWeights &w);
+// whether the tensor-core kernel covers this layer shape (otherwise the SIMT kernel runs it)
+bool tc_supported(int kind, int cin, int cout, int D, int H, int W);
+int tc_conv3d(const TcWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D, int H, int W, int Cout, int kind,
+              const float *bias, const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, cudaStream_t s);
+
+}  // namespace idisp

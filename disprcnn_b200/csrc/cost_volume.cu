@@ -1,0 +1,174 @@
+// cost_volume.cu -- concatenation cost volume + layout converters (HBM-bound, exact copies).
+//
+// Replaces disprcnn/modeling/psmnet/stackhourglass.py:115-128: a CPU-side torch.zeros, an H2D
+// copy of the whole zero volume and 2*D strided slice-copy launches become ONE kernel.
+// Closed form, plane k <-> shift i = k + mindisp/4:
+//   valid(k,x) = x >= max(i,0) && x < W + min(i,0)
+//   cost[b,   c, k,y,x] = valid ? L[b,c,y,x]   : 0
+//   cost[b, C+c, k,y,x] = valid ? R[b,c,y,x-i] : 0
+// Algorithmic bytes: 2C*V*sizeof(T) written per ROI (V = D*Hf*Wf); reads are L2 hits after
+// the first plane.  Every thread writes one 16/32-byte channel-block voxel (blocked layout)
+// or one float4 of a row (NCDHW test hook) -> 128-bit coalesced stores.
+#include "common.cuh"
+
+namespace idisp {
+
+// ---------------- blocked output: [B][2C/8][D][H][W][8] -------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+cost_volume_blocked_kernel(const float *__restrict__ L, const float *__restrict__ R, int B, int C, int Hf,
+                           int Wf, int shift0, int D, T *__restrict__ cost)
+{
+  const int nblk = 2 * C / CB;
+  const int64_t HW = (int64_t)Hf * Wf;
+  const int64_t total = (int64_t)B * nblk * D * HW;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % Wf);
+    const int y = (int)((idx / Wf) % Hf);
+    const int k = (int)((idx / HW) % D);
+    const int cb = (int)((idx / (HW * D)) % nblk);
+    const int b = (int)(idx / (HW * D * nblk));
+    const int i = k + shift0;
+    const bool valid = (x >= max(i, 0)) && (x < Wf + min(i, 0));
+    F8 v;
+    if (valid) {
+      const bool right = cb >= C / CB;
+      const int c0 = (right ? cb - C / CB : cb) * CB;
+      const float *src = (right ? R : L) + ((int64_t)b * C + c0) * HW + (int64_t)y * Wf + (right ? x - i : x);
+#pragma unroll
+      for (int c = 0; c < CB; ++c) v.v[c] = __ldg(src + c * HW);
+    } else {
+#pragma unroll
+      for (int c = 0; c < CB; ++c) v.v[c] = 0.f;
+    }
+    store8<T>(cost + idx * CB, v);
+  }
+}
+
+template <typename T>
+int launch_cost_volume_blocked(const float *L, const float *R, int B, int C, int Hf, int Wf, int mindisp, int D,
+                               T *cost, cudaStream_t s)
+{
+  const int64_t total = (int64_t)B * (2 * C / CB) * D * Hf * Wf;
+  if (total == 0) return IDISP_OK;
+  const int64_t want = ceil_div64(total, 256);
+  const int grid = (int)(want < 148 * 32 ? want : 148 * 32);
+  // Python floor division of a (possibly negative) multiple of 4
+  const int shift0 = mindisp >= 0 ? mindisp / 4 : -((-mindisp + 3) / 4);
+  cost_volume_blocked_kernel<T><<<grid, 256, 0, s>>>(L, R, B, C, Hf, Wf, shift0, D, cost);
+  IDISP_LAUNCH_CHECK();
+  return IDISP_OK;
+}
+template int launch_cost_volume_blocked<float>(const float *, const float *, int, int, int, int, int, int, float *, cudaStream_t);
+template int launch_cost_volume_blocked<__nv_bfloat16>(const float *, const float *, int, int, int, int, int, int, __nv_bfloat16 *, cudaStream_t);
+
+// ---------------- NCDHW f32 output (reference layout; C-ABI test hook) -----------------
+__global__ void __launch_bounds__(256)
+cost_volume_ncdhw_kernel(const float *__restrict__ L, const float *__restrict__ R, int B, int C, int Hf,
+                         int Wf, int shift0, int D, float *__restrict__ cost)
+{
+  const int64_t HW = (int64_t)Hf * Wf;
+  const int64_t total = (int64_t)B * 2 * C * D * HW;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % Wf);
+    const int y = (int)((idx / Wf) % Hf);
+    const int k = (int)((idx / HW) % D);
+    const int c = (int)((idx / (HW * D)) % (2 * C));
+    const int b = (int)(idx / (HW * D * 2 * C));
+    const int i = k + shift0;
+    const bool valid = (x >= max(i, 0)) && (x < Wf + min(i, 0));
+    float v = 0.f;
+    if (valid) {
+      v = c < C ? __ldg(L + ((int64_t)b * C + c) * HW + (int64_t)y * Wf + x)
+                : __ldg(R + ((int64_t)b * C + (c - C)) * HW + (int64_t)y * Wf + (x - i));
+    }
+    cost[idx] = v;
+  }
+}
+
+// ---------------- layout converters NCDHW f32 <-> blocked T ----------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+ncdhw_to_blocked_kernel(const float *__restrict__ src, T *__restrict__ dst, int B, int C, int64_t V)
+{
+  const int nblk = C / CB;
+  const int64_t total = (int64_t)B * nblk * V;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = idx % V;
+    const int cb = (int)((idx / V) % nblk);
+    const int b = (int)(idx / (V * nblk));
+    const float *s = src + ((int64_t)b * C + cb * CB) * V + v;
+    F8 r;
+#pragma unroll
+    for (int c = 0; c < CB; ++c) r.v[c] = __ldg(s + c * V);
+    store8<T>(dst + idx * CB, r);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+blocked_to_ncdhw_kernel(const T *__restrict__ src, float *__restrict__ dst, int B, int C, int64_t V)
+{
+  const int nblk = C / CB;
+  const int64_t total = (int64_t)B * nblk * V;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = idx % V;
+    const int cb = (int)((idx / V) % nblk);
+    const int b = (int)(idx / (V * nblk));
+    const F8 r = load8<T>(src + idx * CB);
+    float *d = dst + ((int64_t)b * C + cb * CB) * V + v;
+#pragma unroll
+    for (int c = 0; c < CB; ++c) d[c * V] = r.v[c];
+  }
+}
+
+template <typename T>
+int launch_ncdhw_to_blocked(const float *src, T *dst, int B, int C, int64_t V, cudaStream_t s)
+{
+  const int64_t total = (int64_t)B * (C / CB) * V;
+  if (total == 0) return IDISP_OK;
+  const int64_t want = ceil_div64(total, 256);
+  ncdhw_to_blocked_kernel<T><<<(int)(want < 148 * 32 ? want : 148 * 32), 256, 0, s>>>(src, dst, B, C, V);
+  IDISP_LAUNCH_CHECK();
+  return IDISP_OK;
+}
+template <typename T>
+int launch_blocked_to_ncdhw(const T *src, float *dst, int B, int C, int64_t V, cudaStream_t s)
+{
+  const int64_t total = (int64_t)B * (C / CB) * V;
+  if (total == 0) return IDISP_OK;
+  const int64_t want = ceil_div64(total, 256);
+  blocked_to_ncdhw_kernel<T><<<(int)(want < 148 * 32 ? want : 148 * 32), 256, 0, s>>>(src, dst, B, C, V);
+  IDISP_LAUNCH_CHECK();
+  return IDISP_OK;
+}
+template int launch_ncdhw_to_blocked<float>(const float *, float *, int, int, int64_t, cudaStream_t);
+template int launch_ncdhw_to_blocked<__nv_bfloat16>(const float *, __nv_bfloat16 *, int, int, int64_t, cudaStream_t);
+template int launch_blocked_to_ncdhw<float>(const float *, float *, int, int, int64_t, cudaStream_t);
+template int launch_blocked_to_ncdhw<__nv_bfloat16>(const __nv_bfloat16 *, float *, int, int, int64_t, cudaStream_t);
+
+}  // namespace idisp
+
+extern "C" int idisp_cost_volume(const float *left, const float *right, int B, int C, int Hf, int Wf,
+                                 int mindisp, int maxdisp, float *cost, void *stream)
+{
+  using namespace idisp;
+  IDISP_REQUIRE(B >= 0 && C > 0 && Hf > 0 && Wf > 0, "cost_volume: bad shape B=%d C=%d Hf=%d Wf=%d", B, C, Hf, Wf);
+  IDISP_REQUIRE(maxdisp > mindisp && mindisp % 4 == 0 && maxdisp % 4 == 0,
+                "cost_volume: mindisp=%d maxdisp=%d must be multiples of 4 with maxdisp>mindisp", mindisp, maxdisp);
+  const int D = (maxdisp - mindisp) / 4;
+  const int shift0 = mindisp >= 0 ? mindisp / 4 : -((-mindisp + 3) / 4);
+  IDISP_REQUIRE(-shift0 < Wf + 1 && shift0 + D - 1 < Wf + 1, "cost_volume: |shift| exceeds feature width %d", Wf);
+  if (B == 0) return IDISP_OK;
+  IDISP_REQUIRE(left && right && cost, "cost_volume: NULL pointer");
+  const int64_t total = (int64_t)B * 2 * C * D * Hf * Wf;
+  const int64_t want = ceil_div64(total, 256);
+  cost_volume_ncdhw_kernel<<<(int)(want < 148 * 32 ? want : 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+      left, right, B, C, Hf, Wf, shift0, D, cost);
+  IDISP_LAUNCH_CHECK();
+  return IDISP_OK;
+}

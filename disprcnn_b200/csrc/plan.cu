@@ -1,0 +1,490 @@
+// plan.cu -- host side of libidisp: error state, weight folding, the 28-layer forward schedule.
+//
+// Schedule and wiring follow disprcnn/modeling/psmnet/stackhourglass.py:130-144 (and the
+// hourglass at :32-51); layer inventory = SURVEY.md Appendix A.  Weights arrive under the
+// reference's own state_dict keys (stackhourglass.py:63-88), BatchNorm3d (eval, eps 1e-5,
+// submodule.py:22) is folded into a per-output-channel scale (multiplied into the kernel) and
+// bias.
+#include <map>
+#include <string>
+#include <vector>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+#include "conv3d_tc.cuh"
+
+namespace idisp {
+
+static thread_local std::string g_err;
+
+void set_error(const char *fmt, ...)
+{
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+  set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return IDISP_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------
+struct LayerSpec {
+  std::string prefix;
+  int kind, cin, cout;
+  bool bn;   // convbn_3d / deconv+BN (prefix.0.weight + prefix.1.*) vs bare Conv3d (prefix.weight)
+};
+
+struct LayerDev {
+  float *w_tap = nullptr;  // [27][cin][cout] f32, BN scale folded in
+  float *bias = nullptr;   // [cout] f32 (nullptr for the bare 32->1 convs)
+  TcWeights tc;            // bf16 re-lay for the tcgen05 kernel (IDISP_PREC_BF16 only)
+};
+
+static std::vector<LayerSpec> make_layers(int C)
+{
+  std::vector<LayerSpec> L;
+  L.push_back({"dres0.0", IDISP_CONV_S1, 2 * C, 32, true});
+  L.push_back({"dres0.2", IDISP_CONV_S1, 32, 32, true});
+  L.push_back({"dres1.0", IDISP_CONV_S1, 32, 32, true});
+  L.push_back({"dres1.2", IDISP_CONV_S1, 32, 32, true});
+  for (const char *h : {"dres2", "dres3", "dres4"}) {
+    const std::string p = h;
+    L.push_back({p + ".conv1.0", IDISP_CONV_S2, 32, 64, true});
+    L.push_back({p + ".conv2", IDISP_CONV_S1, 64, 64, true});
+    L.push_back({p + ".conv3.0", IDISP_CONV_S2, 64, 64, true});
+    L.push_back({p + ".conv4.0", IDISP_CONV_S1, 64, 64, true});
+    L.push_back({p + ".conv5", IDISP_DECONV_S2, 64, 64, true});
+    L.push_back({p + ".conv6", IDISP_DECONV_S2, 64, 32, true});
+  }
+  for (const char *c : {"classif1", "classif2", "classif3"}) L.push_back({std::string(c) + ".0", IDISP_CONV_S1, 32, 32, true});
+  for (const char *c : {"classif1", "classif2", "classif3"}) L.push_back({std::string(c) + ".2", IDISP_CONV_S1, 32, 1, false});
+  return L;
+}
+
+// re-lay a PyTorch conv kernel into tap-major [27][cin][cout] with an optional per-cout scale
+static void relayout_taps(const float *w, int kind, int cin, int cout, const double *scale, std::vector<float> &out)
+{
+  out.assign((size_t)27 * cin * cout, 0.f);
+  for (int co = 0; co < cout; ++co)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int t = 0; t < 27; ++t) {
+        const size_t src = kind == IDISP_DECONV_S2 ? ((size_t)ci * cout + co) * 27 + t   // [Cin][Cout][27]
+                                                   : ((size_t)co * cin + ci) * 27 + t;  // [Cout][Cin][27]
+        const double v = (double)w[src] * (scale ? scale[co] : 1.0);
+        out[((size_t)t * cin + ci) * cout + co] = (float)v;
+      }
+}
+
+}  // namespace idisp
+
+using namespace idisp;
+
+struct idisp_plan {
+  int C, mindisp, maxdisp, precision, D;
+  std::vector<LayerSpec> layers;
+  std::map<std::string, std::vector<float>> host;  // reference-keyed tensors
+  std::vector<LayerDev> dev;
+  float *blob = nullptr;  // one allocation behind all LayerDev f32 pointers
+  bool finalized = false;
+  // state of the last forward (for get_logits)
+  const float *last_logits = nullptr;
+  int last_B = 0, last_Hf = 0, last_Wf = 0;
+  int launches = 0;
+  // host-buffer entry point staging
+  void *stage = nullptr;
+  size_t stage_bytes = 0;
+  // optional per-launch CUDA-event timing (bench.py's roofline leg)
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> ev_layer;  // launch slot -> layer index (-1 cost volume, -2 soft-argmin, 25..27 the 32->1 convs)
+};
+
+extern "C" int idisp_version(void) { return IDISP_VERSION; }
+extern "C" const char *idisp_last_error(void) { return g_err.c_str(); }
+
+extern "C" int idisp_plan_create(int C, int mindisp, int maxdisp, int precision, idisp_plan_t **plan)
+{
+  IDISP_REQUIRE(plan != nullptr, "plan_create: NULL out pointer");
+  *plan = nullptr;
+  IDISP_REQUIRE(C > 0 && (2 * C) % 8 == 0, "plan_create: C=%d must make 2C a multiple of 8", C);
+  IDISP_REQUIRE(maxdisp > mindisp && mindisp % 4 == 0 && maxdisp % 4 == 0,
+                "plan_create: mindisp=%d maxdisp=%d must be multiples of 4, maxdisp>mindisp", mindisp, maxdisp);
+  IDISP_REQUIRE(((maxdisp - mindisp) / 4) % 4 == 0,
+                "plan_create: D=(maxdisp-mindisp)/4=%d must be a multiple of 4 (two stride-2 stages)", (maxdisp - mindisp) / 4);
+  IDISP_REQUIRE(precision == IDISP_PREC_FP32 || precision == IDISP_PREC_BF16, "plan_create: unknown precision %d", precision);
+  idisp_plan *p = new idisp_plan();
+  p->C = C; p->mindisp = mindisp; p->maxdisp = maxdisp; p->precision = precision;
+  p->D = (maxdisp - mindisp) / 4;
+  p->layers = make_layers(C);
+  *plan = p;
+  return IDISP_OK;
+}
+
+extern "C" void idisp_plan_destroy(idisp_plan_t *p)
+{
+  if (!p) return;
+  for (auto &d : p->dev) tc_weights_free(d.tc);
+  for (auto e : p->ev) cudaEventDestroy(e);
+  if (p->blob) cudaFree(p->blob);
+  if (p->stage) cudaFree(p->stage);
+  delete p;
+}
+
+extern "C" int idisp_plan_set_tensor(idisp_plan_t *p, const char *key, const float *data, size_t numel)
+{
+  IDISP_REQUIRE(p && key && (data || numel == 0), "plan_set_tensor: NULL argument");
+  const std::string k = key;
+  bool wanted = false;
+  for (const auto &L : p->layers) {
+    if (k.compare(0, L.prefix.size(), L.prefix) == 0 && k.size() > L.prefix.size() && k[L.prefix.size()] == '.') {
+      wanted = true;
+      break;
+    }
+  }
+  if (!wanted || (k.size() >= 19 && k.compare(k.size() - 19, 19, "num_batches_tracked") == 0)) return IDISP_OK;
+  p->host[k].assign(data, data + numel);
+  p->finalized = false;
+  return IDISP_OK;
+}
+
+static int need(idisp_plan *p, const std::string &key, size_t numel, const float **out)
+{
+  auto it = p->host.find(key);
+  if (it == p->host.end()) {
+    set_error("plan_finalize: missing state_dict entry '%s'", key.c_str());
+    return IDISP_ERR_STATE;
+  }
+  if (it->second.size() != numel) {
+    set_error("plan_finalize: '%s' has %zu elements, expected %zu", key.c_str(), it->second.size(), numel);
+    return IDISP_ERR_STATE;
+  }
+  *out = it->second.data();
+  return IDISP_OK;
+}
+
+extern "C" int idisp_plan_finalize(idisp_plan_t *p, void *stream)
+{
+  IDISP_REQUIRE(p != nullptr, "plan_finalize: NULL plan");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t nl = p->layers.size();
+  std::vector<std::vector<float>> wt(nl), bs(nl);
+  size_t total = 0;
+  for (size_t i = 0; i < nl; ++i) {
+    const LayerSpec &L = p->layers[i];
+    const float *w = nullptr;
+    int rc;
+    std::vector<double> scale(L.cout, 1.0);
+    if (L.bn) {
+      const float *g, *b, *m, *v;
+      if ((rc = need(p, L.prefix + ".0.weight", (size_t)27 * L.cin * L.cout, &w))) return rc;
+      if ((rc = need(p, L.prefix + ".1.weight", L.cout, &g))) return rc;
+      if ((rc = need(p, L.prefix + ".1.bias", L.cout, &b))) return rc;
+      if ((rc = need(p, L.prefix + ".1.running_mean", L.cout, &m))) return rc;
+      if ((rc = need(p, L.prefix + ".1.running_var", L.cout, &v))) return rc;
+      bs[i].resize(L.cout);
+      for (int c = 0; c < L.cout; ++c) {
+        scale[c] = (double)g[c] / std::sqrt((double)v[c] + 1e-5);
+        bs[i][c] = (float)((double)b[c] - (double)m[c] * scale[c]);
+      }
+    } else {
+      if ((rc = need(p, L.prefix + ".weight", (size_t)27 * L.cin * L.cout, &w))) return rc;
+    }
+    relayout_taps(w, L.kind, L.cin, L.cout, L.bn ? scale.data() : nullptr, wt[i]);
+    total += (wt[i].size() + 63) / 64 * 64 + (bs[i].size() + 63) / 64 * 64;
+  }
+  for (auto &d : p->dev) tc_weights_free(d.tc);
+  if (p->blob) { cudaFree(p->blob); p->blob = nullptr; }
+  IDISP_CUDA(cudaMalloc(&p->blob, total * sizeof(float)));
+  p->dev.assign(nl, LayerDev());
+  size_t off = 0;
+  for (size_t i = 0; i < nl; ++i) {
+    p->dev[i].w_tap = p->blob + off;
+    IDISP_CUDA(cudaMemcpyAsync(p->dev[i].w_tap, wt[i].data(), wt[i].size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    off += (wt[i].size() + 63) / 64 * 64;
+    if (!bs[i].empty()) {
+      p->dev[i].bias = p->blob + off;
+      IDISP_CUDA(cudaMemcpyAsync(p->dev[i].bias, bs[i].data(), bs[i].size() * sizeof(float), cudaMemcpyHostToDevice, s));
+      off += (bs[i].size() + 63) / 64 * 64;
+    }
+    if (p->precision == IDISP_PREC_BF16) {
+      const LayerSpec &L = p->layers[i];
+      int rc = tc_weights_prepare(wt[i].data(), L.kind, L.cin, L.cout, p->dev[i].tc, s);
+      if (rc) return rc;
+    }
+  }
+  IDISP_CUDA(cudaStreamSynchronize(s));  // host vectors go out of scope
+  p->finalized = true;
+  return IDISP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// workspace arena (same code computes the size and hands out the pointers)
+// ---------------------------------------------------------------------------------------
+namespace {
+struct Arena {
+  char *base;
+  size_t off = 0;
+  explicit Arena(void *b) : base((char *)b) {}
+  void *take(size_t bytes)
+  {
+    void *p = base ? base + off : nullptr;
+    off += (bytes + 1023) / 1024 * 1024;
+    return p;
+  }
+};
+
+struct Buffers {
+  void *cv, *a, *t0, *cost0, *out, *c;       // full resolution
+  void *h1, *pre1, *prek, *postA, *postB;    // half resolution, 64 ch
+  void *q1, *q2;                             // quarter resolution, 64 ch
+  float *costX, *costY;                      // 1-channel f32 logits
+};
+
+Buffers carve(Arena &A, int C, int B, int D, int Hf, int Wf, size_t esz)
+{
+  const size_t V = (size_t)D * Hf * Wf;
+  const size_t full32 = (size_t)B * 32 * V * esz, half64 = (size_t)B * 64 * (V / 8) * esz, quart64 = (size_t)B * 64 * (V / 64) * esz;
+  Buffers b;
+  b.cv = A.take((size_t)B * 2 * C * V * esz);
+  b.a = A.take(full32); b.t0 = A.take(full32); b.cost0 = A.take(full32); b.out = A.take(full32); b.c = A.take(full32);
+  b.h1 = A.take(half64); b.pre1 = A.take(half64); b.prek = A.take(half64); b.postA = A.take(half64); b.postB = A.take(half64);
+  b.q1 = A.take(quart64); b.q2 = A.take(quart64);
+  b.costX = (float *)A.take((size_t)B * V * 4); b.costY = (float *)A.take((size_t)B * V * 4);
+  return b;
+}
+}  // namespace
+
+extern "C" size_t idisp_plan_workspace_bytes(const idisp_plan_t *p, int B, int Hf, int Wf)
+{
+  if (!p || B <= 0 || Hf <= 0 || Wf <= 0) return 0;
+  Arena A(nullptr);
+  carve(A, p->C, B, p->D, Hf, Wf, p->precision == IDISP_PREC_FP32 ? 4 : 2);
+  return A.off;
+}
+
+template <typename T>
+static int forward_impl(idisp_plan *p, const float *left, const float *right, int B, int Hf, int Wf, int H, int W,
+                        void *workspace, float *out, cudaStream_t s)
+{
+  const int D = p->D, C = p->C;
+  Arena A(workspace);
+  Buffers b = carve(A, C, B, D, Hf, Wf, sizeof(T));
+  int launches = 0;
+  int rc;
+  if (p->timing) p->ev_layer.clear();
+  auto mark = [&](int layer) {  // record an event BEFORE launch slot `launches`
+    if (!p->timing) return;
+    if ((int)p->ev.size() <= launches) { cudaEvent_t e; cudaEventCreate(&e); p->ev.push_back(e); }
+    cudaEventRecord(p->ev[launches], s);
+    if (layer != -99) p->ev_layer.push_back(layer);
+  };
+  auto conv = [&](int li, const void *x, int d, int h, int w, const void *res, int relu, void *y) -> int {
+    const LayerSpec &L = p->layers[li];
+    mark(li);
+    ++launches;
+    if (std::is_same<T, __nv_bfloat16>::value && tc_supported(L.kind, L.cin, L.cout, d, h, w))
+      return tc_conv3d(p->dev[li].tc, (const __nv_bfloat16 *)x, B, L.cin, d, h, w, L.cout, L.kind, p->dev[li].bias,
+                       (const __nv_bfloat16 *)res, relu, (__nv_bfloat16 *)y, s);
+    return launch_conv3d_simt<T>((const T *)x, B, L.cin, d, h, w, p->dev[li].w_tap, L.cout, L.kind, p->dev[li].bias,
+                                 (const T *)res, relu, (T *)y, s);
+  };
+#define RUN(expr) do { if ((rc = (expr)) != IDISP_OK) return rc; } while (0)
+  // cost volume (stackhourglass.py:115-128)
+  mark(-1);
+  RUN(launch_cost_volume_blocked<T>(left, right, B, C, Hf, Wf, p->mindisp, D, (T *)b.cv, s)); ++launches;
+  // dres0, dres1 (:130-131)
+  RUN(conv(0, b.cv, D, Hf, Wf, nullptr, 1, b.a));
+  RUN(conv(1, b.a, D, Hf, Wf, nullptr, 1, b.t0));
+  RUN(conv(2, b.t0, D, Hf, Wf, nullptr, 1, b.a));
+  RUN(conv(3, b.a, D, Hf, Wf, b.t0, 0, b.cost0));
+  // three hourglasses (:133-140); `x` is cost0 / out1 / out2, all outputs land in b.out
+  const int D2 = D / 2, H2 = Hf / 2, W2 = Wf / 2, D4 = D / 4, H4 = Hf / 4, W4 = Wf / 4;
+  for (int k = 0; k < 3; ++k) {
+    const int l0 = 4 + 6 * k;
+    const void *x = k == 0 ? b.cost0 : b.out;
+    void *pre = k == 0 ? b.pre1 : b.prek;
+    const void *postsqu = k == 0 ? nullptr : (k == 1 ? b.postA : b.postB);  // post1 / post2
+    void *post = k == 1 ? b.postB : b.postA;                                  // post1,post3 -> A; post2 -> B
+    const void *presqu = k == 0 ? b.pre1 /* own pre */ : b.pre1;              // pre1 for dres3 AND dres4 (:136,:139)
+    RUN(conv(l0 + 0, x, D, Hf, Wf, nullptr, 1, b.h1));
+    RUN(conv(l0 + 1, b.h1, D2, H2, W2, postsqu, 1, pre));
+    RUN(conv(l0 + 2, pre, D2, H2, W2, nullptr, 1, b.q1));
+    RUN(conv(l0 + 3, b.q1, D4, H4, W4, nullptr, 1, b.q2));
+    RUN(conv(l0 + 4, b.q2, D4, H4, W4, presqu, 1, post));
+    RUN(conv(l0 + 5, post, D2, H2, W2, b.cost0, 0, b.out));
+    // classifier head k on out_k (:142-144), running sum fused
+    RUN(conv(22 + k, b.out, D, Hf, Wf, nullptr, 1, b.c));
+    float *dst = (k == 1) ? b.costY : b.costX;
+    const float *prev = k == 0 ? nullptr : (k == 1 ? b.costX : b.costY);
+    mark(25 + k);
+    RUN(launch_conv3d_to1<T>((const T *)b.c, B, 32, D, Hf, Wf, p->dev[25 + k].w_tap, prev, dst, s)); ++launches;
+  }
+  // upsample + softmax + regression (:169-174)
+  mark(-2);
+  RUN(launch_softargmin(b.costX, B, D, Hf, Wf, p->mindisp, p->maxdisp, H, W, out, s)); ++launches;
+  mark(-99);  // closing event
+#undef RUN
+  p->last_logits = b.costX; p->last_B = B; p->last_Hf = Hf; p->last_Wf = Wf;
+  p->launches = launches;
+  return IDISP_OK;
+}
+
+extern "C" int idisp_plan_forward(idisp_plan_t *p, const float *left, const float *right, int B, int Hf, int Wf,
+                                  int H, int W, void *workspace, size_t workspace_bytes, float *out, void *stream)
+{
+  IDISP_REQUIRE(p != nullptr, "plan_forward: NULL plan");
+  if (!p->finalized) { set_error("plan_forward: plan not finalised (call idisp_plan_finalize after loading weights)"); return IDISP_ERR_STATE; }
+  IDISP_REQUIRE(B >= 0 && Hf > 0 && Wf > 0 && H >= Hf && W >= Wf, "plan_forward: bad shape B=%d Hf=%d Wf=%d H=%d W=%d", B, Hf, Wf, H, W);
+  IDISP_REQUIRE(Hf % 4 == 0 && Wf % 4 == 0, "plan_forward: Hf=%d, Wf=%d must be multiples of 4 (stackhourglass.py:34-49)", Hf, Wf);
+  if (B == 0) return IDISP_OK;
+  IDISP_REQUIRE(left && right && out && workspace, "plan_forward: NULL pointer");
+  const size_t needb = idisp_plan_workspace_bytes(p, B, Hf, Wf);
+  IDISP_REQUIRE(workspace_bytes >= needb, "plan_forward: workspace %zu B < required %zu B", workspace_bytes, needb);
+  if (p->precision == IDISP_PREC_FP32)
+    return forward_impl<float>(p, left, right, B, Hf, Wf, H, W, workspace, out, (cudaStream_t)stream);
+  return forward_impl<__nv_bfloat16>(p, left, right, B, Hf, Wf, H, W, workspace, out, (cudaStream_t)stream);
+}
+
+extern "C" int idisp_plan_forward_host(idisp_plan_t *p, const float *left_host, const float *right_host, int B,
+                                       int Hf, int Wf, int H, int W, float *out_host, void *stream)
+{
+  IDISP_REQUIRE(p != nullptr, "plan_forward_host: NULL plan");
+  if (B == 0) return IDISP_OK;
+  IDISP_REQUIRE(left_host && right_host && out_host && B > 0 && Hf > 0 && Wf > 0 && H > 0 && W > 0, "plan_forward_host: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t fea = (size_t)B * p->C * Hf * Wf * sizeof(float), outb = (size_t)B * H * W * sizeof(float);
+  const size_t ws = idisp_plan_workspace_bytes(p, B, Hf, Wf);
+  auto up = [](size_t x) { return (x + 1023) / 1024 * 1024; };
+  const size_t total = up(fea) * 2 + up(outb) + ws;
+  if (total > p->stage_bytes) {
+    IDISP_CUDA(cudaStreamSynchronize(s));
+    if (p->stage) cudaFree(p->stage);
+    p->stage = nullptr; p->stage_bytes = 0;
+    IDISP_CUDA(cudaMalloc(&p->stage, total));
+    p->stage_bytes = total;
+  }
+  char *base = (char *)p->stage;
+  float *dl = (float *)base, *dr = (float *)(base + up(fea)), *dout = (float *)(base + 2 * up(fea));
+  void *wsp = base + 2 * up(fea) + up(outb);
+  IDISP_CUDA(cudaMemcpyAsync(dl, left_host, fea, cudaMemcpyHostToDevice, s));
+  IDISP_CUDA(cudaMemcpyAsync(dr, right_host, fea, cudaMemcpyHostToDevice, s));
+  int rc = idisp_plan_forward(p, dl, dr, B, Hf, Wf, H, W, wsp, ws, dout, stream);
+  if (rc) return rc;
+  IDISP_CUDA(cudaMemcpyAsync(out_host, dout, outb, cudaMemcpyDeviceToHost, s));
+  return IDISP_OK;
+}
+
+extern "C" int idisp_plan_get_logits(idisp_plan_t *p, float *logits, void *stream)
+{
+  IDISP_REQUIRE(p && logits, "plan_get_logits: NULL argument");
+  if (!p->last_logits) { set_error("plan_get_logits: no forward has run on this plan"); return IDISP_ERR_STATE; }
+  IDISP_CUDA(cudaMemcpyAsync(logits, p->last_logits, (size_t)p->last_B * p->D * p->last_Hf * p->last_Wf * sizeof(float),
+                             cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return IDISP_OK;
+}
+
+extern "C" int idisp_plan_launches_per_forward(const idisp_plan_t *p) { return p ? p->launches : 0; }
+
+extern "C" int idisp_plan_enable_timing(idisp_plan_t *p, int on)
+{
+  IDISP_REQUIRE(p != nullptr, "plan_enable_timing: NULL plan");
+  p->timing = on != 0;
+  return IDISP_OK;
+}
+
+extern "C" int idisp_plan_get_timing(idisp_plan_t *p, float *ms, int *layer, int capacity)
+{
+  IDISP_REQUIRE(p && ms && layer, "plan_get_timing: NULL argument");
+  const int n = (int)p->ev_layer.size();
+  if (!p->timing || n == 0 || (int)p->ev.size() < n + 1) { set_error("plan_get_timing: no timed forward on this plan"); return IDISP_ERR_STATE; }
+  IDISP_REQUIRE(capacity >= n, "plan_get_timing: capacity %d < %d launches", capacity, n);
+  IDISP_CUDA(cudaEventSynchronize(p->ev[n]));
+  for (int i = 0; i < n; ++i) {
+    IDISP_CUDA(cudaEventElapsedTime(&ms[i], p->ev[i], p->ev[i + 1]));
+    layer[i] = p->ev_layer[i];
+  }
+  return IDISP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// per-layer test hook (NCDHW f32 in/out)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+static int conv3d_hook(const float *x, int B, int Cin, int D, int H, int W, const std::vector<float> &w_tap, int Cout,
+                       int kind, const std::vector<float> &bias, const float *residual, int relu, int precision,
+                       float *y, cudaStream_t s)
+{
+  int Do = D, Ho = H, Wo = W;
+  if (kind == IDISP_CONV_S2) { Do = (D + 1) / 2; Ho = (H + 1) / 2; Wo = (W + 1) / 2; }
+  if (kind == IDISP_DECONV_S2) { Do = 2 * D; Ho = 2 * H; Wo = 2 * W; }
+  const int64_t Vi = (int64_t)D * H * W, Vo = (int64_t)Do * Ho * Wo;
+  T *xb = nullptr, *yb = nullptr, *rb = nullptr;
+  float *wd = nullptr, *bd = nullptr, *y1 = nullptr;
+  int rc = IDISP_OK;
+  TcWeights tcw;
+  auto cleanup = [&]() { cudaFree(xb); cudaFree(yb); cudaFree(rb); cudaFree(wd); cudaFree(bd); cudaFree(y1); tc_weights_free(tcw); };
+#define HK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #expr, __FILE__, __LINE__); } } while (0)
+#define HR(expr) do { if ((rc = (expr)) != IDISP_OK) { cudaStreamSynchronize(s); cleanup(); return rc; } } while (0)
+  HK(cudaMalloc(&xb, (size_t)B * Cin * Vi * sizeof(T)));
+  HK(cudaMalloc(&wd, w_tap.size() * sizeof(float)));
+  HK(cudaMemcpyAsync(wd, w_tap.data(), w_tap.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+  HK(cudaMalloc(&bd, bias.size() * sizeof(float)));
+  HK(cudaMemcpyAsync(bd, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+  HR(launch_ncdhw_to_blocked<T>(x, xb, B, Cin, Vi, s));
+  if (Cout == 1) {
+    HR(launch_conv3d_to1<T>(xb, B, Cin, D, H, W, wd, residual, y, s));
+    // bias/relu for the 1-channel hook are not part of any reference layer
+  } else {
+    HK(cudaMalloc(&yb, (size_t)B * Cout * Vo * sizeof(T)));
+    if (residual) {
+      HK(cudaMalloc(&rb, (size_t)B * Cout * Vo * sizeof(T)));
+      HR(launch_ncdhw_to_blocked<T>(residual, rb, B, Cout, Vo, s));
+    }
+    if (precision == IDISP_PREC_BF16 && tc_supported(kind, Cin, Cout, D, H, W)) {
+      HR(tc_weights_prepare(w_tap.data(), kind, Cin, Cout, tcw, s));
+      HR(tc_conv3d(tcw, (const __nv_bfloat16 *)xb, B, Cin, D, H, W, Cout, kind, bd, (const __nv_bfloat16 *)rb, relu,
+                   (__nv_bfloat16 *)yb, s));
+    } else {
+      HR(launch_conv3d_simt<T>(xb, B, Cin, D, H, W, wd, Cout, kind, bd, rb, relu, yb, s));
+    }
+    HR(launch_blocked_to_ncdhw<T>(yb, y, B, Cout, Vo, s));
+  }
+  HK(cudaStreamSynchronize(s));
+  cleanup();
+#undef HK
+#undef HR
+  return IDISP_OK;
+}
+
+extern "C" int idisp_conv3d(const float *x, int B, int Cin, int D, int H, int W, const float *weight, int Cout, int kind,
+                            const float *scale, const float *bias, const float *residual, int relu, int precision,
+                            float *y, void *stream)
+{
+  IDISP_REQUIRE(B >= 0 && Cin > 0 && Cin % 8 == 0 && D > 0 && H > 0 && W > 0, "conv3d: bad input shape B=%d Cin=%d D=%d H=%d W=%d", B, Cin, D, H, W);
+  IDISP_REQUIRE(Cout == 1 || Cout % 8 == 0, "conv3d: Cout=%d must be 1 or a multiple of 8", Cout);
+  IDISP_REQUIRE(kind == IDISP_CONV_S1 || kind == IDISP_CONV_S2 || kind == IDISP_DECONV_S2, "conv3d: unknown kind %d", kind);
+  IDISP_REQUIRE(precision == IDISP_PREC_FP32 || precision == IDISP_PREC_BF16, "conv3d: unknown precision %d", precision);
+  IDISP_REQUIRE(Cout != 1 || (kind == IDISP_CONV_S1 && !scale && !bias && !relu), "conv3d: the 1-channel conv is stride-1, no affine, no ReLU");
+  if (B == 0) return IDISP_OK;
+  IDISP_REQUIRE(x && weight && y, "conv3d: NULL pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t wn = (size_t)27 * Cin * Cout;
+  std::vector<float> hw(wn), hs(Cout, 1.f), hb(Cout, 0.f);
+  IDISP_CUDA(cudaStreamSynchronize(s));
+  IDISP_CUDA(cudaMemcpy(hw.data(), weight, wn * sizeof(float), cudaMemcpyDeviceToHost));
+  if (scale) IDISP_CUDA(cudaMemcpy(hs.data(), scale, Cout * sizeof(float), cudaMemcpyDeviceToHost));
+  if (bias) IDISP_CUDA(cudaMemcpy(hb.data(), bias, Cout * sizeof(float), cudaMemcpyDeviceToHost));
+  std::vector<double> sc(hs.begin(), hs.end());
+  std::vector<float> w_tap;
+  relayout_taps(hw.data(), kind, Cin, Cout, sc.data(), w_tap);
+  if (precision == IDISP_PREC_FP32)
+    return conv3d_hook<float>(x, B, Cin, D, H, W, w_tap, Cout, kind, hb, residual, relu, precision, y, s);
+  return conv3d_hook<__nv_bfloat16>(x, B, Cin, D, H, W, w_tap, Cout, kind, hb, residual, relu, precision, y, s);
+}

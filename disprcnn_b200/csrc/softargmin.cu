@@ -1,0 +1,93 @@
+// softargmin.cu -- fused trilinear upsample (align_corners) + softmax over disparity + expectation.
+//
+// Replaces disprcnn/modeling/psmnet/stackhourglass.py:169-172 (F.interpolate to
+// [maxdisp-mindisp, H, W], squeeze, F.softmax(dim=1)) and submodule.py:51-57
+// (disparityregression).  The reference materialises the upsampled volume, the softmax and a
+// repeated disparity ramp -- 3 x 154 MB per ROI at BASELINE config 2; here the logits
+// [B,D,Hf,Wf] (2.4 MB/ROI) are read through L1/L2 and only the [B,H,W] map (0.8 MB/ROI) is
+// written, so algorithmic bytes = 4*(V + H*W) per ROI and the work is 4D exp per pixel (SFU).
+//
+// Interpolation follows ATen's upsample_trilinear3d exactly: per axis
+// scale=(in-1)/(out-1) in f32, src=scale*o, i0=(int)src, i1=min(i0+1,in-1), l1=src-i0, l0=1-l1,
+// blend nested x -> y -> d.  One thread owns one output pixel: it bilinearly samples the D
+// low-resolution planes at (y,x) (warp-coalesced: 4 neighbouring pixels share their corners),
+// takes their maximum as the softmax stabiliser (an upper bound of every interpolated logit),
+// then streams the 4D output disparities keeping two adjacent plane samples in registers.
+#include "common.cuh"
+
+namespace idisp {
+
+__global__ void __launch_bounds__(256)
+softargmin_kernel(const float *__restrict__ logits, int B, int D, int Hf, int Wf, int mindisp, int Dfull, int H,
+                  int W, float *__restrict__ out)
+{
+  const int64_t total = (int64_t)B * H * W;
+  const float sd = Dfull > 1 ? (float)(D - 1) / (float)(Dfull - 1) : 0.f;
+  const float sh = H > 1 ? (float)(Hf - 1) / (float)(H - 1) : 0.f;
+  const float sw = W > 1 ? (float)(Wf - 1) / (float)(W - 1) : 0.f;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % W);
+    const int y = (int)((idx / W) % H);
+    const int b = (int)(idx / ((int64_t)W * H));
+    const float fy = sh * (float)y, fx = sw * (float)x;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < Hf - 1 ? 1 : 0), x1 = x0 + (x0 < Wf - 1 ? 1 : 0);
+    const float ly1 = fy - (float)y0, ly0 = 1.f - ly1;
+    const float lx1 = fx - (float)x0, lx0 = 1.f - lx1;
+    const float *base = logits + (int64_t)b * D * Hf * Wf;
+    const int o00 = y0 * Wf + x0, o01 = y0 * Wf + x1, o10 = y1 * Wf + x0, o11 = y1 * Wf + x1;
+    const int plane = Hf * Wf;
+    auto sample = [&](int k) {
+      const float *p = base + (int64_t)k * plane;
+      return ly0 * (lx0 * __ldg(p + o00) + lx1 * __ldg(p + o01)) + ly1 * (lx0 * __ldg(p + o10) + lx1 * __ldg(p + o11));
+    };
+    float m = -INFINITY;
+    for (int k = 0; k < D; ++k) m = fmaxf(m, sample(k));
+    float s = 0.f, t = 0.f;
+    int k0 = 0;
+    float p0 = sample(0), p1 = sample(D > 1 ? 1 : 0);
+    for (int d = 0; d < Dfull; ++d) {
+      const float fd = sd * (float)d;
+      const int d0 = (int)fd;
+      if (d0 != k0) {  // advances by at most one plane per step (scale < 1)
+        k0 = d0;
+        p0 = p1;
+        p1 = sample(d0 + (d0 < D - 1 ? 1 : 0));
+      }
+      const float l1 = fd - (float)d0, l0 = 1.f - l1;
+      const float v = l0 * p0 + l1 * p1;
+      const float e = __expf(v - m);
+      s += e;
+      t = fmaf(e, (float)(mindisp + d), t);
+    }
+    out[idx] = t / s;
+  }
+}
+
+int launch_softargmin(const float *logits, int B, int D, int Hf, int Wf, int mindisp, int maxdisp, int H, int W,
+                      float *out, cudaStream_t s)
+{
+  const int64_t total = (int64_t)B * H * W;
+  if (total == 0) return IDISP_OK;
+  const int64_t want = ceil_div64(total, 256);
+  softargmin_kernel<<<(int)(want < 148 * 64 ? want : 148 * 64), 256, 0, s>>>(logits, B, D, Hf, Wf, mindisp,
+                                                                              maxdisp - mindisp, H, W, out);
+  IDISP_LAUNCH_CHECK();
+  return IDISP_OK;
+}
+
+}  // namespace idisp
+
+extern "C" int idisp_softargmin(const float *logits, int B, int D, int Hf, int Wf, int mindisp, int maxdisp, int H,
+                                int W, float *out, void *stream)
+{
+  using namespace idisp;
+  IDISP_REQUIRE(B >= 0 && D > 0 && Hf > 0 && Wf > 0 && H > 0 && W > 0 && maxdisp > mindisp,
+                "softargmin: bad shape B=%d D=%d Hf=%d Wf=%d H=%d W=%d disp=[%d,%d)", B, D, Hf, Wf, H, W, mindisp, maxdisp);
+  // trilinear UP-sampling only (scale <= 1 per axis), which is all the reference does (:169)
+  IDISP_REQUIRE(maxdisp - mindisp >= D && H >= Hf && W >= Wf, "softargmin: output must not be smaller than the logits");
+  if (B == 0) return IDISP_OK;
+  IDISP_REQUIRE(logits && out, "softargmin: NULL pointer");
+  return launch_softargmin(logits, B, D, Hf, Wf, mindisp, maxdisp, H, W, out, (cudaStream_t)stream);
+}

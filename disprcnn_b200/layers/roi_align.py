@@ -1,0 +1,93 @@
+"""ROIAlign operator -- same names, arguments and error behaviour as disprcnn/layers/roi_align.py:13-73.
+
+``roi_align(input, roi, output_size, spatial_scale, sampling_ratio)`` and
+``ROIAlign(output_size, spatial_scale, sampling_ratio).forward(input, rois, spatial_scale=None)``
+call ``idisp_roi_align_forward`` (include/idisp.h) on the current CUDA stream.  The output is a
+fresh tensor, inputs are made contiguous inside (reference: ROIAlign_cuda.cu:271,286,294).
+Backward raises ``RuntimeError`` exactly like the reference's non-CUDA build
+(csrc/ROIAlign.h:44): this is the inference path.
+"""
+import torch
+from torch import nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+from torch.nn.modules.utils import _pair
+
+from .. import _lib
+
+
+def roi_align_forward(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio, mean=None, std=None):
+    """Functional twin of ``disprcnn._C.roi_align_forward`` (csrc/vision.cpp:9) with an optional
+    fused per-channel ``(x - mean) / std`` (disprcnn3d.py:47-49)."""
+    _lib.require_cuda(input, rois, mean, std)
+    if input.dtype != torch.float32 or rois.dtype != torch.float32:
+        raise RuntimeError('roi_align: float32 tensors expected')
+    if rois.dim() != 2 or rois.size(1) != 5:
+        raise RuntimeError('roi_align: rois must be [R,5] (batch_idx,x1,y1,x2,y2)')
+    if input.device != rois.device:
+        raise RuntimeError('roi_align: input and rois must be on the same device')
+    input = input.contiguous()
+    rois = rois.contiguous()
+    N, C, H, W = input.shape
+    R = rois.size(0)
+    out = torch.empty((R, C, pooled_h, pooled_w), dtype=input.dtype, device=input.device)
+    if out.numel() == 0:
+        return out
+    if mean is not None:
+        mean, std = mean.contiguous().float(), std.contiguous().float()
+    with torch.cuda.device(input.device):
+        _lib.check(_lib.load().idisp_roi_align_forward(
+            _lib.ptr(input), N, C, H, W, _lib.ptr(rois), R, float(spatial_scale), int(pooled_h), int(pooled_w),
+            int(sampling_ratio), _lib.ptr(mean), _lib.ptr(std), _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+class _ROIAlign(Function):
+    @staticmethod
+    def forward(ctx, input, roi, output_size, spatial_scale, sampling_ratio):
+        ctx.save_for_backward(roi)
+        ctx.output_size = _pair(output_size)
+        ctx.spatial_scale = spatial_scale
+        ctx.sampling_ratio = sampling_ratio
+        ctx.input_shape = input.size()
+        oh, ow = _pair(output_size)
+        return roi_align_forward(input, roi, spatial_scale, oh, ow, sampling_ratio)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        raise RuntimeError('roi_align backward: not implemented on the B200 inference path '
+                           '(reference: csrc/ROIAlign.h:44 raises for its non-CUDA build)')
+
+
+roi_align = _ROIAlign.apply
+
+
+class ROIAlign(nn.Module):
+    def __init__(self, output_size, spatial_scale, sampling_ratio):
+        super().__init__()
+        self.output_size = output_size
+        self.spatial_scale = spatial_scale
+        self.sampling_ratio = sampling_ratio
+
+    def forward(self, input, rois, spatial_scale=None):
+        if spatial_scale is None:
+            spatial_scale = self.spatial_scale
+        return roi_align(input, rois, self.output_size, spatial_scale, self.sampling_ratio)
+
+    def __repr__(self):
+        return (f'{self.__class__.__name__}(output_size={self.output_size}, '
+                f'spatial_scale={self.spatial_scale}, sampling_ratio={self.sampling_ratio})')
+
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def crop_and_transform_roi_img(im, rois, resolution=224):
+    """Fused form of DispRCNN3D.crop_and_transform_roi_img (disprcnn3d.py:44-50):
+    ROIAlign((res,res), 1.0, 0) on the raw image + ImageNet normalisation in ONE kernel."""
+    rois = torch.as_tensor(rois, dtype=torch.float32, device=im.device).reshape(-1, 5)
+    mean = torch.tensor(IMAGENET_MEAN, dtype=torch.float32, device=im.device)
+    std = torch.tensor(IMAGENET_STD, dtype=torch.float32, device=im.device)
+    return roi_align_forward(im, rois, 1.0, resolution, resolution, 0, mean, std)

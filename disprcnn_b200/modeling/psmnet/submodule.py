@@ -1,0 +1,107 @@
+"""Building blocks of iDispNet -- API mirror of disprcnn/modeling/psmnet/submodule.py.
+
+``convbn_3d`` (submodule.py:19-22) and ``disparityregression`` (:51-57) are the hot-path names;
+``feature_extraction`` (:60-139) is the adjacent 2-D extractor ("next" row):
+it is kept as plain torch modules with the reference's parameter names so reference
+checkpoints load, and runs through torch until its own kernels land.
+
+The 3-D modules built here are PARAMETER HOLDERS with the reference's ``state_dict`` layout; in
+eval mode on a GPU their arithmetic is executed by libidisp (see stackhourglass.PSMNet).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import _lib
+
+
+def convbn(in_planes, out_planes, kernel_size, stride, pad, dilation):
+    conv = nn.Conv2d(in_planes, out_planes, kernel_size, stride, dilation if dilation > 1 else pad, dilation,
+                     bias=False)
+    return nn.Sequential(conv, nn.BatchNorm2d(out_planes))
+
+
+def convbn_3d(in_planes, out_planes, kernel_size, stride, pad):
+    conv = nn.Conv3d(in_planes, out_planes, kernel_size, stride, pad, bias=False)
+    return nn.Sequential(conv, nn.BatchNorm3d(out_planes))
+
+
+def disparityregression(x, maxdisp, mindisp=0):
+    """Expectation over disparity of a probability volume [B, maxdisp-mindisp, H, W] (submodule.py:51-57).
+
+    Kept for API compatibility (training scripts call it on softmax outputs); the eval path of
+    PSMNet never materialises ``x`` -- it uses the fused ``soft_argmin`` below."""
+    assert x.shape[1] == int(maxdisp - mindisp)
+    disp = torch.arange(mindisp, maxdisp, dtype=x.dtype, device=x.device).view(1, -1, 1, 1)
+    return (x * disp).sum(1)
+
+
+def soft_argmin(logits, mindisp, maxdisp, H, W):
+    """Fused F.interpolate(trilinear, align_corners) + softmax + disparityregression
+    (stackhourglass.py:169-172 + submodule.py:51-57) through ``idisp_softargmin``.
+    logits [B,D,Hf,Wf] or [B,1,D,Hf,Wf] f32 CUDA -> [B,H,W]."""
+    _lib.require_cuda(logits)
+    if logits.dim() == 5:
+        logits = logits.squeeze(1)
+    logits = logits.contiguous().float()
+    B, D, Hf, Wf = logits.shape
+    out = torch.empty((B, H, W), dtype=torch.float32, device=logits.device)
+    with torch.cuda.device(logits.device):
+        _lib.check(_lib.load().idisp_softargmin(_lib.ptr(logits), B, D, Hf, Wf, int(mindisp), int(maxdisp), int(H),
+                                               int(W), _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride, downsample, pad, dilation):
+        super().__init__()
+        self.conv1 = nn.Sequential(convbn(inplanes, planes, 3, stride, pad, dilation), nn.ReLU(inplace=True))
+        self.conv2 = convbn(planes, planes, 3, 1, pad, dilation)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        y = self.conv2(self.conv1(x))
+        return y + (x if self.downsample is None else self.downsample(x))
+
+
+class feature_extraction(nn.Module):
+    """2-D CNN + SPP, 3 -> 32 channels at 1/4 resolution (parameter names of submodule.py:60-110)."""
+
+    _SPP = ((56, 'branch1'), (32, 'branch2'), (16, 'branch3'), (8, 'branch4'))
+
+    def __init__(self):
+        super().__init__()
+        self.inplanes = 32
+        relu = lambda: nn.ReLU(inplace=True)
+        self.firstconv = nn.Sequential(convbn(3, 32, 3, 2, 1, 1), relu(), convbn(32, 32, 3, 1, 1, 1), relu(),
+                                       convbn(32, 32, 3, 1, 1, 1), relu())
+        self.layer1 = self._stage(32, 3, 1, 1, 1)
+        self.layer2 = self._stage(64, 16, 2, 1, 1)
+        self.layer3 = self._stage(128, 3, 1, 1, 1)
+        self.layer4 = self._stage(128, 3, 1, 1, 2)
+        for k, name in self._SPP:
+            setattr(self, name, nn.Sequential(nn.AvgPool2d((k, k), stride=(k, k)), convbn(128, 32, 1, 1, 0, 1), relu()))
+        self.lastconv = nn.Sequential(convbn(320, 128, 3, 1, 1, 1), relu(),
+                                      nn.Conv2d(128, 32, kernel_size=1, padding=0, stride=1, bias=False))
+
+    def _stage(self, planes, blocks, stride, pad, dilation):
+        down = None
+        if stride != 1 or self.inplanes != planes:
+            down = nn.Sequential(nn.Conv2d(self.inplanes, planes, kernel_size=1, stride=stride, bias=False),
+                                 nn.BatchNorm2d(planes))
+        mods = [BasicBlock(self.inplanes, planes, stride, down, pad, dilation)]
+        self.inplanes = planes
+        mods += [BasicBlock(planes, planes, 1, None, pad, dilation) for _ in range(1, blocks)]
+        return nn.Sequential(*mods)
+
+    def forward(self, x):
+        raw = self.layer2(self.layer1(self.firstconv(x)))
+        skip = self.layer4(self.layer3(raw))
+        size = skip.shape[-2:]
+        pyramid = [F.interpolate(getattr(self, name)(skip), size, mode='bilinear', align_corners=True)
+                   for _, name in self._SPP]
+        # concat order of submodule.py:134-135: raw, skip, branch4, branch3, branch2, branch1
+        return self.lastconv(torch.cat([raw, skip] + pyramid[::-1], 1))

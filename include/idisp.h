@@ -1,0 +1,138 @@
+/* idisp.h -- C-ABI of the B200-native iDispNet hot path (libidisp.so).
+ *
+ * Drop-in boundary for zju3dv/disprcnn's instance-disparity path.  Every entry point is
+ * plain C: raw device (or, where stated, host) pointers, explicit sizes, a cudaStream_t
+ * passed as void*, int status return (0 = ok; otherwise idisp_last_error() describes the
+ * failure for the calling thread).  Outputs are caller-allocated so the host framework
+ * (PyTorch in the reference) keeps ownership of all memory; the library holds no global
+ * state apart from plan handles.  There is no CPU fallback anywhere behind this header.
+ *
+ * Reference interfaces replaced (paths relative to the reference root):
+ *   idisp_roi_align_forward ... disprcnn/csrc/ROIAlign.h:11-25 (ROIAlign_forward), bound at
+ *                               disprcnn/csrc/vision.cpp:9, called from
+ *                               disprcnn/layers/roi_align.py:21; CUDA kernel
+ *                               disprcnn/csrc/cuda/ROIAlign_cuda.cu:65-122, launcher :257-299.
+ *                               The optional per-channel affine fuses
+ *                               disprcnn/modeling/detector/disprcnn3d.py:47-49.
+ *   idisp_roi_align_backward .. disprcnn/csrc/ROIAlign.h:27-45; training only -> returns
+ *                               IDISP_ERR_UNSUPPORTED like the reference's CPU build (:44).
+ *   idisp_cost_volume ......... disprcnn/modeling/psmnet/stackhourglass.py:115-128.
+ *   idisp_conv3d .............. one convbn_3d / ConvTranspose3d+BN / Conv3d layer:
+ *                               disprcnn/modeling/psmnet/submodule.py:19-22,
+ *                               stackhourglass.py:11-30,63-88 (test hook, NCDHW in/out).
+ *   idisp_softargmin .......... stackhourglass.py:169-172 + submodule.py:51-57.
+ *   idisp_plan_* .............. PSMNet's 3-D stack: stackhourglass.py:63-88 (parameters,
+ *                               reference state_dict keys) and :115-174 (eval forward).
+ */
+#ifndef IDISP_H_
+#define IDISP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IDISP_VERSION 1
+
+enum {
+  IDISP_OK = 0,
+  IDISP_ERR_INVALID = 1,     /* bad argument / shape constraint violated            */
+  IDISP_ERR_CUDA = 2,        /* a CUDA runtime/driver call or kernel launch failed   */
+  IDISP_ERR_UNSUPPORTED = 3, /* not implemented on this path (e.g. ROIAlign backward) */
+  IDISP_ERR_STATE = 4        /* plan not finalised / weights missing                 */
+};
+
+/* Arithmetic mode of the 3-D conv stack (never silently downgraded). */
+enum {
+  IDISP_PREC_FP32 = 0, /* fp32 storage + fp32 FFMA accumulate: parity mode (1e-3 abs)      */
+  IDISP_PREC_BF16 = 1  /* bf16 storage + tcgen05 kind::f16 MMA, fp32 accumulate in TMEM   */
+};
+
+/* conv layer kinds for idisp_conv3d / the plan's layer table */
+enum {
+  IDISP_CONV_S1 = 0, /* Conv3d k3 s1 p1                               */
+  IDISP_CONV_S2 = 1, /* Conv3d k3 s2 p1                               */
+  IDISP_DECONV_S2 = 2 /* ConvTranspose3d k3 s2 p1 output_padding 1     */
+};
+
+typedef struct idisp_plan idisp_plan_t;
+
+int idisp_version(void);
+/* Thread-local description of the last failing call ("" if none). Never NULL. */
+const char *idisp_last_error(void);
+
+/* ROIAlign forward.  input [N,C,H,W] f32 NCHW contiguous, rois [R,5] f32
+ * (batch_idx,x1,y1,x2,y2), out [R,C,pooled_h,pooled_w] f32 -- all device pointers.
+ * mean/inv_std: optional device pointers to C floats; when non-NULL the kernel writes
+ * (v - mean[c]) / std[c] with std[c] passed as-is in `std` (division, like the
+ * reference's in-place sub_/div_).  R == 0 is a no-op (reference early-return :278-281). */
+int idisp_roi_align_forward(const float *input, int N, int C, int H, int W, const float *rois, int R,
+                            float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio,
+                            const float *mean, const float *std, float *out, void *stream);
+int idisp_roi_align_backward(const float *grad, const float *rois, int R, float spatial_scale,
+                             int pooled_h, int pooled_w, int N, int C, int H, int W,
+                             int sampling_ratio, float *grad_input, void *stream);
+
+/* Concatenation cost volume.  left/right [B,C,Hf,Wf] f32 NCHW -> cost [B,2C,D,Hf,Wf] f32
+ * NCDHW with D=(maxdisp-mindisp)/4; mindisp, maxdisp multiples of 4, |shift| < Wf. */
+int idisp_cost_volume(const float *left, const float *right, int B, int C, int Hf, int Wf,
+                      int mindisp, int maxdisp, float *cost, void *stream);
+
+/* One 3x3x3 conv layer with folded affine epilogue (per-layer test hook; NCDHW f32 I/O,
+ * converted to the internal channel-blocked layout inside).
+ *   kind: IDISP_CONV_*.  weight: Conv3d layout [Cout,Cin,3,3,3] (S1,S2) or ConvTranspose3d
+ *   layout [Cin,Cout,3,3,3] (DECONV_S2), device f32.  scale/bias: per-Cout f32 device
+ *   pointers, y = conv(x)*scale + bias (NULL -> 1 / 0); residual (NULL or NCDHW f32 of the
+ *   output shape) is added before the optional ReLU.  precision: IDISP_PREC_*.
+ *   Output dims: S1 same; S2 ceil(n/2); DECONV 2n. */
+int idisp_conv3d(const float *x, int B, int Cin, int D, int H, int W, const float *weight, int Cout,
+                 int kind, const float *scale, const float *bias, const float *residual, int relu,
+                 int precision, float *y, void *stream);
+
+/* Trilinear(align_corners) upsample of logits [B,D,Hf,Wf] f32 to [B,maxdisp-mindisp,H,W],
+ * softmax over disparity, expectation over d in [mindisp,maxdisp) -> out [B,H,W] f32;
+ * the upsampled volume is never materialised. */
+int idisp_softargmin(const float *logits, int B, int D, int Hf, int Wf, int mindisp, int maxdisp,
+                     int H, int W, float *out, void *stream);
+
+/* ---- plan: the 28-layer stack with reference-keyed weights ------------------------- */
+/* C = feature channels per view (dres0.0 has 2C inputs). */
+int idisp_plan_create(int C, int mindisp, int maxdisp, int precision, idisp_plan_t **plan);
+void idisp_plan_destroy(idisp_plan_t *plan);
+/* Hand over one reference state_dict entry by its key (e.g. "dres0.0.0.weight",
+ * "dres2.conv5.1.running_var"); data is a HOST pointer to numel f32 values in the reference's
+ * own layout.  Unknown keys (feature_extraction.*, *.num_batches_tracked) return IDISP_OK
+ * and are ignored, so a whole reference checkpoint can be streamed through. */
+int idisp_plan_set_tensor(idisp_plan_t *plan, const char *key, const float *data, size_t numel);
+/* Fold BN (eps 1e-5) into per-channel scale/bias, re-lay the kernels for the selected
+ * precision, upload.  Fails with IDISP_ERR_STATE naming the first missing key. */
+int idisp_plan_finalize(idisp_plan_t *plan, void *stream);
+/* Bytes of device workspace idisp_plan_forward needs for this shape. */
+size_t idisp_plan_workspace_bytes(const idisp_plan_t *plan, int B, int Hf, int Wf);
+/* left/right [B,C,Hf,Wf] f32 NCHW device -> out [B,H,W] f32 device.
+ * D, Hf, Wf must be multiples of 4 (two stride-2 stages, stackhourglass.py:34-49). */
+int idisp_plan_forward(idisp_plan_t *plan, const float *left, const float *right, int B, int Hf,
+                       int Wf, int H, int W, void *workspace, size_t workspace_bytes, float *out,
+                       void *stream);
+/* Same call with HOST buffers (pinned recommended): H2D of left/right, forward, D2H of out,
+ * all enqueued on `stream`; the plan owns and grows the device staging + workspace. */
+int idisp_plan_forward_host(idisp_plan_t *plan, const float *left_host, const float *right_host,
+                            int B, int Hf, int Wf, int H, int W, float *out_host, void *stream);
+/* Debug/test hook: copy the low-resolution logits cost3 [B,D,Hf,Wf] f32 of the last
+ * idisp_plan_forward on this plan into a device buffer. */
+int idisp_plan_get_logits(idisp_plan_t *plan, float *logits, void *stream);
+/* Number of kernel launches one idisp_plan_forward enqueues (for bench bookkeeping). */
+int idisp_plan_launches_per_forward(const idisp_plan_t *plan);
+/* Per-launch device timing of idisp_plan_forward (CUDA events on the forward's stream between
+ * consecutive launches).  After a forward with timing enabled, get_timing writes, for each of the
+ * launches_per_forward launches, its duration in ms and the layer it ran (0..27 = SURVEY.md
+ * Appendix A order minus one; -1 = cost volume, -2 = soft-argmin).  capacity = array lengths. */
+int idisp_plan_enable_timing(idisp_plan_t *plan, int on);
+int idisp_plan_get_timing(idisp_plan_t *plan, float *ms, int *layer, int capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDISP_H_ */

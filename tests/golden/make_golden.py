@@ -1,0 +1,149 @@
+"""Generate tests/golden/*.npz by EXECUTING THE REFERENCE (authoring container only).
+
+Run:  python tests/golden/make_golden.py
+Needs /root/reference (read-only reference checkout) and, for the ROIAlign vectors,
+oracle/_ref/ref_roialign.so (python oracle/build_ref.py).  The GPU box has neither; it
+only consumes the committed .npz files.
+
+What is executed:
+  * iDispNet: ``disprcnn.modeling.psmnet.stackhourglass.PSMNet`` imported unmodified.
+    ``PSMNet.forward`` (stackhourglass.py:106-174) runs verbatim with
+    ``feature_extraction`` swapped for ``nn.Identity`` so that the inputs ARE the feature
+    maps (BASELINE.json configs 1-3 are feature-input configs); a forward pre-hook on
+    ``dres0`` captures the reference's own cost volume.  That "genuine" forward yields
+    disparity at H,W = Hf,Wf.  The 4x-upsampled variant (H,W = 4Hf,4Wf) re-runs lines
+    :130-174 on the reference's own sub-modules.
+  * The same network in float64 (``.double()``) as arbiter.
+  * ROIAlign: the reference CPU kernel compiled from its own source.
+BatchNorm running statistics are calibrated by two train-mode passes of the reference
+and stored in the fixture (weights themselves are regenerated from tests/golden/recipe.py).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+sys.path.insert(0, '/root/reference')
+
+import recipe  # noqa: E402
+from disprcnn.modeling.psmnet.stackhourglass import PSMNet  # noqa: E402  (the reference)
+from disprcnn.modeling.psmnet import submodule as ref_sub  # noqa: E402
+
+
+def ref_tail(m, cost, H, W):
+    """stackhourglass.py:130-144 + eval branch :169-174 on the reference's own modules."""
+    cost0 = m.dres0(cost)
+    cost0 = m.dres1(cost0) + cost0
+    out1, pre1, post1 = m.dres2(cost0, None, None)
+    out1 = out1 + cost0
+    out2, pre2, post2 = m.dres3(out1, pre1, post1)
+    out2 = out2 + cost0
+    out3, pre3, post3 = m.dres4(out2, pre1, post2)
+    out3 = out3 + cost0
+    cost1 = m.classif1(out1)
+    cost2 = m.classif2(out2) + cost1
+    cost3 = m.classif3(out3) + cost2
+    logits = cost3
+    c = F.interpolate(cost3, [m.maxdisp - m.mindisp, H, W], mode='trilinear', align_corners=True)
+    c = torch.squeeze(c, 1)
+    p = F.softmax(c, dim=1)
+    return ref_sub.disparityregression(p, m.maxdisp, m.mindisp), logits, cost0
+
+
+def build_reference(case):
+    C = case['C']
+    m = PSMNet(case['maxdisp'], case['mindisp'])
+    if C != 32:
+        m.dres0[0] = ref_sub.convbn_3d(2 * C, 32, 3, 1, 1)
+    m.feature_extraction = nn.Identity()
+    sd = recipe.make_state_dict(recipe.stack3d_shapes(C), case['seed'])
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    return m, sd
+
+
+def calibrate(m, case):
+    for mod in m.modules():
+        if isinstance(mod, nn.BatchNorm3d):
+            mod.momentum = None  # cumulative average -> exact batch statistics
+    m.train()
+    with torch.no_grad():
+        for j in range(2):
+            L, R = recipe.make_features(case['B'], case['C'], case['Hf'], case['Wf'], case['seed'] + 100 + j)
+            m((L, R))
+    m.eval()
+
+
+def gen_case(name, case):
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    m, sd0 = build_reference(case)
+    calibrate(m, case)
+    L, R = recipe.make_features(case['B'], case['C'], case['Hf'], case['Wf'], case['seed'])
+    captured = {}
+    hook = m.dres0.register_forward_pre_hook(lambda mod, inp: captured.__setitem__('cost', inp[0].clone()))
+    with torch.no_grad():
+        pred_genuine = m((L, R))  # reference forward verbatim, H,W = Hf,Wf
+    hook.remove()
+    cost = captured['cost']
+    Hf, Wf = case['Hf'], case['Wf']
+    with torch.no_grad():
+        pred_g2, logits, cost0 = ref_tail(m, cost, Hf, Wf)
+        assert torch.equal(pred_g2, pred_genuine)
+        pred_up, _, _ = ref_tail(m, cost, 4 * Hf, 4 * Wf)
+        m64 = m.double()
+        p64_g, logits64, _ = ref_tail(m64, cost.double(), Hf, Wf)
+        p64_up, _, _ = ref_tail(m64, cost.double(), 4 * Hf, 4 * Wf)
+    m.float()
+    out = dict(
+        cost_crc=recipe.checksum(cost), left_crc=recipe.checksum(L), right_crc=recipe.checksum(R),
+        pred_genuine=pred_genuine.numpy(), pred_up=pred_up.numpy(), logits=logits.numpy(),
+        pred_genuine_f64=p64_g.numpy(), pred_up_f64=p64_up.numpy(), logits_f64=logits64.numpy(),
+    )
+    if name.startswith('tiny'):
+        out['cost0'] = cost0.numpy()
+    if name == 'tiny_pos':
+        out['cost'] = cost.numpy()
+    sd = m.state_dict()
+    for k, v in sd.items():
+        if k.endswith('running_mean') or k.endswith('running_var'):
+            out['bn/' + k] = v.numpy()
+    # weights checksum over the recipe tensors (regenerated on the GPU box)
+    wsum = 0
+    for k in sorted(sd0):
+        wsum = (wsum * 31 + int(recipe.checksum(sd0[k])[0])) & 0x7FFFFFFFFFFF
+    out['weights_crc'] = np.array([wsum], dtype=np.int64)
+    e32 = float(np.abs(out['pred_up'] - out['pred_up_f64']).max())
+    print(f'{name}: logits std {float(logits.std()):.3f}  ref fp32-vs-fp64 max|d| {e32:.3e}  '
+          f'disp range [{float(pred_up.min()):.2f},{float(pred_up.max()):.2f}]')
+    out['ref_f32_vs_f64_maxabs'] = np.array([e32])
+    np.savez_compressed(os.path.join(HERE, f'idisp_{name}.npz'), **out)
+
+
+def gen_roi():
+    import build_ref
+    ref = build_ref.build()
+    for name, rc in recipe.ROI_CASES.items():
+        g = recipe._gen(rc['seed'], 'roi_input')
+        inp = torch.randn(rc['N'], rc['C'], rc['H'], rc['W'], generator=g)
+        rois = torch.tensor(rc['rois'], dtype=torch.float32)
+        out = ref.roi_align_forward(inp, rois, rc['scale'], rc['ph'], rc['pw'], rc['sr'])
+        np.savez_compressed(os.path.join(HERE, f'roialign_{name}.npz'), out=out.numpy(),
+                            input_crc=recipe.checksum(inp))
+        print(f'roialign {name}: out {tuple(out.shape)}')
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or list(recipe.CASES) + ['roi']
+    for name in which:
+        if name == 'roi':
+            gen_roi()
+        else:
+            gen_case(name, recipe.CASES[name])

@@ -1,0 +1,71 @@
+"""CPU, world_size 2, gloo: the N>1 host logic (sharding + the disparity all-gather)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from disprcnn_b200.parallel import gather_disparity, shard_range, sharded_forward
+
+
+def test_shard_range_partitions():
+    for B in (0, 1, 5, 32, 33, 255, 256):
+        for G in (1, 2, 3, 8):
+            spans = [shard_range(B, r, G) for r in range(G)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(G - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+class _FakeModel:
+    """Stands in for PSMNet.forward_features: a per-ROI function, so gathering is checkable."""
+
+    def forward_features(self, l, r, H=None, W=None):
+        return (l.sum(1) - r.sum(1)) * 0.5
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, B, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(3)
+        L = torch.randn(B, 4, 6, 7, generator=g)
+        R = torch.randn(B, 4, 6, 7, generator=g)
+        full = sharded_forward(_FakeModel(), L, R)
+        want = _FakeModel().forward_features(L, R)
+        lo, hi = shard_range(B, rank, world)
+        local = sharded_forward(_FakeModel(), L, R, gather=False)
+        ok = torch.equal(full, want) and torch.equal(local, want[lo:hi]) and full.shape[0] == B
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('B', [8, 5])  # equal shards and ragged shards
+def test_gather_world2_gloo(B):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, B, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_gather_without_process_group_is_identity():
+    x = torch.randn(3, 4, 5)
+    assert gather_disparity(x, 3) is x
