@@ -1,33 +1,39 @@
-// conv3d_tc.cu -- tcgen05 (5th-gen tensor core) implicit-GEMM 3x3x3 convolution for sm_100a.
+// conv3d_tc.cu -- tcgen05 (5th-gen tensor core) implicit-GEMM 3x3x3 convolution family for sm_100a.
 //
-// Replaces the cuDNN Conv3d+BatchNorm3d+ReLU(+add) chains of
-// disprcnn/modeling/psmnet/stackhourglass.py:63-88 (applied :130-144) for the stride-1 layers
-// (83 % of the 388 GFLOP/ROI at BASELINE config 2).  No im2col, no materialised patches.
+// Replaces the cuDNN Conv3d / ConvTranspose3d + BatchNorm3d + ReLU (+ add) chains of
+// disprcnn/modeling/psmnet/stackhourglass.py:11-30,63-88 (applied :130-144): stride-1 convs,
+// stride-2 convs, the stride-2 transposed convs and the 32->1 classifier convs -- all 28 layers.
+// No im2col, no materialised patches.
 //
-// GEMM view.  Activations are bf16, channel-blocked-8: [N][C/8][D][H][W][8] (common.cuh); one
-// voxel of one channel block is exactly the 16-byte row of a NO-SWIZZLE K-major UMMA core matrix.
-//   M = 128 output voxels = an 8 (w) x 16 (h) tile of ONE depth plane,
-//   K = Cin per filter tap (two K=16 MMAs per 32 channels),
-//   N = 32 output channels per filter-depth tap kd.
-// A operand.  For an input plane z, TMA (cp.async.bulk.tensor.4d over (8ch*W, H, D, N*Cin/8), box 80 x 18 x 1 x Cin/8,
-//   zero OOB fill == conv padding) lands the haloed tile in shared memory as [Cin/8][18][10][8]:
-//   rows (w) 16 B apart, 8-row groups (h) 160 B apart (SBO), K core matrices 2880 B apart (LBO).
-//   The nine in-plane taps (kh,kw) are the SAME bytes read through descriptors whose start address
-//   is shifted by (kh*10+kw)*16 B -- the halo is loaded once and reused 9 (in-plane) x 3 (depth) times.
-// Depth streaming + kd stacking.  A CTA walks one (n, h-tile, w-tile) column through all D planes.
-//   Input plane z contributes to output planes z-1, z, z+1 with kd = 2, 1, 0, so ONE MMA of
-//   N = 96 = [W(kd=2) | W(kd=1) | W(kd=0)] updates three neighbouring accumulators at once.  This
-//   matters on Blackwell: an SS-mode MMA with N = 32 needs 5 KB of shared-memory operands per 16
-//   tensor cycles (320 B/clk vs the 128 B/clk port); N = 96 needs 7 KB per 48 cycles (146 B/clk).
-//   Accumulators live in a ring of 16 TMEM slots (16 x 32 fp32 columns = all 512), slot = plane mod 16;
-//   a stacked MMA is split only where the ring wraps or an accumulator is touched for the first
-//   time (its accumulate flag must be 0).
+// GEMM view (all modes).  Activations are bf16, channel-blocked-8: [N][C/8][D][H][W][8]
+// (common.cuh); one voxel of one channel block is exactly the 16-byte row of a NO-SWIZZLE K-major
+// UMMA core matrix.  M = 128 rows = an 8 (w) x 16 (h) tile of ONE plane of the "row grid"
+// (output grid for convs, input grid for the transposed conv), K = Cin per filter tap (K=16 per
+// MMA), N = 32 output channels per stacked block.
+// A operand.  TMA (cp.async.bulk.tensor over (8ch*W, H, D, N*Cin/8): 144/160-byte rows, zero OOB
+//   fill == conv padding) lands a haloed plane tile in shared memory as [Cin/8][rows][cols][8]:
+//   GEMM rows (w) 16 B apart, 8-row groups (h) one tile row apart (SBO), K core matrices one
+//   channel-block plane apart (LBO).  Every in-plane tap is the SAME bytes read through a
+//   descriptor whose start address is shifted by (dh*cols+dw)*16 B: the halo is loaded once.
+// Depth streaming + stacking.  A CTA walks one (n, h-tile, w-tile) column through all planes.
+//   stride 1: input plane z feeds output planes z-1,z,z+1 (kd=2,1,0): ONE MMA with
+//             N = 96 = [W(kd=2)|W(kd=1)|W(kd=0)] updates three neighbouring accumulators.
+//   stride 2: the input is first re-laid into its 8 parity sub-volumes (space_to_depth kernel) so
+//             every tap is again a unit-stride tile; odd input planes feed two output planes (N=64).
+//   transposed (stride 2): rows are INPUT positions; each input plane feeds output planes
+//             2z-1,2z,2z+1; per output plane the 4 in-plane output parity classes are 4 x 32
+//             accumulator columns, and taps that share an input shift are stacked (N = 128/64/32).
+//   Accumulators live in a TMEM ring (512 columns = 16 slots x 32 or 4 slots x 128).  The epilogue
+//   zeroes a slot right after reading it, so every MMA accumulates and the issue loop carries no
+//   first-touch logic.  (Measured: the single issuing thread is the scarce resource -- a loop with
+//   per-MMA address arithmetic ran at ~300 cycles/MMA; descriptors are now built once per plane and
+//   advanced by compile-time constants.)
 // Warp roles (256 threads, 1 CTA/SM, persistent over columns): warp 0 = TMA producer, warp 1 = MMA
 //   issuer (one thread), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld 32x32b.x32 ->
-//   +bias (+residual) (ReLU) -> bf16 -> 16-byte stores, 128 B contiguous per 8-voxel row).
-// Pipelines: full/empty mbarriers over the input-plane ring (TMA <-> MMA), acc_full/acc_empty over
-//   the TMEM ring (MMA <-> epilogue); weights (55/110 KB) stay resident in shared memory.
-// Roofline: tensor (dense bf16): 2*128*32*27*Cin FLOP per plane-tile vs 18-36 MMAs of 48 cycles.
+//   +bias (+residual) (ReLU) -> bf16 -> 16-byte stores).
+// Pipelines: full/empty mbarriers over the input ring (TMA <-> MMA), acc_full/acc_empty over the TMEM
+//   ring (MMA <-> epilogue); the layer's weights (55/110 KB) stay resident in shared memory.
+// Roofline: tensor (dense bf16); algorithmic FLOPs = 2*27*Cin*Cout per output voxel (stride 1).
 #include "conv3d_tc.cuh"
 #include "sm100_ptx.cuh"
 
@@ -36,56 +42,82 @@
 namespace idisp {
 
 namespace tc {
-constexpr int TW = 8, TH = 16;              // output tile (w x h) of one plane = 128 GEMM rows
-constexpr int HALO_W = TW + 2, HALO_H = TH + 2;
-constexpr int PLANE_BYTES = HALO_W * HALO_H * 16;  // one channel block of one haloed plane: 2880 B
-constexpr int NT = 32;                      // output channels per CTA and per kd
-constexpr int NSLOT = 16;                   // TMEM accumulator ring (16 x 32 columns)
-constexpr int WCHUNK = 2 * 3 * NT * 16;     // B operand of one (kh,kw,kstep): [2 kcores][96 n][8 ch] bf16 = 3072 B
+enum { M_S1 = 0, M_S2 = 1, M_DEC = 2 };
+constexpr int TW = 8, TH = 16;  // row tile (w x h) = 128 GEMM rows
+constexpr int NT = 32;          // output channels per stacked block
 constexpr int NTHREADS = 256;
 
-template <int CIN> struct Cfg {
-  static constexpr int KS = CIN / 16;           // K=16 steps per tap
-  static constexpr int CBLK = CIN / 8;          // channel blocks
-  static constexpr int STAGE_BYTES = CBLK * PLANE_BYTES;
-  static constexpr int STAGES = CIN == 32 ? 8 : 4;
-  static constexpr int WBYTES = 9 * KS * WCHUNK;
+template <int MODE> struct ModeCfg;
+template <> struct ModeCfg<M_S1> { static constexpr int SUB_W = TW + 2, SUB_H = TH + 2, SUBS = 1, ACC_COLS = 32; };
+// (SUB_H is 18 rather than the 17 rows these modes read so that Cin/8 * SUB_W*SUB_H*16 B stays a multiple of 128 B,
+//  the alignment TMA needs for the second sub-tile of a stage)
+template <> struct ModeCfg<M_S2> { static constexpr int SUB_W = TW + 1, SUB_H = TH + 2, SUBS = 2, ACC_COLS = 32; };
+template <> struct ModeCfg<M_DEC> { static constexpr int SUB_W = TW + 1, SUB_H = TH + 2, SUBS = 1, ACC_COLS = 128; };
+
+template <int CIN, int MODE> struct Cfg {
+  using MC = ModeCfg<MODE>;
+  static constexpr int KS = CIN / 16;    // K=16 MMAs per tap
+  static constexpr int CBLK = CIN / 8;   // channel blocks
+  static constexpr int PLANE_BYTES = MC::SUB_W * MC::SUB_H * 16;  // one channel block of one sub-tile (LBO of A)
+  static constexpr int ROW_BYTES = MC::SUB_W * 16;                // one tile row (SBO of A)
+  static constexpr int SUB_BYTES = CBLK * PLANE_BYTES;
+  static constexpr int STAGE_BYTES = MC::SUBS * SUB_BYTES;
+  static constexpr int WBYTES = 27 * KS * 1024;                   // 27 taps x Cin x 32 couts x bf16
+  static constexpr int NSLOT = 512 / MC::ACC_COLS;
+  static constexpr int STAGES_FIT = (227 * 1024 - WBYTES - 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int BAR_OFF = WBYTES + STAGES * STAGE_BYTES;
   static constexpr int SMEM = BAR_OFF + (2 * STAGES + 2 * NSLOT) * 8 + 16 + NT * 4;
+  static_assert(STAGES >= 2, "input ring needs at least two stages");
+  static_assert(STAGE_BYTES % 128 == 0 && WBYTES % 128 == 0 && SUB_BYTES % 128 == 0, "TMA destinations must stay 128 B aligned");
 };
 
 struct Params {
-  const __nv_bfloat16 *w;         // [NH][9][KS][2][96][8] bf16
+  const __nv_bfloat16 *w;         // packed per mode, [nh][...] (see tc_weights_prepare)
   const float *bias;              // [Cout] or nullptr
   const __nv_bfloat16 *residual;  // blocked, output shape, or nullptr
-  __nv_bfloat16 *y;               // blocked [B][Cout/8][D][H][W][8]
-  int B, D, H, W, Cout, relu;
-  int tiles_h, tiles_w, nh;       // spatial tiling, number of 32-wide output-channel halves
-  int stack;                      // 1: kd-stacked N=96 MMAs, 0: one N=32 MMA per kd (debug / A-B)
+  __nv_bfloat16 *y;               // blocked [B][Cout/8][Do][Ho][Wo][8]
+  const float *res1;              // 32->1 head: running sum [B][D][H][W] f32 or nullptr
+  float *y1;                      // 32->1 head: output [B][D][H][W] f32 (non-null selects this epilogue)
+  int B, Din, Dout, Ho, Wo, Hr, Wr, Cout, relu;  // (Hr,Wr): row grid the 8x16 tiles cover
+  int tiles_h, tiles_w, nh;
 };
 
-template <int CIN>
+// DECONV stacking table: per kd, five MMAs (entries) that share an input shift
+//   e0 shift(0,0) -> classes 0..3 (N=128), e1 shift(0,1) -> classes 2,3 (N=64),
+//   e2 shift(1,0) -> class 1, e3 shift(1,0) -> class 3, e4 shift(1,1) -> class 3   (class = pw*2+ph)
+__host__ __device__ constexpr int dec_rows(int e) { return e == 0 ? 128 : (e == 1 ? 64 : 32); }
+__host__ __device__ constexpr int dec_row_off(int e) { return e == 0 ? 0 : (e == 1 ? 128 : (e == 2 ? 192 : (e == 3 ? 224 : 256))); }
+__host__ __device__ constexpr int dec_dcol(int e) { return e == 0 ? 0 : (e == 1 ? 64 : (e == 2 ? 32 : 96)); }
+__host__ __device__ constexpr int dec_shift_h(int e) { return e >= 2 ? 1 : 0; }
+__host__ __device__ constexpr int dec_shift_w(int e) { return (e == 1 || e == 4) ? 1 : 0; }
+
+__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t byte_off) { return d + (uint64_t)(byte_off >> 4); }
+
+template <int CIN, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
 {
-  using C = Cfg<CIN>;
+  using C = Cfg<CIN, MODE>;
+  using MC = ModeCfg<MODE>;
+  constexpr int NSLOT = C::NSLOT;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = ptx::smem_u32(smem);
   const uint32_t w_addr = smem_base;
   const uint32_t stage_addr0 = smem_base + C::WBYTES;
   const uint32_t bar0 = smem_base + C::BAR_OFF;
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (C::STAGES + s); };
-  auto accf_bar = [&](int r) { return bar0 + 8u * (2 * C::STAGES + r); };
-  auto acce_bar = [&](int r) { return bar0 + 8u * (2 * C::STAGES + NSLOT + r); };
+  auto full_bar = [&](uint32_t s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](uint32_t s) { return bar0 + 8u * (C::STAGES + s); };
+  auto accf_bar = [&](uint32_t r) { return bar0 + 8u * (2 * C::STAGES + r); };
+  auto acce_bar = [&](uint32_t r) { return bar0 + 8u * (2 * C::STAGES + NSLOT + r); };
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + C::BAR_OFF + (2 * C::STAGES + 2 * NSLOT) * 8);
   float *bias_s = reinterpret_cast<float *>(smem + C::BAR_OFF + (2 * C::STAGES + 2 * NSLOT) * 8 + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // this CTA's fixed output-channel half and its strided share of the (n, h-tile, w-tile) columns
-  const int nh = blockIdx.x % p.nh;
+  const int nh = blockIdx.x % p.nh;  // this CTA's fixed 32-wide output-channel slice
   const int cta = blockIdx.x / p.nh, ncta = gridDim.x / p.nh;
   const int ncols = p.B * p.tiles_h * p.tiles_w;
+  const int Din = p.Din, Dout = p.Dout;
 
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
@@ -95,107 +127,210 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<512>(ptx::smem_u32(tmem_ptr_smem));
-  {  // weights of this half -> shared memory (generic proxy), then make them visible to the async proxy
+  {  // this slice's weights -> shared memory (generic proxy), then visible to the async proxy (tensor core)
     const uint4 *src = reinterpret_cast<const uint4 *>(p.w) + (size_t)nh * (C::WBYTES / 16);
     uint4 *dst = reinterpret_cast<uint4 *>(smem);
     for (int i = threadIdx.x; i < C::WBYTES / 16; i += NTHREADS) dst[i] = __ldg(src + i);
-    if (threadIdx.x < NT) bias_s[threadIdx.x] = p.bias ? p.bias[nh * NT + threadIdx.x] : 0.f;
+    if (threadIdx.x < NT) bias_s[threadIdx.x] = (p.bias && nh * NT + (int)threadIdx.x < p.Cout) ? p.bias[nh * NT + threadIdx.x] : 0.f;
     ptx::fence_proxy_async_smem();
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (warp >= 4) {  // accumulators start at zero; afterwards the epilogue re-zeroes each slot it drains
+    uint32_t zero[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) zero[i] = 0u;
+    for (int c = 0; c < 512; c += 32) ptx::tmem_st_32x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + c, zero);
+    ptx::tmem_st_wait();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
 
-  const int D = p.D;
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t q = 0;
       for (int col = cta; col < ncols; col += ncta) {
         const int tw = col % p.tiles_w, th = (col / p.tiles_w) % p.tiles_h, n = col / (p.tiles_w * p.tiles_h);
-        for (int z = 0; z < D; ++z, ++q) {
-          const int s = q % C::STAGES;
-          ptx::mbar_wait(empty_bar(s), ((q / C::STAGES) & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
-          ptx::tma_load_4d(stage_addr0 + s * C::STAGE_BYTES, &xmap, full_bar(s), (tw * TW - 1) * 8, th * TH - 1, z, n * C::CBLK);
+        for (int z = 0; z < Din; ++z) {
+          if (MODE == M_S2) {
+            // two pipeline steps per input plane: even-row (ph=0) and odd-row (ph=1) sub-grids, each {pw=0, pw=1}
+            for (int ph = 0; ph < 2; ++ph, ++q) {
+              const uint32_t s = q % C::STAGES;
+              ptx::mbar_wait(empty_bar(s), ((q / C::STAGES) & 1) ^ 1);
+              ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
+              for (int pw = 0; pw < 2; ++pw)
+                ptx::tma_load_5d(stage_addr0 + s * C::STAGE_BYTES + pw * C::SUB_BYTES, &xmap, full_bar(s), (tw * TW - 1) * 8,
+                                 th * TH - 1, z >> 1, (z & 1) * 4 + ph * 2 + pw, n * C::CBLK);
+            }
+          } else {
+            const uint32_t s = q % C::STAGES;
+            ptx::mbar_wait(empty_bar(s), ((q / C::STAGES) & 1) ^ 1);
+            ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
+            const int halo = MODE == M_S1 ? 1 : 0;
+            ptx::tma_load_4d(stage_addr0 + s * C::STAGE_BYTES, &xmap, full_bar(s), (tw * TW - halo) * 8, th * TH - halo, z, n * C::CBLK);
+            ++q;
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer (single thread) =================
     if (lane == 0) {
+      const uint64_t a_desc0 = ptx::make_smem_desc(stage_addr0, C::PLANE_BYTES, C::ROW_BYTES);
+      auto wait_acc_empty = [&](uint32_t g) { ptx::mbar_wait(acce_bar(g % NSLOT), ((g / NSLOT) & 1) ^ 1); };
       uint32_t q = 0, g0 = 0;
-      for (int col = cta; col < ncols; col += ncta, g0 += D) {
-        for (int z = 0; z < D; ++z, ++q) {
-          // accumulators touched for the first time by this input plane must have been drained
-          if (z == 0) {
-            ptx::mbar_wait(acce_bar(g0 % NSLOT), ((g0 / NSLOT) & 1) ^ 1);
-            if (D > 1) ptx::mbar_wait(acce_bar((g0 + 1) % NSLOT), (((g0 + 1) / NSLOT) & 1) ^ 1);
-          } else if (z + 1 < D) {
-            const uint32_t g = g0 + z + 1;
-            ptx::mbar_wait(acce_bar(g % NSLOT), ((g / NSLOT) & 1) ^ 1);
-          }
-          const int s = q % C::STAGES;
-          ptx::mbar_wait(full_bar(s), (q / C::STAGES) & 1);
-          ptx::tc_fence_after();
-          const uint32_t a_stage = stage_addr0 + s * C::STAGE_BYTES;
-          const int jlo = z == 0 ? 1 : 0, jhi = z == D - 1 ? 1 : 2;  // j <-> output plane z-1+j, kd = 2-j
-#pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            const int kh = tap / 3, kw = tap - 3 * kh;
+      for (int col = cta; col < ncols; col += ncta, g0 += Dout) {
+        for (int z = 0; z < Din; ++z) {
+          if (MODE == M_S1) {
+            if (z == 0) { wait_acc_empty(g0); if (Dout > 1) wait_acc_empty(g0 + 1); }
+            else if (z + 1 < Dout) wait_acc_empty(g0 + z + 1);
+            const uint32_t s = q % C::STAGES;
+            ptx::mbar_wait(full_bar(s), (q / C::STAGES) & 1);
+            ptx::tc_fence_after();
+            // output planes [plo, phi] <- B blocks [plo-(z-1), ...] (block j <-> kd = 2-j); split where the ring wraps
+            const int plo = z > 0 ? z - 1 : 0, phi = z + 1 < Dout ? z + 1 : Dout - 1;
+            const uint32_t slot0 = (g0 + plo) % NSLOT;
+            const int nblk = phi - plo + 1;
+            const int len1 = nblk < (int)(NSLOT - slot0) ? nblk : (int)(NSLOT - slot0), len2 = nblk - len1;
+            const uint32_t d1 = tmem_base + slot0 * NT, d2 = tmem_base;
+            const uint32_t id1 = ptx::make_idesc_bf16(128, NT * len1), id2 = ptx::make_idesc_bf16(128, NT * (len2 > 0 ? len2 : 1));
+            const uint64_t a0 = desc_add(a_desc0, s * C::STAGE_BYTES);
+            const uint64_t b1 = ptx::make_smem_desc(w_addr + (plo - (z - 1)) * NT * 16, 3 * NT * 16, 128);
+            const uint64_t b2 = desc_add(b1, len1 * NT * 16);
 #pragma unroll
-            for (int ks = 0; ks < C::KS; ++ks) {
-              const uint64_t a_desc = ptx::make_smem_desc(a_stage + (kh * HALO_W + kw) * 16 + ks * 2 * PLANE_BYTES, PLANE_BYTES, HALO_W * 16);
-              const uint32_t b_chunk = w_addr + (tap * C::KS + ks) * WCHUNK;
-              const bool first = (tap == 0 && ks == 0);
-              int j = jlo;
-              while (j <= jhi) {
-                const uint32_t slot = (g0 + z - 1 + j) % NSLOT;
-                const bool fresh = first && (z == 0 || j == 2);
-                int len = 1;
-                if (p.stack) {
-                  while (j + len <= jhi && slot + len < NSLOT && (first && (z == 0 || j + len == 2)) == fresh) ++len;
-                }
-                const uint64_t b_desc = ptx::make_smem_desc(b_chunk + j * NT * 16, 3 * NT * 16, 128);
-                ptx::umma_bf16_ss(tmem_base + slot * NT, a_desc, b_desc, ptx::make_idesc_bf16(128, NT * len), fresh ? 0u : 1u);
-                j += len;
+            for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+              for (int ks = 0; ks < C::KS; ++ks) {
+                const uint32_t aoff = ((tap / 3) * MC::SUB_W + (tap % 3)) * 16 + ks * 2 * C::PLANE_BYTES;
+                const uint32_t boff = (tap * C::KS + ks) * 3072;
+                ptx::umma_bf16_ss(d1, desc_add(a0, aoff), desc_add(b1, boff), id1, 1u);
+                if (len2 > 0) ptx::umma_bf16_ss(d2, desc_add(a0, aoff), desc_add(b2, boff), id2, 1u);
               }
             }
+            ptx::umma_commit(empty_bar(s));
+            ++q;
+            if (z >= 1) ptx::umma_commit(accf_bar((g0 + z - 1) % NSLOT));
+            if (z == Din - 1) ptx::umma_commit(accf_bar((g0 + z) % NSLOT));
+          } else if (MODE == M_S2) {
+            const int pz = z >> 1;  // output plane of kd=1 (even z) / kd=2 (odd z); odd z also feeds pz+1 with kd=0
+            const bool odd = z & 1;
+            for (int ph = 0; ph < 2; ++ph, ++q) {
+              if (ph == 0) {
+                if (z == 0) wait_acc_empty(g0);
+                else if (odd && pz + 1 < Dout) wait_acc_empty(g0 + pz + 1);
+              }
+              const uint32_t s = q % C::STAGES;
+              ptx::mbar_wait(full_bar(s), (q / C::STAGES) & 1);
+              ptx::tc_fence_after();
+              // B chunk rows: [kd=2 | kd=0 | kd=1]; odd z -> rows 0.. (planes pz, pz+1), even z -> rows 64.. (plane pz)
+              const uint32_t slot0 = (g0 + pz) % NSLOT;
+              const int nblk = odd ? (pz + 1 < Dout ? 2 : 1) : 1;
+              const int len1 = nblk < (int)(NSLOT - slot0) ? nblk : (int)(NSLOT - slot0), len2 = nblk - len1;
+              const uint32_t d1 = tmem_base + slot0 * NT, d2 = tmem_base;
+              const uint32_t id1 = ptx::make_idesc_bf16(128, NT * len1), id2 = ptx::make_idesc_bf16(128, NT);
+              const uint64_t a0 = desc_add(a_desc0, s * C::STAGE_BYTES);
+              const uint64_t b1 = ptx::make_smem_desc(w_addr + (odd ? 0 : 2 * NT * 16), 3 * NT * 16, 128);
+              const uint64_t b2 = desc_add(b1, len1 * NT * 16);
+#pragma unroll
+              for (int t = 0; t < 6; ++t) {
+                // ph=0 (even input rows): kh=1, kw=t (t<3).  ph=1 (odd rows): kh = 0 (t<3) or 2 (t>=3), kw = t%3
+                if (ph == 0 && t >= 3) break;
+                const int kh = ph == 0 ? 1 : (t < 3 ? 0 : 2), kw = t % 3;
+                const int rh = kh == 0 ? 0 : 1, rw = kw == 0 ? 0 : 1, sub = kw != 1 ? 1 : 0;
+#pragma unroll
+                for (int ks = 0; ks < C::KS; ++ks) {
+                  const uint32_t aoff = sub * C::SUB_BYTES + (rh * MC::SUB_W + rw) * 16 + ks * 2 * C::PLANE_BYTES;
+                  const uint32_t boff = ((kh * 3 + kw) * C::KS + ks) * 3072;
+                  ptx::umma_bf16_ss(d1, desc_add(a0, aoff), desc_add(b1, boff), id1, 1u);
+                  if (len2 > 0) ptx::umma_bf16_ss(d2, desc_add(a0, aoff), desc_add(b2, boff), id2, 1u);
+                }
+              }
+              ptx::umma_commit(empty_bar(s));
+            }
+            if (odd || z == Din - 1) ptx::umma_commit(accf_bar((g0 + pz) % NSLOT));
+          } else {  // M_DEC: rows are input positions; input plane z -> output planes 2z-1 (kd=0), 2z (kd=1), 2z+1 (kd=2)
+            wait_acc_empty(g0 + 2 * z);
+            wait_acc_empty(g0 + 2 * z + 1);
+            const uint32_t s = q % C::STAGES;
+            ptx::mbar_wait(full_bar(s), (q / C::STAGES) & 1);
+            ptx::tc_fence_after();
+            const uint64_t a0 = desc_add(a_desc0, s * C::STAGE_BYTES);
+#pragma unroll
+            for (int kd = 0; kd < 3; ++kd) {
+              const int qo = 2 * z - 1 + kd;
+              if (qo < 0 || qo >= Dout) continue;
+              const uint32_t dbase = tmem_base + ((g0 + qo) % NSLOT) * MC::ACC_COLS;
+#pragma unroll
+              for (int e = 0; e < 5; ++e) {
+#pragma unroll
+                for (int ks = 0; ks < C::KS; ++ks) {
+                  const uint32_t aoff = (dec_shift_h(e) * MC::SUB_W + dec_shift_w(e)) * 16 + ks * 2 * C::PLANE_BYTES;
+                  // weights: [kd][ks][kcore][288 rows][8]; entry e owns rows [row_off, row_off+rows)
+                  const uint32_t boff = ((kd * C::KS + ks) * 2 * 288 + dec_row_off(e)) * 16;
+                  const uint64_t bd = ptx::make_smem_desc(w_addr + boff, 288 * 16, 128);
+                  ptx::umma_bf16_ss(dbase + dec_dcol(e), desc_add(a0, aoff), bd, ptx::make_idesc_bf16(128, dec_rows(e)), 1u);
+                }
+              }
+            }
+            ptx::umma_commit(empty_bar(s));
+            ++q;
+            if (z >= 1) ptx::umma_commit(accf_bar((g0 + 2 * z - 1) % NSLOT));
+            ptx::umma_commit(accf_bar((g0 + 2 * z) % NSLOT));
+            if (z == Din - 1) ptx::umma_commit(accf_bar((g0 + 2 * z + 1) % NSLOT));
           }
-          ptx::umma_commit(empty_bar(s));  // smem stage reusable once these MMAs have read it
-          if (z >= 1) ptx::umma_commit(accf_bar((g0 + z - 1) % NSLOT));  // plane z-1 complete
-          if (z == D - 1) ptx::umma_commit(accf_bar((g0 + z) % NSLOT));   // last plane complete
         }
       }
     }
   } else if (warp >= 4) {
     // ================= epilogue (4 warps = 128 TMEM lanes) =================
     const int quarter = warp & 3;
-    const int m = quarter * 32 + lane;       // GEMM row = TMEM lane
-    const int wl = m & 7, hl = m >> 3;       // voxel inside the 8 x 16 tile
-    const int64_t V = (int64_t)D * p.H * p.W;
+    const int m = quarter * 32 + lane;  // GEMM row = TMEM lane
+    const int wl = m & 7, hl = m >> 3;  // position inside the 8 x 16 row tile
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int64_t Vo = (int64_t)Dout * p.Ho * p.Wo;
     const int cblk_out = p.Cout / 8;
+    uint32_t zero[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) zero[i] = 0u;
     uint32_t g0 = 0;
-    for (int col = cta; col < ncols; col += ncta, g0 += D) {
+    for (int col = cta; col < ncols; col += ncta, g0 += Dout) {
       const int tw = col % p.tiles_w, th = (col / p.tiles_w) % p.tiles_h, n = col / (p.tiles_w * p.tiles_h);
-      const int h = th * TH + hl, w = tw * TW + wl;
-      const bool valid = h < p.H && w < p.W;
-      for (int z = 0; z < D; ++z) {
-        const uint32_t g = g0 + z, r = g % NSLOT;
+      const int hr = th * TH + hl, wr = tw * TW + wl;
+      const bool valid = hr < p.Hr && wr < p.Wr;
+      for (int qo = 0; qo < Dout; ++qo) {
+        const uint32_t g = g0 + qo, r = g % NSLOT;
         ptx::mbar_wait(accf_bar(r), (g / NSLOT) & 1);
         ptx::tc_fence_after();
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + r * NT, v);
-        ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(acce_bar(r));  // accumulator slot may be overwritten
-        if (valid) {
-          const int64_t pos = ((int64_t)z * p.H + h) * p.W + w;
+        constexpr int NCLS = MODE == M_DEC ? 4 : 1;
+#pragma unroll
+        for (int cls = 0; cls < NCLS; ++cls) {
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + lane_addr + r * MC::ACC_COLS + cls * NT;
+          ptx::tmem_ld_32x32(taddr, v);
+          ptx::tmem_ld_wait();
+          ptx::tmem_st_32x32(taddr, zero);  // leave the slot zeroed for its next output plane
+          if (cls == NCLS - 1) {
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(acce_bar(r));
+          }
+          if (!valid) continue;
+          int ho = hr, wo = wr;
+          if (MODE == M_DEC) { ho = 2 * hr + (cls & 1); wo = 2 * wr + (cls >> 1); }  // class = pw*2 + ph
+          const int64_t pos = ((int64_t)qo * p.Ho + ho) * p.Wo + wo;
+          if (p.y1) {  // 32->1 classifier head: channel 0 only, f32, running sum fused (stackhourglass.py:142-144)
+            const int64_t o1 = (int64_t)n * Vo + pos;
+            p.y1[o1] = __uint_as_float(v[0]) + (p.res1 ? p.res1[o1] : 0.f);
+            continue;
+          }
 #pragma unroll
           for (int cb = 0; cb < 4; ++cb) {
-            const int64_t o = (((int64_t)n * cblk_out + nh * 4 + cb) * V + pos) * 8;
+            const int64_t o = (((int64_t)n * cblk_out + nh * 4 + cb) * Vo + pos) * 8;
             F8 r8;
 #pragma unroll
             for (int c = 0; c < 8; ++c) r8.v[c] = __uint_as_float(v[cb * 8 + c]) + bias_s[cb * 8 + c];
@@ -221,6 +356,23 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
   if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
 }
 
+// natural blocked layout -> 8 parity sub-volumes: [N*C/8][D][H][W][8] -> [N*C/8][pd*4+ph*2+pw][D/2][H/2][W/2][8]
+__global__ void __launch_bounds__(256)
+space_to_depth_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, int64_t nblk, int D, int H, int W)
+{
+  const int D2 = D / 2, H2 = H / 2, W2 = W / 2;
+  const int64_t total = nblk * D * H * W;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int w2 = (int)(idx % W2);
+    const int h2 = (int)((idx / W2) % H2);
+    const int d2 = (int)((idx / ((int64_t)W2 * H2)) % D2);
+    const int cls = (int)((idx / ((int64_t)W2 * H2 * D2)) % 8);
+    const int64_t b = idx / ((int64_t)W2 * H2 * D2 * 8);
+    const int d = 2 * d2 + (cls >> 2), h = 2 * h2 + ((cls >> 1) & 1), w = 2 * w2 + (cls & 1);
+    dst[idx] = __ldg(src + ((b * D + d) * H + h) * W + w);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
@@ -241,33 +393,63 @@ static EncodeTiledFn get_encode()
   return fn;
 }
 
-static int debug_nostack()
+static int env_flag(const char *name)
 {
-  static int v = -1;
-  if (v < 0) { const char *e = getenv("IDISP_TC_NOSTACK"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v;
+  const char *e = getenv(name);
+  return (e && e[0] == '1') ? 1 : 0;
 }
+
+static int mode_of(int kind) { return kind == IDISP_CONV_S1 ? M_S1 : (kind == IDISP_CONV_S2 ? M_S2 : M_DEC); }
 
 }  // namespace tc
 
+// Pack [27][cin][cout] f32 (tap = (kd*3+kh)*3+kw, BN scale folded) into the per-mode UMMA B layout, bf16:
+// rows of 8 input channels (16 B), 8-row core matrices contiguous (SBO 128 B), K cores LBO apart.
 int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, TcWeights &out, cudaStream_t s)
 {
   tc_weights_free(out);
   out.kind = kind; out.cin = cin; out.cout = cout;
-  if (!(kind == IDISP_CONV_S1 && (cin == 32 || cin == 64) && (cout == 32 || cout == 64))) return IDISP_OK;  // SIMT layer
-  const int KS = cin / 16, NH = cout / 32;
-  std::vector<__nv_bfloat16> h((size_t)NH * 9 * KS * 2 * 96 * 8);
-  for (int nh = 0; nh < NH; ++nh)
-    for (int t2 = 0; t2 < 9; ++t2)
-      for (int ks = 0; ks < KS; ++ks)
-        for (int kc = 0; kc < 2; ++kc)
-          for (int n = 0; n < 96; ++n)
-            for (int e = 0; e < 8; ++e) {
-              const int j = n / 32, co = n % 32, kd = 2 - j, kh = t2 / 3, kw = t2 % 3;
-              const int ci = ks * 16 + kc * 8 + e;
-              const float v = w_tap[((size_t)((kd * 3 + kh) * 3 + kw) * cin + ci) * cout + nh * 32 + co];
-              h[(((((size_t)nh * 9 + t2) * KS + ks) * 2 + kc) * 96 + n) * 8 + e] = __float2bfloat16_rn(v);
-            }
+  if (!tc_supported(kind, cin, cout, 4, 16, 16)) return IDISP_OK;  // layer stays on the SIMT kernel
+  const int KS = cin / 16, NH = (cout + 31) / 32;
+  const size_t per_nh = (size_t)27 * KS * 512;  // bf16 elements
+  std::vector<__nv_bfloat16> h(NH * per_nh, __float2bfloat16_rn(0.f));
+  auto wv = [&](int kd, int kh, int kw, int ci, int co) -> float {
+    return co < cout ? w_tap[((size_t)((kd * 3 + kh) * 3 + kw) * cin + ci) * cout + co] : 0.f;
+  };
+  for (int nh = 0; nh < NH; ++nh) {
+    __nv_bfloat16 *base = h.data() + nh * per_nh;
+    if (kind == IDISP_CONV_S1 || kind == IDISP_CONV_S2) {
+      // chunk (kh,kw,ks): [2 kcores][96 rows = 3 blocks x 32 couts][8]; block j <-> kd = S1 {2,1,0}, S2 {2,0,1}
+      static const int kd_s1[3] = {2, 1, 0}, kd_s2[3] = {2, 0, 1};
+      const int *kdj = kind == IDISP_CONV_S1 ? kd_s1 : kd_s2;
+      for (int t2 = 0; t2 < 9; ++t2)
+        for (int ks = 0; ks < KS; ++ks)
+          for (int kc = 0; kc < 2; ++kc)
+            for (int n = 0; n < 96; ++n)
+              for (int e = 0; e < 8; ++e)
+                base[((((size_t)t2 * KS + ks) * 2 + kc) * 96 + n) * 8 + e] =
+                    __float2bfloat16_rn(wv(kdj[n / 32], t2 / 3, t2 % 3, ks * 16 + kc * 8 + e, nh * 32 + n % 32));
+    } else {
+      // DECONV: [kd][ks][2 kcores][288 rows][8]; rows = entries e0..e4 (tc::dec_*), blocks = output classes
+      //   class = pw*2+ph; per axis: p=0 -> k=1 (shift 0); p=1 -> k=2 (shift 0), k=0 (shift 1)
+      struct Blk { int kh, kw; };
+      static const Blk blocks[9] = {
+          {1, 1}, {2, 1}, {1, 2}, {2, 2},  // e0 shift(0,0): classes 0 (ph0,pw0), 1 (ph1,pw0), 2 (ph0,pw1), 3 (ph1,pw1)
+          {1, 0}, {2, 0},                  // e1 shift(0,1): classes 2, 3  (pw=1 -> kw=0)
+          {0, 1},                          // e2 shift(1,0): class 1       (ph=1 -> kh=0, pw=0 -> kw=1)
+          {0, 2},                          // e3 shift(1,0): class 3       (kh=0, pw=1 with shift_w 0 -> kw=2)
+          {0, 0}};                         // e4 shift(1,1): class 3
+      for (int kd = 0; kd < 3; ++kd)
+        for (int ks = 0; ks < KS; ++ks)
+          for (int kc = 0; kc < 2; ++kc)
+            for (int row = 0; row < 288; ++row)
+              for (int e = 0; e < 8; ++e) {
+                const Blk b = blocks[row / 32];
+                base[((((size_t)kd * KS + ks) * 2 + kc) * 288 + row) * 8 + e] =
+                    __float2bfloat16_rn(wv(kd, b.kh, b.kw, ks * 16 + kc * 8 + e, nh * 32 + row % 32));
+              }
+    }
+  }
   out.bytes = h.size() * sizeof(__nv_bfloat16);
   IDISP_CUDA(cudaMalloc(&out.dev, out.bytes));
   IDISP_CUDA(cudaMemcpyAsync(out.dev, h.data(), out.bytes, cudaMemcpyHostToDevice, s));
@@ -283,44 +465,72 @@ void tc_weights_free(TcWeights &w)
 
 bool tc_supported(int kind, int cin, int cout, int D, int H, int W)
 {
-  static int disabled = -1;
-  if (disabled < 0) { const char *e = getenv("IDISP_TC_DISABLE"); disabled = (e && e[0] == '1') ? 1 : 0; }
-  if (disabled) return false;
-  return kind == IDISP_CONV_S1 && (cin == 32 || cin == 64) && (cout == 32 || cout == 64) && D >= 1 && H >= 1 && W >= 1;
+  static int disabled = -1, only_s1 = -1;
+  if (disabled < 0) { disabled = tc::env_flag("IDISP_TC_DISABLE"); only_s1 = tc::env_flag("IDISP_TC_ONLY_S1"); }
+  if (disabled || D < 1 || H < 1 || W < 1) return false;
+  if (kind == IDISP_CONV_S1) return (cin == 32 || cin == 64) && (cout == 32 || cout == 64 || (cout == 1 && !only_s1));
+  if (only_s1) return false;
+  if (kind == IDISP_CONV_S2) return (cin == 32 || cin == 64) && (cout == 32 || cout == 64) && D % 2 == 0 && H % 2 == 0 && W % 2 == 0;
+  if (kind == IDISP_DECONV_S2) return cin == 64 && (cout == 32 || cout == 64);
+  return false;
 }
 
-template <int CIN>
-static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, int H, int W, int Cout, const float *bias,
-                     const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, cudaStream_t s)
+size_t tc_scratch_bytes(int kind, int B, int cin, int D, int H, int W)
 {
-  using C = tc::Cfg<CIN>;
+  return kind == IDISP_CONV_S2 ? (size_t)B * cin * D * H * W * sizeof(__nv_bfloat16) : 0;
+}
+
+template <int CIN, int MODE>
+static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, int H, int W, int Cout, const float *bias,
+                     const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1, void *scratch,
+                     cudaStream_t s)
+{
+  using C = tc::Cfg<CIN, MODE>;
+  using MC = tc::ModeCfg<MODE>;
   tc::EncodeTiledFn enc = tc::get_encode();
   if (!enc) { set_error("tc_conv3d: cuTensorMapEncodeTiled not available from the driver"); return IDISP_ERR_CUDA; }
   CUtensorMap map;
-  // (8 ch, W) are contiguous in the blocked layout -> ONE tensor dimension of 8*W elements, so a box row is
-  // 10 voxels x 16 B = 160 contiguous bytes (a 16-byte inner box made TMA issue one request per voxel and
-  // capped the kernel at ~10 cycles per 16 B; measured in profiles/r01_notes.md)
-  const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B * C::CBLK};
-  const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
-  const cuuint32_t box[4] = {8 * tc::HALO_W, tc::HALO_H, 1, (cuuint32_t)C::CBLK};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16 *>(x), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("tc_conv3d: cuTensorMapEncodeTiled failed (%d) for dims W=%d H=%d D=%d", (int)r, W, H, D); return IDISP_ERR_CUDA; }
+  CUresult r;
+  const void *src = x;
+  if (MODE == tc::M_S2) {
+    if (!scratch) { set_error("tc_conv3d: stride-2 layer needs the space-to-depth scratch buffer"); return IDISP_ERR_INVALID; }
+    const int64_t nblk = (int64_t)B * C::CBLK, total = nblk * D * H * W;
+    const int64_t want = ceil_div64(total, 256);
+    tc::space_to_depth_kernel<<<(int)(want < 148 * 32 ? want : 148 * 32), 256, 0, s>>>((const uint4 *)x, (uint4 *)scratch, nblk, D, H, W);
+    IDISP_LAUNCH_CHECK();
+    src = scratch;
+    const int D2 = D / 2, H2 = H / 2, W2 = W / 2;
+    const cuuint64_t dims[5] = {(cuuint64_t)W2 * 8, (cuuint64_t)H2, (cuuint64_t)D2, 8, (cuuint64_t)B * C::CBLK};
+    const cuuint64_t strides[4] = {(cuuint64_t)W2 * 16, (cuuint64_t)H2 * W2 * 16, (cuuint64_t)D2 * H2 * W2 * 16, (cuuint64_t)8 * D2 * H2 * W2 * 16};
+    const cuuint32_t box[5] = {8 * MC::SUB_W, MC::SUB_H, 1, 1, (cuuint32_t)C::CBLK};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    // (8 ch, W) are contiguous in the blocked layout -> ONE tensor dimension of 8*W elements: a box row is SUB_W voxels x 16 B
+    const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B * C::CBLK};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
+    const cuuint32_t box[4] = {8 * MC::SUB_W, MC::SUB_H, 1, (cuuint32_t)C::CBLK};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) { set_error("tc_conv3d: cuTensorMapEncodeTiled failed (%d) for dims W=%d H=%d D=%d mode=%d", (int)r, W, H, D, MODE); return IDISP_ERR_CUDA; }
   tc::Params p;
-  p.w = (const __nv_bfloat16 *)w.dev; p.bias = bias; p.residual = residual; p.y = y;
-  p.B = B; p.D = D; p.H = H; p.W = W; p.Cout = Cout; p.relu = relu;
-  p.tiles_h = ceil_div(H, tc::TH); p.tiles_w = ceil_div(W, tc::TW); p.nh = Cout / 32;
-  p.stack = tc::debug_nostack() ? 0 : 1;
+  p.w = (const __nv_bfloat16 *)w.dev; p.bias = bias; p.residual = residual; p.y = y; p.res1 = res1; p.y1 = y1;
+  p.B = B; p.Din = D; p.Cout = Cout; p.relu = relu;
+  if (MODE == tc::M_S1) { p.Dout = D; p.Ho = H; p.Wo = W; p.Hr = H; p.Wr = W; }
+  if (MODE == tc::M_S2) { p.Dout = D / 2; p.Ho = H / 2; p.Wo = W / 2; p.Hr = H / 2; p.Wr = W / 2; }
+  if (MODE == tc::M_DEC) { p.Dout = 2 * D; p.Ho = 2 * H; p.Wo = 2 * W; p.Hr = H; p.Wr = W; }
+  p.tiles_h = ceil_div(p.Hr, tc::TH); p.tiles_w = ceil_div(p.Wr, tc::TW); p.nh = (Cout + 31) / 32;
   const int ncols = B * p.tiles_h * p.tiles_w;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int per_half = sms / p.nh;
-  if (per_half > ncols) per_half = ncols;
-  const int grid = per_half * p.nh;
-  auto kern = tc::conv3d_tc_kernel<CIN>;
+  int per_slice = sms / p.nh;
+  if (per_slice > ncols) per_slice = ncols;
+  const int grid = per_slice * p.nh;
+  auto kern = tc::conv3d_tc_kernel<CIN, MODE>;
   IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
   kern<<<grid, tc::NTHREADS, C::SMEM, s>>>(map, p);
   IDISP_LAUNCH_CHECK();
@@ -328,15 +538,21 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
 }
 
 int tc_conv3d(const TcWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D, int H, int W, int Cout, int kind,
-              const float *bias, const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, cudaStream_t s)
+              const float *bias, const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1,
+              void *scratch, cudaStream_t s)
 {
-  if (!tc_supported(kind, Cin, Cout, D, H, W) || !w.dev || w.cin != Cin || w.cout != Cout) {
+  if (!tc_supported(kind, Cin, Cout, D, H, W) || !w.dev || w.cin != Cin || w.cout != Cout || w.kind != kind) {
     set_error("tc_conv3d: layer (kind=%d, %d->%d) not prepared for the tensor-core path", kind, Cin, Cout);
     return IDISP_ERR_INVALID;
   }
+  if ((Cout == 1) != (y1 != nullptr)) { set_error("tc_conv3d: the 1-channel head needs the f32 output (and only it)"); return IDISP_ERR_INVALID; }
   if (B == 0) return IDISP_OK;
-  return Cin == 32 ? tc_launch<32>(w, x, B, D, H, W, Cout, bias, residual, relu, y, s)
-                   : tc_launch<64>(w, x, B, D, H, W, Cout, bias, residual, relu, y, s);
+#define IDISP_TC(CI, MD) return tc_launch<CI, MD>(w, x, B, D, H, W, Cout, bias, residual, relu, y, res1, y1, scratch, s)
+  const int mode = tc::mode_of(kind);
+  if (mode == tc::M_S1) { if (Cin == 32) IDISP_TC(32, tc::M_S1); else IDISP_TC(64, tc::M_S1); }
+  if (mode == tc::M_S2) { if (Cin == 32) IDISP_TC(32, tc::M_S2); else IDISP_TC(64, tc::M_S2); }
+  IDISP_TC(64, tc::M_DEC);
+#undef IDISP_TC
 }
 
 }  // namespace idisp

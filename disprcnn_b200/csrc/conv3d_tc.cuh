@@ -16,7 +16,11 @@ int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, TcWeight
 void tc_weights_free(TcWeights &w);
 // whether the tensor-core kernel covers this layer shape (otherwise the SIMT kernel runs it)
 bool tc_supported(int kind, int cin, int cout, int D, int H, int W);
+// device scratch the layer needs (stride-2 convs re-lay their input into parity sub-volumes)
+size_t tc_scratch_bytes(int kind, int B, int cin, int D, int H, int W);
+// Cout == 1 (the classifier head): y1/res1 are [B][D][H][W] f32 and y/residual/bias are unused.
 int tc_conv3d(const TcWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D, int H, int W, int Cout, int kind,
-              const float *bias, const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, cudaStream_t s);
+              const float *bias, const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1,
+              void *scratch, cudaStream_t s);
 
 }  // namespace idisp

@@ -245,6 +245,7 @@ struct Buffers {
   void *h1, *pre1, *prek, *postA, *postB;    // half resolution, 64 ch
   void *q1, *q2;                             // quarter resolution, 64 ch
   float *costX, *costY;                      // 1-channel f32 logits
+  void *split;                               // parity re-lay scratch of the stride-2 tensor-core convs
 };
 
 Buffers carve(Arena &A, int C, int B, int D, int Hf, int Wf, size_t esz)
@@ -257,6 +258,7 @@ Buffers carve(Arena &A, int C, int B, int D, int Hf, int Wf, size_t esz)
   b.h1 = A.take(half64); b.pre1 = A.take(half64); b.prek = A.take(half64); b.postA = A.take(half64); b.postB = A.take(half64);
   b.q1 = A.take(quart64); b.q2 = A.take(quart64);
   b.costX = (float *)A.take((size_t)B * V * 4); b.costY = (float *)A.take((size_t)B * V * 4);
+  b.split = A.take(full32);
   return b;
 }
 }  // namespace
@@ -289,9 +291,11 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
     const LayerSpec &L = p->layers[li];
     mark(li);
     ++launches;
-    if (std::is_same<T, __nv_bfloat16>::value && tc_supported(L.kind, L.cin, L.cout, d, h, w))
+    if (std::is_same<T, __nv_bfloat16>::value && tc_supported(L.kind, L.cin, L.cout, d, h, w)) {
+      if (L.kind == IDISP_CONV_S2) ++launches;  // + the space-to-depth re-lay
       return tc_conv3d(p->dev[li].tc, (const __nv_bfloat16 *)x, B, L.cin, d, h, w, L.cout, L.kind, p->dev[li].bias,
-                       (const __nv_bfloat16 *)res, relu, (__nv_bfloat16 *)y, s);
+                       (const __nv_bfloat16 *)res, relu, (__nv_bfloat16 *)y, nullptr, nullptr, b.split, s);
+    }
     return launch_conv3d_simt<T>((const T *)x, B, L.cin, d, h, w, p->dev[li].w_tap, L.cout, L.kind, p->dev[li].bias,
                                  (const T *)res, relu, (T *)y, s);
   };
@@ -324,7 +328,12 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
     float *dst = (k == 1) ? b.costY : b.costX;
     const float *prev = k == 0 ? nullptr : (k == 1 ? b.costX : b.costY);
     mark(25 + k);
-    RUN(launch_conv3d_to1<T>((const T *)b.c, B, 32, D, Hf, Wf, p->dev[25 + k].w_tap, prev, dst, s)); ++launches;
+    if (std::is_same<T, __nv_bfloat16>::value && tc_supported(IDISP_CONV_S1, 32, 1, D, Hf, Wf))
+      RUN(tc_conv3d(p->dev[25 + k].tc, (const __nv_bfloat16 *)b.c, B, 32, D, Hf, Wf, 1, IDISP_CONV_S1, nullptr, nullptr, 0, nullptr,
+                    prev, dst, nullptr, s));
+    else
+      RUN(launch_conv3d_to1<T>((const T *)b.c, B, 32, D, Hf, Wf, p->dev[25 + k].w_tap, prev, dst, s));
+    ++launches;
   }
   // upsample + softmax + regression (:169-174)
   mark(-2);
@@ -427,9 +436,10 @@ static int conv3d_hook(const float *x, int B, int Cin, int D, int H, int W, cons
   const int64_t Vi = (int64_t)D * H * W, Vo = (int64_t)Do * Ho * Wo;
   T *xb = nullptr, *yb = nullptr, *rb = nullptr;
   float *wd = nullptr, *bd = nullptr, *y1 = nullptr;
+  void *scratch = nullptr;
   int rc = IDISP_OK;
   TcWeights tcw;
-  auto cleanup = [&]() { cudaFree(xb); cudaFree(yb); cudaFree(rb); cudaFree(wd); cudaFree(bd); cudaFree(y1); tc_weights_free(tcw); };
+  auto cleanup = [&]() { cudaFree(xb); cudaFree(yb); cudaFree(rb); cudaFree(wd); cudaFree(bd); cudaFree(y1); cudaFree(scratch); tc_weights_free(tcw); };
 #define HK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #expr, __FILE__, __LINE__); } } while (0)
 #define HR(expr) do { if ((rc = (expr)) != IDISP_OK) { cudaStreamSynchronize(s); cleanup(); return rc; } } while (0)
   HK(cudaMalloc(&xb, (size_t)B * Cin * Vi * sizeof(T)));
@@ -439,7 +449,12 @@ static int conv3d_hook(const float *x, int B, int Cin, int D, int H, int W, cons
   HK(cudaMemcpyAsync(bd, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice, s));
   HR(launch_ncdhw_to_blocked<T>(x, xb, B, Cin, Vi, s));
   if (Cout == 1) {
-    HR(launch_conv3d_to1<T>(xb, B, Cin, D, H, W, wd, residual, y, s));
+    if (precision == IDISP_PREC_BF16 && tc_supported(kind, Cin, Cout, D, H, W)) {
+      HR(tc_weights_prepare(w_tap.data(), kind, Cin, Cout, tcw, s));
+      HR(tc_conv3d(tcw, (const __nv_bfloat16 *)xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, residual, y, nullptr, s));
+    } else {
+      HR(launch_conv3d_to1<T>(xb, B, Cin, D, H, W, wd, residual, y, s));
+    }
     // bias/relu for the 1-channel hook are not part of any reference layer
   } else {
     HK(cudaMalloc(&yb, (size_t)B * Cout * Vo * sizeof(T)));
@@ -449,8 +464,10 @@ static int conv3d_hook(const float *x, int B, int Cin, int D, int H, int W, cons
     }
     if (precision == IDISP_PREC_BF16 && tc_supported(kind, Cin, Cout, D, H, W)) {
       HR(tc_weights_prepare(w_tap.data(), kind, Cin, Cout, tcw, s));
+      const size_t sb = tc_scratch_bytes(kind, B, Cin, D, H, W);
+      if (sb) HK(cudaMalloc(&scratch, sb));
       HR(tc_conv3d(tcw, (const __nv_bfloat16 *)xb, B, Cin, D, H, W, Cout, kind, bd, (const __nv_bfloat16 *)rb, relu,
-                   (__nv_bfloat16 *)yb, s));
+                   (__nv_bfloat16 *)yb, nullptr, nullptr, scratch, s));
     } else {
       HR(launch_conv3d_simt<T>(xb, B, Cin, D, H, W, wd, Cout, kind, bd, rb, relu, yb, s));
     }

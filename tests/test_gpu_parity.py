@@ -117,6 +117,9 @@ CONV_CASES = [
     (0, 16, 32, (4, 4, 12), False, True), (1, 32, 64, (8, 12, 12), False, True), (1, 64, 64, (6, 10, 14), False, True),
     (1, 32, 64, (5, 7, 9), False, True), (2, 64, 64, (3, 4, 5), True, True), (2, 64, 32, (4, 6, 7), True, False),
     (0, 32, 32, (6, 16, 24), False, True), (0, 64, 64, (4, 16, 16), True, True),
+    # shapes that cross tile borders, wrap the TMEM accumulator ring and use every tensor-core mode
+    (0, 32, 32, (36, 24, 20), True, True), (1, 32, 64, (36, 36, 20), False, True), (1, 64, 64, (12, 20, 36), False, True),
+    (2, 64, 32, (7, 20, 12), True, False), (2, 64, 64, (5, 18, 9), True, True),
 ]
 
 
@@ -149,17 +152,20 @@ def test_conv3d_layer_vs_oracle(lib, prec, kind, cin, cout, dhw, use_res, relu):
     assert err < tol, f'{prec} kind={kind} {cin}->{cout}: max|d|={err:.3e} (|ref|max={ref_mag:.2f})'
 
 
-def test_conv3d_to1_vs_oracle(lib):
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+def test_conv3d_to1_vs_oracle(lib, prec):
     from disprcnn_b200 import _lib
     g = torch.Generator().manual_seed(99)
-    x = torch.randn(2, 32, 5, 9, 11, generator=g)
+    x = torch.randn(2, 32, 21, 9, 11, generator=g)
     w = torch.randn(1, 32, 3, 3, 3, generator=g) * 0.05
-    res = torch.randn(2, 1, 5, 9, 11, generator=g)
+    if prec == 'bf16':
+        x, w = x.bfloat16().float(), w.bfloat16().float()
+    res = torch.randn(2, 1, 21, 9, 11, generator=g)
     want = F.conv3d(x, w, None, 1, 1) + res
     y = torch.empty(want.shape, device='cuda')
     xc, wc, rc = x.cuda(), w.cuda(), res.cuda()
-    _lib.check(lib.idisp_conv3d(_lib.ptr(xc), 2, 32, 5, 9, 11, _lib.ptr(wc), 1, 0, None, None, _lib.ptr(rc), 0, 0,
-                                _lib.ptr(y), _lib.stream_ptr()))
+    _lib.check(lib.idisp_conv3d(_lib.ptr(xc), 2, 32, 21, 9, 11, _lib.ptr(wc), 1, 0, None, None, _lib.ptr(rc), 0,
+                                0 if prec == 'fp32' else 1, _lib.ptr(y), _lib.stream_ptr()))
     assert (y.cpu() - want).abs().max().item() < 2e-5
 
 

@@ -17,15 +17,15 @@ sys.path.insert(0, ROOT)
 from disprcnn_b200 import _lib  # noqa: E402
 
 
-def run(x, w, bias=None, res=None, relu=0):
+def run(x, w, bias=None, res=None, relu=0, kind=0, oshape=None):
     lib = _lib.load()
     B, cin, D, H, W = x.shape
-    cout = w.shape[0]
-    y = torch.full((B, cout, D, H, W), float('nan'), device='cuda')
+    cout = w.shape[1] if kind == 2 else w.shape[0]
+    y = torch.full(oshape if oshape is not None else (B, cout, D, H, W), float('nan'), device='cuda')
     xc, wc = x.cuda(), w.cuda()
     bc = bias.cuda() if bias is not None else None
     rc = res.cuda() if res is not None else None
-    _lib.check(lib.idisp_conv3d(_lib.ptr(xc), B, cin, D, H, W, _lib.ptr(wc), cout, 0, None, _lib.ptr(bc), _lib.ptr(rc),
+    _lib.check(lib.idisp_conv3d(_lib.ptr(xc), B, cin, D, H, W, _lib.ptr(wc), cout, kind, None, _lib.ptr(bc), _lib.ptr(rc),
                                 relu, 1, _lib.ptr(y), _lib.stream_ptr()))
     torch.cuda.synchronize()
     return y.cpu()
@@ -67,6 +67,28 @@ def main():
             w[c, c, kd, kh, kw] = 1.0
     elif exp == 'random':
         w = (torch.randn(cout, cin, 3, 3, 3, generator=g) * (2.0 / (27 * cout)) ** 0.5).bfloat16().float()
+    elif exp in ('s2', 'dec', 'to1'):
+        kind = {'s2': 1, 'dec': 2, 'to1': 0}[exp]
+        if exp == 'to1':
+            cout = 1
+        wshape = (cin, cout, 3, 3, 3) if kind == 2 else (cout, cin, 3, 3, 3)
+        w = (torch.randn(wshape, generator=g) * (2.0 / (27 * max(cout, 8))) ** 0.5).bfloat16().float()
+        if kind == 1:
+            want = F.conv3d(x, w, None, 2, 1)
+        elif kind == 2:
+            want = F.conv_transpose3d(x, w, None, 2, 1, 1)
+        else:
+            want = F.conv3d(x, w, None, 1, 1)
+        if exp == 'to1':
+            res = torch.randn(want.shape, generator=g)
+            want = want + res
+            report(exp, run(x, w, None, res, 0, kind, tuple(want.shape)), want, {'shape': [cin, cout, D, H, W]})
+        else:
+            bias = torch.randn(cout, generator=g)
+            res = torch.randn(want.shape, generator=g).bfloat16().float()
+            want = F.relu(want + bias.view(1, -1, 1, 1, 1) + res)
+            report(exp, run(x, w, bias, res, 1, kind, tuple(want.shape)), want, {'shape': [cin, cout, D, H, W]})
+        return
     elif exp == 'random_epi':
         w = (torch.randn(cout, cin, 3, 3, 3, generator=g) * (2.0 / (27 * cout)) ** 0.5).bfloat16().float()
         bias = torch.randn(cout, generator=g)
