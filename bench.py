@@ -232,7 +232,7 @@ def main():
             step_device()
             n = lib.idisp_plan_launches_per_forward(plan)
             ms = (ctypes.c_float * n)()
-            ly = (ctypes.c_int * n)()
+            ly = (ctypes.c_int * n)(*([-100] * n))
             # reading the events waits for this step only; the next step is enqueued right after
             _lib.check(lib.idisp_plan_get_timing(plan, ms, ly, n))
             per_step.append((list(ms), list(ly)))
@@ -246,11 +246,12 @@ def main():
         _lib.check(lib.idisp_plan_enable_timing(plan, 0))
         launches_per_step = lib.idisp_plan_launches_per_forward(plan) + (1 if world > 1 else 0)
         conv_ms = sum(v for msl, lyl in per_step for v, l in zip(msl, lyl) if 0 <= l <= 27)
-        other_ms = sum(v for msl, lyl in per_step for v, l in zip(msl, lyl) if l < 0)
+        other_ms = sum(v for msl, lyl in per_step for v, l in zip(msl, lyl) if -100 < l < 0)
         by_layer = {}
         for msl, lyl in per_step:
             for v, l in zip(msl, lyl):
-                by_layer[l] = by_layer.get(l, 0.0) + v / args.steps
+                if l > -100:
+                    by_layer[l] = by_layer.get(l, 0.0) + v / args.steps
 
         # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----
         def step_host():

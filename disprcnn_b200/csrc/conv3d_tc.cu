@@ -113,7 +113,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + C::BAR_OFF + (2 * C::STAGES + 2 * NSLOT) * 8);
   float *bias_s = reinterpret_cast<float *>(smem + C::BAR_OFF + (2 * C::STAGES + 2 * NSLOT) * 8 + 16);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index made PROVABLY warp-uniform (shfl from lane 0) so the role branches are uniform branches and the
+  // producer / MMA warps can keep their addresses and descriptors in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int nh = blockIdx.x % p.nh;  // this CTA's fixed 32-wide output-channel slice
   const int cta = blockIdx.x / p.nh, ncta = gridDim.x / p.nh;
   const int ncols = p.B * p.tiles_h * p.tiles_w;
@@ -150,8 +152,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
   ptx::tc_fence_after();
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
+    // ================= TMA producer (whole warp converged; one elected lane issues) =================
+    {
+      const bool lead = ptx::elect_one();
       uint32_t q = 0;
       for (int col = cta; col < ncols; col += ncta) {
         const int tw = col % p.tiles_w, th = (col / p.tiles_w) % p.tiles_h, n = col / (p.tiles_w * p.tiles_h);
@@ -161,25 +164,35 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
             for (int ph = 0; ph < 2; ++ph, ++q) {
               const uint32_t s = q % C::STAGES;
               ptx::mbar_wait(empty_bar(s), ((q / C::STAGES) & 1) ^ 1);
-              ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
-              for (int pw = 0; pw < 2; ++pw)
-                ptx::tma_load_5d(stage_addr0 + s * C::STAGE_BYTES + pw * C::SUB_BYTES, &xmap, full_bar(s), (tw * TW - 1) * 8,
-                                 th * TH - 1, z >> 1, (z & 1) * 4 + ph * 2 + pw, n * C::CBLK);
+              if (lead) {
+                ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
+                for (int pw = 0; pw < 2; ++pw)
+                  ptx::tma_load_5d(stage_addr0 + s * C::STAGE_BYTES + pw * C::SUB_BYTES, &xmap, full_bar(s), (tw * TW - 1) * 8,
+                                   th * TH - 1, z >> 1, (z & 1) * 4 + ph * 2 + pw, n * C::CBLK);
+              }
             }
           } else {
             const uint32_t s = q % C::STAGES;
             ptx::mbar_wait(empty_bar(s), ((q / C::STAGES) & 1) ^ 1);
-            ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
             const int halo = MODE == M_S1 ? 1 : 0;
-            ptx::tma_load_4d(stage_addr0 + s * C::STAGE_BYTES, &xmap, full_bar(s), (tw * TW - halo) * 8, th * TH - halo, z, n * C::CBLK);
+            if (lead) {
+              ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
+              ptx::tma_load_4d(stage_addr0 + s * C::STAGE_BYTES, &xmap, full_bar(s), (tw * TW - halo) * 8, th * TH - halo, z, n * C::CBLK);
+            }
             ++q;
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (single thread) =================
-    if (lane == 0) {
+    // ================= MMA issuer =================
+    // The whole warp runs this loop converged and ONE elected lane issues: tcgen05.mma takes its descriptors from
+    // uniform registers, and inside an `if (lane == 0)` region the compiler cannot prove uniformity -- it wrapped
+    // every MMA in an ELECT / 6x R2UR.BROADCAST / BRA.U.ANY waterfall (~190 cycles per MMA, profiles/r01_notes.md).
+    {
+      const bool lead = ptx::elect_one();
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id) { if (lead) ptx::umma_bf16_ss(d, a, b, id, 1u); };
+      auto commit = [&](uint32_t bar) { if (lead) ptx::umma_commit(bar); };
       const uint64_t a_desc0 = ptx::make_smem_desc(stage_addr0, C::PLANE_BYTES, C::ROW_BYTES);
       auto wait_acc_empty = [&](uint32_t g) { ptx::mbar_wait(acce_bar(g % NSLOT), ((g / NSLOT) & 1) ^ 1); };
       uint32_t q = 0, g0 = 0;
@@ -207,14 +220,14 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
               for (int ks = 0; ks < C::KS; ++ks) {
                 const uint32_t aoff = ((tap / 3) * MC::SUB_W + (tap % 3)) * 16 + ks * 2 * C::PLANE_BYTES;
                 const uint32_t boff = (tap * C::KS + ks) * 3072;
-                ptx::umma_bf16_ss(d1, desc_add(a0, aoff), desc_add(b1, boff), id1, 1u);
-                if (len2 > 0) ptx::umma_bf16_ss(d2, desc_add(a0, aoff), desc_add(b2, boff), id2, 1u);
+                mma(d1, desc_add(a0, aoff), desc_add(b1, boff), id1);
+                if (len2 > 0) mma(d2, desc_add(a0, aoff), desc_add(b2, boff), id2);
               }
             }
-            ptx::umma_commit(empty_bar(s));
+            commit(empty_bar(s));
             ++q;
-            if (z >= 1) ptx::umma_commit(accf_bar((g0 + z - 1) % NSLOT));
-            if (z == Din - 1) ptx::umma_commit(accf_bar((g0 + z) % NSLOT));
+            if (z >= 1) commit(accf_bar((g0 + z - 1) % NSLOT));
+            if (z == Din - 1) commit(accf_bar((g0 + z) % NSLOT));
           } else if (MODE == M_S2) {
             const int pz = z >> 1;  // output plane of kd=1 (even z) / kd=2 (odd z); odd z also feeds pz+1 with kd=0
             const bool odd = z & 1;
@@ -245,13 +258,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
                 for (int ks = 0; ks < C::KS; ++ks) {
                   const uint32_t aoff = sub * C::SUB_BYTES + (rh * MC::SUB_W + rw) * 16 + ks * 2 * C::PLANE_BYTES;
                   const uint32_t boff = ((kh * 3 + kw) * C::KS + ks) * 3072;
-                  ptx::umma_bf16_ss(d1, desc_add(a0, aoff), desc_add(b1, boff), id1, 1u);
-                  if (len2 > 0) ptx::umma_bf16_ss(d2, desc_add(a0, aoff), desc_add(b2, boff), id2, 1u);
+                  mma(d1, desc_add(a0, aoff), desc_add(b1, boff), id1);
+                  if (len2 > 0) mma(d2, desc_add(a0, aoff), desc_add(b2, boff), id2);
                 }
               }
-              ptx::umma_commit(empty_bar(s));
+              commit(empty_bar(s));
             }
-            if (odd || z == Din - 1) ptx::umma_commit(accf_bar((g0 + pz) % NSLOT));
+            if (odd || z == Din - 1) commit(accf_bar((g0 + pz) % NSLOT));
           } else {  // M_DEC: rows are input positions; input plane z -> output planes 2z-1 (kd=0), 2z (kd=1), 2z+1 (kd=2)
             wait_acc_empty(g0 + 2 * z);
             wait_acc_empty(g0 + 2 * z + 1);
@@ -272,15 +285,15 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
                   // weights: [kd][ks][kcore][288 rows][8]; entry e owns rows [row_off, row_off+rows)
                   const uint32_t boff = ((kd * C::KS + ks) * 2 * 288 + dec_row_off(e)) * 16;
                   const uint64_t bd = ptx::make_smem_desc(w_addr + boff, 288 * 16, 128);
-                  ptx::umma_bf16_ss(dbase + dec_dcol(e), desc_add(a0, aoff), bd, ptx::make_idesc_bf16(128, dec_rows(e)), 1u);
+                  mma(dbase + dec_dcol(e), desc_add(a0, aoff), bd, ptx::make_idesc_bf16(128, dec_rows(e)));
                 }
               }
             }
-            ptx::umma_commit(empty_bar(s));
+            commit(empty_bar(s));
             ++q;
-            if (z >= 1) ptx::umma_commit(accf_bar((g0 + 2 * z - 1) % NSLOT));
-            ptx::umma_commit(accf_bar((g0 + 2 * z) % NSLOT));
-            if (z == Din - 1) ptx::umma_commit(accf_bar((g0 + 2 * z + 1) % NSLOT));
+            if (z >= 1) commit(accf_bar((g0 + 2 * z - 1) % NSLOT));
+            commit(accf_bar((g0 + 2 * z) % NSLOT));
+            if (z == Din - 1) commit(accf_bar((g0 + 2 * z + 1) % NSLOT));
           }
         }
       }

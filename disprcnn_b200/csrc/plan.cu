@@ -281,10 +281,11 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
   int launches = 0;
   int rc;
   if (p->timing) p->ev_layer.clear();
-  auto mark = [&](int layer) {  // record an event BEFORE launch slot `launches`
+  int nmark = 0;
+  auto mark = [&](int layer) {  // record an event BEFORE the launch(es) of `layer`
     if (!p->timing) return;
-    if ((int)p->ev.size() <= launches) { cudaEvent_t e; cudaEventCreate(&e); p->ev.push_back(e); }
-    cudaEventRecord(p->ev[launches], s);
+    while ((int)p->ev.size() <= nmark) { cudaEvent_t e; cudaEventCreate(&e); p->ev.push_back(e); }
+    cudaEventRecord(p->ev[nmark++], s);
     if (layer != -99) p->ev_layer.push_back(layer);
   };
   auto conv = [&](int li, const void *x, int d, int h, int w, const void *res, int relu, void *y) -> int {
