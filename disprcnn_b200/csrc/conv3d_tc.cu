@@ -37,6 +37,7 @@
 #include "conv3d_tc.cuh"
 #include "sm100_ptx.cuh"
 
+#include <type_traits>
 #include <vector>
 
 namespace idisp {
@@ -81,6 +82,7 @@ struct Params {
   float *y1;                      // 32->1 head: output [B][D][H][W] f32 (non-null selects this epilogue)
   int B, Din, Dout, Ho, Wo, Hr, Wr, Cout, relu;  // (Hr,Wr): row grid the 8x16 tiles cover
   int tiles_h, tiles_w, nh;
+  int dbg;                        // timing experiments only (IDISP_TC_DBG): 1 no MMAs, 2 no TMA loads, 4 no global stores, 8 no tcgen05.ld, 16 no tcgen05.st
 };
 
 // DECONV stacking table: per kd, five MMAs (entries) that share an input shift
@@ -164,7 +166,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
             for (int ph = 0; ph < 2; ++ph, ++q) {
               const uint32_t s = q % C::STAGES;
               ptx::mbar_wait(empty_bar(s), ((q / C::STAGES) & 1) ^ 1);
-              if (lead) {
+              if (lead && (p.dbg & 2)) ptx::mbar_arrive(full_bar(s));
+              else if (lead) {
                 ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
                 for (int pw = 0; pw < 2; ++pw)
                   ptx::tma_load_5d(stage_addr0 + s * C::STAGE_BYTES + pw * C::SUB_BYTES, &xmap, full_bar(s), (tw * TW - 1) * 8,
@@ -175,7 +178,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
             const uint32_t s = q % C::STAGES;
             ptx::mbar_wait(empty_bar(s), ((q / C::STAGES) & 1) ^ 1);
             const int halo = MODE == M_S1 ? 1 : 0;
-            if (lead) {
+            if (lead && (p.dbg & 2)) ptx::mbar_arrive(full_bar(s));
+            else if (lead) {
               ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
               ptx::tma_load_4d(stage_addr0 + s * C::STAGE_BYTES, &xmap, full_bar(s), (tw * TW - halo) * 8, th * TH - halo, z, n * C::CBLK);
             }
@@ -191,43 +195,72 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
     // every MMA in an ELECT / 6x R2UR.BROADCAST / BRA.U.ANY waterfall (~190 cycles per MMA, profiles/r01_notes.md).
     {
       const bool lead = ptx::elect_one();
-      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id) { if (lead) ptx::umma_bf16_ss(d, a, b, id, 1u); };
+      const bool do_mma = lead && !(p.dbg & 1);
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id) { if (do_mma) ptx::umma_bf16_ss(d, a, b, id, 1u); };
       auto commit = [&](uint32_t bar) { if (lead) ptx::umma_commit(bar); };
       const uint64_t a_desc0 = ptx::make_smem_desc(stage_addr0, C::PLANE_BYTES, C::ROW_BYTES);
       auto wait_acc_empty = [&](uint32_t g) { ptx::mbar_wait(acce_bar(g % NSLOT), ((g / NSLOT) & 1) ^ 1); };
       uint32_t q = 0, g0 = 0;
-      for (int col = cta; col < ncols; col += ncta, g0 += Dout) {
-        for (int z = 0; z < Din; ++z) {
-          if (MODE == M_S1) {
-            if (z == 0) { wait_acc_empty(g0); if (Dout > 1) wait_acc_empty(g0 + 1); }
-            else if (z + 1 < Dout) wait_acc_empty(g0 + z + 1);
-            const uint32_t s = q % C::STAGES;
-            ptx::mbar_wait(full_bar(s), (q / C::STAGES) & 1);
-            ptx::tc_fence_after();
-            // output planes [plo, phi] <- B blocks [plo-(z-1), ...] (block j <-> kd = 2-j); split where the ring wraps
-            const int plo = z > 0 ? z - 1 : 0, phi = z + 1 < Dout ? z + 1 : Dout - 1;
-            const uint32_t slot0 = (g0 + plo) % NSLOT;
-            const int nblk = phi - plo + 1;
-            const int len1 = nblk < (int)(NSLOT - slot0) ? nblk : (int)(NSLOT - slot0), len2 = nblk - len1;
-            const uint32_t d1 = tmem_base + slot0 * NT, d2 = tmem_base;
-            const uint32_t id1 = ptx::make_idesc_bf16(128, NT * len1), id2 = ptx::make_idesc_bf16(128, NT * (len2 > 0 ? len2 : 1));
-            const uint64_t a0 = desc_add(a_desc0, s * C::STAGE_BYTES);
-            const uint64_t b1 = ptx::make_smem_desc(w_addr + (plo - (z - 1)) * NT * 16, 3 * NT * 16, 128);
-            const uint64_t b2 = desc_add(b1, len1 * NT * 16);
+      if (MODE == M_S1) {
+        // Software-pipelined: the mbarrier waits of step q+1 (TMA data landed, fresh accumulator slot drained) are
+        // issued in the MIDDLE of step q's MMA stream, so their ~100-cycle round trips hide behind queued MMAs.
+        auto waits = [&](int col_, int z_, uint32_t q_, uint32_t g0_) {
+          if (col_ >= ncols) return;
+          if (z_ == 0) { wait_acc_empty(g0_); if (Dout > 1) wait_acc_empty(g0_ + 1); }
+          else if (z_ + 1 < Dout) wait_acc_empty(g0_ + z_ + 1);
+          ptx::mbar_wait(full_bar(q_ % C::STAGES), (q_ / C::STAGES) & 1);
+        };
+        int col = cta, z = 0;
+        waits(col, 0, 0, 0);
+        while (col < ncols) {
+          ptx::tc_fence_after();
+          const uint32_t s = q % C::STAGES;
+          // output planes [plo, phi] <- B blocks [plo-(z-1), ...] (block j <-> kd = 2-j); split where the ring wraps
+          const int plo = z > 0 ? z - 1 : 0, phi = z + 1 < Dout ? z + 1 : Dout - 1;
+          const uint32_t slot0 = (g0 + plo) % NSLOT;
+          const int nblk = phi - plo + 1;
+          const int len1 = nblk < (int)(NSLOT - slot0) ? nblk : (int)(NSLOT - slot0), len2 = nblk - len1;
+          const uint32_t d1 = tmem_base + slot0 * NT, d2 = tmem_base;
+          const uint32_t id1 = ptx::make_idesc_bf16(128, NT * len1), id2 = ptx::make_idesc_bf16(128, NT * (len2 > 0 ? len2 : 1));
+          const uint64_t a0 = desc_add(a_desc0, s * C::STAGE_BYTES);
+          const uint64_t b1 = ptx::make_smem_desc(w_addr + (plo - (z - 1)) * NT * 16, 3 * NT * 16, 128);
+          const uint64_t b2 = desc_add(b1, len1 * NT * 16);
+          int ncol = col, nz = z + 1;
+          uint32_t ng0 = g0;
+          if (nz == Din) { nz = 0; ncol += ncta; ng0 += Dout; }
+          // (two separate streams: a predicated-off second MMA still costs ~28 issue cycles, measured)
+          if (len2 == 0) {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
+              if (tap == 5) waits(ncol, nz, q + 1, ng0);
+#pragma unroll
+              for (int ks = 0; ks < C::KS; ++ks) {
+                const uint32_t aoff = ((tap / 3) * MC::SUB_W + (tap % 3)) * 16 + ks * 2 * C::PLANE_BYTES;
+                mma(d1, desc_add(a0, aoff), desc_add(b1, (tap * C::KS + ks) * 3072), id1);
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+              if (tap == 5) waits(ncol, nz, q + 1, ng0);
 #pragma unroll
               for (int ks = 0; ks < C::KS; ++ks) {
                 const uint32_t aoff = ((tap / 3) * MC::SUB_W + (tap % 3)) * 16 + ks * 2 * C::PLANE_BYTES;
                 const uint32_t boff = (tap * C::KS + ks) * 3072;
                 mma(d1, desc_add(a0, aoff), desc_add(b1, boff), id1);
-                if (len2 > 0) mma(d2, desc_add(a0, aoff), desc_add(b2, boff), id2);
+                mma(d2, desc_add(a0, aoff), desc_add(b2, boff), id2);
               }
             }
-            commit(empty_bar(s));
-            ++q;
-            if (z >= 1) commit(accf_bar((g0 + z - 1) % NSLOT));
-            if (z == Din - 1) commit(accf_bar((g0 + z) % NSLOT));
+          }
+          commit(empty_bar(s));
+          if (z >= 1) commit(accf_bar((g0 + z - 1) % NSLOT));
+          if (z == Din - 1) commit(accf_bar((g0 + z) % NSLOT));
+          col = ncol; z = nz; g0 = ng0; ++q;
+        }
+      }
+      for (int col = cta; MODE != M_S1 && col < ncols; col += ncta, g0 += Dout) {
+        for (int z = 0; z < Din; ++z) {
+          if (MODE == M_S1) {
           } else if (MODE == M_S2) {
             const int pz = z >> 1;  // output plane of kd=1 (even z) / kd=2 (odd z); odd z also feeds pz+1 with kd=0
             const bool odd = z & 1;
@@ -248,20 +281,29 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
               const uint64_t a0 = desc_add(a_desc0, s * C::STAGE_BYTES);
               const uint64_t b1 = ptx::make_smem_desc(w_addr + (odd ? 0 : 2 * NT * 16), 3 * NT * 16, 128);
               const uint64_t b2 = desc_add(b1, len1 * NT * 16);
+              auto s2_taps = [&](auto PH) {
+                constexpr int ph_ = decltype(PH)::value;
 #pragma unroll
-              for (int t = 0; t < 6; ++t) {
-                // ph=0 (even input rows): kh=1, kw=t (t<3).  ph=1 (odd rows): kh = 0 (t<3) or 2 (t>=3), kw = t%3
-                if (ph == 0 && t >= 3) break;
-                const int kh = ph == 0 ? 1 : (t < 3 ? 0 : 2), kw = t % 3;
-                const int rh = kh == 0 ? 0 : 1, rw = kw == 0 ? 0 : 1, sub = kw != 1 ? 1 : 0;
+                for (int t = 0; t < (ph_ == 0 ? 3 : 6); ++t) {
+                  // ph=0 (even input rows): kh=1, kw=t.  ph=1 (odd rows): kh = 0 (t<3) or 2 (t>=3), kw = t%3
+                  const int kh = ph_ == 0 ? 1 : (t < 3 ? 0 : 2), kw = t % 3;
+                  const int rh = kh == 0 ? 0 : 1, rw = kw == 0 ? 0 : 1, sub = kw != 1 ? 1 : 0;
+                  const uint32_t aoff0 = sub * C::SUB_BYTES + (rh * MC::SUB_W + rw) * 16;
+                  const uint32_t boff0 = (kh * 3 + kw) * C::KS * 3072;
+                  if (len2 == 0) {
 #pragma unroll
-                for (int ks = 0; ks < C::KS; ++ks) {
-                  const uint32_t aoff = sub * C::SUB_BYTES + (rh * MC::SUB_W + rw) * 16 + ks * 2 * C::PLANE_BYTES;
-                  const uint32_t boff = ((kh * 3 + kw) * C::KS + ks) * 3072;
-                  mma(d1, desc_add(a0, aoff), desc_add(b1, boff), id1);
-                  if (len2 > 0) mma(d2, desc_add(a0, aoff), desc_add(b2, boff), id2);
+                    for (int ks = 0; ks < C::KS; ++ks)
+                      mma(d1, desc_add(a0, aoff0 + ks * 2 * C::PLANE_BYTES), desc_add(b1, boff0 + ks * 3072), id1);
+                  } else {
+#pragma unroll
+                    for (int ks = 0; ks < C::KS; ++ks) {
+                      mma(d1, desc_add(a0, aoff0 + ks * 2 * C::PLANE_BYTES), desc_add(b1, boff0 + ks * 3072), id1);
+                      mma(d2, desc_add(a0, aoff0 + ks * 2 * C::PLANE_BYTES), desc_add(b2, boff0 + ks * 3072), id2);
+                    }
+                  }
                 }
-              }
+              };
+              if (ph == 0) s2_taps(std::integral_constant<int, 0>{}); else s2_taps(std::integral_constant<int, 1>{});
               commit(empty_bar(s));
             }
             if (odd || z == Din - 1) commit(accf_bar((g0 + pz) % NSLOT));
@@ -318,24 +360,60 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
         const uint32_t g = g0 + qo, r = g % NSLOT;
         ptx::mbar_wait(accf_bar(r), (g / NSLOT) & 1);
         ptx::tc_fence_after();
-        constexpr int NCLS = MODE == M_DEC ? 4 : 1;
+        if (MODE == M_DEC) {
+          // class = pw*2 + ph.  The two pw classes of one ph are neighbouring output voxels (2w, 2w+1): drain both and
+          // store 32 contiguous bytes per thread and channel block (a lone 16-byte store half-fills its 32 B sector).
 #pragma unroll
-        for (int cls = 0; cls < NCLS; ++cls) {
-          uint32_t v[32];
-          const uint32_t taddr = tmem_base + lane_addr + r * MC::ACC_COLS + cls * NT;
-          ptx::tmem_ld_32x32(taddr, v);
-          ptx::tmem_ld_wait();
-          ptx::tmem_st_32x32(taddr, zero);  // leave the slot zeroed for its next output plane
-          if (cls == NCLS - 1) {
-            ptx::tmem_st_wait();
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(acce_bar(r));
+          for (int ph = 0; ph < 2; ++ph) {
+            uint32_t v0[32], v1[32];
+            const uint32_t t0 = tmem_base + lane_addr + r * MC::ACC_COLS + ph * NT, t1 = t0 + 2 * NT;
+            if (!(p.dbg & 8)) { ptx::tmem_ld_32x32(t0, v0); ptx::tmem_ld_32x32(t1, v1); ptx::tmem_ld_wait(); }
+            if (!(p.dbg & 16)) { ptx::tmem_st_32x32(t0, zero); ptx::tmem_st_32x32(t1, zero); }
+            if (ph == 1) {
+              ptx::tmem_st_wait();
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(acce_bar(r));
+            }
+            if (!valid || (p.dbg & 4)) continue;
+            const int64_t pos = ((int64_t)qo * p.Ho + 2 * hr + ph) * p.Wo + 2 * wr;
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+              const int64_t o = (((int64_t)n * cblk_out + nh * 4 + cb) * Vo + pos) * 8;
+              F8 a8, b8;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                a8.v[c] = __uint_as_float(v0[cb * 8 + c]) + bias_s[cb * 8 + c];
+                b8.v[c] = __uint_as_float(v1[cb * 8 + c]) + bias_s[cb * 8 + c];
+              }
+              if (p.residual) {
+                const F8 qa = load8<__nv_bfloat16>(p.residual + o), qb = load8<__nv_bfloat16>(p.residual + o + 8);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { a8.v[c] += qa.v[c]; b8.v[c] += qb.v[c]; }
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { a8.v[c] = fmaxf(a8.v[c], 0.f); b8.v[c] = fmaxf(b8.v[c], 0.f); }
+              }
+              store8<__nv_bfloat16>(p.y + o, a8);
+              store8<__nv_bfloat16>(p.y + o + 8, b8);
+            }
           }
-          if (!valid) continue;
-          int ho = hr, wo = wr;
-          if (MODE == M_DEC) { ho = 2 * hr + (cls & 1); wo = 2 * wr + (cls >> 1); }  // class = pw*2 + ph
-          const int64_t pos = ((int64_t)qo * p.Ho + ho) * p.Wo + wo;
+        } else {
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + lane_addr + r * MC::ACC_COLS;
+          if (!(p.dbg & 8)) { ptx::tmem_ld_32x32(taddr, v); ptx::tmem_ld_wait(); }
+          else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0u;
+          }
+          if (!(p.dbg & 16)) ptx::tmem_st_32x32(taddr, zero);  // leave the slot zeroed for its next output plane
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(acce_bar(r));
+          if (!valid || (p.dbg & 4)) continue;
+          const int64_t pos = ((int64_t)qo * p.Ho + hr) * p.Wo + wr;
           if (p.y1) {  // 32->1 classifier head: channel 0 only, f32, running sum fused (stackhourglass.py:142-144)
             const int64_t o1 = (int64_t)n * Vo + pos;
             p.y1[o1] = __uint_as_float(v[0]) + (p.res1 ? p.res1[o1] : 0.f);
@@ -369,20 +447,26 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
   if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
 }
 
-// natural blocked layout -> 8 parity sub-volumes: [N*C/8][D][H][W][8] -> [N*C/8][pd*4+ph*2+pw][D/2][H/2][W/2][8]
+// natural blocked layout -> 8 parity sub-volumes: [N*C/8][D][H][W][8] -> [N*C/8][pd*4+ph*2+pw][D/2][H/2][W/2][8].
+// One thread moves the voxel pair (2w2, 2w2+1): a fully used 32-byte read, two 16-byte writes that are contiguous
+// across the warp inside their (pw) sub-volume rows.
 __global__ void __launch_bounds__(256)
 space_to_depth_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, int64_t nblk, int D, int H, int W)
 {
   const int D2 = D / 2, H2 = H / 2, W2 = W / 2;
-  const int64_t total = nblk * D * H * W;
+  const int64_t sub = (int64_t)D2 * H2 * W2;
+  const int64_t total = nblk * D * H * W2;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int w2 = (int)(idx % W2);
-    const int h2 = (int)((idx / W2) % H2);
-    const int d2 = (int)((idx / ((int64_t)W2 * H2)) % D2);
-    const int cls = (int)((idx / ((int64_t)W2 * H2 * D2)) % 8);
-    const int64_t b = idx / ((int64_t)W2 * H2 * D2 * 8);
-    const int d = 2 * d2 + (cls >> 2), h = 2 * h2 + ((cls >> 1) & 1), w = 2 * w2 + (cls & 1);
-    dst[idx] = __ldg(src + ((b * D + d) * H + h) * W + w);
+    const int h = (int)((idx / W2) % H);
+    const int d = (int)((idx / ((int64_t)W2 * H)) % D);
+    const int64_t b = idx / ((int64_t)W2 * H * D);
+    const uint4 *s2 = src + ((b * D + d) * H + h) * W + 2 * w2;
+    const uint4 v0 = __ldg(s2), v1 = __ldg(s2 + 1);
+    const int cls = (d & 1) * 4 + (h & 1) * 2;
+    const int64_t o = (b * 8 + cls) * sub + ((int64_t)(d >> 1) * H2 + (h >> 1)) * W2 + w2;
+    dst[o] = v0;
+    dst[o + sub] = v1;
   }
 }
 
@@ -507,7 +591,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   const void *src = x;
   if (MODE == tc::M_S2) {
     if (!scratch) { set_error("tc_conv3d: stride-2 layer needs the space-to-depth scratch buffer"); return IDISP_ERR_INVALID; }
-    const int64_t nblk = (int64_t)B * C::CBLK, total = nblk * D * H * W;
+    const int64_t nblk = (int64_t)B * C::CBLK, total = nblk * D * H * (W / 2);
     const int64_t want = ceil_div64(total, 256);
     tc::space_to_depth_kernel<<<(int)(want < 148 * 32 ? want : 148 * 32), 256, 0, s>>>((const uint4 *)x, (uint4 *)scratch, nblk, D, H, W);
     IDISP_LAUNCH_CHECK();
@@ -532,6 +616,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   tc::Params p;
   p.w = (const __nv_bfloat16 *)w.dev; p.bias = bias; p.residual = residual; p.y = y; p.res1 = res1; p.y1 = y1;
   p.B = B; p.Din = D; p.Cout = Cout; p.relu = relu;
+  { static int dbg = -1; if (dbg < 0) { const char *e = getenv("IDISP_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   if (MODE == tc::M_S1) { p.Dout = D; p.Ho = H; p.Wo = W; p.Hr = H; p.Wr = W; }
   if (MODE == tc::M_S2) { p.Dout = D / 2; p.Ho = H / 2; p.Wo = W / 2; p.Hr = H / 2; p.Wr = W / 2; }
   if (MODE == tc::M_DEC) { p.Dout = 2 * D; p.Ho = 2 * H; p.Wo = 2 * W; p.Hr = H; p.Wr = W; }
