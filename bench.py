@@ -137,7 +137,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--precision', default=os.environ.get('IDISP_BENCH_PRECISION', 'fp32'), choices=['fp32', 'bf16'])
+    ap.add_argument('--precision', default=os.environ.get('IDISP_BENCH_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -290,6 +290,26 @@ def main():
             'ms_by_layer': {str(k): round(v, 4) for k, v in sorted(by_layer.items())},
             'clocks': clocks,
         }
+        if world == 1 and args.precision == 'bf16' and not os.environ.get('IDISP_TC_DBG'):
+            # the parity (fp32 FFMA) mode on the same inputs and weights: its throughput, and how far the bf16 tensor-core
+            # mode's disparities sit from it (fp32 mode itself is 2-7e-5 px from the reference, tests/test_gpu_parity.py)
+            m32 = make_model('fp32', dev)
+            m32.load_state_dict(m.state_dict())
+            with torch.no_grad():
+                d16 = m.forward_features(L[:4], R[:4])
+                d32 = m32.forward_features(L[:4], R[:4])
+                diff = (d16 - d32).abs()
+                for _ in range(2):
+                    m32.forward_features(L, R)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record(stream)
+                m32.forward_features(L, R)
+                e1.record(stream)
+                torch.cuda.synchronize()
+            result['fp32_parity_mode'] = {'value': B_PER_GPU / (e0.elapsed_time(e1) / 1e3), 'unit': 'ROIs/s',
+                                          'bf16_vs_fp32_disparity_px': {'max': diff.max().item(), 'mean': diff.mean().item()}}
+            del m32
         if world == 1 and not args.no_cpu_baseline:
             sd = {k: v for k, v in m.state_dict().items() if not k.startswith('feature_extraction')}
             val, dt, cores, sample = cpu_port_rois_per_s(sd, 1, 0, budget_s=40.0)

@@ -46,7 +46,6 @@ namespace tc {
 enum { M_S1 = 0, M_S2 = 1, M_DEC = 2 };
 constexpr int TW = 8, TH = 16;  // row tile (w x h) = 128 GEMM rows
 constexpr int NT = 32;          // output channels per stacked block
-constexpr int NTHREADS = 256;
 
 template <int MODE> struct ModeCfg;
 template <> struct ModeCfg<M_S1> { static constexpr int SUB_W = TW + 2, SUB_H = TH + 2, SUBS = 1, ACC_COLS = 32; };
@@ -55,8 +54,14 @@ template <> struct ModeCfg<M_S1> { static constexpr int SUB_W = TW + 2, SUB_H = 
 template <> struct ModeCfg<M_S2> { static constexpr int SUB_W = TW + 1, SUB_H = TH + 2, SUBS = 2, ACC_COLS = 32; };
 template <> struct ModeCfg<M_DEC> { static constexpr int SUB_W = TW + 1, SUB_H = TH + 2, SUBS = 1, ACC_COLS = 128; };
 
-template <int CIN, int MODE> struct Cfg {
+// OCC = CTAs per SM.  OCC 2 (stride-1, Cin 32 only: two 55 KB weight copies fit) gives the tensor pipe a second,
+// independent MMA stream that fills the bubbles one issuing warp leaves at plane boundaries (barrier round trips,
+// commits, descriptor set-up); each CTA then owns 256 TMEM columns and one epilogue group.
+template <int CIN, int MODE, int OCC> struct Cfg {
   using MC = ModeCfg<MODE>;
+  static constexpr int EGROUPS = OCC == 2 ? 1 : 2;        // epilogue groups of 4 warps (alternate output planes)
+  static constexpr int NTHREADS = 128 + 128 * EGROUPS;    // warps 0-3: TMA producer / MMA issuer / TMEM allocator / idle
+  static constexpr int TCOLS = 512 / OCC;                 // TMEM columns of this CTA
   static constexpr int KS = CIN / 16;    // K=16 MMAs per tap
   static constexpr int CBLK = CIN / 8;   // channel blocks
   static constexpr int PLANE_BYTES = MC::SUB_W * MC::SUB_H * 16;  // one channel block of one sub-tile (LBO of A)
@@ -64,8 +69,8 @@ template <int CIN, int MODE> struct Cfg {
   static constexpr int SUB_BYTES = CBLK * PLANE_BYTES;
   static constexpr int STAGE_BYTES = MC::SUBS * SUB_BYTES;
   static constexpr int WBYTES = 27 * KS * 1024;                   // 27 taps x Cin x 32 couts x bf16
-  static constexpr int NSLOT = 512 / MC::ACC_COLS;
-  static constexpr int STAGES_FIT = (227 * 1024 - WBYTES - 1024) / STAGE_BYTES;
+  static constexpr int NSLOT = TCOLS / MC::ACC_COLS;
+  static constexpr int STAGES_FIT = (228 * 1024 / OCC - 1024 - WBYTES - 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int BAR_OFF = WBYTES + STAGES * STAGE_BYTES;
   static constexpr int SMEM = BAR_OFF + (2 * STAGES + 2 * NSLOT) * 8 + 16 + NT * 4;
@@ -80,6 +85,7 @@ struct Params {
   __nv_bfloat16 *y;               // blocked [B][Cout/8][Do][Ho][Wo][8]
   const float *res1;              // 32->1 head: running sum [B][D][H][W] f32 or nullptr
   float *y1;                      // 32->1 head: output [B][D][H][W] f32 (non-null selects this epilogue)
+  __nv_bfloat16 *y_split;         // optional second copy of y in the 8-parity-sub-volume layout a stride-2 consumer reads
   int B, Din, Dout, Ho, Wo, Hr, Wr, Cout, relu;  // (Hr,Wr): row grid the 8x16 tiles cover
   int tiles_h, tiles_w, nh;
   int dbg;                        // timing experiments only (IDISP_TC_DBG): 1 no MMAs, 2 no TMA loads, 4 no global stores, 8 no tcgen05.ld, 16 no tcgen05.st
@@ -94,13 +100,26 @@ __host__ __device__ constexpr int dec_dcol(int e) { return e == 0 ? 0 : (e == 1 
 __host__ __device__ constexpr int dec_shift_h(int e) { return e >= 2 ? 1 : 0; }
 __host__ __device__ constexpr int dec_shift_w(int e) { return (e == 1 || e == 4) ? 1 : 0; }
 
+__device__ __forceinline__ F8 unpack8(const uint4 &a)
+{
+  F8 r;
+  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r.v[2 * i] = __uint_as_float(w[i] << 16);
+    r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+  return r;
+}
+
 __device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t byte_off) { return d + (uint64_t)(byte_off >> 4); }
 
-template <int CIN, int MODE>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int CIN, int MODE, int OCC>
+__global__ void __launch_bounds__((Cfg<CIN, MODE, OCC>::NTHREADS), OCC)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
 {
-  using C = Cfg<CIN, MODE>;
+  using C = Cfg<CIN, MODE, OCC>;
+  constexpr int NTHREADS = C::NTHREADS;
   using MC = ModeCfg<MODE>;
   constexpr int NSLOT = C::NSLOT;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -130,7 +149,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
     for (int r = 0; r < NSLOT; ++r) { ptx::mbar_init(accf_bar(r), 1); ptx::mbar_init(acce_bar(r), 4); }
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc<512>(ptx::smem_u32(tmem_ptr_smem));
+  if (warp == 2) ptx::tmem_alloc<C::TCOLS>(ptx::smem_u32(tmem_ptr_smem));
   {  // this slice's weights -> shared memory (generic proxy), then visible to the async proxy (tensor core)
     const uint4 *src = reinterpret_cast<const uint4 *>(p.w) + (size_t)nh * (C::WBYTES / 16);
     uint4 *dst = reinterpret_cast<uint4 *>(smem);
@@ -142,11 +161,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  if (warp >= 4) {  // accumulators start at zero; afterwards the epilogue re-zeroes each slot it drains
+  if (warp >= 4 && warp < 8) {  // accumulators start at zero; afterwards the epilogue re-zeroes each slot it drains
     uint32_t zero[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) zero[i] = 0u;
-    for (int c = 0; c < 512; c += 32) ptx::tmem_st_32x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + c, zero);
+    for (int c = 0; c < C::TCOLS; c += 32) ptx::tmem_st_32x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + c, zero);
     ptx::tmem_st_wait();
   }
   ptx::tc_fence_before();
@@ -343,6 +362,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
   } else if (warp >= 4) {
     // ================= epilogue (4 warps = 128 TMEM lanes) =================
     const int quarter = warp & 3;
+    const int egroup = (warp >> 2) - 1;  // 0 or 1: the two epilogue groups take alternate output planes, so two planes'
+                                         // TMEM-drain / residual-load / store latency chains are in flight per CTA
     const int m = quarter * 32 + lane;  // GEMM row = TMEM lane
     const int wl = m & 7, hl = m >> 3;  // position inside the 8 x 16 row tile
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
@@ -356,8 +377,21 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
       const int tw = col % p.tiles_w, th = (col / p.tiles_w) % p.tiles_h, n = col / (p.tiles_w * p.tiles_h);
       const int hr = th * TH + hl, wr = tw * TW + wl;
       const bool valid = hr < p.Hr && wr < p.Wr;
-      for (int qo = 0; qo < Dout; ++qo) {
+      for (int qo = egroup; qo < Dout; qo += C::EGROUPS) {
         const uint32_t g = g0 + qo, r = g % NSLOT;
+        // residual operands do not depend on the accumulator: request them BEFORE waiting for it
+        constexpr int NRES = MODE == M_DEC ? 16 : 4;
+        uint4 resv[NRES];
+        if (p.residual && valid) {
+#pragma unroll
+          for (int i = 0; i < NRES; ++i) {
+            // DEC: i = ph*8 + cb*2 + pw -> voxel (2hr+ph, 2wr+pw); conv: i = cb
+            const int cb = MODE == M_DEC ? (i >> 1) & 3 : i;
+            const int64_t pos = MODE == M_DEC ? ((int64_t)qo * p.Ho + 2 * hr + (i >> 3)) * p.Wo + 2 * wr + (i & 1)
+                                              : ((int64_t)qo * p.Ho + hr) * p.Wo + wr;
+            resv[i] = __ldg(reinterpret_cast<const uint4 *>(p.residual + (((int64_t)n * cblk_out + nh * 4 + cb) * Vo + pos) * 8));
+          }
+        }
         ptx::mbar_wait(accf_bar(r), (g / NSLOT) & 1);
         ptx::tc_fence_after();
         if (MODE == M_DEC) {
@@ -387,7 +421,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
                 b8.v[c] = __uint_as_float(v1[cb * 8 + c]) + bias_s[cb * 8 + c];
               }
               if (p.residual) {
-                const F8 qa = load8<__nv_bfloat16>(p.residual + o), qb = load8<__nv_bfloat16>(p.residual + o + 8);
+                const F8 qa = unpack8(resv[ph * 8 + cb * 2]), qb = unpack8(resv[ph * 8 + cb * 2 + 1]);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) { a8.v[c] += qa.v[c]; b8.v[c] += qb.v[c]; }
               }
@@ -397,6 +431,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
               }
               store8<__nv_bfloat16>(p.y + o, a8);
               store8<__nv_bfloat16>(p.y + o + 8, b8);
+              if (p.y_split) {  // classes (qo&1, ph, pw) at (qo>>1, hr, wr): 128 B contiguous per 8-row group
+                const int64_t sub = Vo / 8;
+                const int64_t os = ((((int64_t)n * cblk_out + nh * 4 + cb) * 8 + (qo & 1) * 4 + ph * 2) * sub +
+                                    ((int64_t)(qo >> 1) * (p.Ho / 2) + hr) * (p.Wo / 2) + wr) * 8;
+                store8<__nv_bfloat16>(p.y_split + os, a8);
+                store8<__nv_bfloat16>(p.y_split + os + sub * 8, b8);
+              }
             }
           }
         } else {
@@ -426,7 +467,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
 #pragma unroll
             for (int c = 0; c < 8; ++c) r8.v[c] = __uint_as_float(v[cb * 8 + c]) + bias_s[cb * 8 + c];
             if (p.residual) {
-              const F8 q8 = load8<__nv_bfloat16>(p.residual + o);
+              const F8 q8 = unpack8(resv[cb]);
 #pragma unroll
               for (int c = 0; c < 8; ++c) r8.v[c] += q8.v[c];
             }
@@ -435,6 +476,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
               for (int c = 0; c < 8; ++c) r8.v[c] = fmaxf(r8.v[c], 0.f);
             }
             store8<__nv_bfloat16>(p.y + o, r8);
+            if (p.y_split) {
+              const int64_t sub = Vo / 8;
+              const int64_t os = ((((int64_t)n * cblk_out + nh * 4 + cb) * 8 + (qo & 1) * 4 + (hr & 1) * 2 + (wr & 1)) * sub +
+                                  ((int64_t)(qo >> 1) * (p.Ho / 2) + (hr >> 1)) * (p.Wo / 2) + (wr >> 1)) * 8;
+              store8<__nv_bfloat16>(p.y_split + os, r8);
+            }
           }
         }
       }
@@ -444,7 +491,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
   // ---- teardown ----
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
+  if (warp == 2) ptx::tmem_dealloc<C::TCOLS>(tmem_base);
 }
 
 // natural blocked layout -> 8 parity sub-volumes: [N*C/8][D][H][W][8] -> [N*C/8][pd*4+ph*2+pw][D/2][H/2][W/2][8].
@@ -577,12 +624,12 @@ size_t tc_scratch_bytes(int kind, int B, int cin, int D, int H, int W)
   return kind == IDISP_CONV_S2 ? (size_t)B * cin * D * H * W * sizeof(__nv_bfloat16) : 0;
 }
 
-template <int CIN, int MODE>
+template <int CIN, int MODE, int OCC>
 static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, int H, int W, int Cout, const float *bias,
                      const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1, void *scratch,
-                     cudaStream_t s)
+                     int x_is_split, __nv_bfloat16 *y_split, cudaStream_t s)
 {
-  using C = tc::Cfg<CIN, MODE>;
+  using C = tc::Cfg<CIN, MODE, OCC>;
   using MC = tc::ModeCfg<MODE>;
   tc::EncodeTiledFn enc = tc::get_encode();
   if (!enc) { set_error("tc_conv3d: cuTensorMapEncodeTiled not available from the driver"); return IDISP_ERR_CUDA; }
@@ -590,12 +637,16 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   CUresult r;
   const void *src = x;
   if (MODE == tc::M_S2) {
-    if (!scratch) { set_error("tc_conv3d: stride-2 layer needs the space-to-depth scratch buffer"); return IDISP_ERR_INVALID; }
-    const int64_t nblk = (int64_t)B * C::CBLK, total = nblk * D * H * (W / 2);
-    const int64_t want = ceil_div64(total, 256);
-    tc::space_to_depth_kernel<<<(int)(want < 148 * 32 ? want : 148 * 32), 256, 0, s>>>((const uint4 *)x, (uint4 *)scratch, nblk, D, H, W);
-    IDISP_LAUNCH_CHECK();
-    src = scratch;
+    if (x_is_split) {
+      src = x;  // the producer's epilogue already wrote the parity sub-volumes (Params::y_split)
+    } else {
+      if (!scratch) { set_error("tc_conv3d: stride-2 layer needs the space-to-depth scratch buffer"); return IDISP_ERR_INVALID; }
+      const int64_t nblk = (int64_t)B * C::CBLK, total = nblk * D * H * (W / 2);
+      const int64_t want = ceil_div64(total, 256);
+      tc::space_to_depth_kernel<<<(int)(want < 148 * 32 ? want : 148 * 32), 256, 0, s>>>((const uint4 *)x, (uint4 *)scratch, nblk, D, H, W);
+      IDISP_LAUNCH_CHECK();
+      src = scratch;
+    }
     const int D2 = D / 2, H2 = H / 2, W2 = W / 2;
     const cuuint64_t dims[5] = {(cuuint64_t)W2 * 8, (cuuint64_t)H2, (cuuint64_t)D2, 8, (cuuint64_t)B * C::CBLK};
     const cuuint64_t strides[4] = {(cuuint64_t)W2 * 16, (cuuint64_t)H2 * W2 * 16, (cuuint64_t)D2 * H2 * W2 * 16, (cuuint64_t)8 * D2 * H2 * W2 * 16};
@@ -614,7 +665,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   }
   if (r != CUDA_SUCCESS) { set_error("tc_conv3d: cuTensorMapEncodeTiled failed (%d) for dims W=%d H=%d D=%d mode=%d", (int)r, W, H, D, MODE); return IDISP_ERR_CUDA; }
   tc::Params p;
-  p.w = (const __nv_bfloat16 *)w.dev; p.bias = bias; p.residual = residual; p.y = y; p.res1 = res1; p.y1 = y1;
+  p.w = (const __nv_bfloat16 *)w.dev; p.bias = bias; p.residual = residual; p.y = y; p.res1 = res1; p.y1 = y1; p.y_split = y_split;
   p.B = B; p.Din = D; p.Cout = Cout; p.relu = relu;
   { static int dbg = -1; if (dbg < 0) { const char *e = getenv("IDISP_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   if (MODE == tc::M_S1) { p.Dout = D; p.Ho = H; p.Wo = W; p.Hr = H; p.Wr = W; }
@@ -625,31 +676,37 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int per_slice = sms / p.nh;
+  int per_slice = sms * OCC / p.nh;
   if (per_slice > ncols) per_slice = ncols;
   const int grid = per_slice * p.nh;
-  auto kern = tc::conv3d_tc_kernel<CIN, MODE>;
+  auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC>;
   IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-  kern<<<grid, tc::NTHREADS, C::SMEM, s>>>(map, p);
+  kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, p);
   IDISP_LAUNCH_CHECK();
   return IDISP_OK;
 }
 
 int tc_conv3d(const TcWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D, int H, int W, int Cout, int kind,
               const float *bias, const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1,
-              void *scratch, cudaStream_t s)
+              void *scratch, int x_is_split, __nv_bfloat16 *y_split, cudaStream_t s)
 {
   if (!tc_supported(kind, Cin, Cout, D, H, W) || !w.dev || w.cin != Cin || w.cout != Cout || w.kind != kind) {
     set_error("tc_conv3d: layer (kind=%d, %d->%d) not prepared for the tensor-core path", kind, Cin, Cout);
     return IDISP_ERR_INVALID;
   }
+  if (y_split) {  // output dims must be even for the parity layout
+    const int Do = kind == IDISP_DECONV_S2 ? 2 * D : (kind == IDISP_CONV_S2 ? D / 2 : D), Ho = kind == IDISP_DECONV_S2 ? 2 * H : (kind == IDISP_CONV_S2 ? H / 2 : H),
+              Wo = kind == IDISP_DECONV_S2 ? 2 * W : (kind == IDISP_CONV_S2 ? W / 2 : W);
+    if (Do % 2 || Ho % 2 || Wo % 2 || Cout == 1) { set_error("tc_conv3d: parity-split output needs even output dims"); return IDISP_ERR_INVALID; }
+  }
   if ((Cout == 1) != (y1 != nullptr)) { set_error("tc_conv3d: the 1-channel head needs the f32 output (and only it)"); return IDISP_ERR_INVALID; }
   if (B == 0) return IDISP_OK;
-#define IDISP_TC(CI, MD) return tc_launch<CI, MD>(w, x, B, D, H, W, Cout, bias, residual, relu, y, res1, y1, scratch, s)
+#define IDISP_TC(CI, MD, OC) return tc_launch<CI, MD, OC>(w, x, B, D, H, W, Cout, bias, residual, relu, y, res1, y1, scratch, x_is_split, y_split, s)
   const int mode = tc::mode_of(kind);
-  if (mode == tc::M_S1) { if (Cin == 32) IDISP_TC(32, tc::M_S1); else IDISP_TC(64, tc::M_S1); }
-  if (mode == tc::M_S2) { if (Cin == 32) IDISP_TC(32, tc::M_S2); else IDISP_TC(64, tc::M_S2); }
-  IDISP_TC(64, tc::M_DEC);
+  static const int occ1 = tc::env_flag("IDISP_TC_OCC1");  // A/B switch for the 2-CTA/SM stride-1 variant
+  if (mode == tc::M_S1) { if (Cin == 32) { if (occ1) IDISP_TC(32, tc::M_S1, 1); else IDISP_TC(32, tc::M_S1, 2); } else IDISP_TC(64, tc::M_S1, 1); }
+  if (mode == tc::M_S2) { if (Cin == 32) IDISP_TC(32, tc::M_S2, 1); else IDISP_TC(64, tc::M_S2, 1); }
+  IDISP_TC(64, tc::M_DEC, 1);
 #undef IDISP_TC
 }
 

@@ -21,6 +21,8 @@ size_t tc_scratch_bytes(int kind, int B, int cin, int D, int H, int W);
 // Cout == 1 (the classifier head): y1/res1 are [B][D][H][W] f32 and y/residual/bias are unused.
 int tc_conv3d(const TcWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D, int H, int W, int Cout, int kind,
               const float *bias, const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1,
-              void *scratch, cudaStream_t s);
+              void *scratch, int x_is_split, __nv_bfloat16 *y_split, cudaStream_t s);
+// x_is_split: a stride-2 layer's input pointer already holds the 8 parity sub-volumes (written by its producer's
+// epilogue through y_split), so the space-to-depth pass is skipped.
 
 }  // namespace idisp

@@ -288,18 +288,26 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
     cudaEventRecord(p->ev[nmark++], s);
     if (layer != -99) p->ev_layer.push_back(layer);
   };
-  auto conv = [&](int li, const void *x, int d, int h, int w, const void *res, int relu, void *y) -> int {
+  // split_out: also emit the output as 8 parity sub-volumes into b.split (feeds the next stride-2 tensor-core conv);
+  // x_split: the input IS b.split (written that way by its producer), so no re-lay pass is needed.
+  auto conv = [&](int li, const void *x, int d, int h, int w, const void *res, int relu, void *y, bool split_out = false,
+                  bool x_split = false) -> int {
     const LayerSpec &L = p->layers[li];
     mark(li);
     ++launches;
     if (std::is_same<T, __nv_bfloat16>::value && tc_supported(L.kind, L.cin, L.cout, d, h, w)) {
-      if (L.kind == IDISP_CONV_S2) ++launches;  // + the space-to-depth re-lay
-      return tc_conv3d(p->dev[li].tc, (const __nv_bfloat16 *)x, B, L.cin, d, h, w, L.cout, L.kind, p->dev[li].bias,
-                       (const __nv_bfloat16 *)res, relu, (__nv_bfloat16 *)y, nullptr, nullptr, b.split, s);
+      if (L.kind == IDISP_CONV_S2 && !x_split) ++launches;  // + the space-to-depth re-lay
+      return tc_conv3d(p->dev[li].tc, (const __nv_bfloat16 *)(x_split ? b.split : x), B, L.cin, d, h, w, L.cout, L.kind,
+                       p->dev[li].bias, (const __nv_bfloat16 *)res, relu, (__nv_bfloat16 *)y, nullptr, nullptr, b.split,
+                       x_split ? 1 : 0, split_out ? (__nv_bfloat16 *)b.split : nullptr, s);
     }
     return launch_conv3d_simt<T>((const T *)x, B, L.cin, d, h, w, p->dev[li].w_tap, L.cout, L.kind, p->dev[li].bias,
                                  (const T *)res, relu, (T *)y, s);
   };
+  // the fused parity-split hand-off needs every layer of the chain on the tensor-core path
+  const bool fuse_split = std::is_same<T, __nv_bfloat16>::value && D % 4 == 0 && Hf % 4 == 0 && Wf % 4 == 0 &&
+                          tc_supported(IDISP_CONV_S2, 32, 64, D, Hf, Wf) && tc_supported(IDISP_DECONV_S2, 64, 32, D / 2, Hf / 2, Wf / 2) &&
+                          tc_supported(IDISP_CONV_S1, 32, 32, D, Hf, Wf) && !getenv("IDISP_NO_FUSED_SPLIT");
 #define RUN(expr) do { if ((rc = (expr)) != IDISP_OK) return rc; } while (0)
   // cost volume (stackhourglass.py:115-128)
   mark(-1);
@@ -308,7 +316,7 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
   RUN(conv(0, b.cv, D, Hf, Wf, nullptr, 1, b.a));
   RUN(conv(1, b.a, D, Hf, Wf, nullptr, 1, b.t0));
   RUN(conv(2, b.t0, D, Hf, Wf, nullptr, 1, b.a));
-  RUN(conv(3, b.a, D, Hf, Wf, b.t0, 0, b.cost0));
+  RUN(conv(3, b.a, D, Hf, Wf, b.t0, 0, b.cost0, fuse_split));
   // three hourglasses (:133-140); `x` is cost0 / out1 / out2, all outputs land in b.out
   const int D2 = D / 2, H2 = Hf / 2, W2 = Wf / 2, D4 = D / 4, H4 = Hf / 4, W4 = Wf / 4;
   for (int k = 0; k < 3; ++k) {
@@ -318,12 +326,12 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
     const void *postsqu = k == 0 ? nullptr : (k == 1 ? b.postA : b.postB);  // post1 / post2
     void *post = k == 1 ? b.postB : b.postA;                                  // post1,post3 -> A; post2 -> B
     const void *presqu = k == 0 ? b.pre1 /* own pre */ : b.pre1;              // pre1 for dres3 AND dres4 (:136,:139)
-    RUN(conv(l0 + 0, x, D, Hf, Wf, nullptr, 1, b.h1));
-    RUN(conv(l0 + 1, b.h1, D2, H2, W2, postsqu, 1, pre));
-    RUN(conv(l0 + 2, pre, D2, H2, W2, nullptr, 1, b.q1));
+    RUN(conv(l0 + 0, x, D, Hf, Wf, nullptr, 1, b.h1, false, fuse_split));          // reads b.split (cost0 / out_k)
+    RUN(conv(l0 + 1, b.h1, D2, H2, W2, postsqu, 1, pre, fuse_split));              // writes b.split (pre_k)
+    RUN(conv(l0 + 2, pre, D2, H2, W2, nullptr, 1, b.q1, false, fuse_split));       // reads b.split
     RUN(conv(l0 + 3, b.q1, D4, H4, W4, nullptr, 1, b.q2));
     RUN(conv(l0 + 4, b.q2, D4, H4, W4, presqu, 1, post));
-    RUN(conv(l0 + 5, post, D2, H2, W2, b.cost0, 0, b.out));
+    RUN(conv(l0 + 5, post, D2, H2, W2, b.cost0, 0, b.out, fuse_split && k < 2));   // writes b.split (out_k) for the next hourglass
     // classifier head k on out_k (:142-144), running sum fused
     RUN(conv(22 + k, b.out, D, Hf, Wf, nullptr, 1, b.c));
     float *dst = (k == 1) ? b.costY : b.costX;
@@ -331,7 +339,7 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
     mark(25 + k);
     if (std::is_same<T, __nv_bfloat16>::value && tc_supported(IDISP_CONV_S1, 32, 1, D, Hf, Wf))
       RUN(tc_conv3d(p->dev[25 + k].tc, (const __nv_bfloat16 *)b.c, B, 32, D, Hf, Wf, 1, IDISP_CONV_S1, nullptr, nullptr, 0, nullptr,
-                    prev, dst, nullptr, s));
+                    prev, dst, nullptr, 0, nullptr, s));
     else
       RUN(launch_conv3d_to1<T>((const T *)b.c, B, 32, D, Hf, Wf, p->dev[25 + k].w_tap, prev, dst, s));
     ++launches;
@@ -452,7 +460,7 @@ static int conv3d_hook(const float *x, int B, int Cin, int D, int H, int W, cons
   if (Cout == 1) {
     if (precision == IDISP_PREC_BF16 && tc_supported(kind, Cin, Cout, D, H, W)) {
       HR(tc_weights_prepare(w_tap.data(), kind, Cin, Cout, tcw, s));
-      HR(tc_conv3d(tcw, (const __nv_bfloat16 *)xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, residual, y, nullptr, s));
+      HR(tc_conv3d(tcw, (const __nv_bfloat16 *)xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, residual, y, nullptr, 0, nullptr, s));
     } else {
       HR(launch_conv3d_to1<T>(xb, B, Cin, D, H, W, wd, residual, y, s));
     }
@@ -468,7 +476,7 @@ static int conv3d_hook(const float *x, int B, int Cin, int D, int H, int W, cons
       const size_t sb = tc_scratch_bytes(kind, B, Cin, D, H, W);
       if (sb) HK(cudaMalloc(&scratch, sb));
       HR(tc_conv3d(tcw, (const __nv_bfloat16 *)xb, B, Cin, D, H, W, Cout, kind, bd, (const __nv_bfloat16 *)rb, relu,
-                   (__nv_bfloat16 *)yb, nullptr, nullptr, scratch, s));
+                   (__nv_bfloat16 *)yb, nullptr, nullptr, scratch, 0, nullptr, s));
     } else {
       HR(launch_conv3d_simt<T>(xb, B, Cin, D, H, W, wd, Cout, kind, bd, rb, relu, yb, s));
     }
