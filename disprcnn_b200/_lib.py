@@ -76,6 +76,7 @@ PROTOTYPES = {
     'idisp_plan_launches_per_forward': (_i, [_vp]),
     'idisp_plan_enable_timing': (_i, [_vp, _i]),
     'idisp_plan_get_timing': (_i, [_vp, _vp, _vp, _i]),
+    'idisp_debug_fused_cost_volume': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 
 

@@ -88,6 +88,7 @@ struct Params {
   __nv_bfloat16 *y_split;         // optional second copy of y in the 8-parity-sub-volume layout a stride-2 consumer reads
   int B, Din, Dout, Ho, Wo, Hr, Wr, Cout, relu;  // (Hr,Wr): row grid the 8x16 tiles cover
   int tiles_h, tiles_w, nh;
+  int cv_shift0;                  // mindisp/4: plane k <-> right-view shift i = k + cv_shift0
   int dbg;                        // timing experiments only (IDISP_TC_DBG): 1 no MMAs, 2 no TMA loads, 4 no global stores, 8 no tcgen05.ld, 16 no tcgen05.st
 };
 
@@ -99,6 +100,12 @@ __host__ __device__ constexpr int dec_row_off(int e) { return e == 0 ? 0 : (e ==
 __host__ __device__ constexpr int dec_dcol(int e) { return e == 0 ? 0 : (e == 1 ? 64 : (e == 2 ? 32 : 96)); }
 __host__ __device__ constexpr int dec_shift_h(int e) { return e >= 2 ? 1 : 0; }
 __host__ __device__ constexpr int dec_shift_w(int e) { return (e == 1 || e == 4) ? 1 : 0; }
+
+// Per-plane tensor maps of the fused cost volume travel as a __grid_constant__ kernel parameter (the documented way to
+// hand TMA a descriptor; CUDA >= 12.1 allows 32 KB of parameters).  Non-cost-volume launches pass an empty struct.
+constexpr int CV_MAX_PLANES = 64;
+template <bool CV> struct CvMaps { CUtensorMap m[CV_MAX_PLANES]; };
+template <> struct CvMaps<false> { char unused; };
 
 __device__ __forceinline__ F8 unpack8(const uint4 &a)
 {
@@ -114,9 +121,10 @@ __device__ __forceinline__ F8 unpack8(const uint4 &a)
 
 __device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t byte_off) { return d + (uint64_t)(byte_off >> 4); }
 
-template <int CIN, int MODE, int OCC>
+template <int CIN, int MODE, int OCC, bool CV>
 __global__ void __launch_bounds__((Cfg<CIN, MODE, OCC>::NTHREADS), OCC)
-conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
+conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap rmap,
+                 const __grid_constant__ CvMaps<CV> lmaps, const Params p)
 {
   using C = Cfg<CIN, MODE, OCC>;
   constexpr int NTHREADS = C::NTHREADS;
@@ -145,6 +153,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&xmap);
+    ptx::prefetch_tensormap(&rmap);
     for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
     for (int r = 0; r < NSLOT; ++r) { ptx::mbar_init(accf_bar(r), 1); ptx::mbar_init(acce_bar(r), 4); }
     ptx::fence_barrier_init();
@@ -198,7 +207,20 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
             ptx::mbar_wait(empty_bar(s), ((q / C::STAGES) & 1) ^ 1);
             const int halo = MODE == M_S1 ? 1 : 0;
             if (lead && (p.dbg & 2)) ptx::mbar_arrive(full_bar(s));
-            else if (lead) {
+            else if (CV) {
+              if (lead) {
+              // Fused cost volume (stackhourglass.py:115-128).  Plane k holds, for x in [max(i,0), W+min(i,0)), LEFT[x] in
+              // channel blocks [0, CBLK/2) and RIGHT[x-i] in [CBLK/2, CBLK), zero elsewhere (and zero outside [0,W): conv
+              // padding).  The plane's own 4-D map (origin x = max(i,0), width W-|i|, outermost dim = {left, right} with the
+              // right base advanced by max(-i,0)) makes every masked column plain TMA zero fill: ONE load per plane.
+              const int i = z + p.cv_shift0;
+              const bool dead = i >= p.Wo || -i >= p.Wo;  // fully masked plane: read far out of range (all zero fill)
+              ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
+              if constexpr (CV)
+                ptx::tma_load_4d(stage_addr0 + s * C::STAGE_BYTES, &lmaps.m[z], full_bar(s), dead ? -(1 << 20) : (tw * TW - 1 - (i > 0 ? i : 0)) * 8,
+                                 th * TH - 1, n * (C::CBLK / 2), 0);
+              }
+            } else if (lead) {
               ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
               ptx::tma_load_4d(stage_addr0 + s * C::STAGE_BYTES, &xmap, full_bar(s), (tw * TW - halo) * 8, th * TH - halo, z, n * C::CBLK);
             }
@@ -627,13 +649,14 @@ size_t tc_scratch_bytes(int kind, int B, int cin, int D, int H, int W)
 template <int CIN, int MODE, int OCC>
 static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, int H, int W, int Cout, const float *bias,
                      const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1, void *scratch,
-                     int x_is_split, __nv_bfloat16 *y_split, cudaStream_t s)
+                     int x_is_split, __nv_bfloat16 *y_split, const TcCostVolume *cv, cudaStream_t s)
 {
   using C = tc::Cfg<CIN, MODE, OCC>;
   using MC = tc::ModeCfg<MODE>;
   tc::EncodeTiledFn enc = tc::get_encode();
   if (!enc) { set_error("tc_conv3d: cuTensorMapEncodeTiled not available from the driver"); return IDISP_ERR_CUDA; }
-  CUtensorMap map;
+  CUtensorMap map, rmap;
+  static thread_local tc::CvMaps<true> cvmaps;  // ~8 KB of kernel parameters, encoded per launch (host-only work)
   CUresult r;
   const void *src = x;
   if (MODE == tc::M_S2) {
@@ -654,6 +677,26 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else if (cv) {
+    // fused cost volume: x is unused; one 4-D map per plane over {left, right} x [B*C/8] x [Hf] x [(Wf-|i|)*8]
+    const int halfblk = C::CBLK / 2;
+    if (D > tc::CV_MAX_PLANES) { set_error("tc_conv3d: fused cost volume supports at most %d planes", tc::CV_MAX_PLANES); return IDISP_ERR_INVALID; }
+    const int64_t lr_bytes = (const char *)cv->right - (const char *)cv->left;
+    if (lr_bytes <= 0 || lr_bytes % 16) { set_error("tc_conv3d: right features must follow the left ones in memory (16 B aligned)"); return IDISP_ERR_INVALID; }
+    const cuuint32_t box[4] = {8 * MC::SUB_W, MC::SUB_H, (cuuint32_t)halfblk, 2};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    r = CUDA_SUCCESS;
+    for (int k = 0; r == CUDA_SUCCESS && k < D; ++k) {
+      const int i = k + cv->shift0, ai = i < 0 ? -i : i;
+      const int wk = ai >= W ? 1 : W - ai;  // fully masked planes get a 1-voxel map that the kernel reads far out of range
+      const int lo = ai >= W ? 0 : (i > 0 ? i : 0), ro = ai >= W ? 0 : (i < 0 ? -i : 0);
+      const cuuint64_t dims[4] = {(cuuint64_t)wk * 8, (cuuint64_t)H, (cuuint64_t)B * halfblk, 2};
+      const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)(lr_bytes + (int64_t)(ro - lo) * 16)};
+      r = enc(&cvmaps.m[k], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16 *>(cv->left) + (size_t)lo * 8, dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r == CUDA_SUCCESS) rmap = cvmaps.m[0];
+    map = rmap;
   } else {
     // (8 ch, W) are contiguous in the blocked layout -> ONE tensor dimension of 8*W elements: a box row is SUB_W voxels x 16 B
     const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B * C::CBLK};
@@ -667,6 +710,8 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   tc::Params p;
   p.w = (const __nv_bfloat16 *)w.dev; p.bias = bias; p.residual = residual; p.y = y; p.res1 = res1; p.y1 = y1; p.y_split = y_split;
   p.B = B; p.Din = D; p.Cout = Cout; p.relu = relu;
+  p.cv_shift0 = cv ? cv->shift0 : 0;
+  if (!cv) rmap = map;
   { static int dbg = -1; if (dbg < 0) { const char *e = getenv("IDISP_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   if (MODE == tc::M_S1) { p.Dout = D; p.Ho = H; p.Wo = W; p.Hr = H; p.Wr = W; }
   if (MODE == tc::M_S2) { p.Dout = D / 2; p.Ho = H / 2; p.Wo = W / 2; p.Hr = H / 2; p.Wr = W / 2; }
@@ -679,17 +724,24 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   int per_slice = sms * OCC / p.nh;
   if (per_slice > ncols) per_slice = ncols;
   const int grid = per_slice * p.nh;
-  auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC>;
-  IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-  kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, p);
+  if (MODE == tc::M_S1 && cv) {
+    auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, (MODE == tc::M_S1)>;
+    IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    if constexpr (MODE == tc::M_S1) kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, rmap, cvmaps, p);
+  } else {
+    auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, false>;
+    IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, rmap, tc::CvMaps<false>{}, p);
+  }
   IDISP_LAUNCH_CHECK();
   return IDISP_OK;
 }
 
 int tc_conv3d(const TcWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D, int H, int W, int Cout, int kind,
               const float *bias, const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1,
-              void *scratch, int x_is_split, __nv_bfloat16 *y_split, cudaStream_t s)
+              void *scratch, int x_is_split, __nv_bfloat16 *y_split, const TcCostVolume *cv, cudaStream_t s)
 {
+  if (cv && (kind != IDISP_CONV_S1 || !cv->left || !cv->right)) { set_error("tc_conv3d: bad fused cost-volume arguments"); return IDISP_ERR_INVALID; }
   if (!tc_supported(kind, Cin, Cout, D, H, W) || !w.dev || w.cin != Cin || w.cout != Cout || w.kind != kind) {
     set_error("tc_conv3d: layer (kind=%d, %d->%d) not prepared for the tensor-core path", kind, Cin, Cout);
     return IDISP_ERR_INVALID;
@@ -701,7 +753,7 @@ int tc_conv3d(const TcWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D,
   }
   if ((Cout == 1) != (y1 != nullptr)) { set_error("tc_conv3d: the 1-channel head needs the f32 output (and only it)"); return IDISP_ERR_INVALID; }
   if (B == 0) return IDISP_OK;
-#define IDISP_TC(CI, MD, OC) return tc_launch<CI, MD, OC>(w, x, B, D, H, W, Cout, bias, residual, relu, y, res1, y1, scratch, x_is_split, y_split, s)
+#define IDISP_TC(CI, MD, OC) return tc_launch<CI, MD, OC>(w, x, B, D, H, W, Cout, bias, residual, relu, y, res1, y1, scratch, x_is_split, y_split, cv, s)
   const int mode = tc::mode_of(kind);
   static const int occ1 = tc::env_flag("IDISP_TC_OCC1");  // A/B switch for the 2-CTA/SM stride-1 variant
   if (mode == tc::M_S1) { if (Cin == 32) { if (occ1) IDISP_TC(32, tc::M_S1, 1); else IDISP_TC(32, tc::M_S1, 2); } else IDISP_TC(64, tc::M_S1, 1); }

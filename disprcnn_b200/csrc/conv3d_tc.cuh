@@ -14,6 +14,13 @@ struct TcWeights {
 // w_tap: HOST pointer, [27][cin][cout] f32 with the BN scale already folded in
 int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, TcWeights &out, cudaStream_t s);
 void tc_weights_free(TcWeights &w);
+// Fused cost volume for the first layer (stackhourglass.py:115-128 folded into dres0.0's loader): the per-view features
+// in blocked bf16 [B][C/8][Hf][Wf][8]; D <= 64 planes (the per-plane tensor maps travel as kernel parameters).
+struct TcCostVolume {
+  const __nv_bfloat16 *left = nullptr, *right = nullptr;
+  int shift0 = 0;  // mindisp / 4
+};
+
 // whether the tensor-core kernel covers this layer shape (otherwise the SIMT kernel runs it)
 bool tc_supported(int kind, int cin, int cout, int D, int H, int W);
 // device scratch the layer needs (stride-2 convs re-lay their input into parity sub-volumes)
@@ -21,7 +28,8 @@ size_t tc_scratch_bytes(int kind, int B, int cin, int D, int H, int W);
 // Cout == 1 (the classifier head): y1/res1 are [B][D][H][W] f32 and y/residual/bias are unused.
 int tc_conv3d(const TcWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D, int H, int W, int Cout, int kind,
               const float *bias, const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1,
-              void *scratch, int x_is_split, __nv_bfloat16 *y_split, cudaStream_t s);
+              void *scratch, int x_is_split, __nv_bfloat16 *y_split, const TcCostVolume *cv, cudaStream_t s);
+// cv != nullptr: the layer's input IS the cost volume of (cv->left, cv->right); x is ignored and nothing is materialised.
 // x_is_split: a stride-2 layer's input pointer already holds the 8 parity sub-volumes (written by its producer's
 // epilogue through y_split), so the space-to-depth pass is skipped.
 

@@ -246,6 +246,7 @@ struct Buffers {
   void *q1, *q2;                             // quarter resolution, 64 ch
   float *costX, *costY;                      // 1-channel f32 logits
   void *split;                               // parity re-lay scratch of the stride-2 tensor-core convs
+  void *feaL, *feaR;                         // fused cost volume: blocked bf16 per-view features
 };
 
 Buffers carve(Arena &A, int C, int B, int D, int Hf, int Wf, size_t esz)
@@ -259,6 +260,7 @@ Buffers carve(Arena &A, int C, int B, int D, int Hf, int Wf, size_t esz)
   b.q1 = A.take(quart64); b.q2 = A.take(quart64);
   b.costX = (float *)A.take((size_t)B * V * 4); b.costY = (float *)A.take((size_t)B * V * 4);
   b.split = A.take(full32);
+  b.feaL = A.take((size_t)B * C * Hf * Wf * 2); b.feaR = A.take((size_t)B * C * Hf * Wf * 2);
   return b;
 }
 }  // namespace
@@ -299,7 +301,7 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
       if (L.kind == IDISP_CONV_S2 && !x_split) ++launches;  // + the space-to-depth re-lay
       return tc_conv3d(p->dev[li].tc, (const __nv_bfloat16 *)(x_split ? b.split : x), B, L.cin, d, h, w, L.cout, L.kind,
                        p->dev[li].bias, (const __nv_bfloat16 *)res, relu, (__nv_bfloat16 *)y, nullptr, nullptr, b.split,
-                       x_split ? 1 : 0, split_out ? (__nv_bfloat16 *)b.split : nullptr, s);
+                       x_split ? 1 : 0, split_out ? (__nv_bfloat16 *)b.split : nullptr, nullptr, s);
     }
     return launch_conv3d_simt<T>((const T *)x, B, L.cin, d, h, w, p->dev[li].w_tap, L.cout, L.kind, p->dev[li].bias,
                                  (const T *)res, relu, (T *)y, s);
@@ -310,10 +312,26 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
                           tc_supported(IDISP_CONV_S1, 32, 32, D, Hf, Wf) && !getenv("IDISP_NO_FUSED_SPLIT");
 #define RUN(expr) do { if ((rc = (expr)) != IDISP_OK) return rc; } while (0)
   // cost volume (stackhourglass.py:115-128)
-  mark(-1);
-  RUN(launch_cost_volume_blocked<T>(left, right, B, C, Hf, Wf, p->mindisp, D, (T *)b.cv, s)); ++launches;
-  // dres0, dres1 (:130-131)
-  RUN(conv(0, b.cv, D, Hf, Wf, nullptr, 1, b.a));
+  const bool fuse_cv = std::is_same<T, __nv_bfloat16>::value && tc_supported(IDISP_CONV_S1, 2 * C, 32, D, Hf, Wf) && C % 8 == 0 && D <= 64 &&
+                       !getenv("IDISP_NO_FUSED_CV");
+  if (fuse_cv) {
+    // the [B,2C,D,H,W] volume is never written: dres0.0's TMA producer assembles each plane from the two feature maps
+    mark(-1);
+    RUN(launch_ncdhw_to_blocked<__nv_bfloat16>(left, (__nv_bfloat16 *)b.feaL, B, C, (int64_t)Hf * Wf, s)); ++launches;
+    RUN(launch_ncdhw_to_blocked<__nv_bfloat16>(right, (__nv_bfloat16 *)b.feaR, B, C, (int64_t)Hf * Wf, s)); ++launches;
+    TcCostVolume cvd;
+    cvd.left = (const __nv_bfloat16 *)b.feaL; cvd.right = (const __nv_bfloat16 *)b.feaR;
+    cvd.shift0 = p->mindisp >= 0 ? p->mindisp / 4 : -((-p->mindisp + 3) / 4);
+    mark(0);
+    ++launches;
+    RUN(tc_conv3d(p->dev[0].tc, nullptr, B, 2 * C, D, Hf, Wf, 32, IDISP_CONV_S1, p->dev[0].bias, nullptr, 1, (__nv_bfloat16 *)b.a, nullptr,
+                  nullptr, nullptr, 0, nullptr, &cvd, s));
+  } else {
+    mark(-1);
+    RUN(launch_cost_volume_blocked<T>(left, right, B, C, Hf, Wf, p->mindisp, D, (T *)b.cv, s)); ++launches;
+    RUN(conv(0, b.cv, D, Hf, Wf, nullptr, 1, b.a));
+  }
+  // dres0 (second conv), dres1 (:130-131)
   RUN(conv(1, b.a, D, Hf, Wf, nullptr, 1, b.t0));
   RUN(conv(2, b.t0, D, Hf, Wf, nullptr, 1, b.a));
   RUN(conv(3, b.a, D, Hf, Wf, b.t0, 0, b.cost0, fuse_split));
@@ -339,7 +357,7 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
     mark(25 + k);
     if (std::is_same<T, __nv_bfloat16>::value && tc_supported(IDISP_CONV_S1, 32, 1, D, Hf, Wf))
       RUN(tc_conv3d(p->dev[25 + k].tc, (const __nv_bfloat16 *)b.c, B, 32, D, Hf, Wf, 1, IDISP_CONV_S1, nullptr, nullptr, 0, nullptr,
-                    prev, dst, nullptr, 0, nullptr, s));
+                    prev, dst, nullptr, 0, nullptr, nullptr, s));
     else
       RUN(launch_conv3d_to1<T>((const T *)b.c, B, 32, D, Hf, Wf, p->dev[25 + k].w_tap, prev, dst, s));
     ++launches;
@@ -460,7 +478,7 @@ static int conv3d_hook(const float *x, int B, int Cin, int D, int H, int W, cons
   if (Cout == 1) {
     if (precision == IDISP_PREC_BF16 && tc_supported(kind, Cin, Cout, D, H, W)) {
       HR(tc_weights_prepare(w_tap.data(), kind, Cin, Cout, tcw, s));
-      HR(tc_conv3d(tcw, (const __nv_bfloat16 *)xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, residual, y, nullptr, 0, nullptr, s));
+      HR(tc_conv3d(tcw, (const __nv_bfloat16 *)xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, residual, y, nullptr, 0, nullptr, nullptr, s));
     } else {
       HR(launch_conv3d_to1<T>(xb, B, Cin, D, H, W, wd, residual, y, s));
     }
@@ -476,7 +494,7 @@ static int conv3d_hook(const float *x, int B, int Cin, int D, int H, int W, cons
       const size_t sb = tc_scratch_bytes(kind, B, Cin, D, H, W);
       if (sb) HK(cudaMalloc(&scratch, sb));
       HR(tc_conv3d(tcw, (const __nv_bfloat16 *)xb, B, Cin, D, H, W, Cout, kind, bd, (const __nv_bfloat16 *)rb, relu,
-                   (__nv_bfloat16 *)yb, nullptr, nullptr, scratch, 0, nullptr, s));
+                   (__nv_bfloat16 *)yb, nullptr, nullptr, scratch, 0, nullptr, nullptr, s));
     } else {
       HR(launch_conv3d_simt<T>(xb, B, Cin, D, H, W, wd, Cout, kind, bd, rb, relu, yb, s));
     }
@@ -513,4 +531,51 @@ extern "C" int idisp_conv3d(const float *x, int B, int Cin, int D, int H, int W,
   if (precision == IDISP_PREC_FP32)
     return conv3d_hook<float>(x, B, Cin, D, H, W, w_tap, Cout, kind, hb, residual, relu, precision, y, s);
   return conv3d_hook<__nv_bfloat16>(x, B, Cin, D, H, W, w_tap, Cout, kind, hb, residual, relu, precision, y, s);
+}
+
+// ---------------------------------------------------------------------------------------
+// test hook: the cost volume AS THE TENSOR-CORE PATH SEES IT.  Runs dres0.0's fused TMA loader with centre-tap identity
+// kernels (no BN, no ReLU) so that the layer output equals its input, i.e. the bf16 cost volume, and returns it NCDHW f32.
+// ---------------------------------------------------------------------------------------
+extern "C" int idisp_debug_fused_cost_volume(const float *left, const float *right, int B, int C, int Hf, int Wf, int mindisp,
+                                             int maxdisp, float *cost, void *stream)
+{
+  IDISP_REQUIRE(B > 0 && (C == 16 || C == 32) && Hf > 0 && Wf > 0 && maxdisp > mindisp && mindisp % 4 == 0 && maxdisp % 4 == 0,
+                "debug_fused_cost_volume: unsupported shape (C must be 16 or 32)");
+  IDISP_REQUIRE(left && right && cost, "debug_fused_cost_volume: NULL pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int D = (maxdisp - mindisp) / 4, cin = 2 * C;
+  IDISP_REQUIRE(D <= 64 && tc_supported(IDISP_CONV_S1, cin, 32, D, Hf, Wf), "debug_fused_cost_volume: layer not on the tensor-core path");
+  const int64_t V = (int64_t)D * Hf * Wf;
+  __nv_bfloat16 *fl = nullptr, *fr = nullptr, *yb = nullptr;
+  TcWeights tcw;
+  int rc = IDISP_OK;
+  auto cleanup = [&]() { cudaFree(fl); cudaFree(yb); tc_weights_free(tcw); };
+#define DK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #expr, __FILE__, __LINE__); } } while (0)
+#define DR(expr) do { if ((rc = (expr)) != IDISP_OK) { cudaStreamSynchronize(s); cleanup(); return rc; } } while (0)
+  const size_t fbytes = ((size_t)B * C * Hf * Wf * 2 + 1023) / 1024 * 1024;
+  DK(cudaMalloc(&fl, 2 * fbytes));  // the fused loader wants the right view's features after the left ones
+  fr = fl + fbytes / 2;
+  DK(cudaMalloc(&yb, (size_t)B * 32 * V * 2));
+  DR(launch_ncdhw_to_blocked<__nv_bfloat16>(left, fl, B, C, (int64_t)Hf * Wf, s));
+  DR(launch_ncdhw_to_blocked<__nv_bfloat16>(right, fr, B, C, (int64_t)Hf * Wf, s));
+  TcCostVolume cvd;
+  cvd.left = fl; cvd.right = fr;
+  cvd.shift0 = mindisp >= 0 ? mindisp / 4 : -((-mindisp + 3) / 4);
+  for (int c0 = 0; c0 < cin; c0 += 32) {  // 32 output channels per pass: input channels [c0, c0+32) copied through
+    std::vector<float> w((size_t)27 * cin * 32, 0.f);
+    const char *te = getenv("IDISP_DEBUG_TAP");  // which of the 27 taps carries the identity (default: centre)
+    const int tap = te ? atoi(te) : 13;
+    for (int co = 0; co < 32; ++co) w[((size_t)tap * cin + c0 + co) * 32 + co] = 1.f;
+    DR(tc_weights_prepare(w.data(), IDISP_CONV_S1, cin, 32, tcw, s));
+    DR(tc_conv3d(tcw, nullptr, B, cin, D, Hf, Wf, 32, IDISP_CONV_S1, nullptr, nullptr, 0, yb, nullptr, nullptr, nullptr, 0, nullptr, &cvd, s));
+    // blocked [B][4][V][8] -> channels [c0, c0+32) of NCDHW [B][2C][V]
+    for (int b = 0; b < B; ++b)
+      DR(launch_blocked_to_ncdhw<__nv_bfloat16>(yb + (size_t)b * 32 * V, cost + ((size_t)b * cin + c0) * V, 1, 32, V, s));
+  }
+  DK(cudaStreamSynchronize(s));
+  cleanup();
+#undef DK
+#undef DR
+  return IDISP_OK;
 }

@@ -74,6 +74,20 @@ __device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const CUtensorMap
       : "memory");
 }
 
+// A tensor map that lives in GLOBAL memory (not a kernel parameter) must be acquired by the tensormap proxy before use.
+__device__ __forceinline__ void tensormap_acquire(const CUtensorMap *m)
+{
+  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap *m, uint32_t bar, int c0, int c1, int c2)
+{
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap *m, uint32_t bar, int c0, int c1, int c2, int c3)
 {
   asm volatile(

@@ -132,6 +132,11 @@ int idisp_plan_launches_per_forward(const idisp_plan_t *plan);
 int idisp_plan_enable_timing(idisp_plan_t *plan, int on);
 int idisp_plan_get_timing(idisp_plan_t *plan, float *ms, int *layer, int capacity);
 
+/* Test hook: the cost volume exactly as the tensor-core path assembles it inside dres0.0's TMA loader (never
+ * materialised in the product path): bf16-rounded values, NCDHW f32 out [B,2C,D,Hf,Wf].  C in {16, 32}. */
+int idisp_debug_fused_cost_volume(const float *left, const float *right, int B, int C, int Hf, int Wf,
+                                  int mindisp, int maxdisp, float *cost, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

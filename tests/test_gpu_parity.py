@@ -94,6 +94,28 @@ def test_cost_volume_bit_exact(lib, B, C, Hf, Wf, mind, maxd):
     assert torch.equal(out.cpu(), want)
 
 
+@pytest.mark.parametrize('tap', [13, 12, 14, 0, 26, 10, 22])
+def test_fused_cost_volume_equals_reference(lib, tap, monkeypatch):
+    """The tensor-core path never materialises the cost volume: dres0.0's TMA loader assembles it.  With an identity
+    kernel on one tap the layer output IS the (bf16) cost volume shifted by that tap -- compare with the oracle, exactly."""
+    from disprcnn_b200 import _lib
+    monkeypatch.setenv('IDISP_DEBUG_TAP', str(tap))
+    for (B, C, Hf, Wf, mind, maxd) in [(1, 32, 16, 16, -16, 16), (2, 32, 20, 40, -48, 48), (1, 16, 16, 24, 0, 32), (1, 32, 8, 12, -48, 48)]:
+        g = torch.Generator().manual_seed(tap)
+        L = torch.randn(B, C, Hf, Wf, generator=g).bfloat16().float()
+        R = torch.randn(B, C, Hf, Wf, generator=g).bfloat16().float()
+        D = (maxd - mind) // 4
+        out = torch.full((B, 2 * C, D, Hf, Wf), float('nan'), device='cuda')
+        Lc, Rc = L.cuda(), R.cuda()
+        _lib.check(lib.idisp_debug_fused_cost_volume(_lib.ptr(Lc), _lib.ptr(Rc), B, C, Hf, Wf, mind, maxd, _lib.ptr(out), _lib.stream_ptr()))
+        want = O.cost_volume(L, R, mind, maxd)
+        if tap != 13:
+            k = torch.zeros(2 * C, 1, 3, 3, 3)
+            k[:, 0].view(2 * C, 27)[:, tap] = 1.0
+            want = F.conv3d(want, k, None, 1, 1, 1, 2 * C)
+        assert torch.equal(out.cpu(), want), (tap, B, C, Hf, Wf, mind, maxd, (out.cpu() - want).abs().max().item())
+
+
 # ---------------------------------------------------------------- single conv layers
 def _conv_ref(x, w, kind, scale, bias, res, relu):
     if kind == 0:
