@@ -45,20 +45,26 @@ namespace idisp {
 namespace tc {
 enum { M_S1 = 0, M_S2 = 1, M_DEC = 2 };
 constexpr int TW = 8, TH = 16;  // row tile (w x h) = 128 GEMM rows
-constexpr int NT = 32;          // output channels per stacked block
 
+// ACC_BLOCKS = accumulator blocks (of NT columns) one output plane owns
 template <int MODE> struct ModeCfg;
-template <> struct ModeCfg<M_S1> { static constexpr int SUB_W = TW + 2, SUB_H = TH + 2, SUBS = 1, ACC_COLS = 32; };
+template <> struct ModeCfg<M_S1> { static constexpr int SUB_W = TW + 2, SUB_H = TH + 2, SUBS = 1, ACC_BLOCKS = 1; };
 // (SUB_H is 18 rather than the 17 rows these modes read so that Cin/8 * SUB_W*SUB_H*16 B stays a multiple of 128 B,
 //  the alignment TMA needs for the second sub-tile of a stage)
-template <> struct ModeCfg<M_S2> { static constexpr int SUB_W = TW + 1, SUB_H = TH + 2, SUBS = 2, ACC_COLS = 32; };
-template <> struct ModeCfg<M_DEC> { static constexpr int SUB_W = TW + 1, SUB_H = TH + 2, SUBS = 1, ACC_COLS = 128; };
+template <> struct ModeCfg<M_S2> { static constexpr int SUB_W = TW + 1, SUB_H = TH + 2, SUBS = 2, ACC_BLOCKS = 1; };
+template <> struct ModeCfg<M_DEC> { static constexpr int SUB_W = TW + 1, SUB_H = TH + 2, SUBS = 1, ACC_BLOCKS = 4; };
 
 // OCC = CTAs per SM.  OCC 2 (stride-1, Cin 32 only: two 55 KB weight copies fit) gives the tensor pipe a second,
 // independent MMA stream that fills the bubbles one issuing warp leaves at plane boundaries (barrier round trips,
 // commits, descriptor set-up); each CTA then owns 256 TMEM columns and one epilogue group.
-template <int CIN, int MODE, int OCC> struct Cfg {
+// NT = output channels per stacked block: 32 by default; 16 for the 32->1 heads (their zero-padded kernel then costs
+// N=48 instead of N=96 of shared-memory B traffic per MMA); 64 for the stride-2 32->64 conv (both Cout halves in one MMA,
+// N=128/64 instead of two CTAs re-reading A with N=64/32).
+template <int CIN, int MODE, int OCC, int NT> struct Cfg {
   using MC = ModeCfg<MODE>;
+  static constexpr int ACC_COLS = MC::ACC_BLOCKS * NT;   // TMEM columns of one output plane
+  static constexpr int WCHUNK = 2 * 3 * NT * 16;          // B operand of one (kh,kw,kstep): [2 kcores][3 blocks x NT rows][8] bf16
+  static_assert(MODE != M_DEC || NT == 32, "the transposed-conv stacking table is written for 32-wide blocks");
   static constexpr int EGROUPS = OCC == 2 ? 1 : 2;        // epilogue groups of 4 warps (alternate output planes)
   static constexpr int NTHREADS = 128 + 128 * EGROUPS;    // warps 0-3: TMA producer / MMA issuer / TMEM allocator / idle
   static constexpr int TCOLS = 512 / OCC;                 // TMEM columns of this CTA
@@ -68,8 +74,8 @@ template <int CIN, int MODE, int OCC> struct Cfg {
   static constexpr int ROW_BYTES = MC::SUB_W * 16;                // one tile row (SBO of A)
   static constexpr int SUB_BYTES = CBLK * PLANE_BYTES;
   static constexpr int STAGE_BYTES = MC::SUBS * SUB_BYTES;
-  static constexpr int WBYTES = 27 * KS * 1024;                   // 27 taps x Cin x 32 couts x bf16
-  static constexpr int NSLOT = TCOLS / MC::ACC_COLS;
+  static constexpr int WBYTES = 27 * KS * NT * 32;                // 27 taps x Cin x NT couts x bf16
+  static constexpr int NSLOT = TCOLS / ACC_COLS;
   static constexpr int STAGES_FIT = (228 * 1024 / OCC - 1024 - WBYTES - 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int BAR_OFF = WBYTES + STAGES * STAGE_BYTES;
@@ -121,12 +127,12 @@ __device__ __forceinline__ F8 unpack8(const uint4 &a)
 
 __device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t byte_off) { return d + (uint64_t)(byte_off >> 4); }
 
-template <int CIN, int MODE, int OCC, bool CV>
-__global__ void __launch_bounds__((Cfg<CIN, MODE, OCC>::NTHREADS), OCC)
+template <int CIN, int MODE, int OCC, bool CV, int NT>
+__global__ void __launch_bounds__((Cfg<CIN, MODE, OCC, NT>::NTHREADS), OCC)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap rmap,
                  const __grid_constant__ CvMaps<CV> lmaps, const Params p)
 {
-  using C = Cfg<CIN, MODE, OCC>;
+  using C = Cfg<CIN, MODE, OCC, NT>;
   constexpr int NTHREADS = C::NTHREADS;
   using MC = ModeCfg<MODE>;
   constexpr int NSLOT = C::NSLOT;
@@ -277,7 +283,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
               for (int ks = 0; ks < C::KS; ++ks) {
                 const uint32_t aoff = ((tap / 3) * MC::SUB_W + (tap % 3)) * 16 + ks * 2 * C::PLANE_BYTES;
-                mma(d1, desc_add(a0, aoff), desc_add(b1, (tap * C::KS + ks) * 3072), id1);
+                mma(d1, desc_add(a0, aoff), desc_add(b1, (tap * C::KS + ks) * C::WCHUNK), id1);
               }
             }
           } else {
@@ -287,7 +293,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
               for (int ks = 0; ks < C::KS; ++ks) {
                 const uint32_t aoff = ((tap / 3) * MC::SUB_W + (tap % 3)) * 16 + ks * 2 * C::PLANE_BYTES;
-                const uint32_t boff = (tap * C::KS + ks) * 3072;
+                const uint32_t boff = (tap * C::KS + ks) * C::WCHUNK;
                 mma(d1, desc_add(a0, aoff), desc_add(b1, boff), id1);
                 mma(d2, desc_add(a0, aoff), desc_add(b2, boff), id2);
               }
@@ -330,16 +336,16 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                   const int kh = ph_ == 0 ? 1 : (t < 3 ? 0 : 2), kw = t % 3;
                   const int rh = kh == 0 ? 0 : 1, rw = kw == 0 ? 0 : 1, sub = kw != 1 ? 1 : 0;
                   const uint32_t aoff0 = sub * C::SUB_BYTES + (rh * MC::SUB_W + rw) * 16;
-                  const uint32_t boff0 = (kh * 3 + kw) * C::KS * 3072;
+                  const uint32_t boff0 = (kh * 3 + kw) * C::KS * C::WCHUNK;
                   if (len2 == 0) {
 #pragma unroll
                     for (int ks = 0; ks < C::KS; ++ks)
-                      mma(d1, desc_add(a0, aoff0 + ks * 2 * C::PLANE_BYTES), desc_add(b1, boff0 + ks * 3072), id1);
+                      mma(d1, desc_add(a0, aoff0 + ks * 2 * C::PLANE_BYTES), desc_add(b1, boff0 + ks * C::WCHUNK), id1);
                   } else {
 #pragma unroll
                     for (int ks = 0; ks < C::KS; ++ks) {
-                      mma(d1, desc_add(a0, aoff0 + ks * 2 * C::PLANE_BYTES), desc_add(b1, boff0 + ks * 3072), id1);
-                      mma(d2, desc_add(a0, aoff0 + ks * 2 * C::PLANE_BYTES), desc_add(b2, boff0 + ks * 3072), id2);
+                      mma(d1, desc_add(a0, aoff0 + ks * 2 * C::PLANE_BYTES), desc_add(b1, boff0 + ks * C::WCHUNK), id1);
+                      mma(d2, desc_add(a0, aoff0 + ks * 2 * C::PLANE_BYTES), desc_add(b2, boff0 + ks * C::WCHUNK), id2);
                     }
                   }
                 }
@@ -359,7 +365,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             for (int kd = 0; kd < 3; ++kd) {
               const int qo = 2 * z - 1 + kd;
               if (qo < 0 || qo >= Dout) continue;
-              const uint32_t dbase = tmem_base + ((g0 + qo) % NSLOT) * MC::ACC_COLS;
+              const uint32_t dbase = tmem_base + ((g0 + qo) % NSLOT) * C::ACC_COLS;
 #pragma unroll
               for (int e = 0; e < 5; ++e) {
 #pragma unroll
@@ -402,7 +408,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       for (int qo = egroup; qo < Dout; qo += C::EGROUPS) {
         const uint32_t g = g0 + qo, r = g % NSLOT;
         // residual operands do not depend on the accumulator: request them BEFORE waiting for it
-        constexpr int NRES = MODE == M_DEC ? 16 : 4;
+        constexpr int NRES = MODE == M_DEC ? 16 : (NT >= 8 ? NT / 8 : 1);
         uint4 resv[NRES];
         if (p.residual && valid) {
 #pragma unroll
@@ -411,7 +417,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             const int cb = MODE == M_DEC ? (i >> 1) & 3 : i;
             const int64_t pos = MODE == M_DEC ? ((int64_t)qo * p.Ho + 2 * hr + (i >> 3)) * p.Wo + 2 * wr + (i & 1)
                                               : ((int64_t)qo * p.Ho + hr) * p.Wo + wr;
-            resv[i] = __ldg(reinterpret_cast<const uint4 *>(p.residual + (((int64_t)n * cblk_out + nh * 4 + cb) * Vo + pos) * 8));
+            resv[i] = __ldg(reinterpret_cast<const uint4 *>(p.residual + (((int64_t)n * cblk_out + nh * (NT / 8) + cb) * Vo + pos) * 8));
           }
         }
         ptx::mbar_wait(accf_bar(r), (g / NSLOT) & 1);
@@ -422,7 +428,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
           for (int ph = 0; ph < 2; ++ph) {
             uint32_t v0[32], v1[32];
-            const uint32_t t0 = tmem_base + lane_addr + r * MC::ACC_COLS + ph * NT, t1 = t0 + 2 * NT;
+            const uint32_t t0 = tmem_base + lane_addr + r * C::ACC_COLS + ph * NT, t1 = t0 + 2 * NT;
             if (!(p.dbg & 8)) { ptx::tmem_ld_32x32(t0, v0); ptx::tmem_ld_32x32(t1, v1); ptx::tmem_ld_wait(); }
             if (!(p.dbg & 16)) { ptx::tmem_st_32x32(t0, zero); ptx::tmem_st_32x32(t1, zero); }
             if (ph == 1) {
@@ -463,46 +469,64 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             }
           }
         } else {
-          uint32_t v[32];
-          const uint32_t taddr = tmem_base + lane_addr + r * MC::ACC_COLS;
-          if (!(p.dbg & 8)) { ptx::tmem_ld_32x32(taddr, v); ptx::tmem_ld_wait(); }
-          else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0u;
-          }
-          if (!(p.dbg & 16)) ptx::tmem_st_32x32(taddr, zero);  // leave the slot zeroed for its next output plane
-          ptx::tmem_st_wait();
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(acce_bar(r));
-          if (!valid || (p.dbg & 4)) continue;
+          constexpr int NV = NT < 32 ? NT : 32;      // columns per TMEM load
+          constexpr int NLD = NT / NV;               // loads per plane (NT = 64 -> 2)
+          const uint32_t taddr = tmem_base + lane_addr + r * C::ACC_COLS;
           const int64_t pos = ((int64_t)qo * p.Ho + hr) * p.Wo + wr;
-          if (p.y1) {  // 32->1 classifier head: channel 0 only, f32, running sum fused (stackhourglass.py:142-144)
-            const int64_t o1 = (int64_t)n * Vo + pos;
-            p.y1[o1] = __uint_as_float(v[0]) + (p.res1 ? p.res1[o1] : 0.f);
-            continue;
-          }
 #pragma unroll
-          for (int cb = 0; cb < 4; ++cb) {
-            const int64_t o = (((int64_t)n * cblk_out + nh * 4 + cb) * Vo + pos) * 8;
-            F8 r8;
+          for (int part = 0; part < NLD; ++part) {
+            uint32_t v[32];
+            if (p.dbg & 8) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) r8.v[c] = __uint_as_float(v[cb * 8 + c]) + bias_s[cb * 8 + c];
-            if (p.residual) {
-              const F8 q8 = unpack8(resv[cb]);
+              for (int i = 0; i < 32; ++i) v[i] = 0u;
+            } else if (NT == 16) {
+              uint32_t v16[16];
+              ptx::tmem_ld_32x16(taddr, v16);
+              ptx::tmem_ld_wait();
 #pragma unroll
-              for (int c = 0; c < 8; ++c) r8.v[c] += q8.v[c];
+              for (int i = 0; i < 16; ++i) v[i] = v16[i];
+            } else {
+              ptx::tmem_ld_32x32(taddr + part * 32, v);
+              ptx::tmem_ld_wait();
             }
-            if (p.relu) {
-#pragma unroll
-              for (int c = 0; c < 8; ++c) r8.v[c] = fmaxf(r8.v[c], 0.f);
+            if (!(p.dbg & 16)) {  // leave the slot zeroed for its next output plane
+              if (NT == 16) ptx::tmem_st_32x16(taddr, zero); else ptx::tmem_st_32x32(taddr + part * 32, zero);
             }
-            store8<__nv_bfloat16>(p.y + o, r8);
-            if (p.y_split) {
-              const int64_t sub = Vo / 8;
-              const int64_t os = ((((int64_t)n * cblk_out + nh * 4 + cb) * 8 + (qo & 1) * 4 + (hr & 1) * 2 + (wr & 1)) * sub +
-                                  ((int64_t)(qo >> 1) * (p.Ho / 2) + (hr >> 1)) * (p.Wo / 2) + (wr >> 1)) * 8;
-              store8<__nv_bfloat16>(p.y_split + os, r8);
+            if (part == NLD - 1) {
+              ptx::tmem_st_wait();
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(acce_bar(r));
+            }
+            if (!valid || (p.dbg & 4)) continue;
+            if (p.y1) {  // 32->1 classifier head: channel 0 only, f32, running sum fused (stackhourglass.py:142-144)
+              const int64_t o1 = (int64_t)n * Vo + pos;
+              p.y1[o1] = __uint_as_float(v[0]) + (p.res1 ? p.res1[o1] : 0.f);
+              continue;
+            }
+#pragma unroll
+            for (int cbl = 0; cbl < NV / 8; ++cbl) {
+              const int cb = part * 4 + cbl;  // channel block inside this CTA's NT-wide slice
+              const int64_t o = (((int64_t)n * cblk_out + nh * (NT / 8) + cb) * Vo + pos) * 8;
+              F8 r8;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) r8.v[c] = __uint_as_float(v[cbl * 8 + c]) + bias_s[cb * 8 + c];
+              if (p.residual) {
+                const F8 q8 = unpack8(resv[cb]);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) r8.v[c] += q8.v[c];
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) r8.v[c] = fmaxf(r8.v[c], 0.f);
+              }
+              store8<__nv_bfloat16>(p.y + o, r8);
+              if (p.y_split) {
+                const int64_t sub = Vo / 8;
+                const int64_t os = ((((int64_t)n * cblk_out + nh * (NT / 8) + cb) * 8 + (qo & 1) * 4 + (hr & 1) * 2 + (wr & 1)) * sub +
+                                    ((int64_t)(qo >> 1) * (p.Ho / 2) + (hr >> 1)) * (p.Wo / 2) + (wr >> 1)) * 8;
+                store8<__nv_bfloat16>(p.y_split + os, r8);
+              }
             }
           }
         }
@@ -567,6 +591,15 @@ static int env_flag(const char *name)
 
 static int mode_of(int kind) { return kind == IDISP_CONV_S1 ? M_S1 : (kind == IDISP_CONV_S2 ? M_S2 : M_DEC); }
 
+// output channels per stacked block for a layer (see Cfg): 16 for the 32->1 heads, 64 for the stride-2 32->64 conv
+static int nt_of(int kind, int cin, int cout)
+{
+  if (env_flag("IDISP_TC_NT32")) return 32;  // A/B switch
+  if (kind == IDISP_CONV_S1 && cout == 1) return 16;
+  if (kind == IDISP_CONV_S2 && cin == 32 && cout == 64) return 64;
+  return 32;
+}
+
 }  // namespace tc
 
 // Pack [27][cin][cout] f32 (tap = (kd*3+kh)*3+kw, BN scale folded) into the per-mode UMMA B layout, bf16:
@@ -576,8 +609,10 @@ int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, TcWeight
   tc_weights_free(out);
   out.kind = kind; out.cin = cin; out.cout = cout;
   if (!tc_supported(kind, cin, cout, 4, 16, 16)) return IDISP_OK;  // layer stays on the SIMT kernel
-  const int KS = cin / 16, NH = (cout + 31) / 32;
-  const size_t per_nh = (size_t)27 * KS * 512;  // bf16 elements
+  const int NT = tc::nt_of(kind, cin, cout);
+  out.nt = NT;
+  const int KS = cin / 16, NH = (cout + NT - 1) / NT;
+  const size_t per_nh = (size_t)27 * KS * NT * 16;  // bf16 elements
   std::vector<__nv_bfloat16> h(NH * per_nh, __float2bfloat16_rn(0.f));
   auto wv = [&](int kd, int kh, int kw, int ci, int co) -> float {
     return co < cout ? w_tap[((size_t)((kd * 3 + kh) * 3 + kw) * cin + ci) * cout + co] : 0.f;
@@ -585,16 +620,16 @@ int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, TcWeight
   for (int nh = 0; nh < NH; ++nh) {
     __nv_bfloat16 *base = h.data() + nh * per_nh;
     if (kind == IDISP_CONV_S1 || kind == IDISP_CONV_S2) {
-      // chunk (kh,kw,ks): [2 kcores][96 rows = 3 blocks x 32 couts][8]; block j <-> kd = S1 {2,1,0}, S2 {2,0,1}
+      // chunk (kh,kw,ks): [2 kcores][3 blocks x NT couts][8]; block j <-> kd = S1 {2,1,0}, S2 {2,0,1}
       static const int kd_s1[3] = {2, 1, 0}, kd_s2[3] = {2, 0, 1};
       const int *kdj = kind == IDISP_CONV_S1 ? kd_s1 : kd_s2;
       for (int t2 = 0; t2 < 9; ++t2)
         for (int ks = 0; ks < KS; ++ks)
           for (int kc = 0; kc < 2; ++kc)
-            for (int n = 0; n < 96; ++n)
+            for (int n = 0; n < 3 * NT; ++n)
               for (int e = 0; e < 8; ++e)
-                base[((((size_t)t2 * KS + ks) * 2 + kc) * 96 + n) * 8 + e] =
-                    __float2bfloat16_rn(wv(kdj[n / 32], t2 / 3, t2 % 3, ks * 16 + kc * 8 + e, nh * 32 + n % 32));
+                base[((((size_t)t2 * KS + ks) * 2 + kc) * 3 * NT + n) * 8 + e] =
+                    __float2bfloat16_rn(wv(kdj[n / NT], t2 / 3, t2 % 3, ks * 16 + kc * 8 + e, nh * NT + n % NT));
     } else {
       // DECONV: [kd][ks][2 kcores][288 rows][8]; rows = entries e0..e4 (tc::dec_*), blocks = output classes
       //   class = pw*2+ph; per axis: p=0 -> k=1 (shift 0); p=1 -> k=2 (shift 0), k=0 (shift 1)
@@ -646,12 +681,12 @@ size_t tc_scratch_bytes(int kind, int B, int cin, int D, int H, int W)
   return kind == IDISP_CONV_S2 ? (size_t)B * cin * D * H * W * sizeof(__nv_bfloat16) : 0;
 }
 
-template <int CIN, int MODE, int OCC>
+template <int CIN, int MODE, int OCC, int NT>
 static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, int H, int W, int Cout, const float *bias,
                      const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1, void *scratch,
                      int x_is_split, __nv_bfloat16 *y_split, const TcCostVolume *cv, cudaStream_t s)
 {
-  using C = tc::Cfg<CIN, MODE, OCC>;
+  using C = tc::Cfg<CIN, MODE, OCC, NT>;
   using MC = tc::ModeCfg<MODE>;
   tc::EncodeTiledFn enc = tc::get_encode();
   if (!enc) { set_error("tc_conv3d: cuTensorMapEncodeTiled not available from the driver"); return IDISP_ERR_CUDA; }
@@ -716,7 +751,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   if (MODE == tc::M_S1) { p.Dout = D; p.Ho = H; p.Wo = W; p.Hr = H; p.Wr = W; }
   if (MODE == tc::M_S2) { p.Dout = D / 2; p.Ho = H / 2; p.Wo = W / 2; p.Hr = H / 2; p.Wr = W / 2; }
   if (MODE == tc::M_DEC) { p.Dout = 2 * D; p.Ho = 2 * H; p.Wo = 2 * W; p.Hr = H; p.Wr = W; }
-  p.tiles_h = ceil_div(p.Hr, tc::TH); p.tiles_w = ceil_div(p.Wr, tc::TW); p.nh = (Cout + 31) / 32;
+  p.tiles_h = ceil_div(p.Hr, tc::TH); p.tiles_w = ceil_div(p.Wr, tc::TW); p.nh = (Cout + NT - 1) / NT;
   const int ncols = B * p.tiles_h * p.tiles_w;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -725,11 +760,11 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   if (per_slice > ncols) per_slice = ncols;
   const int grid = per_slice * p.nh;
   if (MODE == tc::M_S1 && cv) {
-    auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, (MODE == tc::M_S1)>;
+    auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, (MODE == tc::M_S1), NT>;
     IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     if constexpr (MODE == tc::M_S1) kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, rmap, cvmaps, p);
   } else {
-    auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, false>;
+    auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, false, NT>;
     IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, rmap, tc::CvMaps<false>{}, p);
   }
@@ -753,12 +788,21 @@ int tc_conv3d(const TcWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D,
   }
   if ((Cout == 1) != (y1 != nullptr)) { set_error("tc_conv3d: the 1-channel head needs the f32 output (and only it)"); return IDISP_ERR_INVALID; }
   if (B == 0) return IDISP_OK;
-#define IDISP_TC(CI, MD, OC) return tc_launch<CI, MD, OC>(w, x, B, D, H, W, Cout, bias, residual, relu, y, res1, y1, scratch, x_is_split, y_split, cv, s)
+#define IDISP_TC(CI, MD, OC, NTT) return tc_launch<CI, MD, OC, NTT>(w, x, B, D, H, W, Cout, bias, residual, relu, y, res1, y1, scratch, x_is_split, y_split, cv, s)
   const int mode = tc::mode_of(kind);
   static const int occ1 = tc::env_flag("IDISP_TC_OCC1");  // A/B switch for the 2-CTA/SM stride-1 variant
-  if (mode == tc::M_S1) { if (Cin == 32) { if (occ1) IDISP_TC(32, tc::M_S1, 1); else IDISP_TC(32, tc::M_S1, 2); } else IDISP_TC(64, tc::M_S1, 1); }
-  if (mode == tc::M_S2) { if (Cin == 32) IDISP_TC(32, tc::M_S2, 1); else IDISP_TC(64, tc::M_S2, 1); }
-  IDISP_TC(64, tc::M_DEC, 1);
+  if (w.nt != tc::nt_of(kind, Cin, Cout)) { set_error("tc_conv3d: weights were packed for a different block width"); return IDISP_ERR_INVALID; }
+  if (mode == tc::M_S1) {
+    if (Cin == 64) IDISP_TC(64, tc::M_S1, 1, 32);
+    if (w.nt == 16) { if (occ1) IDISP_TC(32, tc::M_S1, 1, 16); else IDISP_TC(32, tc::M_S1, 2, 16); }
+    if (occ1) IDISP_TC(32, tc::M_S1, 1, 32); else IDISP_TC(32, tc::M_S1, 2, 32);
+  }
+  if (mode == tc::M_S2) {
+    if (Cin == 64) IDISP_TC(64, tc::M_S2, 1, 32);
+    if (w.nt == 64) IDISP_TC(32, tc::M_S2, 1, 64);
+    IDISP_TC(32, tc::M_S2, 1, 32);
+  }
+  IDISP_TC(64, tc::M_DEC, 1, 32);
 #undef IDISP_TC
 }
 

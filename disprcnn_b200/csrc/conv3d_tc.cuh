@@ -9,6 +9,7 @@ struct TcWeights {
   void *dev = nullptr;
   size_t bytes = 0;
   int kind = -1, cin = 0, cout = 0;
+  int nt = 32;  // output channels per stacked block the packing was made for
 };
 
 // w_tap: HOST pointer, [27][cin][cout] f32 with the BN scale already folded in
