@@ -117,6 +117,35 @@ def cpu_port_rois_per_s(model_sd, n_steps, n_warm, budget_s=150.0):
     return (rows / HF) / dt, dt, cores, f'{n_steps} step(s) of 1 ROI pair x {rows}/{HF} feature rows (D={D}, W={WF}, C={C}), {n_warm} warm-up'
 
 
+def bench_roi_align(dev, hbm_gbs):
+    """The ROIAlign that feeds iDispNet, reported separately: the live variant -- 8 synthetic 3x375x1242
+    images, 32 integer-cornered boxes, 224x224 crops with the ImageNet normalisation fused (disprcnn3d.py:44-50)."""
+    import torch
+    from disprcnn_b200.layers.roi_align import crop_and_transform_roi_img
+    g = torch.Generator().manual_seed(0)
+    im = torch.rand(8, 3, 375, 1242, generator=g).to(dev)
+    x1 = torch.randint(0, 800, (32,), generator=g).float()
+    y1 = torch.randint(0, 150, (32,), generator=g).float()
+    w = torch.randint(60, 400, (32,), generator=g).float()
+    h = torch.randint(60, 200, (32,), generator=g).float()
+    rois = torch.stack([torch.arange(32).float() % 8, x1, y1, x1 + w, y1 + h], 1).to(dev)
+    for _ in range(3):
+        out = crop_and_transform_roi_img(im, rois, 224)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    n = 20
+    for _ in range(n):
+        out = crop_and_transform_roi_img(im, rois, 224)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    out_bytes = out.numel() * 4
+    return {'rois_per_s': 32 / (ms / 1e3), 'ms_per_call': ms, 'workload': '32 ROIs -> 3x224x224 from 8 images 3x375x1242, fused normalise',
+            'algorithmic_bytes': out_bytes, 'achieved_gbs': out_bytes / (ms / 1e3) / 1e9, 'hbm_peak_gbs': hbm_gbs,
+            'note': 'output-write bytes only; the gather reads hit L2 (3.7 MB image set), launch-latency dominated at this size'}
+
+
 def make_model(precision, device):
     import torch
     import torch.nn as nn
@@ -269,6 +298,11 @@ def main():
     conv_flops = FLOP_PER_ROI * B_PER_GPU * args.steps  # this rank's conv launches
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
 
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    if args.precision == 'bf16' and os.path.exists(tpath):
+        tj = json.load(open(tpath))  # DRAM bytes of the 28 conv launches of one step, from the committed ncu --set full capture
+        traffic = {'dram_gb_per_step': tj['dram_read_gb_per_step'] + tj['dram_write_gb_per_step'], 'source': tj['source']}
     if rank == 0:
         result = {
             'metric': 'idispnet_roi_crops_per_s', 'value': value, 'unit': 'ROIs/s', 'n_gpus': world,
@@ -282,7 +316,7 @@ def main():
                     'd2h_bytes_per_step': B_PER_GPU * H * W * 4 * world, 'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': launches_per_step * args.steps,
             'roofline': {'bound': 'tensor', 'kernel': '3-D conv launches (28 layers/step)', 'achieved': achieved,
-                         'peak': tens_sus, 'unit': 'TFLOP/s', 'frac': achieved / tens_sus, 'traffic': None,
+                         'peak': tens_sus, 'unit': 'TFLOP/s', 'frac': achieved / tens_sus, 'traffic': traffic,
                          'peak_source': f'{peak_src} bf16 sustained (burst {tens_burst})',
                          'flop_per_roi': FLOP_PER_ROI, 'conv_ms_per_step': conv_ms / args.steps,
                          'other_ms_per_step': other_ms / args.steps,
@@ -310,6 +344,8 @@ def main():
             result['fp32_parity_mode'] = {'value': B_PER_GPU / (e0.elapsed_time(e1) / 1e3), 'unit': 'ROIs/s',
                                           'bf16_vs_fp32_disparity_px': {'max': diff.max().item(), 'mean': diff.mean().item()}}
             del m32
+        if world == 1:
+            result['roi_align'] = bench_roi_align(dev, hbm)
         if world == 1 and not args.no_cpu_baseline:
             sd = {k: v for k, v in m.state_dict().items() if not k.startswith('feature_extraction')}
             val, dt, cores, sample = cpu_port_rois_per_s(sd, 1, 1, budget_s=45.0)  # 1 warm-up: oneDNN primitive creation is per shape

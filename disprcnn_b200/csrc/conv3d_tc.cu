@@ -92,6 +92,8 @@ struct Params {
   const float *res1;              // 32->1 head: running sum [B][D][H][W] f32 or nullptr
   float *y1;                      // 32->1 head: output [B][D][H][W] f32 (non-null selects this epilogue)
   __nv_bfloat16 *y_split;         // optional second copy of y in the 8-parity-sub-volume layout a stride-2 consumer reads
+  int residual_is_split;          // transposed conv only: `residual` is stored in that parity layout (of the OUTPUT grid)
+  int skip_y;                     // write only y_split (the natural copy has no reader)
   int B, Din, Dout, Ho, Wo, Hr, Wr, Cout, relu;  // (Hr,Wr): row grid the 8x16 tiles cover
   int tiles_h, tiles_w, nh;
   int cv_shift0;                  // mindisp/4: plane k <-> right-view shift i = k + cv_shift0
@@ -417,7 +419,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             const int cb = MODE == M_DEC ? (i >> 1) & 3 : i;
             const int64_t pos = MODE == M_DEC ? ((int64_t)qo * p.Ho + 2 * hr + (i >> 3)) * p.Wo + 2 * wr + (i & 1)
                                               : ((int64_t)qo * p.Ho + hr) * p.Wo + wr;
-            resv[i] = __ldg(reinterpret_cast<const uint4 *>(p.residual + (((int64_t)n * cblk_out + nh * (NT / 8) + cb) * Vo + pos) * 8));
+            int64_t ro = (((int64_t)n * cblk_out + nh * (NT / 8) + cb) * Vo + pos) * 8;
+            if (MODE == M_DEC && p.residual_is_split)  // class (qo&1, ph, pw) at (qo>>1, hr, wr): 128 B contiguous per 8 rows
+              ro = ((((int64_t)n * cblk_out + nh * 4 + cb) * 8 + (qo & 1) * 4 + (i >> 3) * 2 + (i & 1)) * (Vo / 8) +
+                    ((int64_t)(qo >> 1) * (p.Ho / 2) + hr) * (p.Wo / 2) + wr) * 8;
+            resv[i] = __ldg(reinterpret_cast<const uint4 *>(p.residual + ro));
           }
         }
         ptx::mbar_wait(accf_bar(r), (g / NSLOT) & 1);
@@ -520,7 +526,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
                 for (int c = 0; c < 8; ++c) r8.v[c] = fmaxf(r8.v[c], 0.f);
               }
-              store8<__nv_bfloat16>(p.y + o, r8);
+              if (!p.skip_y) store8<__nv_bfloat16>(p.y + o, r8);
               if (p.y_split) {
                 const int64_t sub = Vo / 8;
                 const int64_t os = ((((int64_t)n * cblk_out + nh * (NT / 8) + cb) * 8 + (qo & 1) * 4 + (hr & 1) * 2 + (wr & 1)) * sub +
@@ -695,7 +701,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   CUresult r;
   const void *src = x;
   if (MODE == tc::M_S2) {
-    if (x_is_split) {
+    if (x_is_split & 1) {
       src = x;  // the producer's epilogue already wrote the parity sub-volumes (Params::y_split)
     } else {
       if (!scratch) { set_error("tc_conv3d: stride-2 layer needs the space-to-depth scratch buffer"); return IDISP_ERR_INVALID; }
@@ -743,7 +749,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   }
   if (r != CUDA_SUCCESS) { set_error("tc_conv3d: cuTensorMapEncodeTiled failed (%d) for dims W=%d H=%d D=%d mode=%d", (int)r, W, H, D, MODE); return IDISP_ERR_CUDA; }
   tc::Params p;
-  p.w = (const __nv_bfloat16 *)w.dev; p.bias = bias; p.residual = residual; p.y = y; p.res1 = res1; p.y1 = y1; p.y_split = y_split;
+  p.w = (const __nv_bfloat16 *)w.dev; p.bias = bias; p.residual = residual; p.y = y; p.res1 = res1; p.y1 = y1; p.y_split = y_split; p.residual_is_split = (x_is_split >> 1) & 1; p.skip_y = (x_is_split >> 2) & 1;
   p.B = B; p.Din = D; p.Cout = Cout; p.relu = relu;
   p.cv_shift0 = cv ? cv->shift0 : 0;
   if (!cv) rmap = map;

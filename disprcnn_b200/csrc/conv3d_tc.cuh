@@ -31,7 +31,8 @@ int tc_conv3d(const TcWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D,
               const float *bias, const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1,
               void *scratch, int x_is_split, __nv_bfloat16 *y_split, const TcCostVolume *cv, cudaStream_t s);
 // cv != nullptr: the layer's input IS the cost volume of (cv->left, cv->right); x is ignored and nothing is materialised.
-// x_is_split: a stride-2 layer's input pointer already holds the 8 parity sub-volumes (written by its producer's
-// epilogue through y_split), so the space-to-depth pass is skipped.
+// x_is_split is a bit set: 1 = a stride-2 layer's input pointer already holds the 8 parity sub-volumes (written by its producer's
+// epilogue through y_split), so the space-to-depth pass is skipped; 2 = (transposed conv) `residual` is stored in the parity
+// layout of the output grid; 4 = write only y_split, not y.
 
 }  // namespace idisp

@@ -273,6 +273,17 @@ extern "C" size_t idisp_plan_workspace_bytes(const idisp_plan_t *p, int B, int H
   return A.off;
 }
 
+template <typename MarkFn>
+static int tc_conv3d_split_input(idisp_plan *p, int li, const void *xsplit, int B, int D, int Hf, int Wf, void *y, cudaStream_t s,
+                                 MarkFn &mark, int &launches)
+{
+  const LayerSpec &L = p->layers[li];
+  mark(li);
+  ++launches;
+  return tc_conv3d(p->dev[li].tc, (const __nv_bfloat16 *)xsplit, B, L.cin, D, Hf, Wf, L.cout, L.kind, p->dev[li].bias, nullptr, 1,
+                   (__nv_bfloat16 *)y, nullptr, nullptr, nullptr, 1, nullptr, nullptr, s);
+}
+
 template <typename T>
 static int forward_impl(idisp_plan *p, const float *left, const float *right, int B, int Hf, int Wf, int H, int W,
                         void *workspace, float *out, cudaStream_t s)
@@ -293,7 +304,7 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
   // split_out: also emit the output as 8 parity sub-volumes into b.split (feeds the next stride-2 tensor-core conv);
   // x_split: the input IS b.split (written that way by its producer), so no re-lay pass is needed.
   auto conv = [&](int li, const void *x, int d, int h, int w, const void *res, int relu, void *y, bool split_out = false,
-                  bool x_split = false) -> int {
+                  bool x_split = false, int extra_flags = 0, void *split_dst = nullptr) -> int {
     const LayerSpec &L = p->layers[li];
     mark(li);
     ++launches;
@@ -301,7 +312,7 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
       if (L.kind == IDISP_CONV_S2 && !x_split) ++launches;  // + the space-to-depth re-lay
       return tc_conv3d(p->dev[li].tc, (const __nv_bfloat16 *)(x_split ? b.split : x), B, L.cin, d, h, w, L.cout, L.kind,
                        p->dev[li].bias, (const __nv_bfloat16 *)res, relu, (__nv_bfloat16 *)y, nullptr, nullptr, b.split,
-                       x_split ? 1 : 0, split_out ? (__nv_bfloat16 *)b.split : nullptr, nullptr, s);
+                       (x_split ? 1 : 0) | extra_flags, split_out ? (__nv_bfloat16 *)(split_dst ? split_dst : b.split) : nullptr, nullptr, s);
     }
     return launch_conv3d_simt<T>((const T *)x, B, L.cin, d, h, w, p->dev[li].w_tap, L.cout, L.kind, p->dev[li].bias,
                                  (const T *)res, relu, (T *)y, s);
@@ -334,7 +345,9 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
   // dres0 (second conv), dres1 (:130-131)
   RUN(conv(1, b.a, D, Hf, Wf, nullptr, 1, b.t0));
   RUN(conv(2, b.t0, D, Hf, Wf, nullptr, 1, b.a));
-  RUN(conv(3, b.a, D, Hf, Wf, b.t0, 0, b.cost0, fuse_split));
+  // fused hand-off: cost0 is stored ONLY in the parity layout (in b.cost0): its readers are dres2.conv1 (stride 2) and the
+  // residual adds of the three conv6 epilogues, which all address that layout directly
+  RUN(conv(3, b.a, D, Hf, Wf, b.t0, 0, b.cost0, fuse_split, false, fuse_split ? 4 : 0, b.cost0));
   // three hourglasses (:133-140); `x` is cost0 / out1 / out2, all outputs land in b.out
   const int D2 = D / 2, H2 = Hf / 2, W2 = Wf / 2, D4 = D / 4, H4 = Hf / 4, W4 = Wf / 4;
   for (int k = 0; k < 3; ++k) {
@@ -344,12 +357,15 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
     const void *postsqu = k == 0 ? nullptr : (k == 1 ? b.postA : b.postB);  // post1 / post2
     void *post = k == 1 ? b.postB : b.postA;                                  // post1,post3 -> A; post2 -> B
     const void *presqu = k == 0 ? b.pre1 /* own pre */ : b.pre1;              // pre1 for dres3 AND dres4 (:136,:139)
-    RUN(conv(l0 + 0, x, D, Hf, Wf, nullptr, 1, b.h1, false, fuse_split));          // reads b.split (cost0 / out_k)
+    if (fuse_split && k == 0)  // dres2.conv1 reads cost0's parity layout in place
+      RUN(tc_conv3d_split_input(p, l0, b.cost0, B, D, Hf, Wf, b.h1, s, mark, launches));
+    else
+      RUN(conv(l0 + 0, x, D, Hf, Wf, nullptr, 1, b.h1, false, fuse_split));        // reads b.split (out_k)
     RUN(conv(l0 + 1, b.h1, D2, H2, W2, postsqu, 1, pre, fuse_split));              // writes b.split (pre_k)
     RUN(conv(l0 + 2, pre, D2, H2, W2, nullptr, 1, b.q1, false, fuse_split));       // reads b.split
     RUN(conv(l0 + 3, b.q1, D4, H4, W4, nullptr, 1, b.q2));
     RUN(conv(l0 + 4, b.q2, D4, H4, W4, presqu, 1, post));
-    RUN(conv(l0 + 5, post, D2, H2, W2, b.cost0, 0, b.out, fuse_split && k < 2));   // writes b.split (out_k) for the next hourglass
+    RUN(conv(l0 + 5, post, D2, H2, W2, b.cost0, 0, b.out, fuse_split && k < 2, false, fuse_split ? 2 : 0));  // (+ b.split = out_k)
     // classifier head k on out_k (:142-144), running sum fused
     RUN(conv(22 + k, b.out, D, Hf, Wf, nullptr, 1, b.c));
     float *dst = (k == 1) ? b.costY : b.costX;
