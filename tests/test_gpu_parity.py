@@ -233,6 +233,56 @@ def test_idispnet_bf16_mode_error_is_bounded(lib, name):
     assert e.max() < TOL_BF16 and e.mean() < TOL_BF16_MEAN
 
 
+def test_bf16_fused_paths_equal_unfused_paths(lib, monkeypatch):
+    """The fusions of the tensor-core mode (cost volume inside dres0.0's loader; parity copies written by producer
+    epilogues) move data differently but compute the same bf16 values: results must be bit-identical to the unfused
+    schedule (materialised cost volume, explicit space-to-depth passes)."""
+    case, g, sd, L, R = load_case('tiny')
+    outs = {}
+    for tag, env in (('fused', {}), ('no_cv', {'IDISP_NO_FUSED_CV': '1'}), ('no_split', {'IDISP_NO_FUSED_SPLIT': '1'}),
+                     ('neither', {'IDISP_NO_FUSED_CV': '1', 'IDISP_NO_FUSED_SPLIT': '1'})):
+        for k in ('IDISP_NO_FUSED_CV', 'IDISP_NO_FUSED_SPLIT'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        m = make_psmnet(case, sd, 'bf16')
+        with torch.no_grad():
+            outs[tag] = m.forward_features(L.cuda(), R.cuda()).cpu()
+    for tag in ('no_cv', 'no_split', 'neither'):
+        assert torch.equal(outs[tag], outs['fused']), (tag, (outs[tag] - outs['fused']).abs().max().item())
+
+
+def test_bf16_many_planes_falls_back_to_materialised_cost_volume(lib):
+    """D = 68 planes exceeds the 64 per-plane tensor maps of the fused loader: the plan must take the materialised
+    path and still agree with the oracle."""
+    import torch.nn as nn
+    from disprcnn_b200.modeling.psmnet.stackhourglass import PSMNet
+    mind, maxd, C, Hf, Wf = -136, 136, 32, 8, 16
+    sd = recipe.make_state_dict(recipe.stack3d_shapes(C), 77)
+    L, R = recipe.make_features(1, C, Hf, Wf, 78)
+    with torch.no_grad():
+        want = O.idispnet_from_features(L, R, sd, mind, maxd)
+    for prec, tol in (('fp32', TOL_FP32), ('bf16', TOL_BF16)):
+        m = PSMNet(maxd, mind, precision=prec)
+        m.feature_extraction = nn.Identity()
+        m.load_state_dict(sd, strict=False)
+        m = m.cuda().eval()
+        with torch.no_grad():
+            got = m.forward_features(L.cuda(), R.cuda()).cpu()
+        assert (got - want).abs().max().item() < tol, prec
+
+
+def test_empty_batch_and_roi_independent_batching(lib):
+    case, g, sd, L, R = load_case('tiny')
+    for prec in ('fp32', 'bf16'):
+        m = make_psmnet(case, sd, prec)
+        with torch.no_grad():
+            assert tuple(m.forward_features(L[:0].cuda(), R[:0].cuda()).shape) == (0, 64, 64)
+            full = m.forward_features(L.cuda(), R.cuda())
+            one = m.forward_features(L[1:2].cuda(), R[1:2].cuda())
+        assert torch.equal(one, full[1:2]), prec   # ROIs are independent and the kernels are deterministic
+
+
 def test_host_buffer_entry_matches_device_entry(lib):
     from disprcnn_b200 import _lib
     case, g, sd, L, R = load_case('tiny')
