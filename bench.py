@@ -166,7 +166,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--precision', default=os.environ.get('IDISP_BENCH_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
+    ap.add_argument('--precision', default=os.environ.get('IDISP_BENCH_PRECISION', 'bf16'), choices=['fp32', 'bf16', 'fp16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -300,7 +300,7 @@ def main():
 
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-    if args.precision == 'bf16' and os.path.exists(tpath):
+    if args.precision != 'fp32' and os.path.exists(tpath):
         tj = json.load(open(tpath))  # DRAM bytes of the 28 conv launches of one step, from the committed ncu --set full capture
         traffic = {'dram_gb_per_step': tj['dram_read_gb_per_step'] + tj['dram_write_gb_per_step'], 'source': tj['source']}
     if rank == 0:
@@ -308,7 +308,7 @@ def main():
             'metric': 'idispnet_roi_crops_per_s', 'value': value, 'unit': 'ROIs/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': warm, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32' if args.precision == 'fp32' else 'bf16 (fp32 accumulate)', 'data': 'synthetic',
+            'dtype': 'f32' if args.precision == 'fp32' else f'{args.precision} (fp32 accumulate)', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'global_batch': Bg, 'parallelism': f'dp{world} (ROI shards, one all-gather of disparity maps)',
                        'precision_mode': args.precision,
                        'l2': 'no explicit flush: each step streams >10 GB of activations per GPU, far beyond the 126 MB L2'},
@@ -324,7 +324,7 @@ def main():
             'ms_by_layer': {str(k): round(v, 4) for k, v in sorted(by_layer.items())},
             'clocks': clocks,
         }
-        if world == 1 and args.precision == 'bf16' and not os.environ.get('IDISP_TC_DBG'):
+        if world == 1 and args.precision != 'fp32' and not os.environ.get('IDISP_TC_DBG'):
             # the parity (fp32 FFMA) mode on the same inputs and weights: its throughput, and how far the bf16 tensor-core
             # mode's disparities sit from it (fp32 mode itself is 2-7e-5 px from the reference, tests/test_gpu_parity.py)
             m32 = make_model('fp32', dev)
@@ -342,7 +342,7 @@ def main():
                 e1.record(stream)
                 torch.cuda.synchronize()
             result['fp32_parity_mode'] = {'value': B_PER_GPU / (e0.elapsed_time(e1) / 1e3), 'unit': 'ROIs/s',
-                                          'bf16_vs_fp32_disparity_px': {'max': diff.max().item(), 'mean': diff.mean().item()}}
+                                          f'{args.precision}_vs_fp32_disparity_px': {'max': diff.max().item(), 'mean': diff.mean().item()}}
             del m32
         if world == 1:
             result['roi_align'] = bench_roi_align(dev, hbm)

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -84,7 +85,45 @@ template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16 
   *reinterpret_cast<uint4 *>(p) = a;
 }
 
+// 16-bit storage in either format behind the same (opaque) pointer type: the tensor-core path stores bf16 or fp16
+// (IDISP_PREC_BF16 / IDISP_PREC_FP16); F16 selects the conversion.  Buffers are typed __nv_bfloat16* in both cases.
+template <bool F16> __device__ __forceinline__ F8 unpack8h(const uint4 &a)
+{
+  F8 r;
+  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (F16) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[i]));
+      r.v[2 * i] = f.x; r.v[2 * i + 1] = f.y;
+    } else {
+      r.v[2 * i] = __uint_as_float(w[i] << 16);
+      r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  return r;
+}
+template <bool F16> __device__ __forceinline__ uint4 pack8h(const F8 &r)
+{
+  uint4 a;
+  uint32_t *w = reinterpret_cast<uint32_t *>(&a);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (F16) {
+      const __half2 h = __floats2half2_rn(r.v[2 * i], r.v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t *>(&h);
+    } else {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t *>(&h);
+    }
+  }
+  return a;
+}
+
 // ---- kernels' host launchers (defined in the .cu files) ------------------------------
+// NCDHW f32 <-> blocked 16-bit storage (f16 = 1: IEEE half, 0: bfloat16)
+int launch_ncdhw_to_blocked_h(const float *src, __nv_bfloat16 *dst, int B, int C, int64_t V, int f16, cudaStream_t s);
+int launch_blocked_to_ncdhw_h(const __nv_bfloat16 *src, float *dst, int B, int C, int64_t V, int f16, cudaStream_t s);
 // layout converters (test hooks + plan I/O)
 template <typename T>
 int launch_ncdhw_to_blocked(const float *src, T *dst, int B, int C, int64_t V, cudaStream_t s);

@@ -37,6 +37,7 @@
 #include "conv3d_tc.cuh"
 #include "sm100_ptx.cuh"
 
+#include <cstring>
 #include <type_traits>
 #include <vector>
 
@@ -129,7 +130,7 @@ __device__ __forceinline__ F8 unpack8(const uint4 &a)
 
 __device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t byte_off) { return d + (uint64_t)(byte_off >> 4); }
 
-template <int CIN, int MODE, int OCC, bool CV, int NT>
+template <int CIN, int MODE, int OCC, bool CV, int NT, bool F16>
 __global__ void __launch_bounds__((Cfg<CIN, MODE, OCC, NT>::NTHREADS), OCC)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap rmap,
                  const __grid_constant__ CvMaps<CV> lmaps, const Params p)
@@ -270,7 +271,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           const int nblk = phi - plo + 1;
           const int len1 = nblk < (int)(NSLOT - slot0) ? nblk : (int)(NSLOT - slot0), len2 = nblk - len1;
           const uint32_t d1 = tmem_base + slot0 * NT, d2 = tmem_base;
-          const uint32_t id1 = ptx::make_idesc_bf16(128, NT * len1), id2 = ptx::make_idesc_bf16(128, NT * (len2 > 0 ? len2 : 1));
+          const uint32_t id1 = ptx::make_idesc_h<F16>(128, NT * len1), id2 = ptx::make_idesc_h<F16>(128, NT * (len2 > 0 ? len2 : 1));
           const uint64_t a0 = desc_add(a_desc0, s * C::STAGE_BYTES);
           const uint64_t b1 = ptx::make_smem_desc(w_addr + (plo - (z - 1)) * NT * 16, 3 * NT * 16, 128);
           const uint64_t b2 = desc_add(b1, len1 * NT * 16);
@@ -326,7 +327,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               const int nblk = odd ? (pz + 1 < Dout ? 2 : 1) : 1;
               const int len1 = nblk < (int)(NSLOT - slot0) ? nblk : (int)(NSLOT - slot0), len2 = nblk - len1;
               const uint32_t d1 = tmem_base + slot0 * NT, d2 = tmem_base;
-              const uint32_t id1 = ptx::make_idesc_bf16(128, NT * len1), id2 = ptx::make_idesc_bf16(128, NT);
+              const uint32_t id1 = ptx::make_idesc_h<F16>(128, NT * len1), id2 = ptx::make_idesc_h<F16>(128, NT);
               const uint64_t a0 = desc_add(a_desc0, s * C::STAGE_BYTES);
               const uint64_t b1 = ptx::make_smem_desc(w_addr + (odd ? 0 : 2 * NT * 16), 3 * NT * 16, 128);
               const uint64_t b2 = desc_add(b1, len1 * NT * 16);
@@ -376,7 +377,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                   // weights: [kd][ks][kcore][288 rows][8]; entry e owns rows [row_off, row_off+rows)
                   const uint32_t boff = ((kd * C::KS + ks) * 2 * 288 + dec_row_off(e)) * 16;
                   const uint64_t bd = ptx::make_smem_desc(w_addr + boff, 288 * 16, 128);
-                  mma(dbase + dec_dcol(e), desc_add(a0, aoff), bd, ptx::make_idesc_bf16(128, dec_rows(e)));
+                  mma(dbase + dec_dcol(e), desc_add(a0, aoff), bd, ptx::make_idesc_h<F16>(128, dec_rows(e)));
                 }
               }
             }
@@ -455,7 +456,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 b8.v[c] = __uint_as_float(v1[cb * 8 + c]) + bias_s[cb * 8 + c];
               }
               if (p.residual) {
-                const F8 qa = unpack8(resv[ph * 8 + cb * 2]), qb = unpack8(resv[ph * 8 + cb * 2 + 1]);
+                const F8 qa = unpack8h<F16>(resv[ph * 8 + cb * 2]), qb = unpack8h<F16>(resv[ph * 8 + cb * 2 + 1]);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) { a8.v[c] += qa.v[c]; b8.v[c] += qb.v[c]; }
               }
@@ -463,14 +464,14 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
                 for (int c = 0; c < 8; ++c) { a8.v[c] = fmaxf(a8.v[c], 0.f); b8.v[c] = fmaxf(b8.v[c], 0.f); }
               }
-              store8<__nv_bfloat16>(p.y + o, a8);
-              store8<__nv_bfloat16>(p.y + o + 8, b8);
+              *reinterpret_cast<uint4 *>(p.y + o) = pack8h<F16>(a8);
+              *reinterpret_cast<uint4 *>(p.y + o + 8) = pack8h<F16>(b8);
               if (p.y_split) {  // classes (qo&1, ph, pw) at (qo>>1, hr, wr): 128 B contiguous per 8-row group
                 const int64_t sub = Vo / 8;
                 const int64_t os = ((((int64_t)n * cblk_out + nh * 4 + cb) * 8 + (qo & 1) * 4 + ph * 2) * sub +
                                     ((int64_t)(qo >> 1) * (p.Ho / 2) + hr) * (p.Wo / 2) + wr) * 8;
-                store8<__nv_bfloat16>(p.y_split + os, a8);
-                store8<__nv_bfloat16>(p.y_split + os + sub * 8, b8);
+                *reinterpret_cast<uint4 *>(p.y_split + os) = pack8h<F16>(a8);
+                *reinterpret_cast<uint4 *>(p.y_split + os + sub * 8) = pack8h<F16>(b8);
               }
             }
           }
@@ -518,7 +519,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
               for (int c = 0; c < 8; ++c) r8.v[c] = __uint_as_float(v[cbl * 8 + c]) + bias_s[cb * 8 + c];
               if (p.residual) {
-                const F8 q8 = unpack8(resv[cb]);
+                const F8 q8 = unpack8h<F16>(resv[cb]);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) r8.v[c] += q8.v[c];
               }
@@ -526,12 +527,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
                 for (int c = 0; c < 8; ++c) r8.v[c] = fmaxf(r8.v[c], 0.f);
               }
-              if (!p.skip_y) store8<__nv_bfloat16>(p.y + o, r8);
+              if (!p.skip_y) *reinterpret_cast<uint4 *>(p.y + o) = pack8h<F16>(r8);
               if (p.y_split) {
                 const int64_t sub = Vo / 8;
                 const int64_t os = ((((int64_t)n * cblk_out + nh * (NT / 8) + cb) * 8 + (qo & 1) * 4 + (hr & 1) * 2 + (wr & 1)) * sub +
                                     ((int64_t)(qo >> 1) * (p.Ho / 2) + (hr >> 1)) * (p.Wo / 2) + (wr >> 1)) * 8;
-                store8<__nv_bfloat16>(p.y_split + os, r8);
+                *reinterpret_cast<uint4 *>(p.y_split + os) = pack8h<F16>(r8);
               }
             }
           }
@@ -610,16 +611,24 @@ static int nt_of(int kind, int cin, int cout)
 
 // Pack [27][cin][cout] f32 (tap = (kd*3+kh)*3+kw, BN scale folded) into the per-mode UMMA B layout, bf16:
 // rows of 8 input channels (16 B), 8-row core matrices contiguous (SBO 128 B), K cores LBO apart.
-int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, TcWeights &out, cudaStream_t s)
+int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16, TcWeights &out, cudaStream_t s)
 {
   tc_weights_free(out);
-  out.kind = kind; out.cin = cin; out.cout = cout;
+  out.kind = kind; out.cin = cin; out.cout = cout; out.f16 = f16;
   if (!tc_supported(kind, cin, cout, 4, 16, 16)) return IDISP_OK;  // layer stays on the SIMT kernel
   const int NT = tc::nt_of(kind, cin, cout);
   out.nt = NT;
   const int KS = cin / 16, NH = (cout + NT - 1) / NT;
   const size_t per_nh = (size_t)27 * KS * NT * 16;  // bf16 elements
-  std::vector<__nv_bfloat16> h(NH * per_nh, __float2bfloat16_rn(0.f));
+  // 16-bit storage words (bf16 or IEEE half, same size): convert through cvt()
+  auto cvt = [f16](float v) -> __nv_bfloat16 {
+    if (!f16) return __float2bfloat16_rn(v);
+    const __half hh = __float2half_rn(v);
+    __nv_bfloat16 o;
+    memcpy(&o, &hh, 2);
+    return o;
+  };
+  std::vector<__nv_bfloat16> h(NH * per_nh, cvt(0.f));
   auto wv = [&](int kd, int kh, int kw, int ci, int co) -> float {
     return co < cout ? w_tap[((size_t)((kd * 3 + kh) * 3 + kw) * cin + ci) * cout + co] : 0.f;
   };
@@ -635,7 +644,7 @@ int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, TcWeight
             for (int n = 0; n < 3 * NT; ++n)
               for (int e = 0; e < 8; ++e)
                 base[((((size_t)t2 * KS + ks) * 2 + kc) * 3 * NT + n) * 8 + e] =
-                    __float2bfloat16_rn(wv(kdj[n / NT], t2 / 3, t2 % 3, ks * 16 + kc * 8 + e, nh * NT + n % NT));
+                    cvt(wv(kdj[n / NT], t2 / 3, t2 % 3, ks * 16 + kc * 8 + e, nh * NT + n % NT));
     } else {
       // DECONV: [kd][ks][2 kcores][288 rows][8]; rows = entries e0..e4 (tc::dec_*), blocks = output classes
       //   class = pw*2+ph; per axis: p=0 -> k=1 (shift 0); p=1 -> k=2 (shift 0), k=0 (shift 1)
@@ -653,7 +662,7 @@ int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, TcWeight
               for (int e = 0; e < 8; ++e) {
                 const Blk b = blocks[row / 32];
                 base[((((size_t)kd * KS + ks) * 2 + kc) * 288 + row) * 8 + e] =
-                    __float2bfloat16_rn(wv(kd, b.kh, b.kw, ks * 16 + kc * 8 + e, nh * 32 + row % 32));
+                    cvt(wv(kd, b.kh, b.kw, ks * 16 + kc * 8 + e, nh * 32 + row % 32));
               }
     }
   }
@@ -766,13 +775,25 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   if (per_slice > ncols) per_slice = ncols;
   const int grid = per_slice * p.nh;
   if (MODE == tc::M_S1 && cv) {
-    auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, (MODE == tc::M_S1), NT>;
-    IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    if constexpr (MODE == tc::M_S1) kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, rmap, cvmaps, p);
+    if (w.f16) {
+      auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, (MODE == tc::M_S1), NT, true>;
+      IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+      if constexpr (MODE == tc::M_S1) kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, rmap, cvmaps, p);
+    } else {
+      auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, (MODE == tc::M_S1), NT, false>;
+      IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+      if constexpr (MODE == tc::M_S1) kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, rmap, cvmaps, p);
+    }
   } else {
-    auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, false, NT>;
-    IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, rmap, tc::CvMaps<false>{}, p);
+    if (w.f16) {
+      auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, false, NT, true>;
+      IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+      kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, rmap, tc::CvMaps<false>{}, p);
+    } else {
+      auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, false, NT, false>;
+      IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+      kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, rmap, tc::CvMaps<false>{}, p);
+    }
   }
   IDISP_LAUNCH_CHECK();
   return IDISP_OK;

@@ -10,10 +10,11 @@ struct TcWeights {
   size_t bytes = 0;
   int kind = -1, cin = 0, cout = 0;
   int nt = 32;  // output channels per stacked block the packing was made for
+  int f16 = 0;  // 16-bit storage format of weights AND activations: 0 = bfloat16, 1 = IEEE half
 };
 
 // w_tap: HOST pointer, [27][cin][cout] f32 with the BN scale already folded in
-int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, TcWeights &out, cudaStream_t s);
+int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16, TcWeights &out, cudaStream_t s);
 void tc_weights_free(TcWeights &w);
 // Fused cost volume for the first layer (stackhourglass.py:115-128 folded into dres0.0's loader): the per-view features
 // in blocked bf16 [B][C/8][Hf][Wf][8]; D <= 64 planes (the per-plane tensor maps travel as kernel parameters).

@@ -126,6 +126,62 @@ blocked_to_ncdhw_kernel(const T *__restrict__ src, float *__restrict__ dst, int 
   }
 }
 
+template <bool F16>
+__global__ void __launch_bounds__(256)
+ncdhw_to_blocked_h_kernel(const float *__restrict__ src, uint4 *__restrict__ dst, int B, int C, int64_t V)
+{
+  const int nblk = C / CB;
+  const int64_t total = (int64_t)B * nblk * V;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = idx % V;
+    const int cb = (int)((idx / V) % nblk);
+    const int b = (int)(idx / (V * nblk));
+    const float *s = src + ((int64_t)b * C + cb * CB) * V + v;
+    F8 r;
+#pragma unroll
+    for (int c = 0; c < CB; ++c) r.v[c] = __ldg(s + c * V);
+    dst[idx] = pack8h<F16>(r);
+  }
+}
+template <bool F16>
+__global__ void __launch_bounds__(256)
+blocked_to_ncdhw_h_kernel(const uint4 *__restrict__ src, float *__restrict__ dst, int B, int C, int64_t V)
+{
+  const int nblk = C / CB;
+  const int64_t total = (int64_t)B * nblk * V;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = idx % V;
+    const int cb = (int)((idx / V) % nblk);
+    const int b = (int)(idx / (V * nblk));
+    const F8 r = unpack8h<F16>(__ldg(src + idx));
+    float *d = dst + ((int64_t)b * C + cb * CB) * V + v;
+#pragma unroll
+    for (int c = 0; c < CB; ++c) d[c * V] = r.v[c];
+  }
+}
+int launch_ncdhw_to_blocked_h(const float *src, __nv_bfloat16 *dst, int B, int C, int64_t V, int f16, cudaStream_t s)
+{
+  const int64_t total = (int64_t)B * (C / CB) * V;
+  if (total == 0) return IDISP_OK;
+  const int64_t want = ceil_div64(total, 256);
+  const int grid = (int)(want < 148 * 32 ? want : 148 * 32);
+  if (f16) ncdhw_to_blocked_h_kernel<true><<<grid, 256, 0, s>>>(src, (uint4 *)dst, B, C, V);
+  else ncdhw_to_blocked_h_kernel<false><<<grid, 256, 0, s>>>(src, (uint4 *)dst, B, C, V);
+  IDISP_LAUNCH_CHECK();
+  return IDISP_OK;
+}
+int launch_blocked_to_ncdhw_h(const __nv_bfloat16 *src, float *dst, int B, int C, int64_t V, int f16, cudaStream_t s)
+{
+  const int64_t total = (int64_t)B * (C / CB) * V;
+  if (total == 0) return IDISP_OK;
+  const int64_t want = ceil_div64(total, 256);
+  const int grid = (int)(want < 148 * 32 ? want : 148 * 32);
+  if (f16) blocked_to_ncdhw_h_kernel<true><<<grid, 256, 0, s>>>((const uint4 *)src, dst, B, C, V);
+  else blocked_to_ncdhw_h_kernel<false><<<grid, 256, 0, s>>>((const uint4 *)src, dst, B, C, V);
+  IDISP_LAUNCH_CHECK();
+  return IDISP_OK;
+}
+
 template <typename T>
 int launch_ncdhw_to_blocked(const float *src, T *dst, int B, int C, int64_t V, cudaStream_t s)
 {

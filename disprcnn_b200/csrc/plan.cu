@@ -88,6 +88,7 @@ using namespace idisp;
 
 struct idisp_plan {
   int C, mindisp, maxdisp, precision, D;
+  int f16 = 0;  // 16-bit storage format of the tensor-core path: 0 bf16, 1 IEEE half
   std::vector<LayerSpec> layers;
   std::map<std::string, std::vector<float>> host;  // reference-keyed tensors
   std::vector<LayerDev> dev;
@@ -118,9 +119,9 @@ extern "C" int idisp_plan_create(int C, int mindisp, int maxdisp, int precision,
                 "plan_create: mindisp=%d maxdisp=%d must be multiples of 4, maxdisp>mindisp", mindisp, maxdisp);
   IDISP_REQUIRE(((maxdisp - mindisp) / 4) % 4 == 0,
                 "plan_create: D=(maxdisp-mindisp)/4=%d must be a multiple of 4 (two stride-2 stages)", (maxdisp - mindisp) / 4);
-  IDISP_REQUIRE(precision == IDISP_PREC_FP32 || precision == IDISP_PREC_BF16, "plan_create: unknown precision %d", precision);
+  IDISP_REQUIRE(precision == IDISP_PREC_FP32 || precision == IDISP_PREC_BF16 || precision == IDISP_PREC_FP16, "plan_create: unknown precision %d", precision);
   idisp_plan *p = new idisp_plan();
-  p->C = C; p->mindisp = mindisp; p->maxdisp = maxdisp; p->precision = precision;
+  p->C = C; p->mindisp = mindisp; p->maxdisp = maxdisp; p->precision = precision; p->f16 = precision == IDISP_PREC_FP16;
   p->D = (maxdisp - mindisp) / 4;
   p->layers = make_layers(C);
   *plan = p;
@@ -213,9 +214,9 @@ extern "C" int idisp_plan_finalize(idisp_plan_t *p, void *stream)
       IDISP_CUDA(cudaMemcpyAsync(p->dev[i].bias, bs[i].data(), bs[i].size() * sizeof(float), cudaMemcpyHostToDevice, s));
       off += (bs[i].size() + 63) / 64 * 64;
     }
-    if (p->precision == IDISP_PREC_BF16) {
+    if (p->precision != IDISP_PREC_FP32) {
       const LayerSpec &L = p->layers[i];
-      int rc = tc_weights_prepare(wt[i].data(), L.kind, L.cin, L.cout, p->dev[i].tc, s);
+      int rc = tc_weights_prepare(wt[i].data(), L.kind, L.cin, L.cout, p->f16, p->dev[i].tc, s);
       if (rc) return rc;
     }
   }
@@ -314,6 +315,7 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
                        p->dev[li].bias, (const __nv_bfloat16 *)res, relu, (__nv_bfloat16 *)y, nullptr, nullptr, b.split,
                        (x_split ? 1 : 0) | extra_flags, split_out ? (__nv_bfloat16 *)(split_dst ? split_dst : b.split) : nullptr, nullptr, s);
     }
+    if (p->f16) { set_error("plan_forward: fp16 mode needs tensor-core-supported layer shapes (layer %s)", L.prefix.c_str()); return IDISP_ERR_UNSUPPORTED; }
     return launch_conv3d_simt<T>((const T *)x, B, L.cin, d, h, w, p->dev[li].w_tap, L.cout, L.kind, p->dev[li].bias,
                                  (const T *)res, relu, (T *)y, s);
   };
@@ -328,8 +330,8 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
   if (fuse_cv) {
     // the [B,2C,D,H,W] volume is never written: dres0.0's TMA producer assembles each plane from the two feature maps
     mark(-1);
-    RUN(launch_ncdhw_to_blocked<__nv_bfloat16>(left, (__nv_bfloat16 *)b.feaL, B, C, (int64_t)Hf * Wf, s)); ++launches;
-    RUN(launch_ncdhw_to_blocked<__nv_bfloat16>(right, (__nv_bfloat16 *)b.feaR, B, C, (int64_t)Hf * Wf, s)); ++launches;
+    RUN(launch_ncdhw_to_blocked_h(left, (__nv_bfloat16 *)b.feaL, B, C, (int64_t)Hf * Wf, p->f16, s)); ++launches;
+    RUN(launch_ncdhw_to_blocked_h(right, (__nv_bfloat16 *)b.feaR, B, C, (int64_t)Hf * Wf, p->f16, s)); ++launches;
     TcCostVolume cvd;
     cvd.left = (const __nv_bfloat16 *)b.feaL; cvd.right = (const __nv_bfloat16 *)b.feaR;
     cvd.shift0 = p->mindisp >= 0 ? p->mindisp / 4 : -((-p->mindisp + 3) / 4);
@@ -338,6 +340,7 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
     RUN(tc_conv3d(p->dev[0].tc, nullptr, B, 2 * C, D, Hf, Wf, 32, IDISP_CONV_S1, p->dev[0].bias, nullptr, 1, (__nv_bfloat16 *)b.a, nullptr,
                   nullptr, nullptr, 0, nullptr, &cvd, s));
   } else {
+    if (p->f16) { set_error("plan_forward: fp16 mode needs the fused cost volume (C in {16,32}, D <= 64)"); return IDISP_ERR_UNSUPPORTED; }
     mark(-1);
     RUN(launch_cost_volume_blocked<T>(left, right, B, C, Hf, Wf, p->mindisp, D, (T *)b.cv, s)); ++launches;
     RUN(conv(0, b.cv, D, Hf, Wf, nullptr, 1, b.a));
@@ -374,6 +377,7 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
     if (std::is_same<T, __nv_bfloat16>::value && tc_supported(IDISP_CONV_S1, 32, 1, D, Hf, Wf))
       RUN(tc_conv3d(p->dev[25 + k].tc, (const __nv_bfloat16 *)b.c, B, 32, D, Hf, Wf, 1, IDISP_CONV_S1, nullptr, nullptr, 0, nullptr,
                     prev, dst, nullptr, 0, nullptr, nullptr, s));
+    else if (p->f16) { set_error("plan_forward: fp16 mode needs the tensor-core classifier head"); return IDISP_ERR_UNSUPPORTED; }
     else
       RUN(launch_conv3d_to1<T>((const T *)b.c, B, 32, D, Hf, Wf, p->dev[25 + k].w_tap, prev, dst, s));
     ++launches;
@@ -490,10 +494,14 @@ static int conv3d_hook(const float *x, int B, int Cin, int D, int H, int W, cons
   HK(cudaMemcpyAsync(wd, w_tap.data(), w_tap.size() * sizeof(float), cudaMemcpyHostToDevice, s));
   HK(cudaMalloc(&bd, bias.size() * sizeof(float)));
   HK(cudaMemcpyAsync(bd, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice, s));
-  HR(launch_ncdhw_to_blocked<T>(x, xb, B, Cin, Vi, s));
+  const int f16 = precision == IDISP_PREC_FP16;
+  const bool tcp = precision != IDISP_PREC_FP32 && tc_supported(kind, Cin, Cout, D, H, W);
+  if (f16 && !tcp) { cleanup(); set_error("conv3d: fp16 precision needs a tensor-core-supported layer shape"); return IDISP_ERR_UNSUPPORTED; }
+  if (sizeof(T) == 2) HR(launch_ncdhw_to_blocked_h(x, (__nv_bfloat16 *)xb, B, Cin, Vi, f16, s));
+  else HR(launch_ncdhw_to_blocked<T>(x, xb, B, Cin, Vi, s));
   if (Cout == 1) {
-    if (precision == IDISP_PREC_BF16 && tc_supported(kind, Cin, Cout, D, H, W)) {
-      HR(tc_weights_prepare(w_tap.data(), kind, Cin, Cout, tcw, s));
+    if (tcp) {
+      HR(tc_weights_prepare(w_tap.data(), kind, Cin, Cout, f16, tcw, s));
       HR(tc_conv3d(tcw, (const __nv_bfloat16 *)xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, residual, y, nullptr, 0, nullptr, nullptr, s));
     } else {
       HR(launch_conv3d_to1<T>(xb, B, Cin, D, H, W, wd, residual, y, s));
@@ -503,10 +511,11 @@ static int conv3d_hook(const float *x, int B, int Cin, int D, int H, int W, cons
     HK(cudaMalloc(&yb, (size_t)B * Cout * Vo * sizeof(T)));
     if (residual) {
       HK(cudaMalloc(&rb, (size_t)B * Cout * Vo * sizeof(T)));
-      HR(launch_ncdhw_to_blocked<T>(residual, rb, B, Cout, Vo, s));
+      if (sizeof(T) == 2) HR(launch_ncdhw_to_blocked_h(residual, (__nv_bfloat16 *)rb, B, Cout, Vo, f16, s));
+      else HR(launch_ncdhw_to_blocked<T>(residual, rb, B, Cout, Vo, s));
     }
-    if (precision == IDISP_PREC_BF16 && tc_supported(kind, Cin, Cout, D, H, W)) {
-      HR(tc_weights_prepare(w_tap.data(), kind, Cin, Cout, tcw, s));
+    if (tcp) {
+      HR(tc_weights_prepare(w_tap.data(), kind, Cin, Cout, f16, tcw, s));
       const size_t sb = tc_scratch_bytes(kind, B, Cin, D, H, W);
       if (sb) HK(cudaMalloc(&scratch, sb));
       HR(tc_conv3d(tcw, (const __nv_bfloat16 *)xb, B, Cin, D, H, W, Cout, kind, bd, (const __nv_bfloat16 *)rb, relu,
@@ -514,7 +523,8 @@ static int conv3d_hook(const float *x, int B, int Cin, int D, int H, int W, cons
     } else {
       HR(launch_conv3d_simt<T>(xb, B, Cin, D, H, W, wd, Cout, kind, bd, rb, relu, yb, s));
     }
-    HR(launch_blocked_to_ncdhw<T>(yb, y, B, Cout, Vo, s));
+    if (sizeof(T) == 2) HR(launch_blocked_to_ncdhw_h((const __nv_bfloat16 *)yb, y, B, Cout, Vo, f16, s));
+    else HR(launch_blocked_to_ncdhw<T>(yb, y, B, Cout, Vo, s));
   }
   HK(cudaStreamSynchronize(s));
   cleanup();
@@ -530,7 +540,7 @@ extern "C" int idisp_conv3d(const float *x, int B, int Cin, int D, int H, int W,
   IDISP_REQUIRE(B >= 0 && Cin > 0 && Cin % 8 == 0 && D > 0 && H > 0 && W > 0, "conv3d: bad input shape B=%d Cin=%d D=%d H=%d W=%d", B, Cin, D, H, W);
   IDISP_REQUIRE(Cout == 1 || Cout % 8 == 0, "conv3d: Cout=%d must be 1 or a multiple of 8", Cout);
   IDISP_REQUIRE(kind == IDISP_CONV_S1 || kind == IDISP_CONV_S2 || kind == IDISP_DECONV_S2, "conv3d: unknown kind %d", kind);
-  IDISP_REQUIRE(precision == IDISP_PREC_FP32 || precision == IDISP_PREC_BF16, "conv3d: unknown precision %d", precision);
+  IDISP_REQUIRE(precision == IDISP_PREC_FP32 || precision == IDISP_PREC_BF16 || precision == IDISP_PREC_FP16, "conv3d: unknown precision %d", precision);
   IDISP_REQUIRE(Cout != 1 || (kind == IDISP_CONV_S1 && !scale && !bias && !relu), "conv3d: the 1-channel conv is stride-1, no affine, no ReLU");
   if (B == 0) return IDISP_OK;
   IDISP_REQUIRE(x && weight && y, "conv3d: NULL pointer");
@@ -583,7 +593,7 @@ extern "C" int idisp_debug_fused_cost_volume(const float *left, const float *rig
     const char *te = getenv("IDISP_DEBUG_TAP");  // which of the 27 taps carries the identity (default: centre)
     const int tap = te ? atoi(te) : 13;
     for (int co = 0; co < 32; ++co) w[((size_t)tap * cin + c0 + co) * 32 + co] = 1.f;
-    DR(tc_weights_prepare(w.data(), IDISP_CONV_S1, cin, 32, tcw, s));
+    DR(tc_weights_prepare(w.data(), IDISP_CONV_S1, cin, 32, 0, tcw, s));
     DR(tc_conv3d(tcw, nullptr, B, cin, D, Hf, Wf, 32, IDISP_CONV_S1, nullptr, nullptr, 0, yb, nullptr, nullptr, nullptr, 0, nullptr, &cvd, s));
     // blocked [B][4][V][8] -> channels [c0, c0+32) of NCDHW [B][2C][V]
     for (int b = 0; b < B; ++b)

@@ -134,6 +134,11 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N)
 {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with IEEE half operands (a_format = b_format = 0) when F16
+template <bool F16> __device__ __forceinline__ uint32_t make_idesc_h(int M, int N)
+{
+  return (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread on behalf of the CTA.
 __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)

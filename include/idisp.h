@@ -47,7 +47,9 @@ enum {
 /* Arithmetic mode of the 3-D conv stack (never silently downgraded). */
 enum {
   IDISP_PREC_FP32 = 0, /* fp32 storage + fp32 FFMA accumulate: parity mode (1e-3 abs)      */
-  IDISP_PREC_BF16 = 1  /* bf16 storage + tcgen05 kind::f16 MMA, fp32 accumulate in TMEM   */
+  IDISP_PREC_BF16 = 1, /* bf16 storage + tcgen05 kind::f16 MMA, fp32 accumulate in TMEM   */
+  IDISP_PREC_FP16 = 2  /* IEEE-half storage (11-bit significand, the class of the reference's own TF32 cuDNN path),
+                          same tensor-core kernels; needs |activation| < 65504 and tensor-core-supported shapes */
 };
 
 /* conv layer kinds for idisp_conv3d / the plan's layer table */

@@ -145,7 +145,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+@pytest.mark.parametrize('prec', ['fp32', 'bf16', 'fp16'])
 @pytest.mark.parametrize('kind,cin,cout,dhw,use_res,relu', CONV_CASES)
 def test_conv3d_layer_vs_oracle(lib, prec, kind, cin, cout, dhw, use_res, relu):
     from disprcnn_b200 import _lib
@@ -156,21 +156,26 @@ def test_conv3d_layer_vs_oracle(lib, prec, kind, cin, cout, dhw, use_res, relu):
     w = torch.randn(wshape, generator=g) * (2.0 / (27 * cout)) ** 0.5
     scale = 0.5 + torch.rand(cout, generator=g)
     bias = 0.1 * torch.randn(cout, generator=g)
-    if prec == 'bf16':   # compare like with like: the kernel consumes bf16-rounded operands
-        x = x.bfloat16().float()
+    PREC = {'fp32': 0, 'bf16': 1, 'fp16': 2}[prec]
+    rnd = (lambda t: t) if prec == 'fp32' else ((lambda t: t.bfloat16().float()) if prec == 'bf16' else (lambda t: t.half().float()))
+    if prec == 'fp16' and (cin not in (32, 64) or (kind == 1 and any(v % 2 for v in dhw))):
+        pytest.skip('fp16 mode exists only on the tensor-core kernels (no SIMT fallback)')
+    if prec != 'fp32':   # compare like with like: the kernel consumes 16-bit-rounded operands
+        x = rnd(x)
     want = _conv_ref(x, w, kind, scale, bias, None, False)
     res = torch.randn(want.shape, generator=g) if use_res else None
-    if prec == 'bf16' and res is not None:
-        res = res.bfloat16().float()
+    if prec != 'fp32' and res is not None:
+        res = rnd(res)
     want = _conv_ref(x, w, kind, scale, bias, res, relu)
     y = torch.full(want.shape, float('nan'), device='cuda')
     xc, wc, sc, bc = x.cuda(), w.cuda(), scale.cuda(), bias.cuda()
     rc = res.cuda() if res is not None else None
     _lib.check(lib.idisp_conv3d(_lib.ptr(xc), B, cin, *dhw, _lib.ptr(wc), cout, kind, _lib.ptr(sc), _lib.ptr(bc),
-                                _lib.ptr(rc), int(relu), 0 if prec == 'fp32' else 1, _lib.ptr(y), _lib.stream_ptr()))
+                                _lib.ptr(rc), int(relu), PREC, _lib.ptr(y), _lib.stream_ptr()))
     err = (y.cpu() - want).abs().max().item()
     ref_mag = want.abs().max().item()
-    tol = 2e-5 * max(1.0, ref_mag) if prec == 'fp32' else 2e-2 * max(1.0, ref_mag)  # bf16: weights + output rounding
+    # 16-bit modes: weight rounding + output rounding (bf16: 8-bit, fp16: 11-bit significand)
+    tol = {'fp32': 2e-5, 'bf16': 2e-2, 'fp16': 2.5e-3}[prec] * max(1.0, ref_mag)
     assert err < tol, f'{prec} kind={kind} {cin}->{cout}: max|d|={err:.3e} (|ref|max={ref_mag:.2f})'
 
 
@@ -222,15 +227,17 @@ def test_idispnet_fp32_matches_reference_forward(lib, name):
     assert e_up < TOL_FP32 and e_gen < TOL_FP32
 
 
+@pytest.mark.parametrize('prec', ['bf16', 'fp16'])
 @pytest.mark.parametrize('name', ['tiny', 'c1'])
-def test_idispnet_bf16_mode_error_is_bounded(lib, name):
+def test_idispnet_bf16_mode_error_is_bounded(lib, name, prec):
     case, g, sd, L, R = load_case(name)
-    m = make_psmnet(case, sd, 'bf16')
+    m = make_psmnet(case, sd, prec)
     with torch.no_grad():
         up = m.forward_features(L.cuda(), R.cuda()).cpu().numpy()
     e = np.abs(up - g['pred_up'])
-    print(f'\n[{name}] bf16 mode: max |disp - ref_fp32| {e.max():.3e}, mean {e.mean():.3e}')
-    assert e.max() < TOL_BF16 and e.mean() < TOL_BF16_MEAN
+    print(f'\n[{name}] {prec} mode: max |disp - ref_fp32| {e.max():.3e}, mean {e.mean():.3e}')
+    scale = 1.0 if prec == 'bf16' else 0.125   # fp16 keeps 3 more significand bits
+    assert e.max() < TOL_BF16 * scale and e.mean() < TOL_BF16_MEAN * scale
 
 
 def test_bf16_fused_paths_equal_unfused_paths(lib, monkeypatch):
