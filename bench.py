@@ -166,7 +166,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--precision', default=os.environ.get('IDISP_BENCH_PRECISION', 'fp16'), choices=['fp32', 'bf16', 'fp16'])
+    ap.add_argument('--precision', default=os.environ.get('IDISP_BENCH_PRECISION', 'fp16'), choices=['fp32', 'bf16', 'fp16', 'fp16x2'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))

@@ -20,7 +20,7 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), 'include')
 NVCC_FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-Xcompiler', '-fPIC', '-shared']
 
-PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
+PREC_FP32, PREC_BF16, PREC_FP16, PREC_FP16X2 = 0, 1, 2, 3
 CONV_S1, CONV_S2, DECONV_S2 = 0, 1, 2
 
 _lib = None

@@ -95,6 +95,12 @@ struct Params {
   __nv_bfloat16 *y_split;         // optional second copy of y in the 8-parity-sub-volume layout a stride-2 consumer reads
   int residual_is_split;          // transposed conv only: `residual` is stored in that parity layout (of the OUTPUT grid)
   int skip_y;                     // write only y_split (the natural copy has no reader)
+  // split-precision ("x2") passes: a product of (hi+lo) operands is three launches whose accumulators are chained through an
+  // fp32 partial; the last pass applies the epilogue and stores the result as two 16-bit words (hi blocks, then lo blocks)
+  const float *part_in;           // fp32 partial sums of the earlier pass(es), blocked [B][Cout/8][V][8], or nullptr
+  float *part_out;                // non-null: store this pass's accumulator (+ part_in) there and do nothing else
+  int x2;                         // final pass: y / residual / y_split carry 2*Cout/8 blocks per sample (hi | lo)
+  int in_blk_stride, in_blk_off;  // channel blocks per input sample in memory, and which block this launch's channels start at
   int B, Din, Dout, Ho, Wo, Hr, Wr, Cout, relu;  // (Hr,Wr): row grid the 8x16 tiles cover
   int tiles_h, tiles_w, nh;
   int cv_shift0;                  // mindisp/4: plane k <-> right-view shift i = k + cv_shift0
@@ -130,12 +136,13 @@ __device__ __forceinline__ F8 unpack8(const uint4 &a)
 
 __device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t byte_off) { return d + (uint64_t)(byte_off >> 4); }
 
-template <int CIN, int MODE, int OCC, bool CV, int NT, bool F16>
+template <int CIN, int MODE, int OCC, bool CV, int NT, int FMT>  // FMT: 0 bf16, 1 IEEE half, 2 IEEE half, split-precision pass
 __global__ void __launch_bounds__((Cfg<CIN, MODE, OCC, NT>::NTHREADS), OCC)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap rmap,
                  const __grid_constant__ CvMaps<CV> lmaps, const Params p)
 {
   using C = Cfg<CIN, MODE, OCC, NT>;
+  constexpr bool F16 = FMT != 0, X2 = FMT == 2;
   constexpr int NTHREADS = C::NTHREADS;
   using MC = ModeCfg<MODE>;
   constexpr int NSLOT = C::NSLOT;
@@ -208,7 +215,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
                 for (int pw = 0; pw < 2; ++pw)
                   ptx::tma_load_5d(stage_addr0 + s * C::STAGE_BYTES + pw * C::SUB_BYTES, &xmap, full_bar(s), (tw * TW - 1) * 8,
-                                   th * TH - 1, z >> 1, (z & 1) * 4 + ph * 2 + pw, n * C::CBLK);
+                                   th * TH - 1, z >> 1, (z & 1) * 4 + ph * 2 + pw, n * p.in_blk_stride + p.in_blk_off);
               }
             }
           } else {
@@ -227,11 +234,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
               if constexpr (CV)
                 ptx::tma_load_4d(stage_addr0 + s * C::STAGE_BYTES, &lmaps.m[z], full_bar(s), dead ? -(1 << 20) : (tw * TW - 1 - (i > 0 ? i : 0)) * 8,
-                                 th * TH - 1, n * (C::CBLK / 2), 0);
+                                 th * TH - 1, n * p.in_blk_stride + p.in_blk_off, 0);
               }
             } else if (lead) {
               ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
-              ptx::tma_load_4d(stage_addr0 + s * C::STAGE_BYTES, &xmap, full_bar(s), (tw * TW - halo) * 8, th * TH - halo, z, n * C::CBLK);
+              ptx::tma_load_4d(stage_addr0 + s * C::STAGE_BYTES, &xmap, full_bar(s), (tw * TW - halo) * 8, th * TH - halo, z, n * p.in_blk_stride + p.in_blk_off);
             }
             ++q;
           }
@@ -400,6 +407,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int64_t Vo = (int64_t)Dout * p.Ho * p.Wo;
     const int cblk_out = p.Cout / 8;
+    const int out_blocks = (X2 && p.x2) ? 2 * cblk_out : cblk_out;  // channel blocks per sample in y / residual / y_split
+    const int64_t sub = Vo / 8;                              // voxels of one parity sub-volume
     uint32_t zero[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) zero[i] = 0u;
@@ -408,21 +417,72 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       const int tw = col % p.tiles_w, th = (col / p.tiles_w) % p.tiles_h, n = col / (p.tiles_w * p.tiles_h);
       const int hr = th * TH + hl, wr = tw * TW + wl;
       const bool valid = hr < p.Hr && wr < p.Wr;
+      // Everything after the accumulator: (+ fp32 partial of an earlier pass) -> either the fp32 partial of this pass, or
+      // + bias (+ residual) (ReLU) -> 16-bit store(s).  `cb` = channel block inside this CTA's slice, `pos` = natural
+      // voxel index, (`cls`, `sidx`) = parity class and index inside the parity sub-volume, `pre` = prefetched residual.
+      auto finish = [&](F8 a, int cb, int64_t pos, int cls, int64_t sidx, const uint4 &pre, bool has_pre) {
+        const int cbg = nh * (NT / 8) + cb;
+        const int64_t onat = (((int64_t)n * out_blocks + cbg) * Vo + pos) * 8;
+        const int64_t ospl = ((((int64_t)n * out_blocks + cbg) * 8 + cls) * sub + sidx) * 8;
+        if (X2 && (p.part_in || p.part_out)) {
+          const int64_t op = (((int64_t)n * cblk_out + cbg) * Vo + pos) * 8;
+          if (p.part_in) {
+            const float4 u0 = __ldg(reinterpret_cast<const float4 *>(p.part_in + op)), u1 = __ldg(reinterpret_cast<const float4 *>(p.part_in + op) + 1);
+            a.v[0] += u0.x; a.v[1] += u0.y; a.v[2] += u0.z; a.v[3] += u0.w; a.v[4] += u1.x; a.v[5] += u1.y; a.v[6] += u1.z; a.v[7] += u1.w;
+          }
+          if (p.part_out) {
+            reinterpret_cast<float4 *>(p.part_out + op)[0] = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+            reinterpret_cast<float4 *>(p.part_out + op)[1] = make_float4(a.v[4], a.v[5], a.v[6], a.v[7]);
+            return;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a.v[c] += bias_s[cb * 8 + c];
+        if (p.residual) {
+          const int64_t ro = p.residual_is_split ? ospl : onat;
+          const F8 q = unpack8h<F16>((!X2 || has_pre) ? pre : __ldg(reinterpret_cast<const uint4 *>(p.residual + ro)));
+#pragma unroll
+          for (int c = 0; c < 8; ++c) a.v[c] += q.v[c];
+          if (X2 && p.x2) {  // low half of the residual: cblk_out blocks further
+            const int64_t lo_off = (int64_t)cblk_out * (p.residual_is_split ? 8 * sub : Vo) * 8;
+            const F8 ql = unpack8h<F16>(__ldg(reinterpret_cast<const uint4 *>(p.residual + ro + lo_off)));
+#pragma unroll
+            for (int c = 0; c < 8; ++c) a.v[c] += ql.v[c];
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) a.v[c] = fmaxf(a.v[c], 0.f);
+        }
+        const uint4 hi = pack8h<F16>(a);
+        if (!p.skip_y) *reinterpret_cast<uint4 *>(p.y + onat) = hi;
+        if (p.y_split) *reinterpret_cast<uint4 *>(p.y_split + ospl) = hi;
+        if (X2 && p.x2) {  // split-precision output: second 16-bit word holds what the first one rounded away
+          const F8 h = unpack8h<F16>(hi);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) a.v[c] -= h.v[c];
+          const uint4 lo = pack8h<F16>(a);
+          if (!p.skip_y) *reinterpret_cast<uint4 *>(p.y + onat + (int64_t)cblk_out * Vo * 8) = lo;
+          if (p.y_split) *reinterpret_cast<uint4 *>(p.y_split + ospl + (int64_t)cblk_out * 8 * sub * 8) = lo;
+        }
+      };
       for (int qo = egroup; qo < Dout; qo += C::EGROUPS) {
         const uint32_t g = g0 + qo, r = g % NSLOT;
-        // residual operands do not depend on the accumulator: request them BEFORE waiting for it
+        // residual operands do not depend on the accumulator: request them BEFORE waiting for it (single-precision-word
+        // modes only; the split-precision passes load at use)
         constexpr int NRES = MODE == M_DEC ? 16 : (NT >= 8 ? NT / 8 : 1);
         uint4 resv[NRES];
-        if (p.residual && valid) {
+        const bool prefetch = p.residual && valid && !(X2 && (p.x2 || p.part_out));
+        if (prefetch) {
 #pragma unroll
           for (int i = 0; i < NRES; ++i) {
             // DEC: i = ph*8 + cb*2 + pw -> voxel (2hr+ph, 2wr+pw); conv: i = cb
             const int cb = MODE == M_DEC ? (i >> 1) & 3 : i;
             const int64_t pos = MODE == M_DEC ? ((int64_t)qo * p.Ho + 2 * hr + (i >> 3)) * p.Wo + 2 * wr + (i & 1)
                                               : ((int64_t)qo * p.Ho + hr) * p.Wo + wr;
-            int64_t ro = (((int64_t)n * cblk_out + nh * (NT / 8) + cb) * Vo + pos) * 8;
+            int64_t ro = (((int64_t)n * out_blocks + nh * (NT / 8) + cb) * Vo + pos) * 8;
             if (MODE == M_DEC && p.residual_is_split)  // class (qo&1, ph, pw) at (qo>>1, hr, wr): 128 B contiguous per 8 rows
-              ro = ((((int64_t)n * cblk_out + nh * 4 + cb) * 8 + (qo & 1) * 4 + (i >> 3) * 2 + (i & 1)) * (Vo / 8) +
+              ro = ((((int64_t)n * out_blocks + nh * 4 + cb) * 8 + (qo & 1) * 4 + (i >> 3) * 2 + (i & 1)) * sub +
                     ((int64_t)(qo >> 1) * (p.Ho / 2) + hr) * (p.Wo / 2) + wr) * 8;
             resv[i] = __ldg(reinterpret_cast<const uint4 *>(p.residual + ro));
           }
@@ -446,33 +506,14 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             }
             if (!valid || (p.dbg & 4)) continue;
             const int64_t pos = ((int64_t)qo * p.Ho + 2 * hr + ph) * p.Wo + 2 * wr;
+            const int64_t sidx = ((int64_t)(qo >> 1) * (p.Ho / 2) + hr) * (p.Wo / 2) + wr;
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) {
-              const int64_t o = (((int64_t)n * cblk_out + nh * 4 + cb) * Vo + pos) * 8;
               F8 a8, b8;
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                a8.v[c] = __uint_as_float(v0[cb * 8 + c]) + bias_s[cb * 8 + c];
-                b8.v[c] = __uint_as_float(v1[cb * 8 + c]) + bias_s[cb * 8 + c];
-              }
-              if (p.residual) {
-                const F8 qa = unpack8h<F16>(resv[ph * 8 + cb * 2]), qb = unpack8h<F16>(resv[ph * 8 + cb * 2 + 1]);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) { a8.v[c] += qa.v[c]; b8.v[c] += qb.v[c]; }
-              }
-              if (p.relu) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) { a8.v[c] = fmaxf(a8.v[c], 0.f); b8.v[c] = fmaxf(b8.v[c], 0.f); }
-              }
-              *reinterpret_cast<uint4 *>(p.y + o) = pack8h<F16>(a8);
-              *reinterpret_cast<uint4 *>(p.y + o + 8) = pack8h<F16>(b8);
-              if (p.y_split) {  // classes (qo&1, ph, pw) at (qo>>1, hr, wr): 128 B contiguous per 8-row group
-                const int64_t sub = Vo / 8;
-                const int64_t os = ((((int64_t)n * cblk_out + nh * 4 + cb) * 8 + (qo & 1) * 4 + ph * 2) * sub +
-                                    ((int64_t)(qo >> 1) * (p.Ho / 2) + hr) * (p.Wo / 2) + wr) * 8;
-                *reinterpret_cast<uint4 *>(p.y_split + os) = pack8h<F16>(a8);
-                *reinterpret_cast<uint4 *>(p.y_split + os + sub * 8) = pack8h<F16>(b8);
-              }
+              for (int c = 0; c < 8; ++c) { a8.v[c] = __uint_as_float(v0[cb * 8 + c]); b8.v[c] = __uint_as_float(v1[cb * 8 + c]); }
+              finish(a8, cb, pos, (qo & 1) * 4 + ph * 2, sidx, resv[ph * 8 + cb * 2], prefetch);
+              finish(b8, cb, pos + 1, (qo & 1) * 4 + ph * 2 + 1, sidx, resv[ph * 8 + cb * 2 + 1], prefetch);
             }
           }
         } else {
@@ -480,6 +521,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           constexpr int NLD = NT / NV;               // loads per plane (NT = 64 -> 2)
           const uint32_t taddr = tmem_base + lane_addr + r * C::ACC_COLS;
           const int64_t pos = ((int64_t)qo * p.Ho + hr) * p.Wo + wr;
+          const int64_t sidx = ((int64_t)(qo >> 1) * (p.Ho / 2) + (hr >> 1)) * (p.Wo / 2) + (wr >> 1);
 #pragma unroll
           for (int part = 0; part < NLD; ++part) {
             uint32_t v[32];
@@ -514,26 +556,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
             for (int cbl = 0; cbl < NV / 8; ++cbl) {
               const int cb = part * 4 + cbl;  // channel block inside this CTA's NT-wide slice
-              const int64_t o = (((int64_t)n * cblk_out + nh * (NT / 8) + cb) * Vo + pos) * 8;
               F8 r8;
 #pragma unroll
-              for (int c = 0; c < 8; ++c) r8.v[c] = __uint_as_float(v[cbl * 8 + c]) + bias_s[cb * 8 + c];
-              if (p.residual) {
-                const F8 q8 = unpack8h<F16>(resv[cb]);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) r8.v[c] += q8.v[c];
-              }
-              if (p.relu) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) r8.v[c] = fmaxf(r8.v[c], 0.f);
-              }
-              if (!p.skip_y) *reinterpret_cast<uint4 *>(p.y + o) = pack8h<F16>(r8);
-              if (p.y_split) {
-                const int64_t sub = Vo / 8;
-                const int64_t os = ((((int64_t)n * cblk_out + nh * (NT / 8) + cb) * 8 + (qo & 1) * 4 + (hr & 1) * 2 + (wr & 1)) * sub +
-                                    ((int64_t)(qo >> 1) * (p.Ho / 2) + (hr >> 1)) * (p.Wo / 2) + (wr >> 1)) * 8;
-                *reinterpret_cast<uint4 *>(p.y_split + os) = pack8h<F16>(r8);
-              }
+              for (int c = 0; c < 8; ++c) r8.v[c] = __uint_as_float(v[cbl * 8 + c]);
+              finish(r8, cb, pos, (qo & 1) * 4 + (hr & 1) * 2 + (wr & 1), sidx, resv[cb], prefetch);
             }
           }
         }
@@ -699,9 +725,10 @@ size_t tc_scratch_bytes(int kind, int B, int cin, int D, int H, int W)
 template <int CIN, int MODE, int OCC, int NT>
 static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, int H, int W, int Cout, const float *bias,
                      const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1, void *scratch,
-                     int x_is_split, __nv_bfloat16 *y_split, const TcCostVolume *cv, cudaStream_t s)
+                     int x_is_split, __nv_bfloat16 *y_split, const TcCostVolume *cv, const TcOpts &opts, cudaStream_t s)
 {
   using C = tc::Cfg<CIN, MODE, OCC, NT>;
+  const int blk_stride = opts.in_blk_stride > 0 ? opts.in_blk_stride : (cv ? C::CBLK / 2 : C::CBLK);  // blocks per input sample
   using MC = tc::ModeCfg<MODE>;
   tc::EncodeTiledFn enc = tc::get_encode();
   if (!enc) { set_error("tc_conv3d: cuTensorMapEncodeTiled not available from the driver"); return IDISP_ERR_CUDA; }
@@ -714,14 +741,14 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
       src = x;  // the producer's epilogue already wrote the parity sub-volumes (Params::y_split)
     } else {
       if (!scratch) { set_error("tc_conv3d: stride-2 layer needs the space-to-depth scratch buffer"); return IDISP_ERR_INVALID; }
-      const int64_t nblk = (int64_t)B * C::CBLK, total = nblk * D * H * (W / 2);
+      const int64_t nblk = (int64_t)B * blk_stride, total = nblk * D * H * (W / 2);
       const int64_t want = ceil_div64(total, 256);
       tc::space_to_depth_kernel<<<(int)(want < 148 * 32 ? want : 148 * 32), 256, 0, s>>>((const uint4 *)x, (uint4 *)scratch, nblk, D, H, W);
       IDISP_LAUNCH_CHECK();
       src = scratch;
     }
     const int D2 = D / 2, H2 = H / 2, W2 = W / 2;
-    const cuuint64_t dims[5] = {(cuuint64_t)W2 * 8, (cuuint64_t)H2, (cuuint64_t)D2, 8, (cuuint64_t)B * C::CBLK};
+    const cuuint64_t dims[5] = {(cuuint64_t)W2 * 8, (cuuint64_t)H2, (cuuint64_t)D2, 8, (cuuint64_t)B * blk_stride};
     const cuuint64_t strides[4] = {(cuuint64_t)W2 * 16, (cuuint64_t)H2 * W2 * 16, (cuuint64_t)D2 * H2 * W2 * 16, (cuuint64_t)8 * D2 * H2 * W2 * 16};
     const cuuint32_t box[5] = {8 * MC::SUB_W, MC::SUB_H, 1, 1, (cuuint32_t)C::CBLK};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -740,7 +767,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
       const int i = k + cv->shift0, ai = i < 0 ? -i : i;
       const int wk = ai >= W ? 1 : W - ai;  // fully masked planes get a 1-voxel map that the kernel reads far out of range
       const int lo = ai >= W ? 0 : (i > 0 ? i : 0), ro = ai >= W ? 0 : (i < 0 ? -i : 0);
-      const cuuint64_t dims[4] = {(cuuint64_t)wk * 8, (cuuint64_t)H, (cuuint64_t)B * halfblk, 2};
+      const cuuint64_t dims[4] = {(cuuint64_t)wk * 8, (cuuint64_t)H, (cuuint64_t)B * blk_stride, 2};
       const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)(lr_bytes + (int64_t)(ro - lo) * 16)};
       r = enc(&cvmaps.m[k], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16 *>(cv->left) + (size_t)lo * 8, dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -749,7 +776,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
     map = rmap;
   } else {
     // (8 ch, W) are contiguous in the blocked layout -> ONE tensor dimension of 8*W elements: a box row is SUB_W voxels x 16 B
-    const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B * C::CBLK};
+    const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B * blk_stride};
     const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
     const cuuint32_t box[4] = {8 * MC::SUB_W, MC::SUB_H, 1, (cuuint32_t)C::CBLK};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -761,6 +788,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   p.w = (const __nv_bfloat16 *)w.dev; p.bias = bias; p.residual = residual; p.y = y; p.res1 = res1; p.y1 = y1; p.y_split = y_split; p.residual_is_split = (x_is_split >> 1) & 1; p.skip_y = (x_is_split >> 2) & 1;
   p.B = B; p.Din = D; p.Cout = Cout; p.relu = relu;
   p.cv_shift0 = cv ? cv->shift0 : 0;
+  p.part_in = opts.part_in; p.part_out = opts.part_out; p.x2 = opts.x2; p.in_blk_stride = blk_stride; p.in_blk_off = opts.in_blk_off;
   if (!cv) rmap = map;
   { static int dbg = -1; if (dbg < 0) { const char *e = getenv("IDISP_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   if (MODE == tc::M_S1) { p.Dout = D; p.Ho = H; p.Wo = W; p.Hr = H; p.Wr = W; }
@@ -774,35 +802,39 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   int per_slice = sms * OCC / p.nh;
   if (per_slice > ncols) per_slice = ncols;
   const int grid = per_slice * p.nh;
-  if (MODE == tc::M_S1 && cv) {
-    if (w.f16) {
-      auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, (MODE == tc::M_S1), NT, true>;
-      IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-      if constexpr (MODE == tc::M_S1) kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, rmap, cvmaps, p);
-    } else {
-      auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, (MODE == tc::M_S1), NT, false>;
-      IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-      if constexpr (MODE == tc::M_S1) kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, rmap, cvmaps, p);
-    }
-  } else {
-    if (w.f16) {
-      auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, false, NT, true>;
-      IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-      kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, rmap, tc::CvMaps<false>{}, p);
-    } else {
-      auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, false, NT, false>;
-      IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-      kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, rmap, tc::CvMaps<false>{}, p);
+  const int fmt = !w.f16 ? 0 : ((opts.x2 || opts.part_in || opts.part_out) ? 2 : 1);
+  auto go = [&](auto fmt_c, auto cv_c) -> int {
+    constexpr int FMT = decltype(fmt_c)::value;
+    constexpr bool CVK = decltype(cv_c)::value;
+    auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, CVK, NT, FMT>;
+    IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    if constexpr (CVK) kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, rmap, cvmaps, p);
+    else kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, rmap, tc::CvMaps<false>{}, p);
+    return IDISP_OK;
+  };
+  using std::integral_constant;
+  int lrc = IDISP_OK;
+  if constexpr (MODE == tc::M_S1) {
+    if (cv) {
+      lrc = fmt == 0 ? go(integral_constant<int, 0>{}, std::true_type{}) : fmt == 1 ? go(integral_constant<int, 1>{}, std::true_type{})
+                                                                                   : go(integral_constant<int, 2>{}, std::true_type{});
+      if (lrc) return lrc;
+      IDISP_LAUNCH_CHECK();
+      return IDISP_OK;
     }
   }
+  lrc = fmt == 0 ? go(integral_constant<int, 0>{}, std::false_type{}) : fmt == 1 ? go(integral_constant<int, 1>{}, std::false_type{})
+                                                                               : go(integral_constant<int, 2>{}, std::false_type{});
+  if (lrc) return lrc;
   IDISP_LAUNCH_CHECK();
   return IDISP_OK;
 }
 
 int tc_conv3d(const TcWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D, int H, int W, int Cout, int kind,
               const float *bias, const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1,
-              void *scratch, int x_is_split, __nv_bfloat16 *y_split, const TcCostVolume *cv, cudaStream_t s)
+              void *scratch, int x_is_split, __nv_bfloat16 *y_split, const TcCostVolume *cv, cudaStream_t s, const TcOpts *optsp)
 {
+  const TcOpts opts = optsp ? *optsp : TcOpts();
   if (cv && (kind != IDISP_CONV_S1 || !cv->left || !cv->right)) { set_error("tc_conv3d: bad fused cost-volume arguments"); return IDISP_ERR_INVALID; }
   if (!tc_supported(kind, Cin, Cout, D, H, W) || !w.dev || w.cin != Cin || w.cout != Cout || w.kind != kind) {
     set_error("tc_conv3d: layer (kind=%d, %d->%d) not prepared for the tensor-core path", kind, Cin, Cout);
@@ -815,7 +847,7 @@ int tc_conv3d(const TcWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D,
   }
   if ((Cout == 1) != (y1 != nullptr)) { set_error("tc_conv3d: the 1-channel head needs the f32 output (and only it)"); return IDISP_ERR_INVALID; }
   if (B == 0) return IDISP_OK;
-#define IDISP_TC(CI, MD, OC, NTT) return tc_launch<CI, MD, OC, NTT>(w, x, B, D, H, W, Cout, bias, residual, relu, y, res1, y1, scratch, x_is_split, y_split, cv, s)
+#define IDISP_TC(CI, MD, OC, NTT) return tc_launch<CI, MD, OC, NTT>(w, x, B, D, H, W, Cout, bias, residual, relu, y, res1, y1, scratch, x_is_split, y_split, cv, opts, s)
   const int mode = tc::mode_of(kind);
   static const int occ1 = tc::env_flag("IDISP_TC_OCC1");  // A/B switch for the 2-CTA/SM stride-1 variant
   if (w.nt != tc::nt_of(kind, Cin, Cout)) { set_error("tc_conv3d: weights were packed for a different block width"); return IDISP_ERR_INVALID; }

@@ -23,6 +23,16 @@ struct TcCostVolume {
   int shift0 = 0;  // mindisp / 4
 };
 
+// Split-precision ("x2") pass options.  Activations are then stored as 2*C/8 channel blocks per sample (hi words, then lo
+// words); a layer is three launches -- (x_hi, w_hi), (x_lo, w_hi), (x_hi, w_lo) -- chained through an fp32 partial buffer.
+struct TcOpts {
+  const float *part_in = nullptr;  // fp32 partial of the earlier pass(es), blocked [B][Cout/8][V][8]
+  float *part_out = nullptr;       // non-null: this launch only stores its accumulator (+ part_in) there
+  int x2 = 0;                      // final pass: y / residual / y_split hold hi|lo block groups
+  int in_blk_stride = 0;           // channel blocks per input sample in memory (0: Cin/8)
+  int in_blk_off = 0;              // first channel block this launch reads
+};
+
 // whether the tensor-core kernel covers this layer shape (otherwise the SIMT kernel runs it)
 bool tc_supported(int kind, int cin, int cout, int D, int H, int W);
 // device scratch the layer needs (stride-2 convs re-lay their input into parity sub-volumes)
@@ -30,7 +40,8 @@ size_t tc_scratch_bytes(int kind, int B, int cin, int D, int H, int W);
 // Cout == 1 (the classifier head): y1/res1 are [B][D][H][W] f32 and y/residual/bias are unused.
 int tc_conv3d(const TcWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D, int H, int W, int Cout, int kind,
               const float *bias, const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1,
-              void *scratch, int x_is_split, __nv_bfloat16 *y_split, const TcCostVolume *cv, cudaStream_t s);
+              void *scratch, int x_is_split, __nv_bfloat16 *y_split, const TcCostVolume *cv, cudaStream_t s,
+              const TcOpts *opts = nullptr);
 // cv != nullptr: the layer's input IS the cost volume of (cv->left, cv->right); x is ignored and nothing is materialised.
 // x_is_split is a bit set: 1 = a stride-2 layer's input pointer already holds the 8 parity sub-volumes (written by its producer's
 // epilogue through y_split), so the space-to-depth pass is skipped; 2 = (transposed conv) `residual` is stored in the parity

@@ -159,6 +159,64 @@ blocked_to_ncdhw_h_kernel(const uint4 *__restrict__ src, float *__restrict__ dst
     for (int c = 0; c < CB; ++c) d[c * V] = r.v[c];
   }
 }
+// split precision: [B][2*C/8][V][8] 16-bit words -- blocks [0,C/8) hold hi = half(x), blocks [C/8, 2C/8) hold lo = half(x - hi)
+__global__ void __launch_bounds__(256)
+ncdhw_to_blocked_x2_kernel(const float *__restrict__ src, uint4 *__restrict__ dst, int B, int C, int64_t V)
+{
+  const int nblk = C / CB;
+  const int64_t total = (int64_t)B * nblk * V;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = idx % V;
+    const int cb = (int)((idx / V) % nblk);
+    const int b = (int)(idx / (V * nblk));
+    const float *s = src + ((int64_t)b * C + cb * CB) * V + v;
+    F8 r;
+#pragma unroll
+    for (int c = 0; c < CB; ++c) r.v[c] = __ldg(s + c * V);
+    const uint4 hi = pack8h<true>(r);
+    const F8 h = unpack8h<true>(hi);
+#pragma unroll
+    for (int c = 0; c < CB; ++c) r.v[c] -= h.v[c];
+    const int64_t o = ((int64_t)b * 2 * nblk + cb) * V + v;
+    dst[o] = hi;
+    dst[o + (int64_t)nblk * V] = pack8h<true>(r);
+  }
+}
+__global__ void __launch_bounds__(256)
+blocked_x2_to_ncdhw_kernel(const uint4 *__restrict__ src, float *__restrict__ dst, int B, int C, int64_t V)
+{
+  const int nblk = C / CB;
+  const int64_t total = (int64_t)B * nblk * V;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = idx % V;
+    const int cb = (int)((idx / V) % nblk);
+    const int b = (int)(idx / (V * nblk));
+    const int64_t o = ((int64_t)b * 2 * nblk + cb) * V + v;
+    const F8 h = unpack8h<true>(__ldg(src + o)), l = unpack8h<true>(__ldg(src + o + (int64_t)nblk * V));
+    float *d = dst + ((int64_t)b * C + cb * CB) * V + v;
+#pragma unroll
+    for (int c = 0; c < CB; ++c) d[c * V] = h.v[c] + l.v[c];
+  }
+}
+int launch_ncdhw_to_blocked_x2(const float *src, __nv_bfloat16 *dst, int B, int C, int64_t V, cudaStream_t s)
+{
+  const int64_t total = (int64_t)B * (C / CB) * V;
+  if (total == 0) return IDISP_OK;
+  const int64_t want = ceil_div64(total, 256);
+  ncdhw_to_blocked_x2_kernel<<<(int)(want < 148 * 32 ? want : 148 * 32), 256, 0, s>>>(src, (uint4 *)dst, B, C, V);
+  IDISP_LAUNCH_CHECK();
+  return IDISP_OK;
+}
+int launch_blocked_x2_to_ncdhw(const __nv_bfloat16 *src, float *dst, int B, int C, int64_t V, cudaStream_t s)
+{
+  const int64_t total = (int64_t)B * (C / CB) * V;
+  if (total == 0) return IDISP_OK;
+  const int64_t want = ceil_div64(total, 256);
+  blocked_x2_to_ncdhw_kernel<<<(int)(want < 148 * 32 ? want : 148 * 32), 256, 0, s>>>((const uint4 *)src, dst, B, C, V);
+  IDISP_LAUNCH_CHECK();
+  return IDISP_OK;
+}
+
 int launch_ncdhw_to_blocked_h(const float *src, __nv_bfloat16 *dst, int B, int C, int64_t V, int f16, cudaStream_t s)
 {
   const int64_t total = (int64_t)B * (C / CB) * V;

@@ -44,7 +44,8 @@ struct LayerSpec {
 struct LayerDev {
   float *w_tap = nullptr;  // [27][cin][cout] f32, BN scale folded in
   float *bias = nullptr;   // [cout] f32 (nullptr for the bare 32->1 convs)
-  TcWeights tc;            // bf16 re-lay for the tcgen05 kernel (IDISP_PREC_BF16 only)
+  TcWeights tc;            // 16-bit re-lay for the tcgen05 kernel (tensor-core precisions)
+  TcWeights tc_lo;         // split precision: half(w - half(w)), same layout
 };
 
 static std::vector<LayerSpec> make_layers(int C)
@@ -89,6 +90,7 @@ using namespace idisp;
 struct idisp_plan {
   int C, mindisp, maxdisp, precision, D;
   int f16 = 0;  // 16-bit storage format of the tensor-core path: 0 bf16, 1 IEEE half
+  int x2 = 0;   // split precision: activations/weights are hi+lo pairs of IEEE-half words, three MMA passes per layer
   std::vector<LayerSpec> layers;
   std::map<std::string, std::vector<float>> host;  // reference-keyed tensors
   std::vector<LayerDev> dev;
@@ -119,9 +121,9 @@ extern "C" int idisp_plan_create(int C, int mindisp, int maxdisp, int precision,
                 "plan_create: mindisp=%d maxdisp=%d must be multiples of 4, maxdisp>mindisp", mindisp, maxdisp);
   IDISP_REQUIRE(((maxdisp - mindisp) / 4) % 4 == 0,
                 "plan_create: D=(maxdisp-mindisp)/4=%d must be a multiple of 4 (two stride-2 stages)", (maxdisp - mindisp) / 4);
-  IDISP_REQUIRE(precision == IDISP_PREC_FP32 || precision == IDISP_PREC_BF16 || precision == IDISP_PREC_FP16, "plan_create: unknown precision %d", precision);
+  IDISP_REQUIRE(precision == IDISP_PREC_FP32 || precision == IDISP_PREC_BF16 || precision == IDISP_PREC_FP16 || precision == IDISP_PREC_FP16X2, "plan_create: unknown precision %d", precision);
   idisp_plan *p = new idisp_plan();
-  p->C = C; p->mindisp = mindisp; p->maxdisp = maxdisp; p->precision = precision; p->f16 = precision == IDISP_PREC_FP16;
+  p->C = C; p->mindisp = mindisp; p->maxdisp = maxdisp; p->precision = precision; p->f16 = precision == IDISP_PREC_FP16 || precision == IDISP_PREC_FP16X2; p->x2 = precision == IDISP_PREC_FP16X2;
   p->D = (maxdisp - mindisp) / 4;
   p->layers = make_layers(C);
   *plan = p;
@@ -131,7 +133,7 @@ extern "C" int idisp_plan_create(int C, int mindisp, int maxdisp, int precision,
 extern "C" void idisp_plan_destroy(idisp_plan_t *p)
 {
   if (!p) return;
-  for (auto &d : p->dev) tc_weights_free(d.tc);
+  for (auto &d : p->dev) { tc_weights_free(d.tc); tc_weights_free(d.tc_lo); }
   for (auto e : p->ev) cudaEventDestroy(e);
   if (p->blob) cudaFree(p->blob);
   if (p->stage) cudaFree(p->stage);
@@ -200,7 +202,7 @@ extern "C" int idisp_plan_finalize(idisp_plan_t *p, void *stream)
     relayout_taps(w, L.kind, L.cin, L.cout, L.bn ? scale.data() : nullptr, wt[i]);
     total += (wt[i].size() + 63) / 64 * 64 + (bs[i].size() + 63) / 64 * 64;
   }
-  for (auto &d : p->dev) tc_weights_free(d.tc);
+  for (auto &d : p->dev) { tc_weights_free(d.tc); tc_weights_free(d.tc_lo); }
   if (p->blob) { cudaFree(p->blob); p->blob = nullptr; }
   IDISP_CUDA(cudaMalloc(&p->blob, total * sizeof(float)));
   p->dev.assign(nl, LayerDev());
@@ -218,6 +220,11 @@ extern "C" int idisp_plan_finalize(idisp_plan_t *p, void *stream)
       const LayerSpec &L = p->layers[i];
       int rc = tc_weights_prepare(wt[i].data(), L.kind, L.cin, L.cout, p->f16, p->dev[i].tc, s);
       if (rc) return rc;
+      if (p->x2) {  // low words of the weights: what IEEE half rounded away
+        std::vector<float> lo(wt[i].size());
+        for (size_t j = 0; j < lo.size(); ++j) lo[j] = wt[i][j] - __half2float(__float2half_rn(wt[i][j]));
+        if ((rc = tc_weights_prepare(lo.data(), L.kind, L.cin, L.cout, 1, p->dev[i].tc_lo, s))) return rc;
+      }
     }
   }
   IDISP_CUDA(cudaStreamSynchronize(s));  // host vectors go out of scope
@@ -247,7 +254,8 @@ struct Buffers {
   void *q1, *q2;                             // quarter resolution, 64 ch
   float *costX, *costY;                      // 1-channel f32 logits
   void *split;                               // parity re-lay scratch of the stride-2 tensor-core convs
-  void *feaL, *feaR;                         // fused cost volume: blocked bf16 per-view features
+  void *feaL, *feaR;                         // fused cost volume: blocked 16-bit per-view features
+  float *part;                               // split precision: fp32 partial sums between the three passes of a layer
 };
 
 Buffers carve(Arena &A, int C, int B, int D, int Hf, int Wf, size_t esz)
@@ -261,7 +269,8 @@ Buffers carve(Arena &A, int C, int B, int D, int Hf, int Wf, size_t esz)
   b.q1 = A.take(quart64); b.q2 = A.take(quart64);
   b.costX = (float *)A.take((size_t)B * V * 4); b.costY = (float *)A.take((size_t)B * V * 4);
   b.split = A.take(full32);
-  b.feaL = A.take((size_t)B * C * Hf * Wf * 2); b.feaR = A.take((size_t)B * C * Hf * Wf * 2);
+  b.feaL = A.take((size_t)B * C * Hf * Wf * esz); b.feaR = A.take((size_t)B * C * Hf * Wf * esz);  // esz 2 (one word) or 4 (hi|lo)
+  b.part = (float *)A.take((size_t)B * 32 * V * 4);
   return b;
 }
 }  // namespace
@@ -270,19 +279,39 @@ extern "C" size_t idisp_plan_workspace_bytes(const idisp_plan_t *p, int B, int H
 {
   if (!p || B <= 0 || Hf <= 0 || Wf <= 0) return 0;
   Arena A(nullptr);
-  carve(A, p->C, B, p->D, Hf, Wf, p->precision == IDISP_PREC_FP32 ? 4 : 2);
+  carve(A, p->C, B, p->D, Hf, Wf, (p->precision == IDISP_PREC_FP32 || p->x2) ? 4 : 2);
   return A.off;
 }
 
-template <typename MarkFn>
-static int tc_conv3d_split_input(idisp_plan *p, int li, const void *xsplit, int B, int D, int Hf, int Wf, void *y, cudaStream_t s,
-                                 MarkFn &mark, int &launches)
+// One layer on the tensor-core path: a single launch, or -- split precision -- the three passes (x_hi,w_hi), (x_lo,w_hi),
+// (x_hi,w_lo) chained through the fp32 partial buffer (through y1 itself for the 1-channel heads).
+//   xflags bit0: the input pointer holds the parity sub-volume layout;  eflags: 2 = residual in parity layout, 4 = skip y
+static int tc_layer(idisp_plan *p, int li, const __nv_bfloat16 *xin, int xflags, const TcCostVolume *cv, int B, int d, int h, int w,
+                    const __nv_bfloat16 *res, int relu, __nv_bfloat16 *y, __nv_bfloat16 *ysp, int eflags, const float *res1, float *y1,
+                    void *scratch, float *part, cudaStream_t s, int &launches)
 {
   const LayerSpec &L = p->layers[li];
-  mark(li);
-  ++launches;
-  return tc_conv3d(p->dev[li].tc, (const __nv_bfloat16 *)xsplit, B, L.cin, D, Hf, Wf, L.cout, L.kind, p->dev[li].bias, nullptr, 1,
-                   (__nv_bfloat16 *)y, nullptr, nullptr, nullptr, 1, nullptr, nullptr, s);
+  const float *bias = p->dev[li].bias;
+  if (!p->x2)
+    return tc_conv3d(p->dev[li].tc, xin, B, L.cin, d, h, w, L.cout, L.kind, bias, res, relu, y, res1, y1, scratch, xflags | eflags, ysp, cv, s);
+  launches += 2;
+  const int per_view = cv ? L.cin / 16 : L.cin / 8;  // channel blocks of one precision word (per view for the fused cost volume)
+  TcOpts o;
+  o.in_blk_stride = 2 * per_view;
+  int rc;
+  if (y1) {  // 1-channel head: passes accumulate straight into the f32 logits
+    if ((rc = tc_conv3d(p->dev[li].tc, xin, B, L.cin, d, h, w, L.cout, L.kind, nullptr, nullptr, 0, nullptr, res1, y1, scratch, xflags, nullptr, cv, s, &o))) return rc;
+    o.in_blk_off = per_view;
+    if ((rc = tc_conv3d(p->dev[li].tc, xin, B, L.cin, d, h, w, L.cout, L.kind, nullptr, nullptr, 0, nullptr, y1, y1, scratch, xflags, nullptr, cv, s, &o))) return rc;
+    o.in_blk_off = 0;
+    return tc_conv3d(p->dev[li].tc_lo, xin, B, L.cin, d, h, w, L.cout, L.kind, nullptr, nullptr, 0, nullptr, y1, y1, scratch, xflags, nullptr, cv, s, &o);
+  }
+  o.part_out = part;
+  if ((rc = tc_conv3d(p->dev[li].tc, xin, B, L.cin, d, h, w, L.cout, L.kind, nullptr, nullptr, 0, nullptr, nullptr, nullptr, scratch, xflags, nullptr, cv, s, &o))) return rc;
+  o.part_in = part; o.in_blk_off = per_view;
+  if ((rc = tc_conv3d(p->dev[li].tc, xin, B, L.cin, d, h, w, L.cout, L.kind, nullptr, nullptr, 0, nullptr, nullptr, nullptr, scratch, xflags, nullptr, cv, s, &o))) return rc;
+  o.part_out = nullptr; o.in_blk_off = 0; o.x2 = 1;
+  return tc_conv3d(p->dev[li].tc_lo, xin, B, L.cin, d, h, w, L.cout, L.kind, bias, res, relu, y, nullptr, nullptr, scratch, xflags | eflags, ysp, cv, s, &o);
 }
 
 template <typename T>
@@ -291,7 +320,7 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
 {
   const int D = p->D, C = p->C;
   Arena A(workspace);
-  Buffers b = carve(A, C, B, D, Hf, Wf, sizeof(T));
+  Buffers b = carve(A, C, B, D, Hf, Wf, p->x2 ? 4 : sizeof(T));
   int launches = 0;
   int rc;
   if (p->timing) p->ev_layer.clear();
@@ -311,9 +340,10 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
     ++launches;
     if (std::is_same<T, __nv_bfloat16>::value && tc_supported(L.kind, L.cin, L.cout, d, h, w)) {
       if (L.kind == IDISP_CONV_S2 && !x_split) ++launches;  // + the space-to-depth re-lay
-      return tc_conv3d(p->dev[li].tc, (const __nv_bfloat16 *)(x_split ? b.split : x), B, L.cin, d, h, w, L.cout, L.kind,
-                       p->dev[li].bias, (const __nv_bfloat16 *)res, relu, (__nv_bfloat16 *)y, nullptr, nullptr, b.split,
-                       (x_split ? 1 : 0) | extra_flags, split_out ? (__nv_bfloat16 *)(split_dst ? split_dst : b.split) : nullptr, nullptr, s);
+      const __nv_bfloat16 *xin = (const __nv_bfloat16 *)(x_split ? b.split : x);
+      __nv_bfloat16 *ysp = split_out ? (__nv_bfloat16 *)(split_dst ? split_dst : b.split) : nullptr;
+      return tc_layer(p, li, xin, x_split ? 1 : 0, nullptr, B, d, h, w, (const __nv_bfloat16 *)res, relu, (__nv_bfloat16 *)y, ysp, extra_flags,
+                      nullptr, nullptr, b.split, b.part, s, launches);
     }
     if (p->f16) { set_error("plan_forward: fp16 mode needs tensor-core-supported layer shapes (layer %s)", L.prefix.c_str()); return IDISP_ERR_UNSUPPORTED; }
     return launch_conv3d_simt<T>((const T *)x, B, L.cin, d, h, w, p->dev[li].w_tap, L.cout, L.kind, p->dev[li].bias,
@@ -330,15 +360,19 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
   if (fuse_cv) {
     // the [B,2C,D,H,W] volume is never written: dres0.0's TMA producer assembles each plane from the two feature maps
     mark(-1);
-    RUN(launch_ncdhw_to_blocked_h(left, (__nv_bfloat16 *)b.feaL, B, C, (int64_t)Hf * Wf, p->f16, s)); ++launches;
-    RUN(launch_ncdhw_to_blocked_h(right, (__nv_bfloat16 *)b.feaR, B, C, (int64_t)Hf * Wf, p->f16, s)); ++launches;
+    if (p->x2) {
+      RUN(launch_ncdhw_to_blocked_x2(left, (__nv_bfloat16 *)b.feaL, B, C, (int64_t)Hf * Wf, s)); ++launches;
+      RUN(launch_ncdhw_to_blocked_x2(right, (__nv_bfloat16 *)b.feaR, B, C, (int64_t)Hf * Wf, s)); ++launches;
+    } else {
+      RUN(launch_ncdhw_to_blocked_h(left, (__nv_bfloat16 *)b.feaL, B, C, (int64_t)Hf * Wf, p->f16, s)); ++launches;
+      RUN(launch_ncdhw_to_blocked_h(right, (__nv_bfloat16 *)b.feaR, B, C, (int64_t)Hf * Wf, p->f16, s)); ++launches;
+    }
     TcCostVolume cvd;
     cvd.left = (const __nv_bfloat16 *)b.feaL; cvd.right = (const __nv_bfloat16 *)b.feaR;
     cvd.shift0 = p->mindisp >= 0 ? p->mindisp / 4 : -((-p->mindisp + 3) / 4);
     mark(0);
     ++launches;
-    RUN(tc_conv3d(p->dev[0].tc, nullptr, B, 2 * C, D, Hf, Wf, 32, IDISP_CONV_S1, p->dev[0].bias, nullptr, 1, (__nv_bfloat16 *)b.a, nullptr,
-                  nullptr, nullptr, 0, nullptr, &cvd, s));
+    RUN(tc_layer(p, 0, nullptr, 0, &cvd, B, D, Hf, Wf, nullptr, 1, (__nv_bfloat16 *)b.a, nullptr, 0, nullptr, nullptr, b.split, b.part, s, launches));
   } else {
     if (p->f16) { set_error("plan_forward: fp16 mode needs the fused cost volume (C in {16,32}, D <= 64)"); return IDISP_ERR_UNSUPPORTED; }
     mark(-1);
@@ -361,7 +395,9 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
     void *post = k == 1 ? b.postB : b.postA;                                  // post1,post3 -> A; post2 -> B
     const void *presqu = k == 0 ? b.pre1 /* own pre */ : b.pre1;              // pre1 for dres3 AND dres4 (:136,:139)
     if (fuse_split && k == 0)  // dres2.conv1 reads cost0's parity layout in place
-      RUN(tc_conv3d_split_input(p, l0, b.cost0, B, D, Hf, Wf, b.h1, s, mark, launches));
+    { mark(l0); ++launches;
+      RUN(tc_layer(p, l0, (const __nv_bfloat16 *)b.cost0, 1, nullptr, B, D, Hf, Wf, nullptr, 1, (__nv_bfloat16 *)b.h1, nullptr, 0, nullptr, nullptr,
+                   b.split, b.part, s, launches)); }
     else
       RUN(conv(l0 + 0, x, D, Hf, Wf, nullptr, 1, b.h1, false, fuse_split));        // reads b.split (out_k)
     RUN(conv(l0 + 1, b.h1, D2, H2, W2, postsqu, 1, pre, fuse_split));              // writes b.split (pre_k)
@@ -375,8 +411,8 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
     const float *prev = k == 0 ? nullptr : (k == 1 ? b.costX : b.costY);
     mark(25 + k);
     if (std::is_same<T, __nv_bfloat16>::value && tc_supported(IDISP_CONV_S1, 32, 1, D, Hf, Wf))
-      RUN(tc_conv3d(p->dev[25 + k].tc, (const __nv_bfloat16 *)b.c, B, 32, D, Hf, Wf, 1, IDISP_CONV_S1, nullptr, nullptr, 0, nullptr,
-                    prev, dst, nullptr, 0, nullptr, nullptr, s));
+      RUN(tc_layer(p, 25 + k, (const __nv_bfloat16 *)b.c, 0, nullptr, B, D, Hf, Wf, nullptr, 0, nullptr, nullptr, 0, prev, dst, b.split, b.part, s,
+                   launches));
     else if (p->f16) { set_error("plan_forward: fp16 mode needs the tensor-core classifier head"); return IDISP_ERR_UNSUPPORTED; }
     else
       RUN(launch_conv3d_to1<T>((const T *)b.c, B, 32, D, Hf, Wf, p->dev[25 + k].w_tap, prev, dst, s));
@@ -533,6 +569,63 @@ static int conv3d_hook(const float *x, int B, int Cin, int D, int H, int W, cons
   return IDISP_OK;
 }
 
+// split-precision variant of the hook: hi|lo IEEE-half words, three tensor-core passes (see tc_layer)
+static int conv3d_hook_x2(const float *x, int B, int Cin, int D, int H, int W, const std::vector<float> &w_tap, int Cout, int kind,
+                          const std::vector<float> &bias, const float *residual, int relu, float *y, cudaStream_t s)
+{
+  int Do = D, Ho = H, Wo = W;
+  if (kind == IDISP_CONV_S2) { Do = (D + 1) / 2; Ho = (H + 1) / 2; Wo = (W + 1) / 2; }
+  if (kind == IDISP_DECONV_S2) { Do = 2 * D; Ho = 2 * H; Wo = 2 * W; }
+  const int64_t Vi = (int64_t)D * H * W, Vo = (int64_t)Do * Ho * Wo;
+  if (!tc_supported(kind, Cin, Cout, D, H, W)) { set_error("conv3d: fp16x2 precision needs a tensor-core-supported layer shape"); return IDISP_ERR_UNSUPPORTED; }
+  __nv_bfloat16 *xb = nullptr, *yb = nullptr, *rb = nullptr;
+  float *bd = nullptr, *part = nullptr;
+  void *scratch = nullptr;
+  int rc = IDISP_OK;
+  TcWeights whi, wlo;
+  auto cleanup = [&]() { cudaFree(xb); cudaFree(yb); cudaFree(rb); cudaFree(bd); cudaFree(part); cudaFree(scratch); tc_weights_free(whi); tc_weights_free(wlo); };
+#define HK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #expr, __FILE__, __LINE__); } } while (0)
+#define HR(expr) do { if ((rc = (expr)) != IDISP_OK) { cudaStreamSynchronize(s); cleanup(); return rc; } } while (0)
+  HK(cudaMalloc(&xb, (size_t)B * Cin * Vi * 4));
+  HK(cudaMalloc(&bd, bias.size() * sizeof(float)));
+  HK(cudaMemcpyAsync(bd, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+  HR(launch_ncdhw_to_blocked_x2(x, xb, B, Cin, Vi, s));
+  std::vector<float> lo(w_tap.size());
+  for (size_t j = 0; j < lo.size(); ++j) lo[j] = w_tap[j] - __half2float(__float2half_rn(w_tap[j]));
+  HR(tc_weights_prepare(w_tap.data(), kind, Cin, Cout, 1, whi, s));
+  HR(tc_weights_prepare(lo.data(), kind, Cin, Cout, 1, wlo, s));
+  const size_t sb = 2 * tc_scratch_bytes(kind, B, Cin, D, H, W);
+  if (sb) HK(cudaMalloc(&scratch, sb));
+  TcOpts o;
+  o.in_blk_stride = 2 * (Cin / 8);
+  if (Cout == 1) {
+    HR(tc_conv3d(whi, xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, residual, y, scratch, 0, nullptr, nullptr, s, &o));
+    o.in_blk_off = Cin / 8;
+    HR(tc_conv3d(whi, xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, y, y, scratch, 0, nullptr, nullptr, s, &o));
+    o.in_blk_off = 0;
+    HR(tc_conv3d(wlo, xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, y, y, scratch, 0, nullptr, nullptr, s, &o));
+  } else {
+    HK(cudaMalloc(&yb, (size_t)B * Cout * Vo * 4));
+    HK(cudaMalloc(&part, (size_t)B * Cout * Vo * 4));
+    if (residual) {
+      HK(cudaMalloc(&rb, (size_t)B * Cout * Vo * 4));
+      HR(launch_ncdhw_to_blocked_x2(residual, rb, B, Cout, Vo, s));
+    }
+    o.part_out = part;
+    HR(tc_conv3d(whi, xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, nullptr, nullptr, scratch, 0, nullptr, nullptr, s, &o));
+    o.part_in = part; o.in_blk_off = Cin / 8;
+    HR(tc_conv3d(whi, xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, nullptr, nullptr, scratch, 0, nullptr, nullptr, s, &o));
+    o.part_out = nullptr; o.in_blk_off = 0; o.x2 = 1;
+    HR(tc_conv3d(wlo, xb, B, Cin, D, H, W, Cout, kind, bd, rb, relu, yb, nullptr, nullptr, scratch, 0, nullptr, nullptr, s, &o));
+    HR(launch_blocked_x2_to_ncdhw(yb, y, B, Cout, Vo, s));
+  }
+  HK(cudaStreamSynchronize(s));
+  cleanup();
+#undef HK
+#undef HR
+  return IDISP_OK;
+}
+
 extern "C" int idisp_conv3d(const float *x, int B, int Cin, int D, int H, int W, const float *weight, int Cout, int kind,
                             const float *scale, const float *bias, const float *residual, int relu, int precision,
                             float *y, void *stream)
@@ -540,7 +633,7 @@ extern "C" int idisp_conv3d(const float *x, int B, int Cin, int D, int H, int W,
   IDISP_REQUIRE(B >= 0 && Cin > 0 && Cin % 8 == 0 && D > 0 && H > 0 && W > 0, "conv3d: bad input shape B=%d Cin=%d D=%d H=%d W=%d", B, Cin, D, H, W);
   IDISP_REQUIRE(Cout == 1 || Cout % 8 == 0, "conv3d: Cout=%d must be 1 or a multiple of 8", Cout);
   IDISP_REQUIRE(kind == IDISP_CONV_S1 || kind == IDISP_CONV_S2 || kind == IDISP_DECONV_S2, "conv3d: unknown kind %d", kind);
-  IDISP_REQUIRE(precision == IDISP_PREC_FP32 || precision == IDISP_PREC_BF16 || precision == IDISP_PREC_FP16, "conv3d: unknown precision %d", precision);
+  IDISP_REQUIRE(precision == IDISP_PREC_FP32 || precision == IDISP_PREC_BF16 || precision == IDISP_PREC_FP16 || precision == IDISP_PREC_FP16X2, "conv3d: unknown precision %d", precision);
   IDISP_REQUIRE(Cout != 1 || (kind == IDISP_CONV_S1 && !scale && !bias && !relu), "conv3d: the 1-channel conv is stride-1, no affine, no ReLU");
   if (B == 0) return IDISP_OK;
   IDISP_REQUIRE(x && weight && y, "conv3d: NULL pointer");
@@ -554,6 +647,7 @@ extern "C" int idisp_conv3d(const float *x, int B, int Cin, int D, int H, int W,
   std::vector<double> sc(hs.begin(), hs.end());
   std::vector<float> w_tap;
   relayout_taps(hw.data(), kind, Cin, Cout, sc.data(), w_tap);
+  if (precision == IDISP_PREC_FP16X2) return conv3d_hook_x2(x, B, Cin, D, H, W, w_tap, Cout, kind, hb, residual, relu, y, s);
   if (precision == IDISP_PREC_FP32)
     return conv3d_hook<float>(x, B, Cin, D, H, W, w_tap, Cout, kind, hb, residual, relu, precision, y, s);
   return conv3d_hook<__nv_bfloat16>(x, B, Cin, D, H, W, w_tap, Cout, kind, hb, residual, relu, precision, y, s);

@@ -20,7 +20,7 @@ import torch.nn as nn
 from ... import _lib
 from .submodule import convbn_3d, feature_extraction
 
-PRECISIONS = {'fp32': _lib.PREC_FP32, 'bf16': _lib.PREC_BF16, 'fp16': _lib.PREC_FP16}
+PRECISIONS = {'fp32': _lib.PREC_FP32, 'bf16': _lib.PREC_BF16, 'fp16': _lib.PREC_FP16, 'fp16x2': _lib.PREC_FP16X2}
 
 
 def _deconvbn_3d(cin, cout):
@@ -56,7 +56,7 @@ class PSMNet(nn.Module):
                  feature_channels=32, precision='fp32'):
         """Positional signature of the reference (stackhourglass.py:55-58); two keyword-only extras with
         reference-compatible defaults: ``feature_channels`` (C of the per-view features; dres0.0 takes 2C)
-        and ``precision`` ('fp32' parity mode | 'bf16' / 'fp16' tensor-core modes)."""
+        and ``precision`` ('fp32' parity mode | 'bf16' / 'fp16' tensor-core modes | 'fp16x2' split-precision tensor-core parity mode)."""
         super().__init__()
         if precision not in PRECISIONS:
             raise ValueError(f'precision must be one of {sorted(PRECISIONS)}')

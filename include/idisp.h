@@ -48,6 +48,9 @@ enum {
 enum {
   IDISP_PREC_FP32 = 0, /* fp32 storage + fp32 FFMA accumulate: parity mode (1e-3 abs)      */
   IDISP_PREC_BF16 = 1, /* bf16 storage + tcgen05 kind::f16 MMA, fp32 accumulate in TMEM   */
+  IDISP_PREC_FP16X2 = 3, /* split precision on the tensor cores: every activation and weight is two IEEE-half words
+                            (hi + lo, 22-bit significand); a product is three MMA passes chained through an fp32
+                            partial.  fp32-class results (parity mode at tensor-core speed); same shape limits as FP16 */
   IDISP_PREC_FP16 = 2  /* IEEE-half storage (11-bit significand, the class of the reference's own TF32 cuDNN path),
                           same tensor-core kernels; needs |activation| < 65504 and tensor-core-supported shapes */
 };

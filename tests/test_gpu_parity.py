@@ -145,7 +145,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize('prec', ['fp32', 'bf16', 'fp16'])
+@pytest.mark.parametrize('prec', ['fp32', 'bf16', 'fp16', 'fp16x2'])
 @pytest.mark.parametrize('kind,cin,cout,dhw,use_res,relu', CONV_CASES)
 def test_conv3d_layer_vs_oracle(lib, prec, kind, cin, cout, dhw, use_res, relu):
     from disprcnn_b200 import _lib
@@ -156,15 +156,15 @@ def test_conv3d_layer_vs_oracle(lib, prec, kind, cin, cout, dhw, use_res, relu):
     w = torch.randn(wshape, generator=g) * (2.0 / (27 * cout)) ** 0.5
     scale = 0.5 + torch.rand(cout, generator=g)
     bias = 0.1 * torch.randn(cout, generator=g)
-    PREC = {'fp32': 0, 'bf16': 1, 'fp16': 2}[prec]
-    rnd = (lambda t: t) if prec == 'fp32' else ((lambda t: t.bfloat16().float()) if prec == 'bf16' else (lambda t: t.half().float()))
-    if prec == 'fp16' and (cin not in (32, 64) or (kind == 1 and any(v % 2 for v in dhw))):
+    PREC = {'fp32': 0, 'bf16': 1, 'fp16': 2, 'fp16x2': 3}[prec]
+    rnd = (lambda t: t) if prec in ('fp32', 'fp16x2') else ((lambda t: t.bfloat16().float()) if prec == 'bf16' else (lambda t: t.half().float()))
+    if prec in ('fp16', 'fp16x2') and (cin not in (32, 64) or (kind == 1 and any(v % 2 for v in dhw))):
         pytest.skip('fp16 mode exists only on the tensor-core kernels (no SIMT fallback)')
-    if prec != 'fp32':   # compare like with like: the kernel consumes 16-bit-rounded operands
+    if prec in ('bf16', 'fp16'):   # compare like with like: the kernel consumes 16-bit-rounded operands
         x = rnd(x)
     want = _conv_ref(x, w, kind, scale, bias, None, False)
     res = torch.randn(want.shape, generator=g) if use_res else None
-    if prec != 'fp32' and res is not None:
+    if res is not None:
         res = rnd(res)
     want = _conv_ref(x, w, kind, scale, bias, res, relu)
     y = torch.full(want.shape, float('nan'), device='cuda')
@@ -175,11 +175,12 @@ def test_conv3d_layer_vs_oracle(lib, prec, kind, cin, cout, dhw, use_res, relu):
     err = (y.cpu() - want).abs().max().item()
     ref_mag = want.abs().max().item()
     # 16-bit modes: weight rounding + output rounding (bf16: 8-bit, fp16: 11-bit significand)
-    tol = {'fp32': 2e-5, 'bf16': 2e-2, 'fp16': 2.5e-3}[prec] * max(1.0, ref_mag)
+    # fp16x2: operands and outputs are hi+lo pairs of halves (~22 significand bits), fp32 accumulate: fp32-grade
+    tol = {'fp32': 2e-5, 'bf16': 2e-2, 'fp16': 2.5e-3, 'fp16x2': 2e-5}[prec] * max(1.0, ref_mag)
     assert err < tol, f'{prec} kind={kind} {cin}->{cout}: max|d|={err:.3e} (|ref|max={ref_mag:.2f})'
 
 
-@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+@pytest.mark.parametrize('prec', ['fp32', 'bf16', 'fp16x2'])
 def test_conv3d_to1_vs_oracle(lib, prec):
     from disprcnn_b200 import _lib
     g = torch.Generator().manual_seed(99)
@@ -192,7 +193,7 @@ def test_conv3d_to1_vs_oracle(lib, prec):
     y = torch.empty(want.shape, device='cuda')
     xc, wc, rc = x.cuda(), w.cuda(), res.cuda()
     _lib.check(lib.idisp_conv3d(_lib.ptr(xc), 2, 32, 21, 9, 11, _lib.ptr(wc), 1, 0, None, None, _lib.ptr(rc), 0,
-                                0 if prec == 'fp32' else 1, _lib.ptr(y), _lib.stream_ptr()))
+                                {'fp32': 0, 'bf16': 1, 'fp16x2': 3}[prec], _lib.ptr(y), _lib.stream_ptr()))
     assert (y.cpu() - want).abs().max().item() < 2e-5
 
 
@@ -224,6 +225,21 @@ def test_idispnet_fp32_matches_reference_forward(lib, name):
     e64 = np.abs(up - g['pred_up_f64']).max()
     print(f'\n[{name}] fp32: |disp - ref_fp32| {e_up:.3e} (genuine {e_gen:.3e}), |logit - ref| {e_log:.3e}, '
           f'|disp - ref_fp64| {e64:.3e}; reference fp32-vs-fp64 {float(g["ref_f32_vs_f64_maxabs"][0]):.3e}')
+    assert e_up < TOL_FP32 and e_gen < TOL_FP32
+
+
+@pytest.mark.parametrize('name', ['tiny', 'tiny_pos', 'c1'])
+def test_idispnet_split_precision_tensor_core_mode_meets_parity_bar(lib, name):
+    """'fp16x2': every conv on tcgen05 with hi+lo half operands (3 MMA passes, fp32 accumulate) -- must meet the SAME
+    1e-3 bar as the fp32 SIMT mode against the reference's own forward."""
+    case, g, sd, L, R = load_case(name)
+    m = make_psmnet(case, sd, 'fp16x2')
+    with torch.no_grad():
+        up = m.forward_features(L.cuda(), R.cuda()).cpu().numpy()
+        gen = m((L.cuda(), R.cuda())).cpu().numpy()
+    e_up = np.abs(up - g['pred_up']).max()
+    e_gen = np.abs(gen - g['pred_genuine']).max()
+    print(f'\n[{name}] fp16x2: |disp - ref_fp32| {e_up:.3e} (genuine {e_gen:.3e})')
     assert e_up < TOL_FP32 and e_gen < TOL_FP32
 
 
