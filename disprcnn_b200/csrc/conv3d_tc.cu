@@ -61,8 +61,23 @@ template <> struct ModeCfg<M_DEC> { static constexpr int SUB_W = TW + 1, SUB_H =
 // NT = output channels per stacked block: 32 by default; 16 for the 32->1 heads (their zero-padded kernel then costs
 // N=48 instead of N=96 of shared-memory B traffic per MMA); 64 for the stride-2 32->64 conv (both Cout halves in one MMA,
 // N=128/64 instead of two CTAs re-reading A with N=64/32).
-template <int CIN, int MODE, int OCC, int NT> struct Cfg {
+// XP = split-precision K-concatenation done INSIDE one launch (activations hold hi|lo block groups):
+//   1: A = [x_hi | x_lo | x_hi], B = [w_hi | w_hi | w_lo]  (both weight words resident: Cin = 32 layers)
+//   2: A = [x_hi | x_lo],        B = [w_hi | w_hi]          (Cin = 64 layers: w_lo does not fit next to w_hi; its
+//                                                            x_hi*w_lo term is a second, plain launch chained through a partial)
+// XM = split-precision mode of the launch: 0 none, 1 / 2 = XP above, 3 = a plain-K pass of a multi-launch split layer.
+// Accumulator banks (XM != 0).  The tensor core adds each MMA's K=16 dot products into the fp32 accumulator by TRUNCATION
+// (measured: the disparity error grew ~3x when the two correction terms were accumulated in the same TMEM columns as the
+// main term, i.e. with 3x as many full-magnitude adds per output).  So the main term's chain is split over NMAIN = 3
+// column banks (by kw: 9*KS adds each instead of 27*KS) and the small correction terms get a bank of their own, where
+// their truncation is 2^-11 smaller; the epilogue sums the banks in fp32 round-to-nearest.
+template <int CIN, int MODE, int OCC, int NT, int XM = 0> struct Cfg {
   using MC = ModeCfg<MODE>;
+  static constexpr int XP = XM == 3 ? 0 : XM;
+  static constexpr int NMAIN = (XM != 0 && MODE != M_DEC && NT <= 32 && OCC == 1) ? 3 : 1;
+  static constexpr int NB = NMAIN + ((NMAIN > 1 && XP) ? 1 : 0);
+  static constexpr int AW = XP ? 2 : 1;        // activation words per stage
+  static constexpr int BW = XP == 1 ? 2 : 1;   // weight words resident in shared memory
   static constexpr int ACC_COLS = MC::ACC_BLOCKS * NT;   // TMEM columns of one output plane
   static constexpr int WCHUNK = 2 * 3 * NT * 16;          // B operand of one (kh,kw,kstep): [2 kcores][3 blocks x NT rows][8] bf16
   static_assert(MODE != M_DEC || NT == 32, "the transposed-conv stacking table is written for 32-wide blocks");
@@ -73,10 +88,14 @@ template <int CIN, int MODE, int OCC, int NT> struct Cfg {
   static constexpr int CBLK = CIN / 8;   // channel blocks
   static constexpr int PLANE_BYTES = MC::SUB_W * MC::SUB_H * 16;  // one channel block of one sub-tile (LBO of A)
   static constexpr int ROW_BYTES = MC::SUB_W * 16;                // one tile row (SBO of A)
-  static constexpr int SUB_BYTES = CBLK * PLANE_BYTES;
+  static constexpr int SUB_BYTES = AW * CBLK * PLANE_BYTES;
   static constexpr int STAGE_BYTES = MC::SUBS * SUB_BYTES;
-  static constexpr int WBYTES = 27 * KS * NT * 32;                // 27 taps x Cin x NT couts x bf16
-  static constexpr int NSLOT = TCOLS / ACC_COLS;
+  static constexpr int KSW = BW * KS;                              // weight k-steps per tap
+  static constexpr int KSM = XP == 1 ? 3 * KS : (XP == 2 ? 2 * KS : KS);  // MMAs per tap
+  static constexpr int WBYTES = 27 * KSW * NT * 32;               // 27 taps x Cin (x words) x NT couts x 16 bit
+  static constexpr int NSLOT = TCOLS / (ACC_COLS * NB);
+  static constexpr int BANK_COLS = NSLOT * ACC_COLS;              // TMEM column distance between accumulator banks
+  static_assert(NSLOT >= 4, "the accumulator ring needs four slots");
   static constexpr int STAGES_FIT = (228 * 1024 / OCC - 1024 - WBYTES - 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int BAR_OFF = WBYTES + STAGES * STAGE_BYTES;
@@ -134,15 +153,34 @@ __device__ __forceinline__ F8 unpack8(const uint4 &a)
   return r;
 }
 
+// K-concatenation modes (Cfg::XP): MMA k-step kk of a tap -> activation word / weight k-step / byte offset (inside a
+// sub-tile) of the first of its two channel blocks.  A stage holds [hi blocks | lo blocks]; with the fused cost volume the
+// TMA box lands [left: hi, lo][right: hi, lo], so the logical block order (left, right) is permuted.
+template <int XP, int KS> __host__ __device__ constexpr int xp_a_word(int kk) { return XP == 0 ? 0 : (XP == 1 ? ((kk >= KS && kk < 2 * KS) ? 1 : 0) : kk / KS); }
+template <int XP, int KS> __host__ __device__ constexpr int xp_b_step(int kk) { return XP == 0 ? kk : (XP == 1 ? (kk < KS ? kk : kk - KS) : kk % KS); }
+template <int XP, int KS, bool CV, int PLANE> __host__ __device__ constexpr uint32_t xp_a_off(int kk)
+{
+  const int word = xp_a_word<XP, KS>(kk), blk = 2 * (kk % KS), cblk = 2 * KS, h = cblk / 2;
+  const int phys = (CV && XP) ? ((blk < h ? blk : blk + h) + word * h) : word * cblk + blk;
+  return (uint32_t)(phys * PLANE);
+}
+
 __device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t byte_off) { return d + (uint64_t)(byte_off >> 4); }
 
-template <int CIN, int MODE, int OCC, bool CV, int NT, int FMT>  // FMT: 0 bf16, 1 IEEE half, 2 IEEE half, split-precision pass
+// FMT: 0 bf16, 1 IEEE half, 2 IEEE half split-precision pass (plain K), 3 / 4 the same with in-launch K concatenation XP = 1 / 2
+template <int CIN, int MODE, int OCC, bool CV, int NT, int FMT>
 __global__ void __launch_bounds__((Cfg<CIN, MODE, OCC, NT>::NTHREADS), OCC)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap rmap,
                  const __grid_constant__ CvMaps<CV> lmaps, const Params p)
 {
-  using C = Cfg<CIN, MODE, OCC, NT>;
-  constexpr bool F16 = FMT != 0, X2 = FMT == 2;
+  constexpr int XM = FMT < 2 ? 0 : (FMT == 2 ? 3 : FMT - 2);
+  using C = Cfg<CIN, MODE, OCC, NT, XM>;
+  constexpr int XP = C::XP;
+  constexpr bool F16 = FMT != 0, X2 = FMT >= 2;
+#define A_KOFF(kk) (xp_a_off<XP, C::KS, CV, C::PLANE_BYTES>(kk))
+#define B_KS(kk) (xp_b_step<XP, C::KS>(kk))
+// TMEM column offset of the accumulator bank the MMA of (kw, k-step) adds into
+#define BANK(kw, kk) ((uint32_t)((C::NB > C::NMAIN && (kk) >= C::KS) ? C::NMAIN * C::BANK_COLS : ((kw) % C::NMAIN) * C::BANK_COLS))
   constexpr int NTHREADS = C::NTHREADS;
   using MC = ModeCfg<MODE>;
   constexpr int NSLOT = C::NSLOT;
@@ -291,9 +329,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             for (int tap = 0; tap < 9; ++tap) {
               if (tap == 5) waits(ncol, nz, q + 1, ng0);
 #pragma unroll
-              for (int ks = 0; ks < C::KS; ++ks) {
-                const uint32_t aoff = ((tap / 3) * MC::SUB_W + (tap % 3)) * 16 + ks * 2 * C::PLANE_BYTES;
-                mma(d1, desc_add(a0, aoff), desc_add(b1, (tap * C::KS + ks) * C::WCHUNK), id1);
+              for (int ks = 0; ks < C::KSM; ++ks) {
+                const uint32_t aoff = ((tap / 3) * MC::SUB_W + (tap % 3)) * 16 + A_KOFF(ks);
+                mma(d1 + BANK(tap % 3, ks), desc_add(a0, aoff), desc_add(b1, (tap * C::KSW + B_KS(ks)) * C::WCHUNK), id1);
               }
             }
           } else {
@@ -301,11 +339,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             for (int tap = 0; tap < 9; ++tap) {
               if (tap == 5) waits(ncol, nz, q + 1, ng0);
 #pragma unroll
-              for (int ks = 0; ks < C::KS; ++ks) {
-                const uint32_t aoff = ((tap / 3) * MC::SUB_W + (tap % 3)) * 16 + ks * 2 * C::PLANE_BYTES;
-                const uint32_t boff = (tap * C::KS + ks) * C::WCHUNK;
-                mma(d1, desc_add(a0, aoff), desc_add(b1, boff), id1);
-                mma(d2, desc_add(a0, aoff), desc_add(b2, boff), id2);
+              for (int ks = 0; ks < C::KSM; ++ks) {
+                const uint32_t aoff = ((tap / 3) * MC::SUB_W + (tap % 3)) * 16 + A_KOFF(ks);
+                const uint32_t boff = (tap * C::KSW + B_KS(ks)) * C::WCHUNK;
+                mma(d1 + BANK(tap % 3, ks), desc_add(a0, aoff), desc_add(b1, boff), id1);
+                mma(d2 + BANK(tap % 3, ks), desc_add(a0, aoff), desc_add(b2, boff), id2);
               }
             }
           }
@@ -346,16 +384,16 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                   const int kh = ph_ == 0 ? 1 : (t < 3 ? 0 : 2), kw = t % 3;
                   const int rh = kh == 0 ? 0 : 1, rw = kw == 0 ? 0 : 1, sub = kw != 1 ? 1 : 0;
                   const uint32_t aoff0 = sub * C::SUB_BYTES + (rh * MC::SUB_W + rw) * 16;
-                  const uint32_t boff0 = (kh * 3 + kw) * C::KS * C::WCHUNK;
+                  const uint32_t boff0 = (kh * 3 + kw) * C::KSW * C::WCHUNK;
                   if (len2 == 0) {
 #pragma unroll
-                    for (int ks = 0; ks < C::KS; ++ks)
-                      mma(d1, desc_add(a0, aoff0 + ks * 2 * C::PLANE_BYTES), desc_add(b1, boff0 + ks * C::WCHUNK), id1);
+                    for (int ks = 0; ks < C::KSM; ++ks)
+                      mma(d1 + BANK(kw, ks), desc_add(a0, aoff0 + A_KOFF(ks)), desc_add(b1, boff0 + B_KS(ks) * C::WCHUNK), id1);
                   } else {
 #pragma unroll
-                    for (int ks = 0; ks < C::KS; ++ks) {
-                      mma(d1, desc_add(a0, aoff0 + ks * 2 * C::PLANE_BYTES), desc_add(b1, boff0 + ks * C::WCHUNK), id1);
-                      mma(d2, desc_add(a0, aoff0 + ks * 2 * C::PLANE_BYTES), desc_add(b2, boff0 + ks * C::WCHUNK), id2);
+                    for (int ks = 0; ks < C::KSM; ++ks) {
+                      mma(d1 + BANK(kw, ks), desc_add(a0, aoff0 + A_KOFF(ks)), desc_add(b1, boff0 + B_KS(ks) * C::WCHUNK), id1);
+                      mma(d2 + BANK(kw, ks), desc_add(a0, aoff0 + A_KOFF(ks)), desc_add(b2, boff0 + B_KS(ks) * C::WCHUNK), id2);
                     }
                   }
                 }
@@ -379,10 +417,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
               for (int e = 0; e < 5; ++e) {
 #pragma unroll
-                for (int ks = 0; ks < C::KS; ++ks) {
-                  const uint32_t aoff = (dec_shift_h(e) * MC::SUB_W + dec_shift_w(e)) * 16 + ks * 2 * C::PLANE_BYTES;
+                for (int ks = 0; ks < C::KSM; ++ks) {
+                  const uint32_t aoff = (dec_shift_h(e) * MC::SUB_W + dec_shift_w(e)) * 16 + A_KOFF(ks);
                   // weights: [kd][ks][kcore][288 rows][8]; entry e owns rows [row_off, row_off+rows)
-                  const uint32_t boff = ((kd * C::KS + ks) * 2 * 288 + dec_row_off(e)) * 16;
+                  const uint32_t boff = ((kd * C::KSW + B_KS(ks)) * 2 * 288 + dec_row_off(e)) * 16;
                   const uint64_t bd = ptx::make_smem_desc(w_addr + boff, 288 * 16, 128);
                   mma(dbase + dec_dcol(e), desc_add(a0, aoff), bd, ptx::make_idesc_h<F16>(128, dec_rows(e)));
                 }
@@ -534,12 +572,30 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               ptx::tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = v16[i];
+#pragma unroll
+              for (int bk = 1; bk < C::NB; ++bk) {  // sum the accumulator banks (fp32, round to nearest)
+                ptx::tmem_ld_32x16(taddr + bk * C::BANK_COLS, v16);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v16[i]));
+              }
             } else {
               ptx::tmem_ld_32x32(taddr + part * 32, v);
               ptx::tmem_ld_wait();
+#pragma unroll
+              for (int bk = 1; bk < C::NB; ++bk) {
+                uint32_t u[32];
+                ptx::tmem_ld_32x32(taddr + bk * C::BANK_COLS + part * 32, u);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
+              }
             }
             if (!(p.dbg & 16)) {  // leave the slot zeroed for its next output plane
-              if (NT == 16) ptx::tmem_st_32x16(taddr, zero); else ptx::tmem_st_32x32(taddr + part * 32, zero);
+#pragma unroll
+              for (int bk = 0; bk < C::NB; ++bk) {
+                if (NT == 16) ptx::tmem_st_32x16(taddr + bk * C::BANK_COLS, zero); else ptx::tmem_st_32x32(taddr + bk * C::BANK_COLS + part * 32, zero);
+              }
             }
             if (part == NLD - 1) {
               ptx::tmem_st_wait();
@@ -596,6 +652,10 @@ space_to_depth_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, in
   }
 }
 
+#undef A_KOFF
+#undef B_KS
+#undef BANK
+
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
@@ -637,14 +697,15 @@ static int nt_of(int kind, int cin, int cout)
 
 // Pack [27][cin][cout] f32 (tap = (kd*3+kh)*3+kw, BN scale folded) into the per-mode UMMA B layout, bf16:
 // rows of 8 input channels (16 B), 8-row core matrices contiguous (SBO 128 B), K cores LBO apart.
-int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16, TcWeights &out, cudaStream_t s)
+int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16, TcWeights &out, cudaStream_t s, int words, int nt)
 {
   tc_weights_free(out);
-  out.kind = kind; out.cin = cin; out.cout = cout; out.f16 = f16;
+  out.kind = kind; out.cin = cin; out.cout = cout; out.f16 = f16; out.words = words;
+  if (words != 1 && !(words == 2 && f16)) { set_error("tc_weights_prepare: two-word weights are IEEE half only"); return IDISP_ERR_INVALID; }
   if (!tc_supported(kind, cin, cout, 4, 16, 16)) return IDISP_OK;  // layer stays on the SIMT kernel
-  const int NT = tc::nt_of(kind, cin, cout);
+  const int NT = nt > 0 ? nt : tc::nt_of(kind, cin, cout);
   out.nt = NT;
-  const int KS = cin / 16, NH = (cout + NT - 1) / NT;
+  const int KS = words * cin / 16, NH = (cout + NT - 1) / NT;  // k-steps per tap: the lo word's follow the hi word's
   const size_t per_nh = (size_t)27 * KS * NT * 16;  // bf16 elements
   // 16-bit storage words (bf16 or IEEE half, same size): convert through cvt()
   auto cvt = [f16](float v) -> __nv_bfloat16 {
@@ -656,7 +717,9 @@ int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16,
   };
   std::vector<__nv_bfloat16> h(NH * per_nh, cvt(0.f));
   auto wv = [&](int kd, int kh, int kw, int ci, int co) -> float {
-    return co < cout ? w_tap[((size_t)((kd * 3 + kh) * 3 + kw) * cin + ci) * cout + co] : 0.f;
+    if (co >= cout) return 0.f;
+    const float v = w_tap[((size_t)((kd * 3 + kh) * 3 + kw) * cin + ci % cin) * cout + co];
+    return ci < cin ? v : v - __half2float(__float2half_rn(v));  // second word: what the first one rounded away
   };
   for (int nh = 0; nh < NH; ++nh) {
     __nv_bfloat16 *base = h.data() + nh * per_nh;
@@ -728,6 +791,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
                      int x_is_split, __nv_bfloat16 *y_split, const TcCostVolume *cv, const TcOpts &opts, cudaStream_t s)
 {
   using C = tc::Cfg<CIN, MODE, OCC, NT>;
+  const int aw = opts.xp ? 2 : 1;  // activation words one TMA box fetches (hi|lo block groups are adjacent in memory)
   const int blk_stride = opts.in_blk_stride > 0 ? opts.in_blk_stride : (cv ? C::CBLK / 2 : C::CBLK);  // blocks per input sample
   using MC = tc::ModeCfg<MODE>;
   tc::EncodeTiledFn enc = tc::get_encode();
@@ -750,7 +814,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
     const int D2 = D / 2, H2 = H / 2, W2 = W / 2;
     const cuuint64_t dims[5] = {(cuuint64_t)W2 * 8, (cuuint64_t)H2, (cuuint64_t)D2, 8, (cuuint64_t)B * blk_stride};
     const cuuint64_t strides[4] = {(cuuint64_t)W2 * 16, (cuuint64_t)H2 * W2 * 16, (cuuint64_t)D2 * H2 * W2 * 16, (cuuint64_t)8 * D2 * H2 * W2 * 16};
-    const cuuint32_t box[5] = {8 * MC::SUB_W, MC::SUB_H, 1, 1, (cuuint32_t)C::CBLK};
+    const cuuint32_t box[5] = {8 * MC::SUB_W, MC::SUB_H, 1, 1, (cuuint32_t)(aw * C::CBLK)};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -760,7 +824,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
     if (D > tc::CV_MAX_PLANES) { set_error("tc_conv3d: fused cost volume supports at most %d planes", tc::CV_MAX_PLANES); return IDISP_ERR_INVALID; }
     const int64_t lr_bytes = (const char *)cv->right - (const char *)cv->left;
     if (lr_bytes <= 0 || lr_bytes % 16) { set_error("tc_conv3d: right features must follow the left ones in memory (16 B aligned)"); return IDISP_ERR_INVALID; }
-    const cuuint32_t box[4] = {8 * MC::SUB_W, MC::SUB_H, (cuuint32_t)halfblk, 2};
+    const cuuint32_t box[4] = {8 * MC::SUB_W, MC::SUB_H, (cuuint32_t)(aw * halfblk), 2};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     r = CUDA_SUCCESS;
     for (int k = 0; r == CUDA_SUCCESS && k < D; ++k) {
@@ -778,7 +842,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
     // (8 ch, W) are contiguous in the blocked layout -> ONE tensor dimension of 8*W elements: a box row is SUB_W voxels x 16 B
     const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B * blk_stride};
     const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
-    const cuuint32_t box[4] = {8 * MC::SUB_W, MC::SUB_H, 1, (cuuint32_t)C::CBLK};
+    const cuuint32_t box[4] = {8 * MC::SUB_W, MC::SUB_H, 1, (cuuint32_t)(aw * C::CBLK)};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -802,29 +866,41 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   int per_slice = sms * OCC / p.nh;
   if (per_slice > ncols) per_slice = ncols;
   const int grid = per_slice * p.nh;
-  const int fmt = !w.f16 ? 0 : ((opts.x2 || opts.part_in || opts.part_out) ? 2 : 1);
+  const int fmt = !w.f16 ? 0 : (opts.xp ? 2 + opts.xp : ((opts.x2 || opts.part_in || opts.part_out) ? 2 : 1));
   auto go = [&](auto fmt_c, auto cv_c) -> int {
     constexpr int FMT = decltype(fmt_c)::value;
     constexpr bool CVK = decltype(cv_c)::value;
-    auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, CVK, NT, FMT>;
-    IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    if constexpr (CVK) kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, rmap, cvmaps, p);
-    else kern<<<grid, C::NTHREADS, C::SMEM, s>>>(map, rmap, tc::CvMaps<false>{}, p);
-    return IDISP_OK;
-  };
-  using std::integral_constant;
-  int lrc = IDISP_OK;
-  if constexpr (MODE == tc::M_S1) {
-    if (cv) {
-      lrc = fmt == 0 ? go(integral_constant<int, 0>{}, std::true_type{}) : fmt == 1 ? go(integral_constant<int, 1>{}, std::true_type{})
-                                                                                   : go(integral_constant<int, 2>{}, std::true_type{});
-      if (lrc) return lrc;
-      IDISP_LAUNCH_CHECK();
+    constexpr int XP = FMT == 3 ? 1 : (FMT == 4 ? 2 : 0);
+    // in-launch K concatenation exists where its shared-memory budget closes (see Cfg)
+    constexpr bool ok = XP == 0 || (XP == 1 && CIN == 32 && OCC == 1 && NT <= 32 && MODE != tc::M_DEC) || (XP == 2 && CIN == 64 && OCC == 1 && MODE != tc::M_S2);
+    if constexpr (!ok) {
+      set_error("tc_conv3d: K-concatenation mode %d not built for Cin=%d mode=%d", XP, CIN, MODE);
+      return IDISP_ERR_UNSUPPORTED;
+    } else {
+      using CX = tc::Cfg<CIN, MODE, OCC, NT, (FMT < 2 ? 0 : (FMT == 2 ? 3 : FMT - 2))>;
+      auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, CVK, NT, FMT>;
+      IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CX::SMEM));
+      if constexpr (CVK) kern<<<grid, CX::NTHREADS, CX::SMEM, s>>>(map, rmap, cvmaps, p);
+      else kern<<<grid, CX::NTHREADS, CX::SMEM, s>>>(map, rmap, tc::CvMaps<false>{}, p);
       return IDISP_OK;
     }
+  };
+  auto by_fmt = [&](auto cv_c) -> int {
+    using std::integral_constant;
+    switch (fmt) {
+      case 0: return go(integral_constant<int, 0>{}, cv_c);
+      case 1: return go(integral_constant<int, 1>{}, cv_c);
+      case 2: return go(integral_constant<int, 2>{}, cv_c);
+      case 3: return go(integral_constant<int, 3>{}, cv_c);
+      default: return go(integral_constant<int, 4>{}, cv_c);
+    }
+  };
+  int lrc = IDISP_OK;
+  bool launched = false;
+  if constexpr (MODE == tc::M_S1) {
+    if (cv) { lrc = by_fmt(std::true_type{}); launched = true; }
   }
-  lrc = fmt == 0 ? go(integral_constant<int, 0>{}, std::false_type{}) : fmt == 1 ? go(integral_constant<int, 1>{}, std::false_type{})
-                                                                               : go(integral_constant<int, 2>{}, std::false_type{});
+  if (!launched) lrc = by_fmt(std::false_type{});
   if (lrc) return lrc;
   IDISP_LAUNCH_CHECK();
   return IDISP_OK;
@@ -836,6 +912,7 @@ int tc_conv3d(const TcWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D,
 {
   const TcOpts opts = optsp ? *optsp : TcOpts();
   if (cv && (kind != IDISP_CONV_S1 || !cv->left || !cv->right)) { set_error("tc_conv3d: bad fused cost-volume arguments"); return IDISP_ERR_INVALID; }
+  if (opts.xp < 0 || opts.xp > 2 || w.words != (opts.xp == 1 ? 2 : 1) || (opts.xp && !w.f16)) { set_error("tc_conv3d: weights do not match K-concatenation mode %d", opts.xp); return IDISP_ERR_INVALID; }
   if (!tc_supported(kind, Cin, Cout, D, H, W) || !w.dev || w.cin != Cin || w.cout != Cout || w.kind != kind) {
     set_error("tc_conv3d: layer (kind=%d, %d->%d) not prepared for the tensor-core path", kind, Cin, Cout);
     return IDISP_ERR_INVALID;
@@ -850,11 +927,11 @@ int tc_conv3d(const TcWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D,
 #define IDISP_TC(CI, MD, OC, NTT) return tc_launch<CI, MD, OC, NTT>(w, x, B, D, H, W, Cout, bias, residual, relu, y, res1, y1, scratch, x_is_split, y_split, cv, opts, s)
   const int mode = tc::mode_of(kind);
   static const int occ1 = tc::env_flag("IDISP_TC_OCC1");  // A/B switch for the 2-CTA/SM stride-1 variant
-  if (w.nt != tc::nt_of(kind, Cin, Cout)) { set_error("tc_conv3d: weights were packed for a different block width"); return IDISP_ERR_INVALID; }
   if (mode == tc::M_S1) {
     if (Cin == 64) IDISP_TC(64, tc::M_S1, 1, 32);
-    if (w.nt == 16) { if (occ1) IDISP_TC(32, tc::M_S1, 1, 16); else IDISP_TC(32, tc::M_S1, 2, 16); }
-    if (occ1) IDISP_TC(32, tc::M_S1, 1, 32); else IDISP_TC(32, tc::M_S1, 2, 32);
+    const bool one = occ1 || opts.xp || opts.x2 || opts.part_in || opts.part_out;  // split-precision launches: one CTA per SM (two weight words, banked accumulators)
+    if (w.nt == 16) { if (one) IDISP_TC(32, tc::M_S1, 1, 16); else IDISP_TC(32, tc::M_S1, 2, 16); }
+    if (one) IDISP_TC(32, tc::M_S1, 1, 32); else IDISP_TC(32, tc::M_S1, 2, 32);
   }
   if (mode == tc::M_S2) {
     if (Cin == 64) IDISP_TC(64, tc::M_S2, 1, 32);
@@ -863,6 +940,77 @@ int tc_conv3d(const TcWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D,
   }
   IDISP_TC(64, tc::M_DEC, 1, 32);
 #undef IDISP_TC
+}
+
+// ---------------------------------------------------------------------------------------
+// split precision: x = x_hi + x_lo, w = w_hi + w_lo (IEEE half words), product = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo in fp32
+// ---------------------------------------------------------------------------------------
+// launches per layer: 1 where both weight words fit in shared memory next to a two-word input ring (Cin 32), 2 where only
+// one does (Cin 64: the x_hi*w_lo term is a second launch chained through an fp32 partial), 3 otherwise (stride-2, Cin 64)
+static int split_launches(int kind, int cin)
+{
+  static const int three = tc::env_flag("IDISP_X2_THREE_PASS");  // A/B switch
+  if (three) return 3;
+  if (cin == 32 && kind != IDISP_DECONV_S2) return 1;
+  if (cin == 64 && kind != IDISP_CONV_S2) return 2;
+  return 3;
+}
+
+void tc_split_weights_free(TcSplitWeights &w) { tc_weights_free(w.hi); tc_weights_free(w.lo); tc_weights_free(w.both); }
+
+int tc_split_weights_prepare(const float *w_tap, int kind, int cin, int cout, TcSplitWeights &out, cudaStream_t s)
+{
+  tc_split_weights_free(out);
+  const size_t n = (size_t)27 * cin * cout;
+  std::vector<float> lo(n);
+  for (size_t j = 0; j < n; ++j) lo[j] = w_tap[j] - __half2float(__float2half_rn(w_tap[j]));
+  int rc;
+  if ((rc = tc_weights_prepare(w_tap, kind, cin, cout, 1, out.hi, s))) return rc;
+  if ((rc = tc_weights_prepare(lo.data(), kind, cin, cout, 1, out.lo, s))) return rc;
+  if (split_launches(kind, cin) == 1) {
+    // two-word packing; the stride-2 32->64 conv keeps 32-wide blocks here (2 x 110 KB of 64-wide weights would not fit)
+    const int nt = (kind == IDISP_CONV_S2 && cout == 64) ? 32 : 0;
+    if ((rc = tc_weights_prepare(w_tap, kind, cin, cout, 1, out.both, s, 2, nt))) return rc;
+  }
+  return IDISP_OK;
+}
+
+int tc_conv3d_split(const TcSplitWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D, int H, int W, int Cout, int kind,
+                    const float *bias, const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1,
+                    void *scratch, int flags, __nv_bfloat16 *y_split, const TcCostVolume *cv, float *part, cudaStream_t s, int *launches)
+{
+  const int per_view = cv ? Cin / 16 : Cin / 8;  // channel blocks of one precision word (per view for the fused cost volume)
+  const int nl = split_launches(kind, Cin);
+  if (launches) *launches = nl;
+  TcOpts o;
+  o.in_blk_stride = 2 * per_view;
+  int rc;
+  if (nl == 1) {
+    o.xp = 1;
+    if (y1) return tc_conv3d(w.both, x, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, res1, y1, scratch, flags & 1, nullptr, cv, s, &o);
+    o.x2 = 1;
+    return tc_conv3d(w.both, x, B, Cin, D, H, W, Cout, kind, bias, residual, relu, y, nullptr, nullptr, scratch, flags, y_split, cv, s, &o);
+  }
+  if (y1) {  // 1-channel head: the passes accumulate straight into the f32 logits
+    if (nl == 2) o.xp = 2;
+    if ((rc = tc_conv3d(w.hi, x, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, res1, y1, scratch, flags & 1, nullptr, cv, s, &o))) return rc;
+    if (nl == 3) {
+      o.in_blk_off = per_view;
+      if ((rc = tc_conv3d(w.hi, x, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, y1, y1, scratch, flags & 1, nullptr, cv, s, &o))) return rc;
+    }
+    o.xp = 0; o.in_blk_off = 0;
+    return tc_conv3d(w.lo, x, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, y1, y1, scratch, flags & 1, nullptr, cv, s, &o);
+  }
+  if (!part) { set_error("tc_conv3d_split: this layer needs the fp32 partial buffer"); return IDISP_ERR_INVALID; }
+  o.part_out = part;
+  if (nl == 2) o.xp = 2;
+  if ((rc = tc_conv3d(w.hi, x, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, nullptr, nullptr, scratch, flags & 1, nullptr, cv, s, &o))) return rc;
+  if (nl == 3) {
+    o.part_in = part; o.in_blk_off = per_view;
+    if ((rc = tc_conv3d(w.hi, x, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, nullptr, nullptr, scratch, flags & 1, nullptr, cv, s, &o))) return rc;
+  }
+  o.xp = 0; o.part_in = part; o.part_out = nullptr; o.in_blk_off = 0; o.x2 = 1;
+  return tc_conv3d(w.lo, x, B, Cin, D, H, W, Cout, kind, bias, residual, relu, y, nullptr, nullptr, scratch, flags, y_split, cv, s, &o);
 }
 
 }  // namespace idisp

@@ -11,10 +11,12 @@ struct TcWeights {
   int kind = -1, cin = 0, cout = 0;
   int nt = 32;  // output channels per stacked block the packing was made for
   int f16 = 0;  // 16-bit storage format of weights AND activations: 0 = bfloat16, 1 = IEEE half
+  int words = 1;  // 2: split precision, the lo word's k-steps follow the hi word's inside every tap (TcOpts::xp == 1)
 };
 
 // w_tap: HOST pointer, [27][cin][cout] f32 with the BN scale already folded in
-int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16, TcWeights &out, cudaStream_t s);
+// words = 2 packs half(w) and half(w - half(w)); nt > 0 overrides the layer's default block width
+int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16, TcWeights &out, cudaStream_t s, int words = 1, int nt = 0);
 void tc_weights_free(TcWeights &w);
 // Fused cost volume for the first layer (stackhourglass.py:115-128 folded into dres0.0's loader): the per-view features
 // in blocked bf16 [B][C/8][Hf][Wf][8]; D <= 64 planes (the per-plane tensor maps travel as kernel parameters).
@@ -31,7 +33,23 @@ struct TcOpts {
   int x2 = 0;                      // final pass: y / residual / y_split hold hi|lo block groups
   int in_blk_stride = 0;           // channel blocks per input sample in memory (0: Cin/8)
   int in_blk_off = 0;              // first channel block this launch reads
+  int xp = 0;                      // K concatenation inside the launch: 1 = (x_hi,w_hi)+(x_lo,w_hi)+(x_hi,w_lo) with two-word
+                                   // weights (Cin 32), 2 = (x_hi,w_hi)+(x_lo,w_hi) with one-word weights (Cin 64)
 };
+
+// Split-precision layer = the fewest launches its shared-memory budget allows (see conv3d_tc.cu, Cfg::XP).
+struct TcSplitWeights {
+  TcWeights hi, lo;  // one-word packings of half(w) and half(w - half(w))
+  TcWeights both;    // two-word packing (Cin = 32 layers), empty otherwise
+};
+int tc_split_weights_prepare(const float *w_tap, int kind, int cin, int cout, TcSplitWeights &out, cudaStream_t s);
+void tc_split_weights_free(TcSplitWeights &w);
+// x / residual / y / y_split hold hi|lo block groups (2*C/8 blocks per sample); `part` = fp32 scratch [B][Cout][Vout]
+// (used by the layers that need more than one launch).  Returns the number of kernel launches in *launches.
+int tc_conv3d_split(const TcSplitWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D, int H, int W, int Cout, int kind,
+                    const float *bias, const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1,
+                    void *scratch, int flags, __nv_bfloat16 *y_split, const TcCostVolume *cv, float *part, cudaStream_t s,
+                    int *launches = nullptr);
 
 // whether the tensor-core kernel covers this layer shape (otherwise the SIMT kernel runs it)
 bool tc_supported(int kind, int cin, int cout, int D, int H, int W);

@@ -45,7 +45,7 @@ struct LayerDev {
   float *w_tap = nullptr;  // [27][cin][cout] f32, BN scale folded in
   float *bias = nullptr;   // [cout] f32 (nullptr for the bare 32->1 convs)
   TcWeights tc;            // 16-bit re-lay for the tcgen05 kernel (tensor-core precisions)
-  TcWeights tc_lo;         // split precision: half(w - half(w)), same layout
+  TcSplitWeights sp;       // split precision: hi / lo / two-word packings
 };
 
 static std::vector<LayerSpec> make_layers(int C)
@@ -133,7 +133,7 @@ extern "C" int idisp_plan_create(int C, int mindisp, int maxdisp, int precision,
 extern "C" void idisp_plan_destroy(idisp_plan_t *p)
 {
   if (!p) return;
-  for (auto &d : p->dev) { tc_weights_free(d.tc); tc_weights_free(d.tc_lo); }
+  for (auto &d : p->dev) { tc_weights_free(d.tc); tc_split_weights_free(d.sp); }
   for (auto e : p->ev) cudaEventDestroy(e);
   if (p->blob) cudaFree(p->blob);
   if (p->stage) cudaFree(p->stage);
@@ -202,7 +202,7 @@ extern "C" int idisp_plan_finalize(idisp_plan_t *p, void *stream)
     relayout_taps(w, L.kind, L.cin, L.cout, L.bn ? scale.data() : nullptr, wt[i]);
     total += (wt[i].size() + 63) / 64 * 64 + (bs[i].size() + 63) / 64 * 64;
   }
-  for (auto &d : p->dev) { tc_weights_free(d.tc); tc_weights_free(d.tc_lo); }
+  for (auto &d : p->dev) { tc_weights_free(d.tc); tc_split_weights_free(d.sp); }
   if (p->blob) { cudaFree(p->blob); p->blob = nullptr; }
   IDISP_CUDA(cudaMalloc(&p->blob, total * sizeof(float)));
   p->dev.assign(nl, LayerDev());
@@ -218,13 +218,9 @@ extern "C" int idisp_plan_finalize(idisp_plan_t *p, void *stream)
     }
     if (p->precision != IDISP_PREC_FP32) {
       const LayerSpec &L = p->layers[i];
-      int rc = tc_weights_prepare(wt[i].data(), L.kind, L.cin, L.cout, p->f16, p->dev[i].tc, s);
+      int rc = p->x2 ? tc_split_weights_prepare(wt[i].data(), L.kind, L.cin, L.cout, p->dev[i].sp, s)
+                     : tc_weights_prepare(wt[i].data(), L.kind, L.cin, L.cout, p->f16, p->dev[i].tc, s);
       if (rc) return rc;
-      if (p->x2) {  // low words of the weights: what IEEE half rounded away
-        std::vector<float> lo(wt[i].size());
-        for (size_t j = 0; j < lo.size(); ++j) lo[j] = wt[i][j] - __half2float(__float2half_rn(wt[i][j]));
-        if ((rc = tc_weights_prepare(lo.data(), L.kind, L.cin, L.cout, 1, p->dev[i].tc_lo, s))) return rc;
-      }
     }
   }
   IDISP_CUDA(cudaStreamSynchronize(s));  // host vectors go out of scope
@@ -283,8 +279,8 @@ extern "C" size_t idisp_plan_workspace_bytes(const idisp_plan_t *p, int B, int H
   return A.off;
 }
 
-// One layer on the tensor-core path: a single launch, or -- split precision -- the three passes (x_hi,w_hi), (x_lo,w_hi),
-// (x_hi,w_lo) chained through the fp32 partial buffer (through y1 itself for the 1-channel heads).
+// One layer on the tensor-core path: a single launch, or -- split precision -- the 1-3 launches of tc_conv3d_split
+// (chained through the fp32 partial buffer; through y1 itself for the 1-channel heads).
 //   xflags bit0: the input pointer holds the parity sub-volume layout;  eflags: 2 = residual in parity layout, 4 = skip y
 static int tc_layer(idisp_plan *p, int li, const __nv_bfloat16 *xin, int xflags, const TcCostVolume *cv, int B, int d, int h, int w,
                     const __nv_bfloat16 *res, int relu, __nv_bfloat16 *y, __nv_bfloat16 *ysp, int eflags, const float *res1, float *y1,
@@ -294,24 +290,11 @@ static int tc_layer(idisp_plan *p, int li, const __nv_bfloat16 *xin, int xflags,
   const float *bias = p->dev[li].bias;
   if (!p->x2)
     return tc_conv3d(p->dev[li].tc, xin, B, L.cin, d, h, w, L.cout, L.kind, bias, res, relu, y, res1, y1, scratch, xflags | eflags, ysp, cv, s);
-  launches += 2;
-  const int per_view = cv ? L.cin / 16 : L.cin / 8;  // channel blocks of one precision word (per view for the fused cost volume)
-  TcOpts o;
-  o.in_blk_stride = 2 * per_view;
-  int rc;
-  if (y1) {  // 1-channel head: passes accumulate straight into the f32 logits
-    if ((rc = tc_conv3d(p->dev[li].tc, xin, B, L.cin, d, h, w, L.cout, L.kind, nullptr, nullptr, 0, nullptr, res1, y1, scratch, xflags, nullptr, cv, s, &o))) return rc;
-    o.in_blk_off = per_view;
-    if ((rc = tc_conv3d(p->dev[li].tc, xin, B, L.cin, d, h, w, L.cout, L.kind, nullptr, nullptr, 0, nullptr, y1, y1, scratch, xflags, nullptr, cv, s, &o))) return rc;
-    o.in_blk_off = 0;
-    return tc_conv3d(p->dev[li].tc_lo, xin, B, L.cin, d, h, w, L.cout, L.kind, nullptr, nullptr, 0, nullptr, y1, y1, scratch, xflags, nullptr, cv, s, &o);
-  }
-  o.part_out = part;
-  if ((rc = tc_conv3d(p->dev[li].tc, xin, B, L.cin, d, h, w, L.cout, L.kind, nullptr, nullptr, 0, nullptr, nullptr, nullptr, scratch, xflags, nullptr, cv, s, &o))) return rc;
-  o.part_in = part; o.in_blk_off = per_view;
-  if ((rc = tc_conv3d(p->dev[li].tc, xin, B, L.cin, d, h, w, L.cout, L.kind, nullptr, nullptr, 0, nullptr, nullptr, nullptr, scratch, xflags, nullptr, cv, s, &o))) return rc;
-  o.part_out = nullptr; o.in_blk_off = 0; o.x2 = 1;
-  return tc_conv3d(p->dev[li].tc_lo, xin, B, L.cin, d, h, w, L.cout, L.kind, bias, res, relu, y, nullptr, nullptr, scratch, xflags | eflags, ysp, cv, s, &o);
+  int nl = 1;
+  const int rc = tc_conv3d_split(p->dev[li].sp, xin, B, L.cin, d, h, w, L.cout, L.kind, bias, res, relu, y, res1, y1, scratch, xflags | eflags,
+                                 ysp, cv, part, s, &nl);
+  launches += nl - 1;
+  return rc;
 }
 
 template <typename T>
@@ -582,28 +565,19 @@ static int conv3d_hook_x2(const float *x, int B, int Cin, int D, int H, int W, c
   float *bd = nullptr, *part = nullptr;
   void *scratch = nullptr;
   int rc = IDISP_OK;
-  TcWeights whi, wlo;
-  auto cleanup = [&]() { cudaFree(xb); cudaFree(yb); cudaFree(rb); cudaFree(bd); cudaFree(part); cudaFree(scratch); tc_weights_free(whi); tc_weights_free(wlo); };
+  TcSplitWeights sw;
+  auto cleanup = [&]() { cudaFree(xb); cudaFree(yb); cudaFree(rb); cudaFree(bd); cudaFree(part); cudaFree(scratch); tc_split_weights_free(sw); };
 #define HK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #expr, __FILE__, __LINE__); } } while (0)
 #define HR(expr) do { if ((rc = (expr)) != IDISP_OK) { cudaStreamSynchronize(s); cleanup(); return rc; } } while (0)
   HK(cudaMalloc(&xb, (size_t)B * Cin * Vi * 4));
   HK(cudaMalloc(&bd, bias.size() * sizeof(float)));
   HK(cudaMemcpyAsync(bd, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice, s));
   HR(launch_ncdhw_to_blocked_x2(x, xb, B, Cin, Vi, s));
-  std::vector<float> lo(w_tap.size());
-  for (size_t j = 0; j < lo.size(); ++j) lo[j] = w_tap[j] - __half2float(__float2half_rn(w_tap[j]));
-  HR(tc_weights_prepare(w_tap.data(), kind, Cin, Cout, 1, whi, s));
-  HR(tc_weights_prepare(lo.data(), kind, Cin, Cout, 1, wlo, s));
+  HR(tc_split_weights_prepare(w_tap.data(), kind, Cin, Cout, sw, s));
   const size_t sb = 2 * tc_scratch_bytes(kind, B, Cin, D, H, W);
   if (sb) HK(cudaMalloc(&scratch, sb));
-  TcOpts o;
-  o.in_blk_stride = 2 * (Cin / 8);
   if (Cout == 1) {
-    HR(tc_conv3d(whi, xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, residual, y, scratch, 0, nullptr, nullptr, s, &o));
-    o.in_blk_off = Cin / 8;
-    HR(tc_conv3d(whi, xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, y, y, scratch, 0, nullptr, nullptr, s, &o));
-    o.in_blk_off = 0;
-    HR(tc_conv3d(wlo, xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, y, y, scratch, 0, nullptr, nullptr, s, &o));
+    HR(tc_conv3d_split(sw, xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, residual, y, scratch, 0, nullptr, nullptr, nullptr, s));
   } else {
     HK(cudaMalloc(&yb, (size_t)B * Cout * Vo * 4));
     HK(cudaMalloc(&part, (size_t)B * Cout * Vo * 4));
@@ -611,12 +585,7 @@ static int conv3d_hook_x2(const float *x, int B, int Cin, int D, int H, int W, c
       HK(cudaMalloc(&rb, (size_t)B * Cout * Vo * 4));
       HR(launch_ncdhw_to_blocked_x2(residual, rb, B, Cout, Vo, s));
     }
-    o.part_out = part;
-    HR(tc_conv3d(whi, xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, nullptr, nullptr, scratch, 0, nullptr, nullptr, s, &o));
-    o.part_in = part; o.in_blk_off = Cin / 8;
-    HR(tc_conv3d(whi, xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, nullptr, nullptr, scratch, 0, nullptr, nullptr, s, &o));
-    o.part_out = nullptr; o.in_blk_off = 0; o.x2 = 1;
-    HR(tc_conv3d(wlo, xb, B, Cin, D, H, W, Cout, kind, bd, rb, relu, yb, nullptr, nullptr, scratch, 0, nullptr, nullptr, s, &o));
+    HR(tc_conv3d_split(sw, xb, B, Cin, D, H, W, Cout, kind, bd, rb, relu, yb, nullptr, nullptr, scratch, 0, nullptr, nullptr, part, s));
     HR(launch_blocked_x2_to_ncdhw(yb, y, B, Cout, Vo, s));
   }
   HK(cudaStreamSynchronize(s));

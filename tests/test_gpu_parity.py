@@ -243,6 +243,27 @@ def test_idispnet_split_precision_tensor_core_mode_meets_parity_bar(lib, name):
     assert e_up < TOL_FP32 and e_gen < TOL_FP32
 
 
+def test_full_benchmark_shape_matches_reference_forward(lib):
+    """One ROI pair at BASELINE.json configs[1] (112x112x32ch, D=48 -> 448x448) against the disparity map the REFERENCE
+    itself produced for these inputs (tests/golden/idisp_full.npz, made by executing disprcnn's PSMNet on the CPU)."""
+    case, g, sd, L, R = load_case('full')
+    errs = {}
+    for prec in ('fp32', 'fp16x2', 'fp16', 'bf16'):
+        m = make_psmnet(case, sd, prec)
+        with torch.no_grad():
+            up = m.forward_features(L.cuda(), R.cuda()).cpu().numpy()
+        e = np.abs(up - g['pred_up'])
+        errs[prec] = (float(e.max()), float(e.mean()), float(np.abs(up - g['pred_up_f64']).max()))
+        del m
+    print('\n[full] max / mean |disp - ref_fp32| (and max vs the float64 arbiter): ' +
+          ', '.join(f'{k} {v[0]:.3e} / {v[1]:.3e} ({v[2]:.3e})' for k, v in errs.items()) +
+          f'; reference fp32-vs-fp64 {float(g["ref_f32_vs_f64_maxabs"][0]):.3e}')
+    assert errs['fp32'][0] < TOL_FP32
+    assert errs['fp16x2'][0] < TOL_FP32
+    assert errs['fp16'][0] < TOL_BF16 * 0.125 * 2 and errs['fp16'][1] < TOL_BF16_MEAN * 0.125 * 2   # deeper volume than c1
+    assert errs['bf16'][0] < TOL_BF16 * 2 and errs['bf16'][1] < TOL_BF16_MEAN * 2
+
+
 @pytest.mark.parametrize('prec', ['bf16', 'fp16'])
 @pytest.mark.parametrize('name', ['tiny', 'c1'])
 def test_idispnet_bf16_mode_error_is_bounded(lib, name, prec):
