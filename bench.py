@@ -166,7 +166,9 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--precision', default=os.environ.get('IDISP_BENCH_PRECISION', 'fp16'), choices=['fp32', 'bf16', 'fp16', 'fp16x2'])
+    ap.add_argument('--precision', default=os.environ.get('IDISP_BENCH_PRECISION', 'fp16x2'), choices=['fp32', 'bf16', 'fp16', 'fp16x2'],
+                    help='fp16x2 (default): split-precision tensor-core mode, meets the 1e-3 parity bar; fp16 / bf16: one-word '
+                         'tensor-core modes (faster, 0.07 / 0.4 px from the reference); fp32: SIMT parity mode')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -299,7 +301,9 @@ def main():
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
 
     traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    tpath = os.path.join(ROOT, 'profiles', f'r01_traffic_{args.precision}.json')
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
     if args.precision != 'fp32' and os.path.exists(tpath):
         tj = json.load(open(tpath))  # DRAM bytes of the 28 conv launches of one step, from the committed ncu --set full capture
         traffic = {'dram_gb_per_step': tj['dram_read_gb_per_step'] + tj['dram_write_gb_per_step'], 'source': tj['source']}
@@ -308,7 +312,8 @@ def main():
             'metric': 'idispnet_roi_crops_per_s', 'value': value, 'unit': 'ROIs/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': warm, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32' if args.precision == 'fp32' else f'{args.precision} (fp32 accumulate)', 'data': 'synthetic',
+            'dtype': {'fp32': 'f32', 'fp16x2': 'fp16x2 (operands and activations as hi+lo IEEE-half word pairs, fp32 accumulate: fp32-grade)'}.get(
+                args.precision, f'{args.precision} (fp32 accumulate)'), 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'global_batch': Bg, 'parallelism': f'dp{world} (ROI shards, one all-gather of disparity maps)',
                        'precision_mode': args.precision,
                        'l2': 'no explicit flush: each step streams >10 GB of activations per GPU, far beyond the 126 MB L2'},
@@ -320,7 +325,11 @@ def main():
                          'peak_source': f'{peak_src} bf16 sustained (burst {tens_burst})',
                          'flop_per_roi': FLOP_PER_ROI, 'conv_ms_per_step': conv_ms / args.steps,
                          'other_ms_per_step': other_ms / args.steps,
-                         'whole_step_frac': value / world * FLOP_PER_ROI / 1e12 / tens_sus},
+                         'whole_step_frac': value / world * FLOP_PER_ROI / 1e12 / tens_sus,
+                         # split precision issues three half-precision MMAs per algorithmic product (x_hi*w_hi, x_lo*w_hi,
+                         # x_hi*w_lo): `achieved` counts ALGORITHMIC flops, the tensor pipe executes mma_passes times as many
+                         'mma_passes': 3 if args.precision == 'fp16x2' else 1,
+                         'executed_frac': achieved / tens_sus * (3 if args.precision == 'fp16x2' else 1)},
             'ms_by_layer': {str(k): round(v, 4) for k, v in sorted(by_layer.items())},
             'clocks': clocks,
         }
@@ -343,6 +352,25 @@ def main():
                 torch.cuda.synchronize()
             result['fp32_parity_mode'] = {'value': B_PER_GPU / (e0.elapsed_time(e1) / 1e3), 'unit': 'ROIs/s',
                                           f'{args.precision}_vs_fp32_disparity_px': {'max': diff.max().item(), 'mean': diff.mean().item()}}
+            if args.precision == 'fp16x2':
+                # the one-word tensor-core mode on the same inputs: 3.5x the throughput, but 0.07 px from the reference
+                # (tests/test_gpu_parity.py) -- outside north_star's 1e-3 bar, so it is reported beside the headline, not as it
+                m16 = make_model('fp16', dev)
+                m16.load_state_dict(m.state_dict())
+                with torch.no_grad():
+                    dh = (m16.forward_features(L[:4], R[:4]) - d32).abs()
+                    for _ in range(3):
+                        m16.forward_features(L, R)
+                    torch.cuda.synchronize()
+                    e0.record(stream)
+                    for _ in range(3):
+                        m16.forward_features(L, R)
+                    e1.record(stream)
+                    torch.cuda.synchronize()
+                result['fp16_one_word_mode'] = {'value': 3 * B_PER_GPU / (e0.elapsed_time(e1) / 1e3), 'unit': 'ROIs/s',
+                                                'fp16_vs_fp32_disparity_px': {'max': dh.max().item(), 'mean': dh.mean().item()},
+                                                'note': 'fails the 1e-3 parity bar; not the headline'}
+                del m16
             del m32
         if world == 1:
             result['roi_align'] = bench_roi_align(dev, hbm)

@@ -43,6 +43,10 @@
 
 namespace idisp {
 
+#ifndef IDISP_NMAIN
+#define IDISP_NMAIN 3  // accumulator banks of the main term in the split-precision kernels (see Cfg)
+#endif
+
 namespace tc {
 enum { M_S1 = 0, M_S2 = 1, M_DEC = 2 };
 constexpr int TW = 8, TH = 16;  // row tile (w x h) = 128 GEMM rows
@@ -68,19 +72,19 @@ template <> struct ModeCfg<M_DEC> { static constexpr int SUB_W = TW + 1, SUB_H =
 // XM = split-precision mode of the launch: 0 none, 1 / 2 = XP above, 3 = a plain-K pass of a multi-launch split layer.
 // Accumulator banks (XM != 0).  The tensor core adds each MMA's K=16 dot products into the fp32 accumulator by TRUNCATION
 // (measured: the disparity error grew ~3x when the two correction terms were accumulated in the same TMEM columns as the
-// main term, i.e. with 3x as many full-magnitude adds per output).  So the main term's chain is split over NMAIN = 3
-// column banks (by kw: 9*KS adds each instead of 27*KS) and the small correction terms get a bank of their own, where
+// main term, i.e. with 3x as many full-magnitude adds per output).  So the main term's chain is split over NMAIN
+// column banks (by kw) and the small correction terms get a bank of their own, where
 // their truncation is 2^-11 smaller; the epilogue sums the banks in fp32 round-to-nearest.
 template <int CIN, int MODE, int OCC, int NT, int XM = 0> struct Cfg {
   using MC = ModeCfg<MODE>;
   static constexpr int XP = XM == 3 ? 0 : XM;
-  static constexpr int NMAIN = (XM != 0 && MODE != M_DEC && NT <= 32 && OCC == 1) ? 3 : 1;
+  static constexpr int NMAIN = (XM != 0 && MODE != M_DEC && NT <= 32 && OCC == 1) ? IDISP_NMAIN : 1;
   static constexpr int NB = NMAIN + ((NMAIN > 1 && XP) ? 1 : 0);
   static constexpr int AW = XP ? 2 : 1;        // activation words per stage
   static constexpr int BW = XP == 1 ? 2 : 1;   // weight words resident in shared memory
   static constexpr int ACC_COLS = MC::ACC_BLOCKS * NT;   // TMEM columns of one output plane
   static constexpr int WCHUNK = 2 * 3 * NT * 16;          // B operand of one (kh,kw,kstep): [2 kcores][3 blocks x NT rows][8] bf16
-  static_assert(MODE != M_DEC || NT == 32, "the transposed-conv stacking table is written for 32-wide blocks");
+  static_assert(MODE != M_DEC || NT == 32 || NT == 16, "the transposed-conv stacking table scales from 32-wide blocks");
   static constexpr int EGROUPS = OCC == 2 ? 1 : 2;        // epilogue groups of 4 warps (alternate output planes)
   static constexpr int NTHREADS = 128 + 128 * EGROUPS;    // warps 0-3: TMA producer / MMA issuer / TMEM allocator / idle
   static constexpr int TCOLS = 512 / OCC;                 // TMEM columns of this CTA
@@ -111,6 +115,7 @@ struct Params {
   __nv_bfloat16 *y;               // blocked [B][Cout/8][Do][Ho][Wo][8]
   const float *res1;              // 32->1 head: running sum [B][D][H][W] f32 or nullptr
   float *y1;                      // 32->1 head: output [B][D][H][W] f32 (non-null selects this epilogue)
+  int y1_cols;                    // 32->1 head: accumulator columns summed into the logit (2: column 1 = the w_lo products)
   __nv_bfloat16 *y_split;         // optional second copy of y in the 8-parity-sub-volume layout a stride-2 consumer reads
   int residual_is_split;          // transposed conv only: `residual` is stored in that parity layout (of the OUTPUT grid)
   int skip_y;                     // write only y_split (the natural copy has no reader)
@@ -164,6 +169,9 @@ template <int XP, int KS, bool CV, int PLANE> __host__ __device__ constexpr uint
   const int phys = (CV && XP) ? ((blk < h ? blk : blk + h) + word * h) : word * cblk + blk;
   return (uint32_t)(phys * PLANE);
 }
+
+// operands a split-precision epilogue adds to one voxel block: fp32 partial of the earlier pass, residual hi / lo words
+struct XPre { float4 p0, p1; uint4 rh, rl; };
 
 __device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t byte_off) { return d + (uint64_t)(byte_off >> 4); }
 
@@ -419,10 +427,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
                 for (int ks = 0; ks < C::KSM; ++ks) {
                   const uint32_t aoff = (dec_shift_h(e) * MC::SUB_W + dec_shift_w(e)) * 16 + A_KOFF(ks);
-                  // weights: [kd][ks][kcore][288 rows][8]; entry e owns rows [row_off, row_off+rows)
-                  const uint32_t boff = ((kd * C::KSW + B_KS(ks)) * 2 * 288 + dec_row_off(e)) * 16;
-                  const uint64_t bd = ptx::make_smem_desc(w_addr + boff, 288 * 16, 128);
-                  mma(dbase + dec_dcol(e), desc_add(a0, aoff), bd, ptx::make_idesc_h<F16>(128, dec_rows(e)));
+                  // weights: [kd][ks][kcore][9*NT rows][8]; entry e owns rows [row_off, row_off+rows) (tables written for NT = 32)
+                  const uint32_t boff = ((kd * C::KSW + B_KS(ks)) * 2 * 9 * NT + dec_row_off(e) * NT / 32) * 16;
+                  const uint64_t bd = ptx::make_smem_desc(w_addr + boff, 9 * NT * 16, 128);
+                  mma(dbase + dec_dcol(e) * NT / 32, desc_add(a0, aoff), bd, ptx::make_idesc_h<F16>(128, dec_rows(e) * NT / 32));
                 }
               }
             }
@@ -455,35 +463,50 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       const int tw = col % p.tiles_w, th = (col / p.tiles_w) % p.tiles_h, n = col / (p.tiles_w * p.tiles_h);
       const int hr = th * TH + hl, wr = tw * TW + wl;
       const bool valid = hr < p.Hr && wr < p.Wr;
+      // Split-precision passes: the operands the epilogue adds (fp32 partial of the earlier pass, hi and lo words of the
+      // residual) are independent of the accumulator -> requested as a batch before it is needed (xload), consumed in finish.
+      auto xload = [&](XPre &q, int cb, int64_t pos, int cls, int64_t sidx) {
+        const int cbg = nh * (NT / 8) + cb;
+        if (p.part_in) {
+          const float4 *pp = reinterpret_cast<const float4 *>(p.part_in + (((int64_t)n * cblk_out + cbg) * Vo + pos) * 8);
+          q.p0 = __ldg(pp); q.p1 = __ldg(pp + 1);
+        }
+        if (p.residual) {
+          const int64_t ro = p.residual_is_split ? ((((int64_t)n * out_blocks + cbg) * 8 + cls) * sub + sidx) * 8
+                                                 : (((int64_t)n * out_blocks + cbg) * Vo + pos) * 8;
+          q.rh = __ldg(reinterpret_cast<const uint4 *>(p.residual + ro));
+          if (p.x2) q.rl = __ldg(reinterpret_cast<const uint4 *>(p.residual + ro + (int64_t)cblk_out * (p.residual_is_split ? 8 * sub : Vo) * 8));
+          else q.rl = make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
       // Everything after the accumulator: (+ fp32 partial of an earlier pass) -> either the fp32 partial of this pass, or
       // + bias (+ residual) (ReLU) -> 16-bit store(s).  `cb` = channel block inside this CTA's slice, `pos` = natural
-      // voxel index, (`cls`, `sidx`) = parity class and index inside the parity sub-volume, `pre` = prefetched residual.
-      auto finish = [&](F8 a, int cb, int64_t pos, int cls, int64_t sidx, const uint4 &pre, bool has_pre) {
+      // voxel index, (`cls`, `sidx`) = parity class and index inside the parity sub-volume, `pre` = prefetched residual
+      // (one-word modes), `xq` = prefetched operands of a split-precision pass.
+      auto finish = [&](F8 a, int cb, int64_t pos, int cls, int64_t sidx, const uint4 &pre, const XPre &xq) {
         const int cbg = nh * (NT / 8) + cb;
         const int64_t onat = (((int64_t)n * out_blocks + cbg) * Vo + pos) * 8;
         const int64_t ospl = ((((int64_t)n * out_blocks + cbg) * 8 + cls) * sub + sidx) * 8;
         if (X2 && (p.part_in || p.part_out)) {
-          const int64_t op = (((int64_t)n * cblk_out + cbg) * Vo + pos) * 8;
           if (p.part_in) {
-            const float4 u0 = __ldg(reinterpret_cast<const float4 *>(p.part_in + op)), u1 = __ldg(reinterpret_cast<const float4 *>(p.part_in + op) + 1);
-            a.v[0] += u0.x; a.v[1] += u0.y; a.v[2] += u0.z; a.v[3] += u0.w; a.v[4] += u1.x; a.v[5] += u1.y; a.v[6] += u1.z; a.v[7] += u1.w;
+            a.v[0] += xq.p0.x; a.v[1] += xq.p0.y; a.v[2] += xq.p0.z; a.v[3] += xq.p0.w;
+            a.v[4] += xq.p1.x; a.v[5] += xq.p1.y; a.v[6] += xq.p1.z; a.v[7] += xq.p1.w;
           }
           if (p.part_out) {
-            reinterpret_cast<float4 *>(p.part_out + op)[0] = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
-            reinterpret_cast<float4 *>(p.part_out + op)[1] = make_float4(a.v[4], a.v[5], a.v[6], a.v[7]);
+            float4 *po = reinterpret_cast<float4 *>(p.part_out + (((int64_t)n * cblk_out + cbg) * Vo + pos) * 8);
+            po[0] = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+            po[1] = make_float4(a.v[4], a.v[5], a.v[6], a.v[7]);
             return;
           }
         }
 #pragma unroll
         for (int c = 0; c < 8; ++c) a.v[c] += bias_s[cb * 8 + c];
         if (p.residual) {
-          const int64_t ro = p.residual_is_split ? ospl : onat;
-          const F8 q = unpack8h<F16>((!X2 || has_pre) ? pre : __ldg(reinterpret_cast<const uint4 *>(p.residual + ro)));
+          const F8 q = unpack8h<F16>(X2 ? xq.rh : pre);
 #pragma unroll
           for (int c = 0; c < 8; ++c) a.v[c] += q.v[c];
-          if (X2 && p.x2) {  // low half of the residual: cblk_out blocks further
-            const int64_t lo_off = (int64_t)cblk_out * (p.residual_is_split ? 8 * sub : Vo) * 8;
-            const F8 ql = unpack8h<F16>(__ldg(reinterpret_cast<const uint4 *>(p.residual + ro + lo_off)));
+          if (X2) {  // low word of the residual
+            const F8 ql = unpack8h<F16>(xq.rl);
 #pragma unroll
             for (int c = 0; c < 8; ++c) a.v[c] += ql.v[c];
           }
@@ -510,7 +533,31 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         // modes only; the split-precision passes load at use)
         constexpr int NRES = MODE == M_DEC ? 16 : (NT >= 8 ? NT / 8 : 1);
         uint4 resv[NRES];
-        const bool prefetch = p.residual && valid && !(X2 && (p.x2 || p.part_out));
+        const bool prefetch = !X2 && p.residual && valid;
+        constexpr int NXQ = (X2 && MODE != M_DEC && NT >= 8 && NT <= 32) ? NT / 8 : 1;
+        XPre xq[NXQ];
+        if (X2 && MODE != M_DEC && NT <= 32 && valid && !p.y1) {
+          const int64_t pos = ((int64_t)qo * p.Ho + hr) * p.Wo + wr;
+          const int64_t sidx = ((int64_t)(qo >> 1) * (p.Ho / 2) + (hr >> 1)) * (p.Wo / 2) + (wr >> 1);
+#pragma unroll
+          for (int cb = 0; cb < NXQ; ++cb) xload(xq[cb], cb, pos, (qo & 1) * 4 + (hr & 1) * 2 + (wr & 1), sidx);
+        }
+        if (MODE == M_DEC && X2 && valid && (p.part_in || p.residual)) {
+          // the plane's 16 voxel blocks per thread are consumed class by class below; ask L2 for all of them now
+#pragma unroll
+          for (int i = 0; i < 4 * (NT / 8); ++i) {
+            const int cb = i % (NT / 8), ph = (i / (NT / 8)) >> 1, pw = (i / (NT / 8)) & 1, cbg = nh * (NT / 8) + cb;
+            const int64_t pos = ((int64_t)qo * p.Ho + 2 * hr + ph) * p.Wo + 2 * wr + pw;
+            if (p.part_in) ptx::prefetch_l2(p.part_in + (((int64_t)n * cblk_out + cbg) * Vo + pos) * 8);
+            if (p.residual) {
+              const int64_t ro = p.residual_is_split ? ((((int64_t)n * out_blocks + cbg) * 8 + (qo & 1) * 4 + ph * 2 + pw) * sub +
+                                                         ((int64_t)(qo >> 1) * (p.Ho / 2) + hr) * (p.Wo / 2) + wr) * 8
+                                                      : (((int64_t)n * out_blocks + cbg) * Vo + pos) * 8;
+              ptx::prefetch_l2(p.residual + ro);
+              if (p.x2) ptx::prefetch_l2(p.residual + ro + (int64_t)cblk_out * (p.residual_is_split ? 8 * sub : Vo) * 8);
+            }
+          }
+        }
         if (prefetch) {
 #pragma unroll
           for (int i = 0; i < NRES; ++i) {
@@ -527,7 +574,52 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         }
         ptx::mbar_wait(accf_bar(r), (g / NSLOT) & 1);
         ptx::tc_fence_after();
-        if (MODE == M_DEC) {
+        if (MODE == M_DEC && X2) {
+          // split-precision pass: one parity class (32 accumulator columns, column block = pw*2 + ph) at a time; its
+          // partial / residual operands are requested as one batch before the TMEM read
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const int ph = c4 >> 1, pw = c4 & 1;
+            constexpr int NCB = NT / 8;  // channel blocks of this CTA's slice
+            const int64_t pos = ((int64_t)qo * p.Ho + 2 * hr + ph) * p.Wo + 2 * wr + pw;
+            const int64_t sidx = ((int64_t)(qo >> 1) * (p.Ho / 2) + hr) * (p.Wo / 2) + wr;
+            const int cls = (qo & 1) * 4 + ph * 2 + pw;
+            XPre dq[NCB];
+            if (valid) {
+#pragma unroll
+              for (int cb = 0; cb < NCB; ++cb) xload(dq[cb], cb, pos, cls, sidx);
+            }
+            uint32_t v[32];
+            const uint32_t t0 = tmem_base + lane_addr + r * C::ACC_COLS + (pw * 2 + ph) * NT;
+            if (!(p.dbg & 8)) {
+              if (NT == 16) {
+                uint32_t v16[16];
+                ptx::tmem_ld_32x16(t0, v16);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = v16[i];
+              } else {
+                ptx::tmem_ld_32x32(t0, v);
+                ptx::tmem_ld_wait();
+              }
+            }
+            if (!(p.dbg & 16)) { if (NT == 16) ptx::tmem_st_32x16(t0, zero); else ptx::tmem_st_32x32(t0, zero); }
+            if (c4 == 3) {
+              ptx::tmem_st_wait();
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(acce_bar(r));
+            }
+            if (!valid || (p.dbg & 4)) continue;
+#pragma unroll
+            for (int cb = 0; cb < NCB; ++cb) {
+              F8 a8;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) a8.v[c] = __uint_as_float(v[cb * 8 + c]);
+              finish(a8, cb, pos, cls, sidx, resv[0], dq[cb]);
+            }
+          }
+        } else if (MODE == M_DEC) {
           // class = pw*2 + ph.  The two pw classes of one ph are neighbouring output voxels (2w, 2w+1): drain both and
           // store 32 contiguous bytes per thread and channel block (a lone 16-byte store half-fills its 32 B sector).
 #pragma unroll
@@ -550,8 +642,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               F8 a8, b8;
 #pragma unroll
               for (int c = 0; c < 8; ++c) { a8.v[c] = __uint_as_float(v0[cb * 8 + c]); b8.v[c] = __uint_as_float(v1[cb * 8 + c]); }
-              finish(a8, cb, pos, (qo & 1) * 4 + ph * 2, sidx, resv[ph * 8 + cb * 2], prefetch);
-              finish(b8, cb, pos + 1, (qo & 1) * 4 + ph * 2 + 1, sidx, resv[ph * 8 + cb * 2 + 1], prefetch);
+              finish(a8, cb, pos, (qo & 1) * 4 + ph * 2, sidx, resv[ph * 8 + cb * 2], xq[0]);
+              finish(b8, cb, pos + 1, (qo & 1) * 4 + ph * 2 + 1, sidx, resv[ph * 8 + cb * 2 + 1], xq[0]);
             }
           }
         } else {
@@ -581,9 +673,17 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               }
             } else {
               ptx::tmem_ld_32x32(taddr + part * 32, v);
-              ptx::tmem_ld_wait();
+              if (C::NB > 1) {  // banks 0 and 1 with ONE round trip (the drain latency bounds how few ring slots suffice)
+                uint32_t u[32];
+                ptx::tmem_ld_32x32(taddr + C::BANK_COLS + part * 32, u);
+                ptx::tmem_ld_wait();
 #pragma unroll
-              for (int bk = 1; bk < C::NB; ++bk) {
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
+              } else {
+                ptx::tmem_ld_wait();
+              }
+#pragma unroll
+              for (int bk = 2; bk < C::NB; ++bk) {
                 uint32_t u[32];
                 ptx::tmem_ld_32x32(taddr + bk * C::BANK_COLS + part * 32, u);
                 ptx::tmem_ld_wait();
@@ -606,7 +706,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             if (!valid || (p.dbg & 4)) continue;
             if (p.y1) {  // 32->1 classifier head: channel 0 only, f32, running sum fused (stackhourglass.py:142-144)
               const int64_t o1 = (int64_t)n * Vo + pos;
-              p.y1[o1] = __uint_as_float(v[0]) + (p.res1 ? p.res1[o1] : 0.f);
+              p.y1[o1] = __uint_as_float(v[0]) + (p.y1_cols == 2 ? __uint_as_float(v[1]) : 0.f) + (p.res1 ? p.res1[o1] : 0.f);
               continue;
             }
 #pragma unroll
@@ -615,7 +715,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               F8 r8;
 #pragma unroll
               for (int c = 0; c < 8; ++c) r8.v[c] = __uint_as_float(v[cbl * 8 + c]);
-              finish(r8, cb, pos, (qo & 1) * 4 + (hr & 1) * 2 + (wr & 1), sidx, resv[cb], prefetch);
+              if (X2 && NXQ == 1 && NT > 8) {  // (64-wide blocks: no batch, operands requested at use)
+                XPre one;
+                xload(one, cb, pos, (qo & 1) * 4 + (hr & 1) * 2 + (wr & 1), sidx);
+                finish(r8, cb, pos, (qo & 1) * 4 + (hr & 1) * 2 + (wr & 1), sidx, resv[cb], one);
+              } else {
+                finish(r8, cb, pos, (qo & 1) * 4 + (hr & 1) * 2 + (wr & 1), sidx, resv[cb], xq[cb < NXQ ? cb : 0]);
+              }
             }
           }
         }
@@ -697,10 +803,11 @@ static int nt_of(int kind, int cin, int cout)
 
 // Pack [27][cin][cout] f32 (tap = (kd*3+kh)*3+kw, BN scale folded) into the per-mode UMMA B layout, bf16:
 // rows of 8 input channels (16 B), 8-row core matrices contiguous (SBO 128 B), K cores LBO apart.
-int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16, TcWeights &out, cudaStream_t s, int words, int nt)
+int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16, TcWeights &out, cudaStream_t s, int words, int nt, int ncat)
 {
   tc_weights_free(out);
-  out.kind = kind; out.cin = cin; out.cout = cout; out.f16 = f16; out.words = words;
+  out.kind = kind; out.cin = cin; out.cout = cout; out.f16 = f16; out.words = words; out.ncat = ncat;
+  if (ncat && !(cout == 1 && f16 && words == 1)) { set_error("tc_weights_prepare: the lo word goes to output column 1 only for the 1-channel head"); return IDISP_ERR_INVALID; }
   if (words != 1 && !(words == 2 && f16)) { set_error("tc_weights_prepare: two-word weights are IEEE half only"); return IDISP_ERR_INVALID; }
   if (!tc_supported(kind, cin, cout, 4, 16, 16)) return IDISP_OK;  // layer stays on the SIMT kernel
   const int NT = nt > 0 ? nt : tc::nt_of(kind, cin, cout);
@@ -717,6 +824,10 @@ int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16,
   };
   std::vector<__nv_bfloat16> h(NH * per_nh, cvt(0.f));
   auto wv = [&](int kd, int kh, int kw, int ci, int co) -> float {
+    if (ncat && co == 1) {  // 1-channel head, split precision: column 1 = what column 0's half rounded away
+      const float v = w_tap[((size_t)((kd * 3 + kh) * 3 + kw) * cin + ci) * cout];
+      return v - __half2float(__float2half_rn(v));
+    }
     if (co >= cout) return 0.f;
     const float v = w_tap[((size_t)((kd * 3 + kh) * 3 + kw) * cin + ci % cin) * cout + co];
     return ci < cin ? v : v - __half2float(__float2half_rn(v));  // second word: what the first one rounded away
@@ -735,7 +846,7 @@ int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16,
                 base[((((size_t)t2 * KS + ks) * 2 + kc) * 3 * NT + n) * 8 + e] =
                     cvt(wv(kdj[n / NT], t2 / 3, t2 % 3, ks * 16 + kc * 8 + e, nh * NT + n % NT));
     } else {
-      // DECONV: [kd][ks][2 kcores][288 rows][8]; rows = entries e0..e4 (tc::dec_*), blocks = output classes
+      // DECONV: [kd][ks][2 kcores][9*NT rows][8]; rows = entries e0..e4 (tc::dec_*), blocks = output classes
       //   class = pw*2+ph; per axis: p=0 -> k=1 (shift 0); p=1 -> k=2 (shift 0), k=0 (shift 1)
       struct Blk { int kh, kw; };
       static const Blk blocks[9] = {
@@ -747,11 +858,11 @@ int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16,
       for (int kd = 0; kd < 3; ++kd)
         for (int ks = 0; ks < KS; ++ks)
           for (int kc = 0; kc < 2; ++kc)
-            for (int row = 0; row < 288; ++row)
+            for (int row = 0; row < 9 * NT; ++row)
               for (int e = 0; e < 8; ++e) {
-                const Blk b = blocks[row / 32];
-                base[((((size_t)kd * KS + ks) * 2 + kc) * 288 + row) * 8 + e] =
-                    cvt(wv(kd, b.kh, b.kw, ks * 16 + kc * 8 + e, nh * 32 + row % 32));
+                const Blk b = blocks[row / NT];
+                base[((((size_t)kd * KS + ks) * 2 + kc) * 9 * NT + row) * 8 + e] =
+                    cvt(wv(kd, b.kh, b.kw, ks * 16 + kc * 8 + e, nh * NT + row % NT));
               }
     }
   }
@@ -850,7 +961,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   if (r != CUDA_SUCCESS) { set_error("tc_conv3d: cuTensorMapEncodeTiled failed (%d) for dims W=%d H=%d D=%d mode=%d", (int)r, W, H, D, MODE); return IDISP_ERR_CUDA; }
   tc::Params p;
   p.w = (const __nv_bfloat16 *)w.dev; p.bias = bias; p.residual = residual; p.y = y; p.res1 = res1; p.y1 = y1; p.y_split = y_split; p.residual_is_split = (x_is_split >> 1) & 1; p.skip_y = (x_is_split >> 2) & 1;
-  p.B = B; p.Din = D; p.Cout = Cout; p.relu = relu;
+  p.B = B; p.Din = D; p.Cout = Cout; p.relu = relu; p.y1_cols = w.ncat ? 2 : 1;
   p.cv_shift0 = cv ? cv->shift0 : 0;
   p.part_in = opts.part_in; p.part_out = opts.part_out; p.x2 = opts.x2; p.in_blk_stride = blk_stride; p.in_blk_off = opts.in_blk_off;
   if (!cv) rmap = map;
@@ -872,7 +983,8 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
     constexpr bool CVK = decltype(cv_c)::value;
     constexpr int XP = FMT == 3 ? 1 : (FMT == 4 ? 2 : 0);
     // in-launch K concatenation exists where its shared-memory budget closes (see Cfg)
-    constexpr bool ok = XP == 0 || (XP == 1 && CIN == 32 && OCC == 1 && NT <= 32 && MODE != tc::M_DEC) || (XP == 2 && CIN == 64 && OCC == 1 && MODE != tc::M_S2);
+    constexpr bool ok = (XP == 0 && (MODE != tc::M_DEC || NT == 32)) || (XP == 1 && CIN == 32 && OCC == 1 && NT <= 32 && MODE != tc::M_DEC) ||
+                        (XP == 1 && MODE == tc::M_DEC && NT == 16) || (XP == 2 && (CIN == 64 || NT == 16) && OCC == 1 && MODE != tc::M_S2);
     if constexpr (!ok) {
       set_error("tc_conv3d: K-concatenation mode %d not built for Cin=%d mode=%d", XP, CIN, MODE);
       return IDISP_ERR_UNSUPPORTED;
@@ -938,6 +1050,7 @@ int tc_conv3d(const TcWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D,
     if (w.nt == 64) IDISP_TC(32, tc::M_S2, 1, 64);
     IDISP_TC(32, tc::M_S2, 1, 32);
   }
+  if (w.nt == 16) IDISP_TC(64, tc::M_DEC, 1, 16);
   IDISP_TC(64, tc::M_DEC, 1, 32);
 #undef IDISP_TC
 }
@@ -952,6 +1065,7 @@ static int split_launches(int kind, int cin)
   static const int three = tc::env_flag("IDISP_X2_THREE_PASS");  // A/B switch
   if (three) return 3;
   if (cin == 32 && kind != IDISP_DECONV_S2) return 1;
+  if (cin == 64 && kind == IDISP_DECONV_S2) return 1;  // 16-wide blocks: both weight words of a 16-channel slice fit
   if (cin == 64 && kind != IDISP_CONV_S2) return 2;
   return 3;
 }
@@ -967,9 +1081,12 @@ int tc_split_weights_prepare(const float *w_tap, int kind, int cin, int cout, Tc
   int rc;
   if ((rc = tc_weights_prepare(w_tap, kind, cin, cout, 1, out.hi, s))) return rc;
   if ((rc = tc_weights_prepare(lo.data(), kind, cin, cout, 1, out.lo, s))) return rc;
-  if (split_launches(kind, cin) == 1) {
+  if (cout == 1 && split_launches(kind, cin) == 1) {
+    // 1-channel head: w_lo rides in the (otherwise zero) output column 1, so x_hi feeds both weight words in ONE MMA
+    if ((rc = tc_weights_prepare(w_tap, kind, cin, cout, 1, out.both, s, 1, 0, 1))) return rc;
+  } else if (split_launches(kind, cin) == 1) {
     // two-word packing; the stride-2 32->64 conv keeps 32-wide blocks here (2 x 110 KB of 64-wide weights would not fit)
-    const int nt = (kind == IDISP_CONV_S2 && cout == 64) ? 32 : 0;
+    const int nt = (kind == IDISP_CONV_S2 && cout == 64) ? 32 : (kind == IDISP_DECONV_S2 ? 16 : 0);
     if ((rc = tc_weights_prepare(w_tap, kind, cin, cout, 1, out.both, s, 2, nt))) return rc;
   }
   return IDISP_OK;
@@ -986,7 +1103,7 @@ int tc_conv3d_split(const TcSplitWeights &w, const __nv_bfloat16 *x, int B, int 
   o.in_blk_stride = 2 * per_view;
   int rc;
   if (nl == 1) {
-    o.xp = 1;
+    o.xp = w.both.ncat ? 2 : 1;
     if (y1) return tc_conv3d(w.both, x, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, res1, y1, scratch, flags & 1, nullptr, cv, s, &o);
     o.x2 = 1;
     return tc_conv3d(w.both, x, B, Cin, D, H, W, Cout, kind, bias, residual, relu, y, nullptr, nullptr, scratch, flags, y_split, cv, s, &o);

@@ -11,12 +11,14 @@ struct TcWeights {
   int kind = -1, cin = 0, cout = 0;
   int nt = 32;  // output channels per stacked block the packing was made for
   int f16 = 0;  // 16-bit storage format of weights AND activations: 0 = bfloat16, 1 = IEEE half
+  int ncat = 0;   // 1-channel head, split precision: output column 1 holds half(w - half(w)) (see tc_split_weights_prepare)
   int words = 1;  // 2: split precision, the lo word's k-steps follow the hi word's inside every tap (TcOpts::xp == 1)
 };
 
 // w_tap: HOST pointer, [27][cin][cout] f32 with the BN scale already folded in
 // words = 2 packs half(w) and half(w - half(w)); nt > 0 overrides the layer's default block width
-int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16, TcWeights &out, cudaStream_t s, int words = 1, int nt = 0);
+int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16, TcWeights &out, cudaStream_t s, int words = 1, int nt = 0,
+                       int ncat = 0);
 void tc_weights_free(TcWeights &w);
 // Fused cost volume for the first layer (stackhourglass.py:115-128 folded into dres0.0's loader): the per-view features
 // in blocked bf16 [B][C/8][Hf][Wf][8]; D <= 64 planes (the per-plane tensor maps travel as kernel parameters).

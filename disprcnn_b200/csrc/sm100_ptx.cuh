@@ -61,6 +61,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 }
 
 // ---------------- TMA (cp.async.bulk.tensor, tiled mode) ----------------
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *m)
 {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
