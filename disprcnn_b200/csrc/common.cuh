@@ -146,6 +146,10 @@ template <typename T>
 int launch_conv3d_to1(const T *x, int B, int Cin, int D, int H, int W, const float *w_tap,
                       const float *residual, float *y, cudaStream_t s);
 
+// the same on split-precision activations (hi|lo IEEE-half block groups), f32 weights, f32 FMA
+int launch_conv3d_to1_x2(const __nv_bfloat16 *x, int B, int Cin, int D, int H, int W, const float *w_tap, const float *residual,
+                         float *y, cudaStream_t s);
+
 int launch_softargmin(const float *logits, int B, int D, int Hf, int Wf, int mindisp, int maxdisp, int H,
                       int W, float *out, cudaStream_t s);
 

@@ -214,7 +214,8 @@ template int launch_conv3d_simt<__nv_bfloat16>(const __nv_bfloat16 *, int, int, 
 // running sum of the previous head fused (:143-144).  1.04 GFLOP/ROI at config 2: CUDA cores,
 // one thread per output voxel, w [27][Cin] in shared memory, output/residual plain [B][D][H][W] f32.
 // ---------------------------------------------------------------------------------------
-template <typename T, int CIN>
+// X2: x holds split-precision activations (IEEE-half hi blocks, then lo blocks: [N][2*CIN/8][V][8]); the value is hi + lo.
+template <typename T, int CIN, bool X2 = false>
 __global__ void __launch_bounds__(128)
 conv3d_to1_kernel(const T *__restrict__ x, const float *__restrict__ w_tap, const float *__restrict__ residual,
                   float *__restrict__ y, int D, int H, int W)
@@ -227,7 +228,7 @@ conv3d_to1_kernel(const T *__restrict__ x, const float *__restrict__ w_tap, cons
   if (p >= H * W) return;
   const int h = p / W, w = p - h * W;
   const int64_t V = (int64_t)D * H * W;
-  const T *xn = x + (int64_t)n * (CIN / 8) * V * 8;
+  const T *xn = x + (int64_t)n * ((X2 ? 2 : 1) * CIN / 8) * V * 8;
   float acc = 0.f;
   for (int kd = 0; kd < 3; ++kd) {
     const int di = d + kd - 1;
@@ -243,7 +244,15 @@ conv3d_to1_kernel(const T *__restrict__ x, const float *__restrict__ w_tap, cons
         const int64_t off = (((int64_t)di * H + hi) * W + wi) * 8;
 #pragma unroll
         for (int cb = 0; cb < CIN / 8; ++cb) {
-          const F8 a = load8<T>(xn + (int64_t)cb * V * 8 + off);
+          F8 a;
+          if (X2) {
+            a = unpack8h<true>(__ldg(reinterpret_cast<const uint4 *>(xn + (int64_t)cb * V * 8 + off)));
+            const F8 lo = unpack8h<true>(__ldg(reinterpret_cast<const uint4 *>(xn + (int64_t)(cb + CIN / 8) * V * 8 + off)));
+#pragma unroll
+            for (int c = 0; c < 8; ++c) a.v[c] += lo.v[c];
+          } else {
+            a = load8<T>(xn + (int64_t)cb * V * 8 + off);
+          }
 #pragma unroll
           for (int c = 0; c < 8; ++c) acc = fmaf(a.v[c], wt[cb * 8 + c], acc);
         }
@@ -263,6 +272,16 @@ int launch_conv3d_to1(const T *x, int B, int Cin, int D, int H, int W, const flo
   if (Cin != 32) { set_error("conv3d_to1: Cin=%d unsupported (32 only)", Cin); return IDISP_ERR_INVALID; }
   dim3 grid(ceil_div(H * W, 128), D, B);
   conv3d_to1_kernel<T, 32><<<grid, 128, 0, s>>>(x, w_tap, residual, y, D, H, W);
+  IDISP_LAUNCH_CHECK();
+  return IDISP_OK;
+}
+int launch_conv3d_to1_x2(const __nv_bfloat16 *x, int B, int Cin, int D, int H, int W, const float *w_tap, const float *residual,
+                         float *y, cudaStream_t s)
+{
+  if (B == 0) return IDISP_OK;
+  if (Cin != 32) { set_error("conv3d_to1: Cin=%d unsupported (32 only)", Cin); return IDISP_ERR_INVALID; }
+  dim3 grid(ceil_div(H * W, 128), D, B);
+  conv3d_to1_kernel<__nv_bfloat16, 32, true><<<grid, 128, 0, s>>>(x, w_tap, residual, y, D, H, W);
   IDISP_LAUNCH_CHECK();
   return IDISP_OK;
 }

@@ -393,7 +393,12 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
     float *dst = (k == 1) ? b.costY : b.costX;
     const float *prev = k == 0 ? nullptr : (k == 1 ? b.costX : b.costY);
     mark(25 + k);
-    if (std::is_same<T, __nv_bfloat16>::value && tc_supported(IDISP_CONV_S1, 32, 1, D, Hf, Wf))
+    static const int x2_simt_heads = getenv("IDISP_X2_SIMT_HEADS") ? 1 : 0;  // A/B switch
+    if (p->x2 && x2_simt_heads)
+      // split precision, 1-channel head on the CUDA cores straight from the hi|lo words (f32 weights and FMAs).  Measured at
+      // B=32: 3.8 ms against 1.36 ms for the tensor-core form (w_lo in output column 1) -- kept only as a cross-check.
+      RUN(launch_conv3d_to1_x2((const __nv_bfloat16 *)b.c, B, 32, D, Hf, Wf, p->dev[25 + k].w_tap, prev, dst, s));
+    else if (std::is_same<T, __nv_bfloat16>::value && tc_supported(IDISP_CONV_S1, 32, 1, D, Hf, Wf))
       RUN(tc_layer(p, 25 + k, (const __nv_bfloat16 *)b.c, 0, nullptr, B, D, Hf, Wf, nullptr, 0, nullptr, nullptr, 0, prev, dst, b.split, b.part, s,
                    launches));
     else if (p->f16) { set_error("plan_forward: fp16 mode needs the tensor-core classifier head"); return IDISP_ERR_UNSUPPORTED; }
