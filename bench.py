@@ -146,6 +146,37 @@ def bench_roi_align(dev, hbm_gbs):
             'note': 'output-write bytes only; the gather reads hit L2 (3.7 MB image set), launch-latency dominated at this size'}
 
 
+def bench_cost_volume(dev, hbm_gbs, L, R):
+    """The standalone correlation kernel (stackhourglass.py:115-128 in the reference's NCDHW layout, C-ABI idisp_cost_volume):
+    8 ROI pairs of the benchmark shape -> 1.23 GB written per call.  (The tensor-core modes never materialise this volume: the
+    first conv's TMA loader assembles it; this entry exists for callers that want the tensor itself.)"""
+    import torch
+    from disprcnn_b200 import _lib
+    lib = _lib.load()
+    n = 8
+    D = (MAXD - MIND) // 4
+    cost = torch.empty(n, 2 * C, D, HF, WF, device=dev)
+    Ln, Rn = L[:n].contiguous(), R[:n].contiguous()
+
+    def run():
+        _lib.check(lib.idisp_cost_volume(_lib.ptr(Ln), _lib.ptr(Rn), n, C, HF, WF, MIND, MAXD, _lib.ptr(cost), _lib.stream_ptr()))
+    for _ in range(3):
+        run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    k = 10
+    for _ in range(k):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / k
+    nbytes = cost.numel() * 4
+    return {'ms_per_call': ms, 'workload': f'{n} ROI pairs 112x112x32ch, D=48 -> [{n},64,48,112,112] f32', 'algorithmic_bytes': nbytes,
+            'achieved_gbs': nbytes / (ms / 1e3) / 1e9, 'hbm_peak_gbs': hbm_gbs, 'frac': nbytes / (ms / 1e3) / 1e9 / hbm_gbs,
+            'rois_per_s': n / (ms / 1e3)}
+
+
 def make_model(precision, device):
     import torch
     import torch.nn as nn
@@ -374,6 +405,7 @@ def main():
             del m32
         if world == 1:
             result['roi_align'] = bench_roi_align(dev, hbm)
+            result['cost_volume'] = bench_cost_volume(dev, hbm, L, R)
         if world == 1 and not args.no_cpu_baseline:
             sd = {k: v for k, v in m.state_dict().items() if not k.startswith('feature_extraction')}
             val, dt, cores, sample = cpu_port_rois_per_s(sd, 1, 1, budget_s=45.0)  # 1 warm-up: oneDNN primitive creation is per shape

@@ -10,6 +10,7 @@
 // the first plane.  Every thread writes one 16/32-byte channel-block voxel (blocked layout)
 // or one float4 of a row (NCDHW test hook) -> 128-bit coalesced stores.
 #include "common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace idisp {
 
@@ -63,7 +64,57 @@ int launch_cost_volume_blocked(const float *L, const float *R, int B, int C, int
 template int launch_cost_volume_blocked<float>(const float *, const float *, int, int, int, int, int, int, float *, cudaStream_t);
 template int launch_cost_volume_blocked<__nv_bfloat16>(const float *, const float *, int, int, int, int, int, int, __nv_bfloat16 *, cudaStream_t);
 
-// ---------------- NCDHW f32 output (reference layout; C-ABI test hook) -----------------
+// ---------------- NCDHW f32 output (the reference's layout; C-ABI entry idisp_cost_volume) -----------------
+// One CTA owns RY feature rows of one (b, c): the rows of BOTH views are contiguous in NCHW, so two linear TMA copies
+// (cp.async.bulk, one mbarrier) stage them in shared memory once; the CTA then writes those rows into all D planes of
+// channels c (left, unshifted) and C+c (right, shifted by the plane's disparity, read from shared memory) with 128-bit
+// stores -- RY*Wf*4 contiguous bytes per plane and channel.  Algorithmic bytes: 2C*V*4 written per ROI (154 MB at config 2).
+constexpr int CV_RY = 8;
+
+__global__ void __launch_bounds__(256)
+cost_volume_ncdhw_tma_kernel(const float *__restrict__ L, const float *__restrict__ R, int C, int Hf, int Wf, int shift0, int D,
+                             float *__restrict__ cost)
+{
+  extern __shared__ __align__(128) float cv_smem[];  // [2][RY*Wf] + mbarrier
+  const int tiles_y = (Hf + CV_RY - 1) / CV_RY;
+  const int ty = blockIdx.x % tiles_y, c = (blockIdx.x / tiles_y) % C, b = blockIdx.x / (tiles_y * C);
+  const int y0 = ty * CV_RY, rows = min(CV_RY, Hf - y0);
+  const int n = rows * Wf;  // floats per view
+  float *sl = cv_smem, *sr = cv_smem + CV_RY * Wf;
+  const uint32_t bar = ptx::smem_u32(cv_smem + 2 * CV_RY * Wf);
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(bar, 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int64_t src = (((int64_t)b * C + c) * Hf + y0) * Wf;
+    ptx::mbar_arrive_expect_tx(bar, 2u * n * 4u);
+    ptx::bulk_g2s(ptx::smem_u32(sl), L + src, n * 4u, bar);
+    ptx::bulk_g2s(ptx::smem_u32(sr), R + src, n * 4u, bar);
+  }
+  ptx::mbar_wait(bar, 0);
+  const int w4 = Wf / 4, per_plane = rows * w4;
+  const int64_t HW = (int64_t)Hf * Wf;
+  float *outl = cost + (((int64_t)b * 2 * C + c) * D) * HW + (int64_t)y0 * Wf;
+  float *outr = cost + (((int64_t)b * 2 * C + C + c) * D) * HW + (int64_t)y0 * Wf;
+  for (int it = threadIdx.x; it < D * per_plane; it += 256) {
+    const int k = it / per_plane, rem = it - k * per_plane;
+    const int yr = rem / w4, x = (rem - yr * w4) * 4;
+    const int i = k + shift0, lo = max(i, 0), hi = Wf + min(i, 0);  // valid x in [lo, hi)
+    const float *pl = sl + yr * Wf + x, *pr = sr + yr * Wf + x - i;
+    float4 vl, vr;
+    vl.x = (x + 0 >= lo && x + 0 < hi) ? pl[0] : 0.f; vr.x = (x + 0 >= lo && x + 0 < hi) ? pr[0] : 0.f;
+    vl.y = (x + 1 >= lo && x + 1 < hi) ? pl[1] : 0.f; vr.y = (x + 1 >= lo && x + 1 < hi) ? pr[1] : 0.f;
+    vl.z = (x + 2 >= lo && x + 2 < hi) ? pl[2] : 0.f; vr.z = (x + 2 >= lo && x + 2 < hi) ? pr[2] : 0.f;
+    vl.w = (x + 3 >= lo && x + 3 < hi) ? pl[3] : 0.f; vr.w = (x + 3 >= lo && x + 3 < hi) ? pr[3] : 0.f;
+    const int64_t o = (int64_t)k * HW + (int64_t)yr * Wf + x;
+    __stcs(reinterpret_cast<float4 *>(outl + o), vl);  // streaming: written once, read by the next layer from HBM
+    __stcs(reinterpret_cast<float4 *>(outr + o), vr);
+  }
+}
+
+// any width (Wf % 4 != 0 breaks the 16-byte alignment of rows): one element per thread
 __global__ void __launch_bounds__(256)
 cost_volume_ncdhw_kernel(const float *__restrict__ L, const float *__restrict__ R, int B, int C, int Hf,
                          int Wf, int shift0, int D, float *__restrict__ cost)
@@ -279,6 +330,17 @@ extern "C" int idisp_cost_volume(const float *left, const float *right, int B, i
   IDISP_REQUIRE(-shift0 < Wf + 1 && shift0 + D - 1 < Wf + 1, "cost_volume: |shift| exceeds feature width %d", Wf);
   if (B == 0) return IDISP_OK;
   IDISP_REQUIRE(left && right && cost, "cost_volume: NULL pointer");
+  const bool aligned = Wf % 4 == 0 && (((uintptr_t)left | (uintptr_t)right | (uintptr_t)cost) & 15) == 0;
+  if (aligned && !getenv("IDISP_CV_SCALAR")) {
+    const int tiles_y = (Hf + CV_RY - 1) / CV_RY;
+    const size_t smem = (size_t)2 * CV_RY * Wf * 4 + 16;
+    if (smem <= 200 * 1024) {
+      IDISP_CUDA(cudaFuncSetAttribute(cost_volume_ncdhw_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cost_volume_ncdhw_tma_kernel<<<B * C * tiles_y, 256, smem, (cudaStream_t)stream>>>(left, right, C, Hf, Wf, shift0, D, cost);
+      IDISP_LAUNCH_CHECK();
+      return IDISP_OK;
+    }
+  }
   const int64_t total = (int64_t)B * 2 * C * D * Hf * Wf;
   const int64_t want = ceil_div64(total, 256);
   cost_volume_ncdhw_kernel<<<(int)(want < 148 * 32 ? want : 148 * 32), 256, 0, (cudaStream_t)stream>>>(

@@ -60,6 +60,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
   }
 }
 
+// ---------------- TMA, linear (cp.async.bulk): `bytes` (multiple of 16, 16 B aligned both sides) global -> shared ----------------
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+
 // ---------------- TMA (cp.async.bulk.tensor, tiled mode) ----------------
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *m)

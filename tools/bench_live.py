@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 from disprcnn_b200.modeling.psmnet.stackhourglass import PSMNet
 
 out = {}
-for prec in ('bf16', 'fp32'):
+for prec in ('fp16x2', 'fp16', 'bf16', 'fp32'):
     torch.manual_seed(0)
     m = PSMNet(48, -48, precision=prec)
     m.feature_extraction = nn.Identity()
