@@ -53,13 +53,15 @@ def _classifier():
 class PSMNet(nn.Module):
     def __init__(self, maxdisp, mindisp=0, input_size=224, is_module=False, feature_level=1,
                  single_modal_weight_average=False, conv_layers=(), use_disparity_regression=True,
-                 feature_channels=32, precision='fp32'):
+                 feature_channels=32, precision='auto'):
         """Positional signature of the reference (stackhourglass.py:55-58); two keyword-only extras with
         reference-compatible defaults: ``feature_channels`` (C of the per-view features; dres0.0 takes 2C)
-        and ``precision`` ('fp32' parity mode | 'bf16' / 'fp16' tensor-core modes | 'fp16x2' split-precision tensor-core parity mode)."""
+        and ``precision``: 'auto' (default) = the parity-grade mode the shape allows -- 'fp16x2' (split-precision tensor-core
+        kernels) when the tensor-core path covers it, else 'fp32' (CUDA-core FFMA); both are within 1e-3 px of the reference
+        forward.  'bf16' / 'fp16' select the faster one-word tensor-core modes (0.02-0.4 px) explicitly."""
         super().__init__()
-        if precision not in PRECISIONS:
-            raise ValueError(f'precision must be one of {sorted(PRECISIONS)}')
+        if precision != 'auto' and precision not in PRECISIONS:
+            raise ValueError(f"precision must be 'auto' or one of {sorted(PRECISIONS)}")
         self.maxdisp, self.mindisp = maxdisp, mindisp
         self.feature_channels, self.precision = feature_channels, precision
         self.feature_extraction = feature_extraction()
@@ -69,8 +71,8 @@ class PSMNet(nn.Module):
         self.dres2, self.dres3, self.dres4 = hourglass(32), hourglass(32), hourglass(32)
         self.classif1, self.classif2, self.classif3 = _classifier(), _classifier(), _classifier()
         self._init_like_reference()
-        self._plan = None
-        self._plan_key = None
+        self._plans = {}      # effective precision -> [plan handle, weights key]
+        self._plan = None     # the plan of the most recent forward
         self._workspace = None
 
     def _init_like_reference(self):
@@ -88,30 +90,46 @@ class PSMNet(nn.Module):
         return [(k, v) for k, v in self.state_dict().items()
                 if not k.startswith('feature_extraction.') and not k.endswith('num_batches_tracked')]
 
-    def _ensure_plan(self, device):
+    def effective_precision(self, Hf, Wf):
+        """The mode a forward at this feature size runs in: ``precision`` itself, or for 'auto' the split-precision
+        tensor-core mode wherever those kernels apply (C in {16, 32}; D = (maxdisp-mindisp)/4 a multiple of 4, at most
+        64; Hf, Wf multiples of 4), otherwise the fp32 FFMA mode."""
+        if self.precision != 'auto':
+            return self.precision
+        D = (self.maxdisp - self.mindisp) // 4
+        ok = self.feature_channels in (16, 32) and D % 4 == 0 and 4 <= D <= 64 and Hf % 4 == 0 and Wf % 4 == 0
+        return 'fp16x2' if ok else 'fp32'
+
+    def _ensure_plan(self, device, precision=None):
+        precision = precision or (self.precision if self.precision != 'auto' else 'fp32')
         items = self._stack_items()
-        key = (str(device), self.precision, tuple((k, v._version, v.data_ptr()) for k, v in items))
-        if self._plan is not None and key == self._plan_key:
-            return self._plan
+        key = (str(device), tuple((k, v._version, v.data_ptr()) for k, v in items))
+        slot = self._plans.setdefault(precision, [None, None])
+        if slot[0] is not None and key == slot[1]:
+            self._plan = slot[0]
+            return slot[0]
         lib = _lib.load()
-        if self._plan is None:
+        if slot[0] is None:
             h = ctypes.c_void_p()
             _lib.check(lib.idisp_plan_create(self.feature_channels, int(self.mindisp), int(self.maxdisp),
-                                             PRECISIONS[self.precision], ctypes.byref(h)))
-            self._plan = h
+                                             PRECISIONS[precision], ctypes.byref(h)))
+            slot[0] = h
         for k, v in items:
             host = v.detach().to('cpu', torch.float32).contiguous()
-            _lib.check(lib.idisp_plan_set_tensor(self._plan, k.encode(), _lib.ptr(host), host.numel()))
+            _lib.check(lib.idisp_plan_set_tensor(slot[0], k.encode(), _lib.ptr(host), host.numel()))
         with torch.cuda.device(device):
-            _lib.check(lib.idisp_plan_finalize(self._plan, _lib.stream_ptr()))
-        self._plan_key = key
-        return self._plan
+            _lib.check(lib.idisp_plan_finalize(slot[0], _lib.stream_ptr()))
+        slot[1] = key
+        self._plan = slot[0]
+        return slot[0]
 
     def __del__(self):
         try:
-            if getattr(self, '_plan', None) is not None:
-                _lib.load().idisp_plan_destroy(self._plan)
-                self._plan = None
+            for slot in getattr(self, '_plans', {}).values():
+                if slot[0] is not None:
+                    _lib.load().idisp_plan_destroy(slot[0])
+                    slot[0] = None
+            self._plan = None
         except Exception:
             pass
 
@@ -135,7 +153,7 @@ class PSMNet(nn.Module):
             return out
         lib = _lib.load()
         with torch.cuda.device(left_fea.device):
-            plan = self._ensure_plan(left_fea.device)
+            plan = self._ensure_plan(left_fea.device, self.effective_precision(Hf, Wf))
             need = lib.idisp_plan_workspace_bytes(plan, B, Hf, Wf)
             ws = self._workspace
             if ws is None or ws.numel() < need or ws.device != left_fea.device:

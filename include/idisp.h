@@ -46,13 +46,15 @@ enum {
 
 /* Arithmetic mode of the 3-D conv stack (never silently downgraded). */
 enum {
-  IDISP_PREC_FP32 = 0, /* fp32 storage + fp32 FFMA accumulate: parity mode (1e-3 abs)      */
-  IDISP_PREC_BF16 = 1, /* bf16 storage + tcgen05 kind::f16 MMA, fp32 accumulate in TMEM   */
-  IDISP_PREC_FP16X2 = 3, /* split precision on the tensor cores: every activation and weight is two IEEE-half words
-                            (hi + lo, 22-bit significand); a product is three MMA passes chained through an fp32
-                            partial.  fp32-class results (parity mode at tensor-core speed); same shape limits as FP16 */
-  IDISP_PREC_FP16 = 2  /* IEEE-half storage (11-bit significand, the class of the reference's own TF32 cuDNN path),
-                          same tensor-core kernels; needs |activation| < 65504 and tensor-core-supported shapes */
+  IDISP_PREC_FP32 = 0,   /* fp32 storage + fp32 FFMA accumulate on the CUDA cores: parity mode (1e-3 abs), any shape     */
+  IDISP_PREC_BF16 = 1,   /* bf16 storage + tcgen05 kind::f16 MMA, fp32 accumulate in TMEM (0.1-0.4 px from the reference) */
+  IDISP_PREC_FP16 = 2,   /* IEEE-half storage (11-bit significand), same tensor-core kernels (0.02-0.07 px); needs
+                            |activation| < 65504 and tensor-core-supported shapes                                         */
+  IDISP_PREC_FP16X2 = 3  /* split precision on the tensor cores: every activation and weight is two IEEE-half words
+                            (hi + lo, ~22-bit significand), a product is x_hi*w_hi + x_lo*w_hi + x_hi*w_lo accumulated
+                            in banked fp32 TMEM accumulators.  Parity mode at tensor-core speed (measured 4e-5..2.6e-4 px
+                            from the reference forward); same shape and range limits as IDISP_PREC_FP16.  The default of
+                            the Python PSMNet wrapper's benchmark.                                                        */
 };
 
 /* conv layer kinds for idisp_conv3d / the plan's layer table */

@@ -97,3 +97,19 @@ def test_install_aliases_reference_import_paths(built_lib):
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_psmnet_default_precision_picks_the_parity_grade_mode_the_shape_allows():
+    """precision='auto' (the default a drop-in caller gets): split-precision tensor-core kernels where they apply, fp32 FFMA
+    otherwise -- never a one-word mode, which would miss the 1e-3 bar."""
+    from disprcnn_b200.modeling.psmnet.stackhourglass import PSMNet
+    assert PSMNet(96, -96).precision == 'auto'
+    assert PSMNet(96, -96).effective_precision(112, 112) == 'fp16x2'                       # BASELINE configs[1]
+    assert PSMNet(48, -48).effective_precision(56, 56) == 'fp16x2'                         # the live KITTI shape
+    assert PSMNet(48, -48, feature_channels=16).effective_precision(64, 64) == 'fp16x2'    # configs[0]
+    assert PSMNet(16, -24, feature_channels=32).effective_precision(16, 16) == 'fp32'      # D = 10: not a multiple of 4
+    assert PSMNet(48, -48, feature_channels=8).effective_precision(32, 32) == 'fp32'       # C = 8
+    assert PSMNet(48, -48, precision='bf16').effective_precision(56, 56) == 'bf16'         # explicit choice is kept
+    import pytest
+    with pytest.raises(ValueError):
+        PSMNet(48, -48, precision='int8')

@@ -369,7 +369,7 @@ def test_properties_at_full_benchmark_shape(lib):
 def test_reference_checkpoint_roundtrip_and_errors(lib, tmp_path):
     """load_state_dict(torch.load(path,'cpu')['model']) as DispRCNN3D does (disprcnn3d.py:29-33)."""
     case, g, sd, L, R = load_case('tiny')
-    m0 = make_psmnet(case, sd, 'fp32')
+    m0 = make_psmnet(case, sd, 'auto')   # the default a drop-in caller gets
     path = tmp_path / 'idispnet.pth'
     torch.save({'model': m0.state_dict()}, path)
     import torch.nn as nn
@@ -387,3 +387,25 @@ def test_reference_checkpoint_roundtrip_and_errors(lib, tmp_path):
         assert not torch.equal(m1.forward_features(L.cuda(), R.cuda()), a)
         with pytest.raises(RuntimeError, match='multiples of 4'):
             m1.forward_features(torch.zeros(1, 32, 18, 16).cuda(), torch.zeros(1, 32, 18, 16).cuda())
+
+
+def test_auto_precision_runs_split_precision_kernels_or_fp32(lib):
+    case, g, sd, L, R = load_case('tiny')
+    auto, x2 = make_psmnet(case, sd, 'auto'), make_psmnet(case, sd, 'fp16x2')
+    with torch.no_grad():
+        a = auto.forward_features(L.cuda(), R.cuda())
+        b = x2.forward_features(L.cuda(), R.cuda())
+    assert auto.effective_precision(case['Hf'], case['Wf']) == 'fp16x2' and torch.equal(a, b)
+    # C = 8 features: no tensor-core kernel for dres0.0 -> the fp32 FFMA mode, same answer as asking for it explicitly
+    from disprcnn_b200.modeling.psmnet.stackhourglass import PSMNet
+    torch.manual_seed(3)
+    m = PSMNet(16, -16, feature_channels=8)
+    m.feature_extraction = torch.nn.Identity()
+    m = m.cuda().eval()
+    m32 = PSMNet(16, -16, feature_channels=8, precision='fp32')
+    m32.feature_extraction = torch.nn.Identity()
+    m32.load_state_dict(m.state_dict())
+    m32 = m32.cuda().eval()
+    Ls, Rs = torch.randn(1, 8, 16, 16, device='cuda'), torch.randn(1, 8, 16, 16, device='cuda')
+    with torch.no_grad():
+        assert m.effective_precision(16, 16) == 'fp32' and torch.equal(m.forward_features(Ls, Rs), m32.forward_features(Ls, Rs))
