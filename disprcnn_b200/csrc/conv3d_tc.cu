@@ -43,6 +43,9 @@
 
 namespace idisp {
 
+#ifndef IDISP_TRI
+#define IDISP_TRI 1  // per-step accumulator triples in the stride-1 split-precision kernels (see Cfg::TRI); 0: banked plane ring
+#endif
 #ifndef IDISP_NMAIN
 #define IDISP_NMAIN 3  // accumulator banks of the main term in the split-precision kernels (see Cfg)
 #endif
@@ -78,7 +81,13 @@ template <> struct ModeCfg<M_DEC> { static constexpr int SUB_W = TW + 1, SUB_H =
 template <int CIN, int MODE, int OCC, int NT, int XM = 0> struct Cfg {
   using MC = ModeCfg<MODE>;
   static constexpr int XP = XM == 3 ? 0 : XM;
-  static constexpr int NMAIN = (XM != 0 && MODE != M_DEC && NT <= 32 && OCC == 1) ? IDISP_NMAIN : 1;
+  // TRI (stride-1, 32-wide blocks, split precision): accumulators are not per output plane but per STEP.  Input plane z adds its
+  // three kd contributions into a fresh, aligned triple of column blocks [plane z-1 | z | z+1] (one N=96 MMA, never split by a
+  // ring wrap -- with four banks the 4-slot plane ring split half of them into N=64 + N=32, 88 instead of 56 port cycles); the
+  // epilogue drains the triple after every step and carries the two open planes' sums in registers (fp32 round-to-nearest).
+  // Each column then sees only 9*KS truncating adds, and the correction terms get a triple of their own.
+  static constexpr bool TRI = IDISP_TRI && XM != 0 && MODE == M_S1 && NT == 32 && OCC == 1;
+  static constexpr int NMAIN = (!TRI && XM != 0 && MODE != M_DEC && NT <= 32 && OCC == 1) ? IDISP_NMAIN : 1;
   static constexpr int NB = NMAIN + ((NMAIN > 1 && XP) ? 1 : 0);
   static constexpr int AW = XP ? 2 : 1;        // activation words per stage
   static constexpr int BW = XP == 1 ? 2 : 1;   // weight words resident in shared memory
@@ -97,9 +106,10 @@ template <int CIN, int MODE, int OCC, int NT, int XM = 0> struct Cfg {
   static constexpr int KSW = BW * KS;                              // weight k-steps per tap
   static constexpr int KSM = XP == 1 ? 3 * KS : (XP == 2 ? 2 * KS : KS);  // MMAs per tap
   static constexpr int WBYTES = 27 * KSW * NT * 32;               // 27 taps x Cin (x words) x NT couts x 16 bit
-  static constexpr int NSLOT = TCOLS / (ACC_COLS * NB);
+  static constexpr int NSLOT = TRI ? 2 : TCOLS / (ACC_COLS * NB);   // TRI: two step-triples (MMA fills one while the other drains)
+  static constexpr int TRI_SMALL = 2 * 3 * NT;                    // TRI: column offset of the correction terms' triples
   static constexpr int BANK_COLS = NSLOT * ACC_COLS;              // TMEM column distance between accumulator banks
-  static_assert(NSLOT >= 4, "the accumulator ring needs four slots");
+  static_assert(TRI || NSLOT >= 4, "the accumulator ring needs four slots");
   static constexpr int STAGES_FIT = (228 * 1024 / OCC - 1024 - WBYTES - 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int BAR_OFF = WBYTES + STAGES * STAGE_BYTES;
@@ -217,7 +227,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     ptx::prefetch_tensormap(&xmap);
     ptx::prefetch_tensormap(&rmap);
     for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-    for (int r = 0; r < NSLOT; ++r) { ptx::mbar_init(accf_bar(r), 1); ptx::mbar_init(acce_bar(r), 4); }
+    for (int r = 0; r < NSLOT; ++r) { ptx::mbar_init(accf_bar(r), 1); ptx::mbar_init(acce_bar(r), C::TRI ? 4 * C::EGROUPS : 4); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<C::TCOLS>(ptx::smem_u32(tmem_ptr_smem));
@@ -304,7 +314,40 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       const uint64_t a_desc0 = ptx::make_smem_desc(stage_addr0, C::PLANE_BYTES, C::ROW_BYTES);
       auto wait_acc_empty = [&](uint32_t g) { ptx::mbar_wait(acce_bar(g % NSLOT), ((g / NSLOT) & 1) ^ 1); };
       uint32_t q = 0, g0 = 0;
-      if (MODE == M_S1) {
+      if constexpr (C::TRI) {
+        // one stage and one accumulator triple per step; the waits of step q+1 are issued in the middle of step q's stream
+        auto waits = [&](int col_, uint32_t q_) {
+          if (col_ >= ncols) return;
+          ptx::mbar_wait(acce_bar(q_ % NSLOT), ((q_ / NSLOT) & 1) ^ 1);
+          ptx::mbar_wait(full_bar(q_ % C::STAGES), (q_ / C::STAGES) & 1);
+        };
+        int col = cta, z = 0;
+        waits(col, 0);
+        while (col < ncols) {
+          ptx::tc_fence_after();
+          const uint32_t s = q % C::STAGES, t = q % NSLOT;
+          const int plo = z > 0 ? z - 1 : 0, phi = z + 1 < Dout ? z + 1 : Dout - 1;  // output planes this input plane feeds
+          const int j0 = plo - (z - 1), nblk = phi - plo + 1;                           // first block / blocks of [kd=2|kd=1|kd=0]
+          const uint32_t dm = tmem_base + t * 3 * NT + j0 * NT, ds = dm + C::TRI_SMALL;
+          const uint32_t id1 = ptx::make_idesc_h<F16>(128, NT * nblk);
+          const uint64_t a0 = desc_add(a_desc0, s * C::STAGE_BYTES);
+          const uint64_t b1 = ptx::make_smem_desc(w_addr + j0 * NT * 16, 3 * NT * 16, 128);
+          int ncol = col, nz = z + 1;
+          if (nz == Din) { nz = 0; ncol += ncta; }
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            if (tap == 5) waits(ncol, q + 1);
+#pragma unroll
+            for (int ks = 0; ks < C::KSM; ++ks) {
+              const uint32_t aoff = ((tap / 3) * MC::SUB_W + (tap % 3)) * 16 + A_KOFF(ks);
+              mma((XP != 0 && ks >= C::KS) ? ds : dm, desc_add(a0, aoff), desc_add(b1, (tap * C::KSW + B_KS(ks)) * C::WCHUNK), id1);
+            }
+          }
+          commit(empty_bar(s));
+          commit(accf_bar(t));
+          col = ncol; z = nz; ++q;
+        }
+      } else if (MODE == M_S1) {
         // Software-pipelined: the mbarrier waits of step q+1 (TMA data landed, fresh accumulator slot drained) are
         // issued in the MIDDLE of step q's MMA stream, so their ~100-cycle round trips hide behind queued MMAs.
         auto waits = [&](int col_, int z_, uint32_t q_, uint32_t g0_) {
@@ -361,7 +404,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           col = ncol; z = nz; g0 = ng0; ++q;
         }
       }
-      for (int col = cta; MODE != M_S1 && col < ncols; col += ncta, g0 += Dout) {
+      for (int col = cta; MODE != M_S1 && !C::TRI && col < ncols; col += ncta, g0 += Dout) {
         for (int z = 0; z < Din; ++z) {
           if (MODE == M_S1) {
           } else if (MODE == M_S2) {
@@ -458,7 +501,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     uint32_t zero[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) zero[i] = 0u;
-    uint32_t g0 = 0;
+    uint32_t g0 = 0, tq = 0;  // tq: step counter of the TRI mode (one accumulator triple per input plane)
     for (int col = cta; col < ncols; col += ncta, g0 += Dout) {
       const int tw = col % p.tiles_w, th = (col / p.tiles_w) % p.tiles_h, n = col / (p.tiles_w * p.tiles_h);
       const int hr = th * TH + hl, wr = tw * TW + wl;
@@ -527,7 +570,86 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           if (p.y_split) *reinterpret_cast<uint4 *>(p.y_split + ospl + (int64_t)cblk_out * 8 * sub * 8) = lo;
         }
       };
-      for (int qo = egroup; qo < Dout; qo += C::EGROUPS) {
+      if constexpr (C::TRI) {
+        // Both epilogue groups drain EVERY step's triple; group `egroup` owns output channels [16*egroup, 16*egroup+16) of the
+        // CTA's 32.  P0 / P1: running sums of the two open planes (z and z+1 after step z).
+        float P0[16], P1[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { P0[i] = 0.f; P1[i] = 0.f; }
+        for (int z = 0; z < Dout; ++z, ++tq) {
+          const uint32_t t = tq % NSLOT;
+          const int qf = z - 1;  // the plane this step completes (also plane z itself at the last step)
+          XPre xq[2];
+          if (valid && qf >= 0) {
+            const int64_t pos = ((int64_t)qf * p.Ho + hr) * p.Wo + wr;
+            const int64_t sidx = ((int64_t)(qf >> 1) * (p.Ho / 2) + (hr >> 1)) * (p.Wo / 2) + (wr >> 1);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) xload(xq[i], egroup * 2 + i, pos, (qf & 1) * 4 + (hr & 1) * 2 + (wr & 1), sidx);
+          }
+          ptx::mbar_wait(accf_bar(t), (tq / NSLOT) & 1);
+          ptx::tc_fence_after();
+          const uint32_t tb = tmem_base + lane_addr + t * 3 * NT + egroup * 16;
+          uint32_t b0[16], b1[16], b2[16];
+          ptx::tmem_ld_32x16(tb, b0);
+          ptx::tmem_ld_32x16(tb + NT, b1);
+          ptx::tmem_ld_32x16(tb + 2 * NT, b2);
+          ptx::tmem_ld_wait();
+          if (XP != 0) {  // correction terms: their own triple, summed in fp32 (round to nearest)
+            uint32_t u0[16], u1[16], u2[16];
+            ptx::tmem_ld_32x16(tb + C::TRI_SMALL, u0);
+            ptx::tmem_ld_32x16(tb + C::TRI_SMALL + NT, u1);
+            ptx::tmem_ld_32x16(tb + C::TRI_SMALL + 2 * NT, u2);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              b0[i] = __float_as_uint(__uint_as_float(b0[i]) + __uint_as_float(u0[i]));
+              b1[i] = __float_as_uint(__uint_as_float(b1[i]) + __uint_as_float(u1[i]));
+              b2[i] = __float_as_uint(__uint_as_float(b2[i]) + __uint_as_float(u2[i]));
+            }
+          }
+          ptx::tmem_st_32x16(tb, zero); ptx::tmem_st_32x16(tb + NT, zero); ptx::tmem_st_32x16(tb + 2 * NT, zero);
+          if (XP != 0) {
+            ptx::tmem_st_32x16(tb + C::TRI_SMALL, zero); ptx::tmem_st_32x16(tb + C::TRI_SMALL + NT, zero);
+            ptx::tmem_st_32x16(tb + C::TRI_SMALL + 2 * NT, zero);
+          }
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(acce_bar(t));
+          // plane z-1 = P0 + block 0 (complete);  plane z: P1 + block 1;  plane z+1: block 2 (first contribution)
+          if (valid && qf >= 0) {
+            const int64_t pos = ((int64_t)qf * p.Ho + hr) * p.Wo + wr;
+            const int64_t sidx = ((int64_t)(qf >> 1) * (p.Ho / 2) + (hr >> 1)) * (p.Wo / 2) + (wr >> 1);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              F8 a8;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) a8.v[c] = P0[i * 8 + c] + __uint_as_float(b0[i * 8 + c]);
+              finish(a8, egroup * 2 + i, pos, (qf & 1) * 4 + (hr & 1) * 2 + (wr & 1), sidx, xq[0].rh, xq[i]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { P0[i] = P1[i] + __uint_as_float(b1[i]); P1[i] = __uint_as_float(b2[i]); }
+          if (z == Dout - 1) {  // no step z+1: plane z is complete as well
+            if (valid) {
+              const int64_t pos = ((int64_t)z * p.Ho + hr) * p.Wo + wr;
+              const int64_t sidx = ((int64_t)(z >> 1) * (p.Ho / 2) + (hr >> 1)) * (p.Wo / 2) + (wr >> 1);
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                XPre one;
+                xload(one, egroup * 2 + i, pos, (z & 1) * 4 + (hr & 1) * 2 + (wr & 1), sidx);
+                F8 a8;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) a8.v[c] = P0[i * 8 + c];
+                finish(a8, egroup * 2 + i, pos, (z & 1) * 4 + (hr & 1) * 2 + (wr & 1), sidx, one.rh, one);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { P0[i] = 0.f; P1[i] = 0.f; }
+          }
+        }
+      }
+      for (int qo = egroup; !C::TRI && qo < Dout; qo += C::EGROUPS) {
         const uint32_t g = g0 + qo, r = g % NSLOT;
         // residual operands do not depend on the accumulator: request them BEFORE waiting for it (single-precision-word
         // modes only; the split-precision passes load at use)
