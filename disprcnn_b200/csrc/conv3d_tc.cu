@@ -86,7 +86,7 @@ template <int CIN, int MODE, int OCC, int NT, int XM = 0> struct Cfg {
   // ring wrap -- with four banks the 4-slot plane ring split half of them into N=64 + N=32, 88 instead of 56 port cycles); the
   // epilogue drains the triple after every step and carries the two open planes' sums in registers (fp32 round-to-nearest).
   // Each column then sees only 9*KS truncating adds, and the correction terms get a triple of their own.
-  static constexpr bool TRI = IDISP_TRI && XM != 0 && MODE == M_S1 && NT == 32 && OCC == 1;
+  static constexpr bool TRI = IDISP_TRI && XM != 0 && MODE == M_S1 && (NT == 32 || NT == 16) && OCC == 1;
   static constexpr int NMAIN = (!TRI && XM != 0 && MODE != M_DEC && NT <= 32 && OCC == 1) ? IDISP_NMAIN : 1;
   static constexpr int NB = NMAIN + ((NMAIN > 1 && XP) ? 1 : 0);
   static constexpr int AW = XP ? 2 : 1;        // activation words per stage
@@ -572,7 +572,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       };
       if constexpr (C::TRI) {
         // Both epilogue groups drain EVERY step's triple; group `egroup` owns output channels [16*egroup, 16*egroup+16) of the
-        // CTA's 32.  P0 / P1: running sums of the two open planes (z and z+1 after step z).
+        // CTA's 32 (16-wide blocks, i.e. the 1-channel head: group 0 owns all of them, group 1 only keeps the barrier count).
+        // P0 / P1: running sums of the two open planes (z and z+1 after step z).
+        const bool owner = NT == 32 || egroup == 0;
+        const int cbase = NT == 32 ? egroup * 16 : 0;   // first accumulator column (of a block) this group drains
         float P0[16], P1[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) { P0[i] = 0.f; P1[i] = 0.f; }
@@ -580,7 +583,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           const uint32_t t = tq % NSLOT;
           const int qf = z - 1;  // the plane this step completes (also plane z itself at the last step)
           XPre xq[2];
-          if (valid && qf >= 0) {
+          if (valid && qf >= 0 && !p.y1) {
             const int64_t pos = ((int64_t)qf * p.Ho + hr) * p.Wo + wr;
             const int64_t sidx = ((int64_t)(qf >> 1) * (p.Ho / 2) + (hr >> 1)) * (p.Wo / 2) + (wr >> 1);
 #pragma unroll
@@ -588,62 +591,68 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           }
           ptx::mbar_wait(accf_bar(t), (tq / NSLOT) & 1);
           ptx::tc_fence_after();
-          const uint32_t tb = tmem_base + lane_addr + t * 3 * NT + egroup * 16;
           uint32_t b0[16], b1[16], b2[16];
-          ptx::tmem_ld_32x16(tb, b0);
-          ptx::tmem_ld_32x16(tb + NT, b1);
-          ptx::tmem_ld_32x16(tb + 2 * NT, b2);
-          ptx::tmem_ld_wait();
-          if (XP != 0) {  // correction terms: their own triple, summed in fp32 (round to nearest)
-            uint32_t u0[16], u1[16], u2[16];
-            ptx::tmem_ld_32x16(tb + C::TRI_SMALL, u0);
-            ptx::tmem_ld_32x16(tb + C::TRI_SMALL + NT, u1);
-            ptx::tmem_ld_32x16(tb + C::TRI_SMALL + 2 * NT, u2);
+          if (owner) {
+            const uint32_t tb = tmem_base + lane_addr + t * 3 * NT + cbase;
+            ptx::tmem_ld_32x16(tb, b0);
+            ptx::tmem_ld_32x16(tb + NT, b1);
+            ptx::tmem_ld_32x16(tb + 2 * NT, b2);
             ptx::tmem_ld_wait();
+            if (XP != 0) {  // correction terms: their own triple, summed in fp32 (round to nearest)
+              uint32_t u0[16], u1[16], u2[16];
+              ptx::tmem_ld_32x16(tb + C::TRI_SMALL, u0);
+              ptx::tmem_ld_32x16(tb + C::TRI_SMALL + NT, u1);
+              ptx::tmem_ld_32x16(tb + C::TRI_SMALL + 2 * NT, u2);
+              ptx::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              b0[i] = __float_as_uint(__uint_as_float(b0[i]) + __uint_as_float(u0[i]));
-              b1[i] = __float_as_uint(__uint_as_float(b1[i]) + __uint_as_float(u1[i]));
-              b2[i] = __float_as_uint(__uint_as_float(b2[i]) + __uint_as_float(u2[i]));
+              for (int i = 0; i < 16; ++i) {
+                b0[i] = __float_as_uint(__uint_as_float(b0[i]) + __uint_as_float(u0[i]));
+                b1[i] = __float_as_uint(__uint_as_float(b1[i]) + __uint_as_float(u1[i]));
+                b2[i] = __float_as_uint(__uint_as_float(b2[i]) + __uint_as_float(u2[i]));
+              }
             }
+            ptx::tmem_st_32x16(tb, zero); ptx::tmem_st_32x16(tb + NT, zero); ptx::tmem_st_32x16(tb + 2 * NT, zero);
+            if (XP != 0) {
+              ptx::tmem_st_32x16(tb + C::TRI_SMALL, zero); ptx::tmem_st_32x16(tb + C::TRI_SMALL + NT, zero);
+              ptx::tmem_st_32x16(tb + C::TRI_SMALL + 2 * NT, zero);
+            }
+            ptx::tmem_st_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { b0[i] = 0u; b1[i] = 0u; b2[i] = 0u; }
           }
-          ptx::tmem_st_32x16(tb, zero); ptx::tmem_st_32x16(tb + NT, zero); ptx::tmem_st_32x16(tb + 2 * NT, zero);
-          if (XP != 0) {
-            ptx::tmem_st_32x16(tb + C::TRI_SMALL, zero); ptx::tmem_st_32x16(tb + C::TRI_SMALL + NT, zero);
-            ptx::tmem_st_32x16(tb + C::TRI_SMALL + 2 * NT, zero);
-          }
-          ptx::tmem_st_wait();
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(acce_bar(t));
           // plane z-1 = P0 + block 0 (complete);  plane z: P1 + block 1;  plane z+1: block 2 (first contribution)
-          if (valid && qf >= 0) {
-            const int64_t pos = ((int64_t)qf * p.Ho + hr) * p.Wo + wr;
-            const int64_t sidx = ((int64_t)(qf >> 1) * (p.Ho / 2) + (hr >> 1)) * (p.Wo / 2) + (wr >> 1);
+          auto emit = [&](int q_, const float *sum, const uint32_t *blk, const XPre *pre2) {
+            const int64_t pos = ((int64_t)q_ * p.Ho + hr) * p.Wo + wr;
+            if (p.y1) {  // 32->1 classifier head: channel 0 (+ column 1 = the w_lo products), f32, running sum fused
+              if (owner) {
+                const int64_t o1 = (int64_t)n * Vo + pos;
+                float v1 = sum[0] + (blk ? __uint_as_float(blk[0]) : 0.f);
+                if (p.y1_cols == 2) v1 += sum[1] + (blk ? __uint_as_float(blk[1]) : 0.f);
+                p.y1[o1] = v1 + (p.res1 ? p.res1[o1] : 0.f);
+              }
+              return;
+            }
+            const int64_t sidx = ((int64_t)(q_ >> 1) * (p.Ho / 2) + (hr >> 1)) * (p.Wo / 2) + (wr >> 1);
+            const int cls = (q_ & 1) * 4 + (hr & 1) * 2 + (wr & 1);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
+              XPre one;
+              if (!pre2) xload(one, egroup * 2 + i, pos, cls, sidx);
               F8 a8;
 #pragma unroll
-              for (int c = 0; c < 8; ++c) a8.v[c] = P0[i * 8 + c] + __uint_as_float(b0[i * 8 + c]);
-              finish(a8, egroup * 2 + i, pos, (qf & 1) * 4 + (hr & 1) * 2 + (wr & 1), sidx, xq[0].rh, xq[i]);
+              for (int c = 0; c < 8; ++c) a8.v[c] = sum[i * 8 + c] + (blk ? __uint_as_float(blk[i * 8 + c]) : 0.f);
+              finish(a8, egroup * 2 + i, pos, cls, sidx, one.rh, pre2 ? pre2[i] : one);
             }
-          }
+          };
+          if (valid && qf >= 0) emit(qf, P0, b0, xq);
 #pragma unroll
           for (int i = 0; i < 16; ++i) { P0[i] = P1[i] + __uint_as_float(b1[i]); P1[i] = __uint_as_float(b2[i]); }
           if (z == Dout - 1) {  // no step z+1: plane z is complete as well
-            if (valid) {
-              const int64_t pos = ((int64_t)z * p.Ho + hr) * p.Wo + wr;
-              const int64_t sidx = ((int64_t)(z >> 1) * (p.Ho / 2) + (hr >> 1)) * (p.Wo / 2) + (wr >> 1);
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                XPre one;
-                xload(one, egroup * 2 + i, pos, (z & 1) * 4 + (hr & 1) * 2 + (wr & 1), sidx);
-                F8 a8;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) a8.v[c] = P0[i * 8 + c];
-                finish(a8, egroup * 2 + i, pos, (z & 1) * 4 + (hr & 1) * 2 + (wr & 1), sidx, one.rh, one);
-              }
-            }
+            if (valid) emit(z, P0, nullptr, nullptr);
 #pragma unroll
             for (int i = 0; i < 16; ++i) { P0[i] = 0.f; P1[i] = 0.f; }
           }
