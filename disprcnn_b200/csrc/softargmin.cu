@@ -65,11 +65,14 @@ softargmin_kernel(const float *__restrict__ logits, int B, int D, int Hf, int Wf
   }
 }
 
-// Specialisation for the reference's geometry Dfull = 4*D (D = 24 or 48): the D plane samples live in registers (all
-// loads issued up front), and the depth interpolation indices/weights d0(d), l1(d) are compile-time constants of the
-// fully unrolled 4D loop -- per upsampled disparity 2 FMAs for the blend, 1 FFMA + 1 MUFU for exp, 2 for the sums.
+// Specialisation for the reference's geometry Dfull = 4*D (D = 24 or 48).  The depth interpolation indices/weights d0(d), l1(d) are
+// compile-time constants of the fully unrolled 4D loop.  Two passes over the D plane samples (each a bilinear blend of 4 L1/L2-
+// resident logits): pass 1 takes their maximum (the softmax stabiliser -- an upper bound of every interpolated value), pass 2
+// streams the 4D output disparities through a rolling window of TWO samples.  Keeping all D samples in registers instead (the
+// first version) cost 168 registers = 3 warps per scheduler, and the kernel ran at a third of its issue rate; re-sampling is
+// 48 x 11 instructions per pixel against 192 x 6 for the exponentials.
 template <int D>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 softargmin_x4_kernel(const float *__restrict__ logits, int B, int Hf, int Wf, int mindisp, int H, int W, float *__restrict__ out)
 {
   constexpr int Dfull = 4 * D;
@@ -89,26 +92,27 @@ softargmin_x4_kernel(const float *__restrict__ logits, int B, int Hf, int Wf, in
     const int plane = Hf * Wf;
     const float *p00 = logits + (int64_t)b * D * plane + y0 * Wf + x0;
     const int d01 = x1 - x0, d10 = (y1 - y0) * Wf;
-    float P[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
+    auto sample = [&](int k) {
       const float *q = p00 + k * plane;
-      P[k] = ly0 * (lx0 * __ldg(q) + lx1 * __ldg(q + d01)) + ly1 * (lx0 * __ldg(q + d10) + lx1 * __ldg(q + d10 + d01));
-    }
-    float m = P[0];
+      return ly0 * (lx0 * __ldg(q) + lx1 * __ldg(q + d01)) + ly1 * (lx0 * __ldg(q + d10) + lx1 * __ldg(q + d10 + d01));
+    };
+    float m = sample(0);
 #pragma unroll
-    for (int k = 1; k < D; ++k) m = fmaxf(m, P[k]);
+    for (int k = 1; k < D; ++k) m = fmaxf(m, sample(k));
     const float mneg = -m * 1.4426950408889634f;
-    // four independent (sum, weighted-sum) chains: with one chain the 4-cycle add latency of 2 x 192 dependent
-    // accumulations, not the 192 MUFU.EX2, set the pace at the 3 warps per scheduler the 48 live samples allow
+    // four independent (sum, weighted-sum) chains: with one chain the add latency of 2 x 192 dependent accumulations sets the pace
     float s4[4] = {0.f, 0.f, 0.f, 0.f}, t4[4] = {0.f, 0.f, 0.f, 0.f};
+    float Pk = sample(0), Pk1 = sample(D > 1 ? 1 : 0);
 #pragma unroll
     for (int d = 0; d < Dfull; ++d) {
       const float fd = sd * (float)d;      // compile-time per unrolled iteration
       const int d0 = (int)fd;
-      const int d1 = d0 + (d0 < D - 1 ? 1 : 0);
+      if (d > 0 && d0 != (int)(sd * (float)(d - 1))) {  // (compile-time) the window advances by one plane
+        Pk = Pk1;
+        Pk1 = sample(d0 + (d0 < D - 1 ? 1 : 0));
+      }
       const float l1 = fd - (float)d0, l0 = 1.f - l1;
-      const float v = l0 * P[d0] + l1 * P[d1];
+      const float v = l0 * Pk + l1 * Pk1;
       float e;  // one MUFU.EX2 (arguments are <= 0; flushing the far tail to zero is what softmax does to it anyway)
       asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v, 1.4426950408889634f, mneg)));
       s4[d & 3] += e;
@@ -125,10 +129,10 @@ int launch_softargmin(const float *logits, int B, int D, int Hf, int Wf, int min
   const int64_t total = (int64_t)B * H * W;
   if (total == 0) return IDISP_OK;
   if (maxdisp - mindisp == 4 * D && (D == 24 || D == 48) && !getenv("IDISP_SOFTARGMIN_GENERIC")) {
-    const int64_t want128 = ceil_div64(total, 128);
-    const int grid = (int)(want128 < 148 * 128 ? want128 : 148 * 128);
-    if (D == 24) softargmin_x4_kernel<24><<<grid, 128, 0, s>>>(logits, B, Hf, Wf, mindisp, H, W, out);
-    else softargmin_x4_kernel<48><<<grid, 128, 0, s>>>(logits, B, Hf, Wf, mindisp, H, W, out);
+    const int64_t want256 = ceil_div64(total, 256);
+    const int grid = (int)(want256 < 148 * 64 ? want256 : 148 * 64);
+    if (D == 24) softargmin_x4_kernel<24><<<grid, 256, 0, s>>>(logits, B, Hf, Wf, mindisp, H, W, out);
+    else softargmin_x4_kernel<48><<<grid, 256, 0, s>>>(logits, B, Hf, Wf, mindisp, H, W, out);
     IDISP_LAUNCH_CHECK();
     return IDISP_OK;
   }
