@@ -60,7 +60,9 @@ template <> struct ModeCfg<M_S1> { static constexpr int SUB_W = TW + 2, SUB_H = 
 // (SUB_H is 18 rather than the 17 rows these modes read so that Cin/8 * SUB_W*SUB_H*16 B stays a multiple of 128 B,
 //  the alignment TMA needs for the second sub-tile of a stage)
 template <> struct ModeCfg<M_S2> { static constexpr int SUB_W = TW + 1, SUB_H = TH + 2, SUBS = 2, ACC_BLOCKS = 1; };
-template <> struct ModeCfg<M_DEC> { static constexpr int SUB_W = TW + 1, SUB_H = TH + 2, SUBS = 1, ACC_BLOCKS = 4; };
+// (transposed conv: Cin = 64 only, so the 17 rows it reads already make 128 B-multiple sub-tiles; the smaller stage buys the
+//  two-word split-precision form a third pipeline stage next to its 110 KB of weights)
+template <> struct ModeCfg<M_DEC> { static constexpr int SUB_W = TW + 1, SUB_H = TH + 1, SUBS = 1, ACC_BLOCKS = 4; };
 
 // OCC = CTAs per SM.  OCC 2 (stride-1, Cin 32 only: two 55 KB weight copies fit) gives the tensor pipe a second,
 // independent MMA stream that fills the bubbles one issuing warp leaves at plane boundaries (barrier round trips,
