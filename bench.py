@@ -122,7 +122,7 @@ def cpu_port_rois_per_s(model_sd, n_steps, n_warm, budget_s=150.0):
     run(28)               # first call pays oneDNN primitive creation
     t_probe = run(28)     # a quarter ROI; larger slices parallelise better on many cores, so scaling up is conservative
     # "all the host threads it can use": oneDNN's 3-D convs do not always get faster with every hardware thread of a big box
-    # (measured: 128 threads ran several times slower than 32 on the GPU box) -- keep the thread count that is fastest
+    # (with all 128 threads the GPU box measured 0.06-0.09 ROIs/s, an 8-core container 0.7-0.8) -- keep the fastest thread count
     best = cores
     for cand in sorted({max(1, cores // 2), 64, 32, 16}):
         if cand >= cores:
