@@ -12,6 +12,7 @@ below only owns the parameters.  No CPU path, no cuDNN on the 3-D stack.  Traini
 of scope for this path and raises.
 """
 import ctypes
+import warnings
 import math
 
 import torch
@@ -71,6 +72,7 @@ class PSMNet(nn.Module):
         self.dres2, self.dres3, self.dres4 = hourglass(32), hourglass(32), hourglass(32)
         self.classif1, self.classif2, self.classif3 = _classifier(), _classifier(), _classifier()
         self._init_like_reference()
+        self.check_range = True   # 'auto' only: verify the split-precision result is finite (one device reduction + sync per call)
         self._plans = {}      # effective precision -> [plan handle, weights key]
         self._plan = None     # the plan of the most recent forward
         self._workspace = None
@@ -152,8 +154,9 @@ class PSMNet(nn.Module):
         if B == 0:
             return out
         lib = _lib.load()
-        with torch.cuda.device(left_fea.device):
-            plan = self._ensure_plan(left_fea.device, self.effective_precision(Hf, Wf))
+
+        def run(precision):
+            plan = self._ensure_plan(left_fea.device, precision)
             need = lib.idisp_plan_workspace_bytes(plan, B, Hf, Wf)
             ws = self._workspace
             if ws is None or ws.numel() < need or ws.device != left_fea.device:
@@ -161,6 +164,15 @@ class PSMNet(nn.Module):
                 ws = self._workspace = torch.empty(need, dtype=torch.uint8, device=left_fea.device)
             _lib.check(lib.idisp_plan_forward(plan, _lib.ptr(left_fea), _lib.ptr(right_fea), B, Hf, Wf, H, W,
                                               _lib.ptr(ws), ws.numel(), _lib.ptr(out), _lib.stream_ptr()))
+
+        with torch.cuda.device(left_fea.device):
+            precision = self.effective_precision(Hf, Wf)
+            run(precision)
+            if self.precision == 'auto' and precision == 'fp16x2' and self.check_range and not bool(torch.isfinite(out).all()):
+                # the hi words are IEEE halves: an activation beyond 65504 overflows them.  Not seen with BatchNorm-ed iDispNet
+                # weights, but 'auto' promises a parity-grade answer, so such a batch is redone by the fp32 FFMA kernels.
+                warnings.warn('PSMNet: activations left the fp16 range of the split-precision mode; batch recomputed in fp32')
+                run('fp32')
         return out
 
     def last_logits(self, B, Hf, Wf):

@@ -409,3 +409,16 @@ def test_auto_precision_runs_split_precision_kernels_or_fp32(lib):
     Ls, Rs = torch.randn(1, 8, 16, 16, device='cuda'), torch.randn(1, 8, 16, 16, device='cuda')
     with torch.no_grad():
         assert m.effective_precision(16, 16) == 'fp32' and torch.equal(m.forward_features(Ls, Rs), m32.forward_features(Ls, Rs))
+
+
+def test_auto_precision_recomputes_in_fp32_when_the_fp16_range_is_left(lib):
+    """The split-precision words are IEEE halves: features scaled far beyond what BatchNorm-ed weights produce overflow them.
+    'auto' then redoes the batch with the fp32 FFMA kernels (and says so) instead of returning non-finite disparities."""
+    case, g, sd, L, R = load_case('tiny')
+    auto, f32, x2 = make_psmnet(case, sd, 'auto'), make_psmnet(case, sd, 'fp32'), make_psmnet(case, sd, 'fp16x2')
+    Lb, Rb = (L * 3e5).cuda(), (R * 3e5).cuda()
+    with torch.no_grad():
+        assert not torch.isfinite(x2.forward_features(Lb, Rb)).all()      # the explicit mode reports what the hardware did
+        with pytest.warns(UserWarning, match='fp16 range'):
+            a = auto.forward_features(Lb, Rb)
+        assert torch.isfinite(a).all() and torch.equal(a, f32.forward_features(Lb, Rb))
