@@ -123,3 +123,42 @@ extern "C" int idisp_roi_align_backward(const float *, const float *, int, float
   idisp::set_error("roi_align_backward: not implemented on the B200 inference path");
   return IDISP_ERR_UNSUPPORTED;
 }
+
+// ---------------------------------------------------------------------------------------
+// Stereo ROI preparation on the device (disprcnn3d.py:126-146 + utils/stereo_utils.py:219-229): the reference walks the
+// boxes in Python (.tolist() = one device->host sync per image) to build the aligned left/right crop rectangles.  Same
+// integer arithmetic here, one thread per ROI, no host round trip: floor/ceil to integers, clamp to the image, common width
+// max_width = min(max(x2-x1, x2p-x1p), W-x1, W-x1p); left ROI (i, x1, y1, x1+mw, y2), right ROI (i, x1p, y1, x1p+mw, y2).
+// ---------------------------------------------------------------------------------------
+namespace idisp {
+__global__ void stereo_rois_kernel(const float *__restrict__ lb, const float *__restrict__ rb, const int *__restrict__ img, int R,
+                                   int width, int height, float *__restrict__ rois_l, float *__restrict__ rois_r,
+                                   long long *__restrict__ xs)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  int x1 = (int)floorf(lb[r * 4 + 0]), y1 = (int)floorf(lb[r * 4 + 1]), x2 = (int)ceilf(lb[r * 4 + 2]), y2 = (int)ceilf(lb[r * 4 + 3]);
+  int x1p = (int)floorf(rb[r * 4 + 0]), x2p = (int)ceilf(rb[r * 4 + 2]);
+  x1 = max(0, x1); x1p = max(0, x1p); y1 = max(0, y1);
+  y2 = min(y2, height - 1); x2 = min(x2, width - 1); x2p = min(x2p, width - 1);
+  int mw = max(x2 - x1, x2p - x1p);
+  mw = min(mw, min(width - x1, width - x1p));
+  const float fi = (float)img[r];
+  rois_l[r * 5 + 0] = fi; rois_l[r * 5 + 1] = (float)x1;  rois_l[r * 5 + 2] = (float)y1; rois_l[r * 5 + 3] = (float)(x1 + mw);  rois_l[r * 5 + 4] = (float)y2;
+  rois_r[r * 5 + 0] = fi; rois_r[r * 5 + 1] = (float)x1p; rois_r[r * 5 + 2] = (float)y1; rois_r[r * 5 + 3] = (float)(x1p + mw); rois_r[r * 5 + 4] = (float)y2;
+  if (xs) { xs[r] = x1; xs[R + r] = x1p; xs[2 * R + r] = x1 + mw; xs[3 * R + r] = x1p + mw; }
+}
+}  // namespace idisp
+
+extern "C" int idisp_stereo_rois(const float *left_boxes, const float *right_boxes, const int *image_index, int R, int width,
+                                 int height, float *rois_left, float *rois_right, long long *x1_x1p_x2_x2p, void *stream)
+{
+  using namespace idisp;
+  IDISP_REQUIRE(R >= 0 && width > 0 && height > 0, "stereo_rois: bad arguments R=%d width=%d height=%d", R, width, height);
+  if (R == 0) return IDISP_OK;
+  IDISP_REQUIRE(left_boxes && right_boxes && image_index && rois_left && rois_right, "stereo_rois: NULL pointer");
+  stereo_rois_kernel<<<ceil_div(R, 128), 128, 0, (cudaStream_t)stream>>>(left_boxes, right_boxes, image_index, R, width, height, rois_left,
+                                                                         rois_right, x1_x1p_x2_x2p);
+  IDISP_LAUNCH_CHECK();
+  return IDISP_OK;
+}

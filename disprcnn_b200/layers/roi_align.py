@@ -91,3 +91,36 @@ def crop_and_transform_roi_img(im, rois, resolution=224):
     mean = torch.tensor(IMAGENET_MEAN, dtype=torch.float32, device=im.device)
     std = torch.tensor(IMAGENET_STD, dtype=torch.float32, device=im.device)
     return roi_align_forward(im, rois, 1.0, resolution, resolution, 0, mean, std)
+
+
+def prepare_stereo_rois(left_boxes, right_boxes, image_index, width, height):
+    """Device-side form of the box alignment loop in ``DispRCNN3D.prepare_psmnet_input_and_target`` (disprcnn3d.py:126-146):
+    ``left_boxes`` / ``right_boxes`` [R,4] CUDA f32 (the concatenated ``BoxList.bbox`` of a batch), ``image_index`` [R] (which
+    image each box belongs to).  Returns ``(rois_left, rois_right, x1s, x1ps, x2s, x2ps)``: the [R,5] crop rectangles for
+    ``crop_and_transform_roi_img`` and the four int64 column tensors the reference keeps -- with no ``.tolist()`` host sync."""
+    _lib.require_cuda(left_boxes, right_boxes, image_index)
+    lb = left_boxes.reshape(-1, 4).contiguous().float()
+    rb = right_boxes.reshape(-1, 4).contiguous().float()
+    if lb.shape != rb.shape:
+        raise RuntimeError(f'prepare_stereo_rois: {tuple(lb.shape)} left boxes vs {tuple(rb.shape)} right boxes')
+    idx = image_index.reshape(-1).to(torch.int32).contiguous()
+    R = lb.size(0)
+    if idx.numel() != R:
+        raise RuntimeError('prepare_stereo_rois: one image index per box expected')
+    rl = torch.empty((R, 5), dtype=torch.float32, device=lb.device)
+    rr = torch.empty((R, 5), dtype=torch.float32, device=lb.device)
+    xs = torch.empty((4, R), dtype=torch.int64, device=lb.device)
+    with torch.cuda.device(lb.device):
+        _lib.check(_lib.load().idisp_stereo_rois(_lib.ptr(lb), _lib.ptr(rb), _lib.ptr(idx), R, int(width), int(height),
+                                                 _lib.ptr(rl), _lib.ptr(rr), _lib.ptr(xs), _lib.stream_ptr()))
+    return rl, rr, xs[0], xs[1], xs[2], xs[3]
+
+
+def crop_stereo_rois(left_images, right_images, left_boxes, right_boxes, image_index, resolution=224):
+    """Eval branch of ``prepare_psmnet_input_and_target`` (disprcnn3d.py:113-159) without the host loop: aligned boxes on the
+    device, then the fused ROIAlign + ImageNet normalisation of both views.  Returns
+    ``(left_roi_images, right_roi_images, x1s, x1ps, x2s, x2ps)``."""
+    H, W = left_images.shape[-2:]
+    rl, rr, x1s, x1ps, x2s, x2ps = prepare_stereo_rois(left_boxes, right_boxes, image_index, W, H)
+    return (crop_and_transform_roi_img(left_images, rl, resolution), crop_and_transform_roi_img(right_images, rr, resolution),
+            x1s, x1ps, x2s, x2ps)

@@ -70,6 +70,15 @@ int idisp_version(void);
 /* Thread-local description of the last failing call ("" if none). Never NULL. */
 const char *idisp_last_error(void);
 
+/* Stereo ROI preparation (replaces the Python loop of DispRCNN3D.prepare_psmnet_input_and_target,
+ * disprcnn/modeling/detector/disprcnn3d.py:126-146, and expand_box_to_integer, utils/stereo_utils.py:219-229, which pulls
+ * every box to the host with .tolist()).  left_boxes / right_boxes [R,4] f32 (x1,y1,x2,y2), image_index [R] int32 -- device
+ * pointers.  Writes the aligned crop rectangles rois_left / rois_right [R,5] f32 (batch_idx,x1,y1,x2,y2: same top/bottom,
+ * same width) ready for idisp_roi_align_forward, and -- if non-NULL -- x1_x1p_x2_x2p [4][R] int64 (the x1s, x1ps, x2s, x2ps the
+ * caller keeps for the disparity -> depth conversion, disprcnn3d.py:150-153).  Integer arithmetic, bit-exact. */
+int idisp_stereo_rois(const float *left_boxes, const float *right_boxes, const int *image_index, int R, int width, int height,
+                      float *rois_left, float *rois_right, long long *x1_x1p_x2_x2p, void *stream);
+
 /* ROIAlign forward.  input [N,C,H,W] f32 NCHW contiguous, rois [R,5] f32
  * (batch_idx,x1,y1,x2,y2), out [R,C,pooled_h,pooled_w] f32 -- all device pointers.
  * mean/inv_std: optional device pointers to C floats; when non-NULL the kernel writes

@@ -45,6 +45,9 @@ def test_argument_validation_without_gpu(built_lib):
     assert lib.idisp_roi_align_forward(None, 1, 3, 8, 8, None, 2, 1.0, 0, 7, 0, None, None, None, None) == 1
     assert lib.idisp_roi_align_forward(None, 1, 3, 8, 8, None, 0, 1.0, 7, 7, 0, None, None, None, None) == 0  # R=0 no-op
     assert lib.idisp_roi_align_backward(None, None, 0, 1.0, 7, 7, 1, 3, 8, 8, 0, None, None) == 3
+    assert lib.idisp_stereo_rois(None, None, None, 0, 1242, 375, None, None, None, None) == 0           # R=0 no-op
+    assert lib.idisp_stereo_rois(None, None, None, 2, 1242, 375, None, None, None, None) == 1 and 'NULL' in _lib.last_error()
+    assert lib.idisp_stereo_rois(None, None, None, 2, 0, 375, None, None, None, None) == 1
     assert lib.idisp_softargmin(None, 1, 8, 4, 4, 0, 4, 16, 16, None, None) == 1  # Dfull < D
     assert lib.idisp_conv3d(None, 1, 12, 4, 4, 4, None, 32, 0, None, None, None, 0, 0, None, None) == 1  # Cin % 8
 

@@ -422,3 +422,37 @@ def test_auto_precision_recomputes_in_fp32_when_the_fp16_range_is_left(lib):
         with pytest.warns(UserWarning, match='fp16 range'):
             a = auto.forward_features(Lb, Rb)
         assert torch.isfinite(a).all() and torch.equal(a, f32.forward_features(Lb, Rb))
+
+
+def test_stereo_roi_preparation_on_device_matches_the_reference_loop(lib):
+    """disprcnn3d.py:126-146 on the device (idisp_stereo_rois) against the oracle's restatement of the Python loop, then the
+    whole eval branch (aligned boxes -> ROIAlign + normalise of both views) against the oracle's crops."""
+    from disprcnn_b200.layers.roi_align import crop_stereo_rois, prepare_stereo_rois
+    g = torch.Generator().manual_seed(77)
+    Wd, Hd, nimg = 310, 94, 3
+    lbs, rbs, idx = [], [], []
+    for i in range(nimg):
+        n = 5 + i
+        x1 = torch.rand(n, generator=g) * 280 - 10          # some boxes start left of the image
+        y1 = torch.rand(n, generator=g) * 70 - 5
+        w = 4 + torch.rand(n, generator=g) * 120            # some reach past the right border
+        h = 4 + torch.rand(n, generator=g) * 60
+        off = torch.rand(n, generator=g) * 40
+        lb = torch.stack([x1, y1, x1 + w, y1 + h], 1)
+        rb = torch.stack([x1 - off, y1, x1 - off + w * (0.8 + 0.4 * torch.rand(n, generator=g)), y1 + h], 1)
+        lbs.append(lb); rbs.append(rb); idx += [i] * n
+    want_l, want_r = O.align_stereo_boxes([b.tolist() for b in lbs], [b.tolist() for b in rbs], Wd, Hd)
+    LB, RB, IDX = torch.cat(lbs).cuda(), torch.cat(rbs).cuda(), torch.tensor(idx).cuda()
+    rl, rr, x1s, x1ps, x2s, x2ps = prepare_stereo_rois(LB, RB, IDX, Wd, Hd)
+    assert torch.equal(rl.cpu(), torch.tensor(want_l, dtype=torch.float32))
+    assert torch.equal(rr.cpu(), torch.tensor(want_r, dtype=torch.float32))
+    assert x1s.dtype == torch.int64 and torch.equal(x1s.cpu(), torch.tensor([r[1] for r in want_l]))
+    assert torch.equal(x1ps.cpu(), torch.tensor([r[1] for r in want_r])) and torch.equal(x2s.cpu(), torch.tensor([r[3] for r in want_l]))
+    assert torch.equal(x2ps.cpu(), torch.tensor([r[3] for r in want_r]))
+    iml, imr = recipe.make_images(nimg, Hd, Wd, 5), recipe.make_images(nimg, Hd, Wd, 6)
+    cl, cr, *_ = crop_stereo_rois(iml.cuda(), imr.cuda(), LB, RB, IDX, 32)
+    assert np.array_equal(cl.cpu().numpy(), O.crop_and_transform_roi_img(iml.numpy(), np.asarray(want_l, np.float32), 32))
+    assert np.array_equal(cr.cpu().numpy(), O.crop_and_transform_roi_img(imr.numpy(), np.asarray(want_r, np.float32), 32))
+    # empty batch: nothing to do, empty tensors back
+    e = prepare_stereo_rois(LB[:0], RB[:0], IDX[:0], Wd, Hd)
+    assert e[0].shape == (0, 5) and e[2].numel() == 0
