@@ -71,6 +71,7 @@ PROTOTYPES = {
     'idisp_plan_set_tensor': (_i, [_vp, ctypes.c_char_p, _vp, _sz]),
     'idisp_plan_finalize': (_i, [_vp, _vp]),
     'idisp_plan_workspace_bytes': (_sz, [_vp, _i, _i, _i]),
+    'idisp_plan_range_exceeded': (_i, [_vp, ctypes.POINTER(ctypes.c_int), _vp]),
     'idisp_plan_forward': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
     'idisp_plan_forward_host': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     'idisp_plan_get_logits': (_i, [_vp, _vp, _vp]),

@@ -125,7 +125,8 @@ template <bool F16> __device__ __forceinline__ uint4 pack8h(const F8 &r)
 int launch_ncdhw_to_blocked_h(const float *src, __nv_bfloat16 *dst, int B, int C, int64_t V, int f16, cudaStream_t s);
 int launch_blocked_to_ncdhw_h(const __nv_bfloat16 *src, float *dst, int B, int C, int64_t V, int f16, cudaStream_t s);
 // split precision (two IEEE-half words per value): [B][2*C/8][V][8], hi blocks then lo blocks
-int launch_ncdhw_to_blocked_x2(const float *src, __nv_bfloat16 *dst, int B, int C, int64_t V, cudaStream_t s);
+// range_flag (device int, optional): set to 1 if a value does not fit the IEEE-half range
+int launch_ncdhw_to_blocked_x2(const float *src, __nv_bfloat16 *dst, int B, int C, int64_t V, cudaStream_t s, int *range_flag = nullptr);
 int launch_blocked_x2_to_ncdhw(const __nv_bfloat16 *src, float *dst, int B, int C, int64_t V, cudaStream_t s);
 // layout converters (test hooks + plan I/O)
 template <typename T>

@@ -136,6 +136,7 @@ struct Params {
   const float *part_in;           // fp32 partial sums of the earlier pass(es), blocked [B][Cout/8][V][8], or nullptr
   float *part_out;                // non-null: store this pass's accumulator (+ part_in) there and do nothing else
   int x2;                         // final pass: y / residual / y_split carry 2*Cout/8 blocks per sample (hi | lo)
+  int *range_flag;                // optional device int: set to 1 when a value to be stored as IEEE half exceeds its range
   int in_blk_stride, in_blk_off;  // channel blocks per input sample in memory, and which block this launch's channels start at
   int B, Din, Dout, Ho, Wo, Hr, Wr, Cout, relu;  // (Hr,Wr): row grid the 8x16 tiles cover
   int tiles_h, tiles_w, nh;
@@ -559,6 +560,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         if (p.relu) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) a.v[c] = fmaxf(a.v[c], 0.f);
+        }
+        if (F16 && p.range_flag) {  // fp16 words: beyond 65504 (or NaN) the stored activation is no longer the computed one
+          bool bad = false;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) bad |= !(fabsf(a.v[c]) <= 65504.f);
+          if (bad) *p.range_flag = 1;
         }
         const uint4 hi = pack8h<F16>(a);
         if (!p.skip_y) *reinterpret_cast<uint4 *>(p.y + onat) = hi;
@@ -1097,6 +1104,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   p.B = B; p.Din = D; p.Cout = Cout; p.relu = relu; p.y1_cols = w.ncat ? 2 : 1;
   p.cv_shift0 = cv ? cv->shift0 : 0;
   p.part_in = opts.part_in; p.part_out = opts.part_out; p.x2 = opts.x2; p.in_blk_stride = blk_stride; p.in_blk_off = opts.in_blk_off;
+  p.range_flag = opts.range_flag;
   if (!cv) rmap = map;
   { static int dbg = -1; if (dbg < 0) { const char *e = getenv("IDISP_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   if (MODE == tc::M_S1) { p.Dout = D; p.Ho = H; p.Wo = W; p.Hr = H; p.Wr = W; }
@@ -1227,13 +1235,15 @@ int tc_split_weights_prepare(const float *w_tap, int kind, int cin, int cout, Tc
 
 int tc_conv3d_split(const TcSplitWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D, int H, int W, int Cout, int kind,
                     const float *bias, const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1,
-                    void *scratch, int flags, __nv_bfloat16 *y_split, const TcCostVolume *cv, float *part, cudaStream_t s, int *launches)
+                    void *scratch, int flags, __nv_bfloat16 *y_split, const TcCostVolume *cv, float *part, cudaStream_t s, int *launches,
+                    int *range_flag)
 {
   const int per_view = cv ? Cin / 16 : Cin / 8;  // channel blocks of one precision word (per view for the fused cost volume)
   const int nl = split_launches(kind, Cin);
   if (launches) *launches = nl;
   TcOpts o;
   o.in_blk_stride = 2 * per_view;
+  o.range_flag = range_flag;
   int rc;
   if (nl == 1) {
     o.xp = w.both.ncat ? 2 : 1;

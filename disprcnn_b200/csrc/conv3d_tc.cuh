@@ -35,6 +35,7 @@ struct TcOpts {
   int x2 = 0;                      // final pass: y / residual / y_split hold hi|lo block groups
   int in_blk_stride = 0;           // channel blocks per input sample in memory (0: Cin/8)
   int in_blk_off = 0;              // first channel block this launch reads
+  int *range_flag = nullptr;       // device int set to 1 if an activation leaves the IEEE-half range (fp16 modes)
   int xp = 0;                      // K concatenation inside the launch: 1 = (x_hi,w_hi)+(x_lo,w_hi)+(x_hi,w_lo) with two-word
                                    // weights (Cin 32), 2 = (x_hi,w_hi)+(x_lo,w_hi) with one-word weights (Cin 64)
 };
@@ -51,7 +52,7 @@ void tc_split_weights_free(TcSplitWeights &w);
 int tc_conv3d_split(const TcSplitWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D, int H, int W, int Cout, int kind,
                     const float *bias, const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1,
                     void *scratch, int flags, __nv_bfloat16 *y_split, const TcCostVolume *cv, float *part, cudaStream_t s,
-                    int *launches = nullptr);
+                    int *launches = nullptr, int *range_flag = nullptr);
 
 // whether the tensor-core kernel covers this layer shape (otherwise the SIMT kernel runs it)
 bool tc_supported(int kind, int cin, int cout, int D, int H, int W);

@@ -212,7 +212,7 @@ blocked_to_ncdhw_h_kernel(const uint4 *__restrict__ src, float *__restrict__ dst
 }
 // split precision: [B][2*C/8][V][8] 16-bit words -- blocks [0,C/8) hold hi = half(x), blocks [C/8, 2C/8) hold lo = half(x - hi)
 __global__ void __launch_bounds__(256)
-ncdhw_to_blocked_x2_kernel(const float *__restrict__ src, uint4 *__restrict__ dst, int B, int C, int64_t V)
+ncdhw_to_blocked_x2_kernel(const float *__restrict__ src, uint4 *__restrict__ dst, int B, int C, int64_t V, int *__restrict__ range_flag)
 {
   const int nblk = C / CB;
   const int64_t total = (int64_t)B * nblk * V;
@@ -224,6 +224,12 @@ ncdhw_to_blocked_x2_kernel(const float *__restrict__ src, uint4 *__restrict__ ds
     F8 r;
 #pragma unroll
     for (int c = 0; c < CB; ++c) r.v[c] = __ldg(s + c * V);
+    if (range_flag) {  // a value outside the IEEE-half range (or non-finite) cannot be split into hi + lo words
+      bool bad = false;
+#pragma unroll
+      for (int c = 0; c < CB; ++c) bad |= !(fabsf(r.v[c]) <= 65504.f);
+      if (bad) *range_flag = 1;
+    }
     const uint4 hi = pack8h<true>(r);
     const F8 h = unpack8h<true>(hi);
 #pragma unroll
@@ -249,12 +255,12 @@ blocked_x2_to_ncdhw_kernel(const uint4 *__restrict__ src, float *__restrict__ ds
     for (int c = 0; c < CB; ++c) d[c * V] = h.v[c] + l.v[c];
   }
 }
-int launch_ncdhw_to_blocked_x2(const float *src, __nv_bfloat16 *dst, int B, int C, int64_t V, cudaStream_t s)
+int launch_ncdhw_to_blocked_x2(const float *src, __nv_bfloat16 *dst, int B, int C, int64_t V, cudaStream_t s, int *range_flag)
 {
   const int64_t total = (int64_t)B * (C / CB) * V;
   if (total == 0) return IDISP_OK;
   const int64_t want = ceil_div64(total, 256);
-  ncdhw_to_blocked_x2_kernel<<<(int)(want < 148 * 32 ? want : 148 * 32), 256, 0, s>>>(src, (uint4 *)dst, B, C, V);
+  ncdhw_to_blocked_x2_kernel<<<(int)(want < 148 * 32 ? want : 148 * 32), 256, 0, s>>>(src, (uint4 *)dst, B, C, V, range_flag);
   IDISP_LAUNCH_CHECK();
   return IDISP_OK;
 }

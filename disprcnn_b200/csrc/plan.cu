@@ -104,6 +104,7 @@ struct idisp_plan {
   void *stage = nullptr;
   size_t stage_bytes = 0;
   // optional per-launch CUDA-event timing (bench.py's roofline leg)
+  int *range_flag = nullptr;  // device int: an fp16-mode forward saw a value outside the IEEE-half range
   bool timing = false;
   std::vector<cudaEvent_t> ev;
   std::vector<int> ev_layer;  // launch slot -> layer index (-1 cost volume, -2 soft-argmin, 25..27 the 32->1 convs)
@@ -136,6 +137,7 @@ extern "C" void idisp_plan_destroy(idisp_plan_t *p)
   for (auto &d : p->dev) { tc_weights_free(d.tc); tc_split_weights_free(d.sp); }
   for (auto e : p->ev) cudaEventDestroy(e);
   if (p->blob) cudaFree(p->blob);
+  if (p->range_flag) cudaFree(p->range_flag);
   if (p->stage) cudaFree(p->stage);
   delete p;
 }
@@ -288,11 +290,14 @@ static int tc_layer(idisp_plan *p, int li, const __nv_bfloat16 *xin, int xflags,
 {
   const LayerSpec &L = p->layers[li];
   const float *bias = p->dev[li].bias;
-  if (!p->x2)
-    return tc_conv3d(p->dev[li].tc, xin, B, L.cin, d, h, w, L.cout, L.kind, bias, res, relu, y, res1, y1, scratch, xflags | eflags, ysp, cv, s);
+  if (!p->x2) {
+    TcOpts o;
+    o.range_flag = p->f16 ? p->range_flag : nullptr;
+    return tc_conv3d(p->dev[li].tc, xin, B, L.cin, d, h, w, L.cout, L.kind, bias, res, relu, y, res1, y1, scratch, xflags | eflags, ysp, cv, s, &o);
+  }
   int nl = 1;
   const int rc = tc_conv3d_split(p->dev[li].sp, xin, B, L.cin, d, h, w, L.cout, L.kind, bias, res, relu, y, res1, y1, scratch, xflags | eflags,
-                                 ysp, cv, part, s, &nl);
+                                 ysp, cv, part, s, &nl, p->range_flag);
   launches += nl - 1;
   return rc;
 }
@@ -306,6 +311,10 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
   Buffers b = carve(A, C, B, D, Hf, Wf, p->x2 ? 4 : sizeof(T));
   int launches = 0;
   int rc;
+  if (p->f16) {  // fp16-word modes: a device flag collects "value left the IEEE-half range" over this forward
+    if (!p->range_flag) IDISP_CUDA(cudaMalloc(&p->range_flag, sizeof(int)));
+    IDISP_CUDA(cudaMemsetAsync(p->range_flag, 0, sizeof(int), s));
+  }
   if (p->timing) p->ev_layer.clear();
   int nmark = 0;
   auto mark = [&](int layer) {  // record an event BEFORE the launch(es) of `layer`
@@ -344,8 +353,8 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
     // the [B,2C,D,H,W] volume is never written: dres0.0's TMA producer assembles each plane from the two feature maps
     mark(-1);
     if (p->x2) {
-      RUN(launch_ncdhw_to_blocked_x2(left, (__nv_bfloat16 *)b.feaL, B, C, (int64_t)Hf * Wf, s)); ++launches;
-      RUN(launch_ncdhw_to_blocked_x2(right, (__nv_bfloat16 *)b.feaR, B, C, (int64_t)Hf * Wf, s)); ++launches;
+      RUN(launch_ncdhw_to_blocked_x2(left, (__nv_bfloat16 *)b.feaL, B, C, (int64_t)Hf * Wf, s, p->range_flag)); ++launches;
+      RUN(launch_ncdhw_to_blocked_x2(right, (__nv_bfloat16 *)b.feaR, B, C, (int64_t)Hf * Wf, s, p->range_flag)); ++launches;
     } else {
       RUN(launch_ncdhw_to_blocked_h(left, (__nv_bfloat16 *)b.feaL, B, C, (int64_t)Hf * Wf, p->f16, s)); ++launches;
       RUN(launch_ncdhw_to_blocked_h(right, (__nv_bfloat16 *)b.feaR, B, C, (int64_t)Hf * Wf, p->f16, s)); ++launches;
@@ -430,6 +439,17 @@ extern "C" int idisp_plan_forward(idisp_plan_t *p, const float *left, const floa
   if (p->precision == IDISP_PREC_FP32)
     return forward_impl<float>(p, left, right, B, Hf, Wf, H, W, workspace, out, (cudaStream_t)stream);
   return forward_impl<__nv_bfloat16>(p, left, right, B, Hf, Wf, H, W, workspace, out, (cudaStream_t)stream);
+}
+
+extern "C" int idisp_plan_range_exceeded(idisp_plan_t *p, int *exceeded, void *stream)
+{
+  IDISP_REQUIRE(p != nullptr && exceeded != nullptr, "plan_range_exceeded: NULL argument");
+  *exceeded = 0;
+  if (!p->range_flag) return IDISP_OK;  // fp32 / bf16 plans, or no forward yet
+  cudaStream_t s = (cudaStream_t)stream;
+  IDISP_CUDA(cudaMemcpyAsync(exceeded, p->range_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  IDISP_CUDA(cudaStreamSynchronize(s));
+  return IDISP_OK;
 }
 
 extern "C" int idisp_plan_forward_host(idisp_plan_t *p, const float *left_host, const float *right_host, int B,

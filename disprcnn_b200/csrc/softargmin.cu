@@ -42,8 +42,20 @@ softargmin_kernel(const float *__restrict__ logits, int B, int D, int Hf, int Wf
       const float *p = base + (int64_t)k * plane;
       return ly0 * (lx0 * __ldg(p + o00) + lx1 * __ldg(p + o01)) + ly1 * (lx0 * __ldg(p + o10) + lx1 * __ldg(p + o11));
     };
+    // softmax stabiliser = the maximum of the INTERPOLATED logits themselves (same expression as below): the maximum of the
+    // plane samples is only an upper bound, and with sharply peaked logits every exp(v - bound) could underflow -> 0/0
     float m = -INFINITY;
-    for (int k = 0; k < D; ++k) m = fmaxf(m, sample(k));
+    {
+      int k0 = 0;
+      float p0 = sample(0), p1 = sample(D > 1 ? 1 : 0);
+      for (int d = 0; d < Dfull; ++d) {
+        const float fd = sd * (float)d;
+        const int d0 = (int)fd;
+        if (d0 != k0) { k0 = d0; p0 = p1; p1 = sample(d0 + (d0 < D - 1 ? 1 : 0)); }
+        const float l1 = fd - (float)d0, l0 = 1.f - l1;
+        m = fmaxf(m, l0 * p0 + l1 * p1);
+      }
+    }
     float s = 0.f, t = 0.f;
     int k0 = 0;
     float p0 = sample(0), p1 = sample(D > 1 ? 1 : 0);
@@ -67,12 +79,12 @@ softargmin_kernel(const float *__restrict__ logits, int B, int D, int Hf, int Wf
 
 // Specialisation for the reference's geometry Dfull = 4*D (D = 24 or 48).  The depth interpolation indices/weights d0(d), l1(d) are
 // compile-time constants of the fully unrolled 4D loop.  Two passes over the D plane samples (each a bilinear blend of 4 L1/L2-
-// resident logits): pass 1 takes their maximum (the softmax stabiliser -- an upper bound of every interpolated value), pass 2
-// streams the 4D output disparities through a rolling window of TWO samples.  Keeping all D samples in registers instead (the
+// resident logits), each streaming the 4D output disparities through a rolling window of TWO samples: pass 1 takes the maximum
+// of the interpolated logits (the softmax stabiliser), pass 2 accumulates the exponentials.  Keeping all D samples in registers instead (the
 // first version) cost 168 registers = 3 warps per scheduler, and the kernel ran at a third of its issue rate; re-sampling is
 // 48 x 11 instructions per pixel against 192 x 6 for the exponentials.
 template <int D>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)  // <= 85 registers: the unrolled loops must not hoist all 4*D*... loads at once
 softargmin_x4_kernel(const float *__restrict__ logits, int B, int Hf, int Wf, int mindisp, int H, int W, float *__restrict__ out)
 {
   constexpr int Dfull = 4 * D;
@@ -92,14 +104,35 @@ softargmin_x4_kernel(const float *__restrict__ logits, int B, int Hf, int Wf, in
     const int plane = Hf * Wf;
     const float *p00 = logits + (int64_t)b * D * plane + y0 * Wf + x0;
     const int d01 = x1 - x0, d10 = (y1 - y0) * Wf;
+    const float *pbase = p00;
     auto sample = [&](int k) {
-      const float *q = p00 + k * plane;
+      const float *q = pbase + k * plane;
       return ly0 * (lx0 * __ldg(q) + lx1 * __ldg(q + d01)) + ly1 * (lx0 * __ldg(q + d10) + lx1 * __ldg(q + d10 + d01));
     };
-    float m = sample(0);
+    // pass 1: the softmax stabiliser = maximum of the interpolated logits themselves (the SAME expression pass 2 evaluates, so
+    // the largest term is exactly exp(0) and the sum cannot underflow; the maximum of the plane samples is only an upper bound)
+    float m = -INFINITY;
+    {
+      float Pk = sample(0), Pk1 = sample(D > 1 ? 1 : 0);
 #pragma unroll
-    for (int k = 1; k < D; ++k) m = fmaxf(m, sample(k));
+      for (int d = 0; d < Dfull; ++d) {
+        const float fd = sd * (float)d;
+        const int d0 = (int)fd;
+        if (d > 0 && d0 != (int)(sd * (float)(d - 1))) {
+          Pk = Pk1;
+          Pk1 = sample(d0 + (d0 < D - 1 ? 1 : 0));
+        }
+        // between two planes the interpolant is monotone in d: only the first and the last d of a segment can hold the maximum
+        // (compile-time test; a last-ulp difference to the true maximum only makes the largest term 1 + eps)
+        const bool first = d == 0 || d0 != (int)(sd * (float)(d - 1)), last = d == Dfull - 1 || d0 != (int)(sd * (float)(d + 1));
+        if (first || last) {
+          const float l1 = fd - (float)d0, l0 = 1.f - l1;
+          m = fmaxf(m, l0 * Pk + l1 * Pk1);
+        }
+      }
+    }
     const float mneg = -m * 1.4426950408889634f;
+    asm volatile("" : "+l"(pbase));  // pass 2 RE-samples (L1 hits): keeping pass 1's 48 samples alive would cost the occupancy
     // four independent (sum, weighted-sum) chains: with one chain the add latency of 2 x 192 dependent accumulations sets the pace
     float s4[4] = {0.f, 0.f, 0.f, 0.f}, t4[4] = {0.f, 0.f, 0.f, 0.f};
     float Pk = sample(0), Pk1 = sample(D > 1 ? 1 : 0);

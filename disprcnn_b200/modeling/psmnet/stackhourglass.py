@@ -72,7 +72,7 @@ class PSMNet(nn.Module):
         self.dres2, self.dres3, self.dres4 = hourglass(32), hourglass(32), hourglass(32)
         self.classif1, self.classif2, self.classif3 = _classifier(), _classifier(), _classifier()
         self._init_like_reference()
-        self.check_range = True   # 'auto' only: verify the split-precision result is finite (one device reduction + sync per call)
+        self.check_range = True   # 'auto' only: ask the plan whether the fp16 range was left (one 4-byte D2H + sync per call)
         self._plans = {}      # effective precision -> [plan handle, weights key]
         self._plan = None     # the plan of the most recent forward
         self._workspace = None
@@ -168,12 +168,23 @@ class PSMNet(nn.Module):
         with torch.cuda.device(left_fea.device):
             precision = self.effective_precision(Hf, Wf)
             run(precision)
-            if self.precision == 'auto' and precision == 'fp16x2' and self.check_range and not bool(torch.isfinite(out).all()):
-                # the hi words are IEEE halves: an activation beyond 65504 overflows them.  Not seen with BatchNorm-ed iDispNet
-                # weights, but 'auto' promises a parity-grade answer, so such a batch is redone by the fp32 FFMA kernels.
+            if self.precision == 'auto' and precision == 'fp16x2' and self.check_range and self.range_exceeded():
+                # the hi words are IEEE halves: an activation beyond 65504 overflows them (and ReLU turns the resulting NaN
+                # into 0: finite but wrong).  Not seen with BatchNorm-ed iDispNet weights, but 'auto' promises a parity-grade
+                # answer, so such a batch is redone by the fp32 FFMA kernels.
                 warnings.warn('PSMNet: activations left the fp16 range of the split-precision mode; batch recomputed in fp32')
                 run('fp32')
         return out
+
+    def range_exceeded(self):
+        """fp16-word modes: did the most recent forward see a value outside the IEEE-half range (idisp_plan_range_exceeded)?
+        Synchronises the current stream."""
+        if self._plan is None:
+            return False
+        flag = ctypes.c_int(0)
+        with torch.cuda.device(self._workspace.device):
+            _lib.check(_lib.load().idisp_plan_range_exceeded(self._plan, ctypes.byref(flag), _lib.stream_ptr()))
+        return bool(flag.value)
 
     def last_logits(self, B, Hf, Wf):
         """cost3 [B,D,Hf,Wf] of the most recent forward (debug/test hook)."""

@@ -132,6 +132,13 @@ size_t idisp_plan_workspace_bytes(const idisp_plan_t *plan, int B, int Hf, int W
 int idisp_plan_forward(idisp_plan_t *plan, const float *left, const float *right, int B, int Hf,
                        int Wf, int H, int W, void *workspace, size_t workspace_bytes, float *out,
                        void *stream);
+/* fp16-word modes (IDISP_PREC_FP16, IDISP_PREC_FP16X2): did the most recent idisp_plan_forward on this plan produce an
+ * activation (or take an input feature) outside the IEEE-half range, |v| > 65504 or non-finite?  Such a value is stored as
+ * inf and -- because ReLU's max(NaN, 0) is 0 -- can end in finite but wrong disparities.  Writes 0/1 to *exceeded (host
+ * pointer); synchronises `stream`.  Always 0 for fp32 / bf16 plans.  The Python wrapper's precision='auto' uses it to redo such
+ * a batch with the fp32 kernels. */
+int idisp_plan_range_exceeded(idisp_plan_t *plan, int *exceeded, void *stream);
+
 /* Same call with HOST buffers (pinned recommended): H2D of left/right, forward, D2H of out,
  * all enqueued on `stream`; the plan owns and grows the device staging + workspace. */
 int idisp_plan_forward_host(idisp_plan_t *plan, const float *left_host, const float *right_host,

@@ -416,12 +416,19 @@ def test_auto_precision_recomputes_in_fp32_when_the_fp16_range_is_left(lib):
     'auto' then redoes the batch with the fp32 FFMA kernels (and says so) instead of returning non-finite disparities."""
     case, g, sd, L, R = load_case('tiny')
     auto, f32, x2 = make_psmnet(case, sd, 'auto'), make_psmnet(case, sd, 'fp32'), make_psmnet(case, sd, 'fp16x2')
-    Lb, Rb = (L * 3e5).cuda(), (R * 3e5).cuda()
+    Lb, Rb = L.clone().cuda(), R.clone().cuda()
+    Lb[0, 3, 5, 7] = 1.0e5   # one feature beyond the IEEE-half range (65504)
     with torch.no_grad():
-        assert not torch.isfinite(x2.forward_features(Lb, Rb)).all()      # the explicit mode reports what the hardware did
+        x2.forward_features(L.cuda(), R.cuda())
+        assert not x2.range_exceeded()                                     # the fixture itself is well inside the range
+        x2.forward_features(Lb, Rb)                                        # ReLU(NaN) = 0: the output may even be finite ...
+        assert x2.range_exceeded()                                         # ... which is why the plan keeps a range flag
         with pytest.warns(UserWarning, match='fp16 range'):
             a = auto.forward_features(Lb, Rb)
-        assert torch.isfinite(a).all() and torch.equal(a, f32.forward_features(Lb, Rb))
+        b = f32.forward_features(Lb, Rb)
+        assert torch.isfinite(b).all(), 'fp32 mode itself is not finite on these features'
+        assert torch.isfinite(a).all()
+        assert torch.equal(a, b), f'auto differs from fp32 by {(a - b).abs().max().item()}'
 
 
 def test_stereo_roi_preparation_on_device_matches_the_reference_loop(lib):
@@ -456,3 +463,17 @@ def test_stereo_roi_preparation_on_device_matches_the_reference_loop(lib):
     # empty batch: nothing to do, empty tensors back
     e = prepare_stereo_rois(LB[:0], RB[:0], IDX[:0], Wd, Hd)
     assert e[0].shape == (0, 5) and e[2].numel() == 0
+
+
+@pytest.mark.parametrize('B,D,Hf,Wf,mind,maxd,H,W', [(1, 48, 12, 16, -96, 96, 48, 64), (2, 8, 16, 16, -16, 16, 64, 64), (1, 12, 9, 7, -8, 40, 33, 29)])
+def test_softargmin_with_sharply_peaked_logits_stays_finite(lib, B, D, Hf, Wf, mind, maxd, H, W):
+    """Adjacent planes hundreds of logits apart: every interpolated value except the largest underflows in the softmax.  The
+    stabiliser must be the maximum of the INTERPOLATED logits (as in F.softmax on the upsampled volume, stackhourglass.py:169-172);
+    the maximum of the plane samples is only an upper bound and gave 0/0 here."""
+    from disprcnn_b200.modeling.psmnet.submodule import soft_argmin
+    g = torch.Generator().manual_seed(5 * D + Hf)
+    logits = torch.randn(B, 1, D, Hf, Wf, generator=g) * 400.0
+    want = O.upsample_softargmin(logits, mind, maxd, H, W)
+    got = soft_argmin(logits.cuda(), mind, maxd, H, W).cpu()
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max().item() < 5e-3
