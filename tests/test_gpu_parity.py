@@ -477,3 +477,32 @@ def test_softargmin_with_sharply_peaked_logits_stays_finite(lib, B, D, Hf, Wf, m
     got = soft_argmin(logits.cuda(), mind, maxd, H, W).cpu()
     assert torch.isfinite(got).all()
     assert (got - want).abs().max().item() < 5e-3
+
+
+def test_split_precision_mode_at_full_benchmark_shape_tracks_the_fp32_mode(lib):
+    """B=4 ROI pairs of BASELINE configs[1] with bench.py's random-init model: the tensor-core parity mode stays within the
+    1e-3 px bar of the fp32 FFMA mode (measured 3.4-3.7e-4), and its ROIs are independent bit for bit."""
+    import torch.nn as nn
+    from disprcnn_b200.modeling.psmnet.stackhourglass import PSMNet
+    torch.manual_seed(0)
+    m32 = PSMNet(96, -96, precision='fp32')
+    m32.feature_extraction = nn.Identity()
+    with torch.no_grad():
+        for c in (m32.classif1, m32.classif2, m32.classif3):
+            c[2].weight.mul_(0.1)
+    m32 = m32.cuda().eval()
+    mx2 = PSMNet(96, -96, precision='fp16x2')
+    mx2.feature_extraction = nn.Identity()
+    mx2.load_state_dict(m32.state_dict())
+    mx2 = mx2.cuda().eval()
+    g = torch.Generator().manual_seed(1234)
+    L = torch.randn(4, 32, 112, 112, generator=g).relu().cuda()
+    R = torch.randn(4, 32, 112, 112, generator=g).relu().cuda()
+    with torch.no_grad():
+        a, b = mx2.forward_features(L, R), m32.forward_features(L, R)
+        assert not mx2.range_exceeded()
+        d = (a - b).abs()
+        print(f'\n[full, B=4, random init] fp16x2 vs fp32 FFMA: max {d.max().item():.3e} mean {d.mean().item():.3e}')
+        assert d.max().item() < TOL_FP32
+        perm = torch.tensor([3, 1, 0, 2], device='cuda')
+        assert torch.equal(mx2.forward_features(L[perm], R[perm]), a[perm])
