@@ -33,7 +33,13 @@
 //   +bias (+residual) (ReLU) -> bf16 -> 16-byte stores).
 // Pipelines: full/empty mbarriers over the input ring (TMA <-> MMA), acc_full/acc_empty over the TMEM
 //   ring (MMA <-> epilogue); the layer's weights (55/110 KB) stay resident in shared memory.
-// Roofline: tensor (dense bf16); algorithmic FLOPs = 2*27*Cin*Cout per output voxel (stride 1).
+// Roofline: tensor (dense bf16/fp16); algorithmic FLOPs = 2*27*Cin*Cout per output voxel (stride 1).
+//
+// Storage formats (template parameter FMT): bf16 or IEEE-half words (one word per value), or SPLIT PRECISION -- every activation
+// and weight is two IEEE-half words (hi + lo, block groups [hi | lo] per sample), a product is x_hi*w_hi + x_lo*w_hi + x_hi*w_lo
+// accumulated in fp32: the tensor-core mode that meets the 1e-3 px parity bar (Cfg::XP: the three terms as extra k-steps of ONE
+// launch where both weight words fit in shared memory; Cfg::TRI / accumulator banks: tcgen05.mma adds into the fp32 accumulator
+// by truncation, so no accumulator column may collect a long chain of full-magnitude adds -- see Cfg and DESIGN.md 4b).
 #include "conv3d_tc.cuh"
 #include "sm100_ptx.cuh"
 
