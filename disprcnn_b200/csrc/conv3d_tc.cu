@@ -1268,6 +1268,16 @@ int tc_conv3d_split(const TcSplitWeights &w, const __nv_bfloat16 *x, int B, int 
     return tc_conv3d(w.lo, x, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, y1, y1, scratch, flags & 1, nullptr, cv, s, &o);
   }
   if (!part) { set_error("tc_conv3d_split: this layer needs the fp32 partial buffer"); return IDISP_ERR_INVALID; }
+  static const int heavy_first = tc::env_flag("IDISP_X2_HEAVY_FIRST");  // A/B switch: the order before this scheduling
+  if (nl == 2 && !heavy_first) {
+    // light launch first: x_hi*w_lo (one term, its epilogue only stores the fp32 partial); then the two-term launch, whose
+    // twice-as-long MMA phase hides the real epilogue (partial + residual reads, hi|lo stores).  The other order left the
+    // epilogue-heavy work to the MMA-light launch (dres0.0: 2.96 + 1.74 ms).
+    o.part_out = part;
+    if ((rc = tc_conv3d(w.lo, x, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, nullptr, nullptr, scratch, flags & 1, nullptr, cv, s, &o))) return rc;
+    o.xp = 2; o.part_in = part; o.part_out = nullptr; o.x2 = 1;
+    return tc_conv3d(w.hi, x, B, Cin, D, H, W, Cout, kind, bias, residual, relu, y, nullptr, nullptr, scratch, flags, y_split, cv, s, &o);
+  }
   o.part_out = part;
   if (nl == 2) o.xp = 2;
   if ((rc = tc_conv3d(w.hi, x, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, nullptr, nullptr, scratch, flags & 1, nullptr, cv, s, &o))) return rc;
