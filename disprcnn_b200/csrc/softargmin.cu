@@ -77,10 +77,80 @@ softargmin_kernel(const float *__restrict__ logits, int B, int D, int Hf, int Wf
   }
 }
 
+// ---- pieces of the Dfull = 4*D specialisation (below) ----
+struct SampleCtx {  // bilinear sampling of one low-resolution plane at this thread's output pixel
+  const float *p00;
+  int plane, d01, d10;
+  float lx0, lx1, ly0, ly1;
+  __device__ __forceinline__ float operator()(int k) const
+  {
+    const float *q = p00 + k * plane;
+    return ly0 * (lx0 * __ldg(q) + lx1 * __ldg(q + d01)) + ly1 * (lx0 * __ldg(q + d10) + lx1 * __ldg(q + d10 + d01));
+  }
+};
+
+// sum and disparity-weighted sum of exp(v(d) - m) over the 4D interpolated logits; rolling window of two plane samples
+template <int D>
+__device__ __forceinline__ void softargmin_accumulate(const SampleCtx &sample, float mneg, int mindisp, float &s_out, float &t_out)
+{
+  constexpr int Dfull = 4 * D;
+  constexpr float sd = (float)(D - 1) / (float)(Dfull - 1);
+  // four independent (sum, weighted-sum) chains: with one chain the add latency of 2 x 192 dependent accumulations sets the pace
+  float s4[4] = {0.f, 0.f, 0.f, 0.f}, t4[4] = {0.f, 0.f, 0.f, 0.f};
+  float Pk = sample(0), Pk1 = sample(D > 1 ? 1 : 0);
+#pragma unroll
+  for (int d = 0; d < Dfull; ++d) {
+    const float fd = sd * (float)d;      // compile-time per unrolled iteration
+    const int d0 = (int)fd;
+    if (d > 0 && d0 != (int)(sd * (float)(d - 1))) {  // (compile-time) the window advances by one plane
+      Pk = Pk1;
+      Pk1 = sample(d0 + (d0 < D - 1 ? 1 : 0));
+    }
+    const float l1 = fd - (float)d0, l0 = 1.f - l1;
+    const float v = l0 * Pk + l1 * Pk1;
+    float e;  // one MUFU.EX2 (arguments are <= 0; flushing the far tail to zero is what softmax does to it anyway)
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v, 1.4426950408889634f, mneg)));
+    s4[d & 3] += e;
+    t4[d & 3] = fmaf(e, (float)(mindisp + d), t4[d & 3]);
+  }
+  s_out = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  t_out = (t4[0] + t4[1]) + (t4[2] + t4[3]);
+}
+
+// rare path (kept out of line so that it does not weigh on the fast path's registers): exact maximum of the interpolated
+// logits -- the SAME expression the accumulation evaluates, so the largest term is exp(0) -- then the accumulation again
+template <int D>
+__device__ __noinline__ float softargmin_exact(SampleCtx sample, int mindisp)
+{
+  constexpr int Dfull = 4 * D;
+  constexpr float sd = (float)(D - 1) / (float)(Dfull - 1);
+  float m = -INFINITY;
+  float Pk = sample(0), Pk1 = sample(D > 1 ? 1 : 0);
+#pragma unroll
+  for (int d = 0; d < Dfull; ++d) {
+    const float fd = sd * (float)d;
+    const int d0 = (int)fd;
+    if (d > 0 && d0 != (int)(sd * (float)(d - 1))) {
+      Pk = Pk1;
+      Pk1 = sample(d0 + (d0 < D - 1 ? 1 : 0));
+    }
+    // between two planes the interpolant is monotone in d: only the first and the last d of a segment can hold the maximum
+    const bool first = d == 0 || d0 != (int)(sd * (float)(d - 1)), last = d == Dfull - 1 || d0 != (int)(sd * (float)(d + 1));
+    if (first || last) {
+      const float l1 = fd - (float)d0, l0 = 1.f - l1;
+      m = fmaxf(m, l0 * Pk + l1 * Pk1);
+    }
+  }
+  asm volatile("" : "+l"(sample.p00));
+  float s, t;
+  softargmin_accumulate<D>(sample, -m * 1.4426950408889634f, mindisp, s, t);
+  return t / s;
+}
+
 // Specialisation for the reference's geometry Dfull = 4*D (D = 24 or 48).  The depth interpolation indices/weights d0(d), l1(d) are
 // compile-time constants of the fully unrolled 4D loop.  Two passes over the D plane samples (each a bilinear blend of 4 L1/L2-
-// resident logits), each streaming the 4D output disparities through a rolling window of TWO samples: pass 1 takes the maximum
-// of the interpolated logits (the softmax stabiliser), pass 2 accumulates the exponentials.  Keeping all D samples in registers instead (the
+// resident logits): pass 1 takes their maximum (upper bound of the interpolated logits), pass 2 streams the 4D output disparities
+// through a rolling window of TWO samples and accumulates the exponentials (with an exact-maximum fallback, see below).  Keeping all D samples in registers instead (the
 // first version) cost 168 registers = 3 warps per scheduler, and the kernel ran at a third of its issue rate; re-sampling is
 // 48 x 11 instructions per pixel against 192 x 6 for the exponentials.
 template <int D>
@@ -104,55 +174,18 @@ softargmin_x4_kernel(const float *__restrict__ logits, int B, int Hf, int Wf, in
     const int plane = Hf * Wf;
     const float *p00 = logits + (int64_t)b * D * plane + y0 * Wf + x0;
     const int d01 = x1 - x0, d10 = (y1 - y0) * Wf;
-    const float *pbase = p00;
-    auto sample = [&](int k) {
-      const float *q = pbase + k * plane;
-      return ly0 * (lx0 * __ldg(q) + lx1 * __ldg(q + d01)) + ly1 * (lx0 * __ldg(q + d10) + lx1 * __ldg(q + d10 + d01));
-    };
-    // pass 1: the softmax stabiliser = maximum of the interpolated logits themselves (the SAME expression pass 2 evaluates, so
-    // the largest term is exactly exp(0) and the sum cannot underflow; the maximum of the plane samples is only an upper bound)
-    float m = -INFINITY;
-    {
-      float Pk = sample(0), Pk1 = sample(D > 1 ? 1 : 0);
+    SampleCtx sample{p00, plane, d01, d10, lx0, lx1, ly0, ly1};
+    // softmax stabiliser.  Fast path: the maximum M of the D plane samples -- an upper bound of every interpolated logit, one
+    // independent sample per plane.  It is NOT safe on its own: with sharply peaked logits every exp(v - M) can underflow
+    // (sum = 0 -> 0/0), so a vanishing sum falls back to softargmin_exact, as F.softmax on the upsampled volume
+    // (stackhourglass.py:169-172) would behave.
+    float M = sample(0);
 #pragma unroll
-      for (int d = 0; d < Dfull; ++d) {
-        const float fd = sd * (float)d;
-        const int d0 = (int)fd;
-        if (d > 0 && d0 != (int)(sd * (float)(d - 1))) {
-          Pk = Pk1;
-          Pk1 = sample(d0 + (d0 < D - 1 ? 1 : 0));
-        }
-        // between two planes the interpolant is monotone in d: only the first and the last d of a segment can hold the maximum
-        // (compile-time test; a last-ulp difference to the true maximum only makes the largest term 1 + eps)
-        const bool first = d == 0 || d0 != (int)(sd * (float)(d - 1)), last = d == Dfull - 1 || d0 != (int)(sd * (float)(d + 1));
-        if (first || last) {
-          const float l1 = fd - (float)d0, l0 = 1.f - l1;
-          m = fmaxf(m, l0 * Pk + l1 * Pk1);
-        }
-      }
-    }
-    const float mneg = -m * 1.4426950408889634f;
-    asm volatile("" : "+l"(pbase));  // pass 2 RE-samples (L1 hits): keeping pass 1's 48 samples alive would cost the occupancy
-    // four independent (sum, weighted-sum) chains: with one chain the add latency of 2 x 192 dependent accumulations sets the pace
-    float s4[4] = {0.f, 0.f, 0.f, 0.f}, t4[4] = {0.f, 0.f, 0.f, 0.f};
-    float Pk = sample(0), Pk1 = sample(D > 1 ? 1 : 0);
-#pragma unroll
-    for (int d = 0; d < Dfull; ++d) {
-      const float fd = sd * (float)d;      // compile-time per unrolled iteration
-      const int d0 = (int)fd;
-      if (d > 0 && d0 != (int)(sd * (float)(d - 1))) {  // (compile-time) the window advances by one plane
-        Pk = Pk1;
-        Pk1 = sample(d0 + (d0 < D - 1 ? 1 : 0));
-      }
-      const float l1 = fd - (float)d0, l0 = 1.f - l1;
-      const float v = l0 * Pk + l1 * Pk1;
-      float e;  // one MUFU.EX2 (arguments are <= 0; flushing the far tail to zero is what softmax does to it anyway)
-      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v, 1.4426950408889634f, mneg)));
-      s4[d & 3] += e;
-      t4[d & 3] = fmaf(e, (float)(mindisp + d), t4[d & 3]);
-    }
-    const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]), t = (t4[0] + t4[1]) + (t4[2] + t4[3]);
-    out[idx] = t / s;
+    for (int k = 1; k < D; ++k) M = fmaxf(M, sample(k));
+    asm volatile("" : "+l"(sample.p00));  // the accumulation RE-samples (L1 hits): keeping the D samples alive would cost the occupancy
+    float s, t;
+    softargmin_accumulate<D>(sample, -M * 1.4426950408889634f, mindisp, s, t);
+    out[idx] = (s >= 1e-30f) ? t / s : softargmin_exact<D>(sample, mindisp);
   }
 }
 
