@@ -107,7 +107,7 @@ def gen_case(name, case):
         pred_genuine=pred_genuine.numpy(), pred_up=pred_up.numpy(), logits=logits.numpy(),
         pred_genuine_f64=p64_g.numpy(), pred_up_f64=p64_up.numpy(), logits_f64=logits64.numpy(),
     )
-    if name == 'full':  # keep the fixture small: disparity maps only (+ the float64 arbiter's)
+    if name in ('full', 'live'):  # keep the fixture small: disparity maps only (+ the float64 arbiter's)
         for k in ('logits', 'logits_f64', 'pred_genuine_f64'):
             out.pop(k)
         out['pred_up_f64'] = out['pred_up_f64'].astype(np.float32)

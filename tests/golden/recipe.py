@@ -103,6 +103,8 @@ CASES = {
     'tiny': dict(B=2, C=32, Hf=16, Wf=16, mindisp=-16, maxdisp=16, seed=11),
     'tiny_pos': dict(B=1, C=32, Hf=12, Wf=20, mindisp=0, maxdisp=32, seed=12),
     'c1': dict(B=1, C=16, Hf=64, Wf=64, mindisp=-48, maxdisp=48, seed=13),
+    # the shape tools/test_net.py really runs (KITTI configs: 224x224 crops -> 56x56x32ch features, D=24 -> 224x224), 2 ROI pairs
+    'live': dict(B=2, C=32, Hf=56, Wf=56, mindisp=-48, maxdisp=48, seed=15),
     # one ROI pair of BASELINE.json configs[1] (the benchmark shape): 112x112x32ch, D=48 -> 448x448
     'full': dict(B=1, C=32, Hf=112, Wf=112, mindisp=-96, maxdisp=96, seed=14),
 }

@@ -506,3 +506,18 @@ def test_split_precision_mode_at_full_benchmark_shape_tracks_the_fp32_mode(lib):
         assert d.max().item() < TOL_FP32
         perm = torch.tensor([3, 1, 0, 2], device='cuda')
         assert torch.equal(mx2.forward_features(L[perm], R[perm]), a[perm])
+
+
+def test_live_kitti_shape_matches_reference_forward(lib):
+    """The shape tools/test_net.py runs on KITTI (224x224 crops -> 56x56x32ch features, D=24 -> 224x224; 2 ROI pairs) against the
+    reference's own output (tests/golden/idisp_live.npz): both parity-grade modes and the default 'auto'."""
+    case, g, sd, L, R = load_case('live')
+    for prec in ('fp32', 'fp16x2', 'auto'):
+        m = make_psmnet(case, sd, prec)
+        with torch.no_grad():
+            up = m.forward_features(L.cuda(), R.cuda()).cpu().numpy()
+        e = np.abs(up - g['pred_up'])
+        print(f'\n[live] {prec}: max |disp - ref_fp32| {e.max():.3e} mean {e.mean():.3e}')
+        assert e.max() < TOL_FP32
+        if prec == 'auto':
+            assert m.effective_precision(case['Hf'], case['Wf']) == 'fp16x2'

@@ -13,7 +13,7 @@ from helpers import GOLDEN, load_case
 ORACLE_DIR = os.path.dirname(os.path.abspath(O.__file__))
 
 
-@pytest.mark.parametrize('name', ['tiny', 'tiny_pos', 'c1'])
+@pytest.mark.parametrize('name', ['tiny', 'tiny_pos', 'c1', 'live'])
 def test_cost_volume_matches_reference(name):
     case, g, sd, L, R = load_case(name)
     cost = O.cost_volume(L, R, case['mindisp'], case['maxdisp'])
@@ -22,7 +22,7 @@ def test_cost_volume_matches_reference(name):
         assert np.array_equal(cost.numpy(), g['cost'])
 
 
-@pytest.mark.parametrize('name', ['tiny', 'tiny_pos', 'c1'])
+@pytest.mark.parametrize('name', ['tiny', 'tiny_pos', 'c1', 'live'])
 def test_stack_and_regression_match_reference(name):
     case, g, sd, L, R = load_case(name)
     torch.set_num_threads(8)
@@ -32,7 +32,8 @@ def test_stack_and_regression_match_reference(name):
         up = O.upsample_softargmin(logits, case['mindisp'], case['maxdisp'], 4 * case['Hf'], 4 * case['Wf'])
         gen = O.upsample_softargmin(logits, case['mindisp'], case['maxdisp'], case['Hf'], case['Wf'])
     # same torch CPU ops as the reference modules -> agreement far below the 1e-3 parity tolerance
-    assert np.abs(logits.numpy() - g['logits']).max() < 2e-5
+    if 'logits' in g.files:   # (the larger fixtures keep only the disparity maps)
+        assert np.abs(logits.numpy() - g['logits']).max() < 2e-5
     assert np.abs(up.numpy() - g['pred_up']).max() < 5e-5
     assert np.abs(gen.numpy() - g['pred_genuine']).max() < 5e-5
     if 'cost0' in g.files:
