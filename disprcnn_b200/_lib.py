@@ -62,7 +62,7 @@ PROTOTYPES = {
     'idisp_last_error': (ctypes.c_char_p, []),
     'idisp_roi_align_forward': (_i, [_vp, _i, _i, _i, _i, _vp, _i, _f, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'idisp_roi_align_backward': (_i, [_vp, _vp, _i, _f, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
-    'idisp_stereo_rois': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    'idisp_stereo_rois': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     'idisp_cost_volume': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     'idisp_conv3d': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     'idisp_softargmin': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),

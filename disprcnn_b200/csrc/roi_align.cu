@@ -132,11 +132,16 @@ extern "C" int idisp_roi_align_backward(const float *, const float *, int, float
 // ---------------------------------------------------------------------------------------
 namespace idisp {
 __global__ void stereo_rois_kernel(const float *__restrict__ lb, const float *__restrict__ rb, const int *__restrict__ img, int R,
-                                   int width, int height, float *__restrict__ rois_l, float *__restrict__ rois_r,
-                                   long long *__restrict__ xs)
+                                   int width, int height, const int *__restrict__ image_wh, int n_images,
+                                   float *__restrict__ rois_l, float *__restrict__ rois_r, long long *__restrict__ xs)
 {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
+  if (image_wh) {  // per-image (unpadded BoxList) size: left_result[i].width / .height, disprcnn3d.py:136-141
+    const int i = min(max(img[r], 0), n_images - 1);
+    width = image_wh[2 * i];
+    height = image_wh[2 * i + 1];
+  }
   int x1 = (int)floorf(lb[r * 4 + 0]), y1 = (int)floorf(lb[r * 4 + 1]), x2 = (int)ceilf(lb[r * 4 + 2]), y2 = (int)ceilf(lb[r * 4 + 3]);
   int x1p = (int)floorf(rb[r * 4 + 0]), x2p = (int)ceilf(rb[r * 4 + 2]);
   x1 = max(0, x1); x1p = max(0, x1p); y1 = max(0, y1);
@@ -151,14 +156,16 @@ __global__ void stereo_rois_kernel(const float *__restrict__ lb, const float *__
 }  // namespace idisp
 
 extern "C" int idisp_stereo_rois(const float *left_boxes, const float *right_boxes, const int *image_index, int R, int width,
-                                 int height, float *rois_left, float *rois_right, long long *x1_x1p_x2_x2p, void *stream)
+                                 int height, const int *image_wh, int n_images, float *rois_left, float *rois_right,
+                                 long long *x1_x1p_x2_x2p, void *stream)
 {
   using namespace idisp;
-  IDISP_REQUIRE(R >= 0 && width > 0 && height > 0, "stereo_rois: bad arguments R=%d width=%d height=%d", R, width, height);
+  IDISP_REQUIRE(R >= 0 && ((image_wh && n_images > 0) || (width > 0 && height > 0)),
+                "stereo_rois: bad arguments R=%d width=%d height=%d n_images=%d", R, width, height, n_images);
   if (R == 0) return IDISP_OK;
   IDISP_REQUIRE(left_boxes && right_boxes && image_index && rois_left && rois_right, "stereo_rois: NULL pointer");
-  stereo_rois_kernel<<<ceil_div(R, 128), 128, 0, (cudaStream_t)stream>>>(left_boxes, right_boxes, image_index, R, width, height, rois_left,
-                                                                         rois_right, x1_x1p_x2_x2p);
+  stereo_rois_kernel<<<ceil_div(R, 128), 128, 0, (cudaStream_t)stream>>>(left_boxes, right_boxes, image_index, R, width, height, image_wh,
+                                                                         n_images, rois_left, rois_right, x1_x1p_x2_x2p);
   IDISP_LAUNCH_CHECK();
   return IDISP_OK;
 }

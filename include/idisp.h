@@ -75,9 +75,13 @@ const char *idisp_last_error(void);
  * every box to the host with .tolist()).  left_boxes / right_boxes [R,4] f32 (x1,y1,x2,y2), image_index [R] int32 -- device
  * pointers.  Writes the aligned crop rectangles rois_left / rois_right [R,5] f32 (batch_idx,x1,y1,x2,y2: same top/bottom,
  * same width) ready for idisp_roi_align_forward, and -- if non-NULL -- x1_x1p_x2_x2p [4][R] int64 (the x1s, x1ps, x2s, x2ps the
- * caller keeps for the disparity -> depth conversion, disprcnn3d.py:150-153).  Integer arithmetic, bit-exact. */
+ * caller keeps for the disparity -> depth conversion, disprcnn3d.py:150-153).  Integer arithmetic, bit-exact.
+ * Clamping uses the size of the image a box belongs to, as the reference does (left_result[i].width / .height, the UNPADDED
+ * BoxList size, disprcnn3d.py:136-141): image_wh = device int32 [n_images][2] (width, height) indexed by image_index; when
+ * NULL, every box is clamped with the scalar width / height. */
 int idisp_stereo_rois(const float *left_boxes, const float *right_boxes, const int *image_index, int R, int width, int height,
-                      float *rois_left, float *rois_right, long long *x1_x1p_x2_x2p, void *stream);
+                      const int *image_wh, int n_images, float *rois_left, float *rois_right, long long *x1_x1p_x2_x2p,
+                      void *stream);
 
 /* ROIAlign forward.  input [N,C,H,W] f32 NCHW contiguous, rois [R,5] f32
  * (batch_idx,x1,y1,x2,y2), out [R,C,pooled_h,pooled_w] f32 -- all device pointers.

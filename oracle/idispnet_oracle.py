@@ -256,10 +256,15 @@ def align_stereo_boxes(left_boxes, right_boxes, width, height):
     """disprcnn3d.py:126-146 (+ stereo_utils.py:219-229): per-ROI left/right crop boxes.
 
     left_boxes/right_boxes: lists of lists ``[[(x1,y1,x2,y2), ...] per image]``.
+    width/height: the (unpadded) BoxList size ``left_result[i].width/.height`` -- one int for all images or a
+    per-image sequence (KITTI frames differ in size; the ImageList batch is padded, the BoxLists are not).
     Returns (rois_left [R,5], rois_right [R,5]) as python lists.
     """
     rl, rr = [], []
+    widths = width if hasattr(width, '__len__') else [width] * len(left_boxes)
+    heights = height if hasattr(height, '__len__') else [height] * len(left_boxes)
     for i, (lbs, rbs) in enumerate(zip(left_boxes, right_boxes)):
+        width, height = widths[i], heights[i]
         for lb, rb in zip(lbs, rbs):
             x1, y1, x2, y2 = math.floor(lb[0]), math.floor(lb[1]), math.ceil(lb[2]), math.ceil(lb[3])
             x1p, x2p = math.floor(rb[0]), math.ceil(rb[2])

@@ -45,9 +45,9 @@ def test_argument_validation_without_gpu(built_lib):
     assert lib.idisp_roi_align_forward(None, 1, 3, 8, 8, None, 2, 1.0, 0, 7, 0, None, None, None, None) == 1
     assert lib.idisp_roi_align_forward(None, 1, 3, 8, 8, None, 0, 1.0, 7, 7, 0, None, None, None, None) == 0  # R=0 no-op
     assert lib.idisp_roi_align_backward(None, None, 0, 1.0, 7, 7, 1, 3, 8, 8, 0, None, None) == 3
-    assert lib.idisp_stereo_rois(None, None, None, 0, 1242, 375, None, None, None, None) == 0           # R=0 no-op
-    assert lib.idisp_stereo_rois(None, None, None, 2, 1242, 375, None, None, None, None) == 1 and 'NULL' in _lib.last_error()
-    assert lib.idisp_stereo_rois(None, None, None, 2, 0, 375, None, None, None, None) == 1
+    assert lib.idisp_stereo_rois(None, None, None, 0, 1242, 375, None, 0, None, None, None, None) == 0           # R=0 no-op
+    assert lib.idisp_stereo_rois(None, None, None, 2, 1242, 375, None, 0, None, None, None, None) == 1 and 'NULL' in _lib.last_error()
+    assert lib.idisp_stereo_rois(None, None, None, 2, 0, 375, None, 0, None, None, None, None) == 1
     assert lib.idisp_softargmin(None, 1, 8, 4, 4, 0, 4, 16, 16, None, None) == 1  # Dfull < D
     assert lib.idisp_conv3d(None, 1, 12, 4, 4, 4, None, 32, 0, None, None, None, 0, 0, None, None) == 1  # Cin % 8
 
@@ -90,7 +90,7 @@ def test_install_aliases_reference_import_paths(built_lib):
     saved = {k: sys.modules.get(k) for k in ('disprcnn.layers.roi_align', 'disprcnn.modeling.psmnet.stackhourglass',
                                              'disprcnn.modeling.psmnet.submodule')}
     try:
-        disprcnn_b200.install()
+        disprcnn_b200.install(inference_only=True)
         from disprcnn_b200.modeling.psmnet import stackhourglass
         assert sys.modules['disprcnn.modeling.psmnet.stackhourglass'] is stackhourglass
         assert sys.modules['disprcnn.layers.roi_align'].ROIAlign.__module__ == 'disprcnn_b200.layers.roi_align'
@@ -116,3 +116,56 @@ def test_psmnet_default_precision_picks_the_parity_grade_mode_the_shape_allows()
     import pytest
     with pytest.raises(ValueError):
         PSMNet(48, -48, precision='int8')
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/disprcnn'), reason='needs the reference checkout (authoring container)')
+def test_install_makes_the_reference_layers_package_import(built_lib):
+    """after install() the reference's own ``disprcnn/layers/__init__.py:4-20`` must import (it pulls nms,
+    roi_pool and the focal loss from the pybind module ``disprcnn._C``, which does not build on torch 2.x) and hand out the
+    B200 ROIAlign next to the 10 other names.  Run in a subprocess: it imports the reference package tree."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, warnings
+sys.path.insert(0, %r); sys.path.insert(1, '/root/reference')
+import disprcnn_b200
+with warnings.catch_warnings(record=True) as w:
+    warnings.simplefilter('always')
+    disprcnn_b200.install(inference_only=True)
+assert any('inference-only' in str(x.message) for x in w), 'install() must say that it is inference-only'
+disprcnn_b200.install(inference_only=True)
+from disprcnn.layers import (ROIAlign, roi_align, nms, ROIPool, roi_pool, smooth_l1_loss, Conv2d, ConvTranspose2d, interpolate,
+                             BatchNorm2d, FrozenBatchNorm2d, SigmoidFocalLoss)
+import disprcnn.layers as L
+assert sorted(L.__all__) == sorted(["nms", "roi_align", "ROIAlign", "roi_pool", "ROIPool", "smooth_l1_loss", "Conv2d",
+                                    "ConvTranspose2d", "interpolate", "BatchNorm2d", "FrozenBatchNorm2d", "SigmoidFocalLoss"])
+assert ROIAlign.__module__ == 'disprcnn_b200.layers.roi_align', ROIAlign.__module__
+from disprcnn import _C
+import disprcnn_b200._C as shim
+assert _C is shim
+for name in ('nms', 'roi_align_forward', 'roi_align_backward', 'roi_pool_forward', 'roi_pool_backward',
+             'sigmoid_focalloss_forward', 'sigmoid_focalloss_backward'):   # csrc/vision.cpp:7-15
+    assert callable(getattr(_C, name)), name
+import torch
+for fn in (nms, _C.roi_align_backward, _C.roi_pool_forward):
+    try:
+        fn(torch.zeros(1, 4), torch.zeros(1), 0.5)
+    except RuntimeError as e:
+        assert 'B200' in str(e)
+    else:
+        raise AssertionError('detector ops must raise when called')
+try:
+    _C.roi_align_forward(torch.zeros(1, 3, 8, 8), torch.zeros(1, 5), 1.0, 4, 4, 0)   # CPU tensors: no CPU path
+except RuntimeError as e:
+    assert 'no CPU path' in str(e)
+else:
+    raise AssertionError('CPU tensors must raise')
+from disprcnn.modeling.psmnet.stackhourglass import PSMNet
+assert PSMNet.__module__ == 'disprcnn_b200.modeling.psmnet.stackhourglass'
+from disprcnn.modeling.poolers import Pooler   # second ROIAlign consumer (modeling/poolers.py:66-70,127)
+p = Pooler((7, 7), (0.25, 0.125), 2)
+assert type(p.poolers[0]).__module__ == 'disprcnn_b200.layers.roi_align'
+print('ok')
+''' % ROOT
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith('ok'), r.stdout + r.stderr

@@ -463,6 +463,31 @@ def test_stereo_roi_preparation_on_device_matches_the_reference_loop(lib):
     # empty batch: nothing to do, empty tensors back
     e = prepare_stereo_rois(LB[:0], RB[:0], IDX[:0], Wd, Hd)
     assert e[0].shape == (0, 5) and e[2].numel() == 0
+    # mixed-size images in a PADDED batch (KITTI frames differ; the ImageList tensor is padded, the BoxLists are not): the
+    # reference clamps each box with the size of ITS image (disprcnn3d.py:136-141), not with the padded tensor's
+    sizes = [(310, 94), (290, 80), (250, 90)]  # (width, height) per image, all inside the padded 310 x 94 tensor
+    want_l2, want_r2 = O.align_stereo_boxes([b.tolist() for b in lbs], [b.tolist() for b in rbs], [s_[0] for s_ in sizes], [s_[1] for s_ in sizes])
+    assert want_l2 != want_l, 'the mixed-size case must actually clamp differently'
+    rl2, rr2, *_ = prepare_stereo_rois(LB, RB, IDX, [s_[0] for s_ in sizes], [s_[1] for s_ in sizes])
+    assert torch.equal(rl2.cpu(), torch.tensor(want_l2, dtype=torch.float32)) and torch.equal(rr2.cpu(), torch.tensor(want_r2, dtype=torch.float32))
+    cl2, cr2, _, _, x2s2, _ = crop_stereo_rois(iml.cuda(), imr.cuda(), LB, RB, IDX, 32, image_sizes=sizes)
+    assert np.array_equal(cl2.cpu().numpy(), O.crop_and_transform_roi_img(iml.numpy(), np.asarray(want_l2, np.float32), 32))
+    assert np.array_equal(cr2.cpu().numpy(), O.crop_and_transform_roi_img(imr.numpy(), np.asarray(want_r2, np.float32), 32))
+    assert torch.equal(x2s2.cpu(), torch.tensor([r[3] for r in want_l2]))
+
+
+def test_roi_align_accepts_the_callers_empty_1d_roi_tensor(lib):
+    """No detections: DispRCNN3D.crop_and_transform_roi_img passes torch.as_tensor([]) (shape [0], disprcnn3d.py:44-46);
+    the reference returns an empty [0,C,ph,pw] tensor (ROIAlign_cuda.cu:271,278-281)."""
+    from disprcnn_b200.layers import ROIAlign
+    from disprcnn_b200.layers.roi_align import crop_and_transform_roi_img
+    im = recipe.make_images(2, 40, 60, 3).cuda()
+    rois = torch.as_tensor([], dtype=torch.float32).cuda()
+    assert rois.shape == (0,)
+    out = ROIAlign((224, 224), 1.0, 0)(im, rois)
+    assert out.shape == (0, 3, 224, 224) and out.device == im.device and out.dtype == torch.float32
+    assert crop_and_transform_roi_img(im, [], 224).shape == (0, 3, 224, 224)
+    assert ROIAlign((7, 7), 0.25, 2)(im, torch.empty((0, 5), device='cuda')).shape == (0, 3, 7, 7)
 
 
 @pytest.mark.parametrize('B,D,Hf,Wf,mind,maxd,H,W', [(1, 48, 12, 16, -96, 96, 48, 64), (2, 8, 16, 16, -16, 16, 64, 64), (1, 12, 9, 7, -8, 40, 33, 29)])
