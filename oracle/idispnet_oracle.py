@@ -23,6 +23,8 @@ Reference locations restated here (paths relative to the reference root):
   classif1..3 ............ stackhourglass.py:78-88, applied :142-144
   trilinear + softmax .... stackhourglass.py:169-172
   disparityregression .... submodule.py:51-57
+  feature_extraction ..... submodule.py:60-139 (convbn :13-16, BasicBlock :25-48)
+  PSMNet.forward ......... stackhourglass.py:106-174 (image crops -> extractor -> the rows above)
   ROIAlign (CPU kernel) .. disprcnn/csrc/cpu/ROIAlign_cpu.cpp:18-219
   crop + normalise ....... disprcnn/modeling/detector/disprcnn3d.py:44-50
   ROI box alignment ...... disprcnn3d.py:126-146, utils/stereo_utils.py:219-229
@@ -155,6 +157,65 @@ def idispnet_from_features(left_fea, right_fea, sd, mindisp, maxdisp, H=None, W=
     cost = cost_volume(left_fea, right_fea, mindisp, maxdisp)
     cost3 = stack3d(cost, sd)
     return upsample_softargmin(cost3, mindisp, maxdisp, H, W)
+
+
+# ----------------------------------------------------------------------------
+# 2-D feature extractor (submodule.py:60-139) and the whole PSMNet.forward (stackhourglass.py:106-174)
+# ----------------------------------------------------------------------------
+def _bn2d(x, sd, prefix):
+    return F.batch_norm(x, sd[prefix + '.running_mean'], sd[prefix + '.running_var'], sd[prefix + '.weight'], sd[prefix + '.bias'],
+                        False, 0.0, BN_EPS)
+
+
+def _convbn2d(x, sd, prefix, stride, pad, dilation):
+    """submodule.py:13-16: Conv2d(k, stride, padding = dilation if dilation > 1 else pad, dilation, bias=False) + BatchNorm2d."""
+    w = sd[prefix + '.0.weight']
+    return _bn2d(F.conv2d(x, w, None, stride, dilation if dilation > 1 else pad, dilation), sd, prefix + '.1')
+
+
+def _basic_block(x, sd, p, stride, pad, dilation):
+    """submodule.py:25-48: conv1 (convbn + ReLU), conv2 (convbn), optional 1x1 downsample of the input, add (NO ReLU after)."""
+    out = F.relu(_convbn2d(x, sd, p + '.conv1.0', stride, pad, dilation))
+    out = _convbn2d(out, sd, p + '.conv2', 1, pad, dilation)
+    if (p + '.downsample.0.weight') in sd:
+        x = _bn2d(F.conv2d(x, sd[p + '.downsample.0.weight'], None, stride), sd, p + '.downsample.1')
+    return out + x
+
+
+def feature_extraction(x, sd, prefix='feature_extraction.', return_intermediates=False):
+    """submodule.py:112-139.  x [B,3,H,W] -> [B,32,H/4,W/4]."""
+    pre = prefix
+    o = F.relu(_convbn2d(x, sd, pre + 'firstconv.0', 2, 1, 1))
+    o = F.relu(_convbn2d(o, sd, pre + 'firstconv.2', 1, 1, 1))
+    o = F.relu(_convbn2d(o, sd, pre + 'firstconv.4', 1, 1, 1))
+    first = o
+    for b in range(3):
+        o = _basic_block(o, sd, f'{pre}layer1.{b}', 1, 1, 1)
+    for b in range(16):
+        o = _basic_block(o, sd, f'{pre}layer2.{b}', 2 if b == 0 else 1, 1, 1)
+    raw = o
+    for b in range(3):
+        o = _basic_block(o, sd, f'{pre}layer3.{b}', 1, 1, 1)
+    for b in range(3):
+        o = _basic_block(o, sd, f'{pre}layer4.{b}', 1, 1, 2)
+    skip = o
+    size = skip.shape[-2:]
+    branches = {}
+    for k, name in ((56, 'branch1'), (32, 'branch2'), (16, 'branch3'), (8, 'branch4')):
+        bo = F.relu(_convbn2d(F.avg_pool2d(skip, (k, k), (k, k)), sd, f'{pre}{name}.1', 1, 0, 1))
+        branches[name] = F.interpolate(bo, size, mode='bilinear', align_corners=True)
+    cat = torch.cat((raw, skip, branches['branch4'], branches['branch3'], branches['branch2'], branches['branch1']), 1)
+    o = F.relu(_convbn2d(cat, sd, pre + 'lastconv.0', 1, 1, 1))
+    out = F.conv2d(o, sd[pre + 'lastconv.2.weight'])
+    if return_intermediates:
+        return out, dict(first=first, raw=raw, skip=skip, cat=cat)
+    return out
+
+
+def psmnet_forward(left, right, sd, mindisp, maxdisp):
+    """stackhourglass.py:106-174 in eval mode: image crops [B,3,H,W] x2 -> disparity [B,H,W] (pred3)."""
+    H, W = left.shape[-2:]
+    return idispnet_from_features(feature_extraction(left, sd), feature_extraction(right, sd), sd, mindisp, maxdisp, H, W)
 
 
 # ----------------------------------------------------------------------------

@@ -14,6 +14,9 @@ What is executed:
     disparity at H,W = Hf,Wf.  The 4x-upsampled variant (H,W = 4Hf,4Wf) re-runs lines
     :130-174 on the reference's own sub-modules.
   * The same network in float64 (``.double()``) as arbiter.
+  * The live drop-in call (``psm_*``): ``PSMNet.forward`` UNMODIFIED -- real ``feature_extraction`` on [R,3,224,224] crop pairs
+    (what ``DispRCNN3D._forward_eval`` does, disprcnn3d.py:266-284) -- plus the reference's own per-view features.
+  * ``raw_*``: the 3-D stack with the reference's DEFAULT initialisation (stackhourglass.py:90-104), uncalibrated.
   * ROIAlign: the reference CPU kernel compiled from its own source.
 BatchNorm running statistics are calibrated by two train-mode passes of the reference
 and stored in the fixture (weights themselves are regenerated from tests/golden/recipe.py).
@@ -131,6 +134,101 @@ def gen_case(name, case):
     np.savez_compressed(os.path.join(HERE, f'idisp_{name}.npz'), **out)
 
 
+def _weights_crc(sd0):
+    wsum = 0
+    for k in sorted(sd0):
+        wsum = (wsum * 31 + int(recipe.checksum(sd0[k])[0])) & 0x7FFFFFFFFFFF
+    return np.array([wsum], dtype=np.int64)
+
+
+def gen_psm(name, case):
+    """The live drop-in call (disprcnn3d.py:266-284 -> stackhourglass.py:106-174): image crop pairs [R,3,224,224] through the
+    UNMODIFIED reference PSMNet.forward -- real feature_extraction (submodule.py:60-139) + cost volume + 3-D stack + regression.
+    Also stores the reference's own per-view features (forward hook on feature_extraction) for the extractor's parity test."""
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    m = PSMNet(case['maxdisp'], case['mindisp'])
+    shapes = dict(recipe.stack3d_shapes(32))
+    shapes.update(recipe.feature2d_shapes())
+    sd0 = recipe.make_state_dict(shapes, case['seed'])
+    missing, unexpected = m.load_state_dict(sd0, strict=True)
+    for mod in m.modules():
+        if isinstance(mod, (nn.BatchNorm2d, nn.BatchNorm3d)):
+            mod.momentum = None
+    m.train()
+    with torch.no_grad():
+        for j in range(2):
+            L, R = recipe.make_stereo_crops(case['R'], case['size'], case['seed'] + 100 + j)
+            m((L, R))
+    m.eval()
+    L, R = recipe.make_stereo_crops(case['R'], case['size'], case['seed'])
+    feas = []
+    hook = m.feature_extraction.register_forward_hook(lambda mod, inp, out: feas.append(out.clone()))
+    with torch.no_grad():
+        pred = m({'left': L, 'right': R})      # dict form, as DispRCNN3D calls it (disprcnn3d.py:273)
+        pred_seq = m((L, R))                   # 2-sequence form (stackhourglass.py:110-111)
+    hook.remove()
+    assert torch.equal(pred, pred_seq) and len(feas) == 4
+    with torch.no_grad():
+        # float64 arbiter: the reference forward allocates its cost volume as a FloatTensor (stackhourglass.py:117), so the
+        # double twin runs the same steps by hand: extractor -> cost volume (oracle restatement of :115-128) -> :130-174
+        import idispnet_oracle as O
+        m64 = m.double()
+        f64 = [m64.feature_extraction(L.double()), m64.feature_extraction(R.double())]
+        cost64 = O.cost_volume(f64[0], f64[1], case['mindisp'], case['maxdisp'])
+        pred64, _, _ = ref_tail(m64, cost64, case['size'], case['size'])
+    m.float()
+    with torch.no_grad():  # the same hand-run chain in float32 reproduces the genuine forward bit for bit
+        p32, _, _ = ref_tail(m, O.cost_volume(feas[0], feas[1], case['mindisp'], case['maxdisp']), case['size'], case['size'])
+        assert torch.equal(p32, pred)
+    out = dict(pred=pred.numpy(), pred_f64=pred64.numpy().astype(np.float32), fea_left=feas[0].numpy(), fea_right=feas[1].numpy(),
+               fea_left_f64=f64[0].numpy().astype(np.float32),
+               left_crc=recipe.checksum(L), right_crc=recipe.checksum(R), weights_crc=_weights_crc(sd0))
+    for k, v in m.state_dict().items():
+        if k.endswith('running_mean') or k.endswith('running_var'):
+            out['bn/' + k] = v.numpy()
+    e32 = float(np.abs(out['pred'] - pred64.numpy()).max())
+    ef = float(np.abs(out['fea_left'] - f64[0].numpy()).max())
+    out['ref_f32_vs_f64_maxabs'] = np.array([e32])
+    print(f'{name}: disp range [{float(pred.min()):.2f},{float(pred.max()):.2f}] std {float(pred.std()):.2f}; ref fp32-vs-fp64 max|d| {e32:.3e}; '
+          f'features |max| {float(feas[0].abs().max()):.2f}, fp32-vs-fp64 {ef:.3e}')
+    np.savez_compressed(os.path.join(HERE, f'{name}.npz'), **out)
+
+
+def gen_raw(name, case):
+    """Default-initialised weights (stackhourglass.py:90-104): no calibration, nothing damped -- logits of std
+    ~17, where the reference's own fp32 forward is already ~3e-3 px from its float64 twin."""
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    m = PSMNet(case['maxdisp'], case['mindisp'])
+    m.feature_extraction = nn.Identity()
+    sd0 = recipe.make_state_dict(recipe.stack3d_shapes(case['C']), case['seed'], raw=True)
+    missing, unexpected = m.load_state_dict(sd0, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    m.eval()
+    L, R = recipe.make_features(case['B'], case['C'], case['Hf'], case['Wf'], case['seed'])
+    captured = {}
+    hook = m.dres0.register_forward_pre_hook(lambda mod, inp: captured.__setitem__('cost', inp[0].clone()))
+    with torch.no_grad():
+        pred_genuine = m((L, R))
+    hook.remove()
+    cost = captured['cost']
+    Hf, Wf = case['Hf'], case['Wf']
+    with torch.no_grad():
+        pred_up, logits, _ = ref_tail(m, cost, 4 * Hf, 4 * Wf)
+        m64 = m.double()
+        p64_up, logits64, _ = ref_tail(m64, cost.double(), 4 * Hf, 4 * Wf)
+        p64_g, _, _ = ref_tail(m64, cost.double(), Hf, Wf)
+    m.float()
+    e32 = float(np.abs(pred_up.numpy() - p64_up.numpy()).max())
+    out = dict(pred_up=pred_up.numpy(), pred_genuine=pred_genuine.numpy(), pred_up_f64=p64_up.numpy().astype(np.float32),
+               pred_genuine_f64=p64_g.numpy().astype(np.float32),
+               left_crc=recipe.checksum(L), right_crc=recipe.checksum(R), weights_crc=_weights_crc(sd0),
+               ref_f32_vs_f64_maxabs=np.array([e32]), logits_std=np.array([float(logits.std())]))
+    print(f'{name}: logits std {float(logits.std()):.3f}  ref fp32-vs-fp64 max|d| {e32:.3e}  disp range [{float(pred_up.min()):.2f},{float(pred_up.max()):.2f}]')
+    np.savez_compressed(os.path.join(HERE, f'{name}.npz'), **out)
+
+
 def gen_roi():
     import build_ref
     ref = build_ref.build()
@@ -145,9 +243,13 @@ def gen_roi():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or list(recipe.CASES) + ['roi']
+    which = sys.argv[1:] or list(recipe.CASES) + list(recipe.PSM_CASES) + list(recipe.RAW_CASES) + ['roi']
     for name in which:
         if name == 'roi':
             gen_roi()
+        elif name in recipe.PSM_CASES:
+            gen_psm(name, recipe.PSM_CASES[name])
+        elif name in recipe.RAW_CASES:
+            gen_raw(name, recipe.RAW_CASES[name])
         else:
             gen_case(name, recipe.CASES[name])

@@ -18,17 +18,32 @@ def _gen(seed, key):
     return g
 
 
-def make_state_dict(shapes, seed, classif_damp=0.1):
+def make_state_dict(shapes, seed, classif_damp=0.1, raw=False):
     """shapes: {state_dict key: shape}.  'Trained-like' weights:
 
     He-normal conv kernels, BN affine parameters jittered around (1, 0), identity BN
     running statistics (the generator calibrates them and stores the calibrated values),
     final classifier kernels damped so the soft-argmin is smooth.
+
+    raw=True: the reference's DEFAULT INITIALISATION instead (stackhourglass.py:90-104) -- He-normal Conv2d/Conv3d kernels,
+    PyTorch's own kaiming-uniform(a=sqrt(5)) for the transposed convs the init loop skips, BN (1, 0) with identity running
+    statistics, nothing damped, nothing calibrated (the raw fixture next to the trained-like one).
     """
     sd = {}
     for key in sorted(shapes):
         shape = tuple(shapes[key])
         g = _gen(seed, key)
+        if raw and not key.endswith('num_batches_tracked') and not key.endswith('running_mean') and not key.endswith('running_var'):
+            if len(shape) >= 4:
+                ksz = int(np.prod(shape[2:]))
+                if ('.conv5.' in key) or ('.conv6.' in key):   # ConvTranspose3d [Cin,Cout,k,k,k]: fan_in = size(1)*k^3
+                    bound = 1.0 / math.sqrt(shape[1] * ksz)
+                    sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+                else:
+                    sd[key] = torch.randn(shape, generator=g) * math.sqrt(2.0 / (ksz * shape[0]))
+            else:
+                sd[key] = torch.ones(shape) if key.endswith('.weight') else torch.zeros(shape)
+            continue
         if key.endswith('num_batches_tracked'):
             t = torch.zeros(shape, dtype=torch.int64)
         elif key.endswith('running_mean'):
@@ -59,6 +74,24 @@ def make_features(B, C, Hf, Wf, seed, relu=True):
     if relu:
         L, R = L.relu(), R.relu()
     return L.contiguous(), R.contiguous()
+
+
+def make_stereo_crops(R, size, seed, max_shift=12):
+    """R left/right ROI crop pairs [R,3,size,size] as DispRCNN3D hands them to PSMNet (disprcnn3d.py:44-50: ROIAlign-ed image
+    crops, ImageNet-normalised): a smooth random texture per ROI, the right view = the left one shifted by a per-ROI number of
+    pixels plus a little independent noise, so the network sees a real correspondence problem."""
+    g = _gen(seed, 'crops')
+    pad = 2 * max_shift
+    base = torch.rand(R, 3, size + 8, size + pad + 8, generator=g)
+    base = torch.nn.functional.avg_pool2d(base, 5, 1, 2) * 0.6 + torch.nn.functional.avg_pool2d(base, 9, 1, 4) * 0.4
+    base = (base - base.mean()) / base.std() * 0.25 + 0.45
+    noise = torch.randn(R, 3, size, size, generator=g) * 0.01
+    shifts = torch.randint(-max_shift, max_shift + 1, (R,), generator=g)
+    left = torch.stack([base[r, :, 4:4 + size, 4 + max_shift:4 + max_shift + size] for r in range(R)])
+    right = torch.stack([base[r, :, 4:4 + size, 4 + max_shift + int(shifts[r]):4 + max_shift + int(shifts[r]) + size] for r in range(R)]) + noise
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    return ((left.clamp(0, 1) - mean) / std).contiguous(), ((right.clamp(0, 1) - mean) / std).contiguous()
 
 
 def make_images(B, H, W, seed):
@@ -97,6 +130,54 @@ def stack3d_shapes(C):
         shapes[c + '.2.weight'] = (1, 32, 3, 3, 3)
     return shapes
 
+
+def feature2d_shapes(prefix='feature_extraction.'):
+    """state_dict keys -> shapes of the 2-D extractor (disprcnn/modeling/psmnet/submodule.py:60-110), written out by hand so
+    the GPU box regenerates the weights without the reference: firstconv (3 convbn), layer1 3 x / layer2 16 x / layer3 3 x /
+    layer4 3 x BasicBlock (conv1 = convbn+ReLU, conv2 = convbn, 1x1 downsample at layer2.0 and layer3.0), four SPP branches
+    (1x1 convbn 128->32), lastconv (convbn 320->128 3x3, Conv2d 128->32 1x1)."""
+    shapes = {}
+
+    def bn(p, c):
+        for k in ('weight', 'bias', 'running_mean', 'running_var'):
+            shapes[p + '.' + k] = (c,)
+        shapes[p + '.num_batches_tracked'] = ()
+
+    def convbn(p, cin, cout, k):
+        shapes[p + '.0.weight'] = (cout, cin, k, k)
+        bn(p + '.1', cout)
+
+    convbn(prefix + 'firstconv.0', 3, 32, 3)
+    convbn(prefix + 'firstconv.2', 32, 32, 3)
+    convbn(prefix + 'firstconv.4', 32, 32, 3)
+    inpl = 32
+    for name, planes, blocks, stride in (('layer1', 32, 3, 1), ('layer2', 64, 16, 2), ('layer3', 128, 3, 1), ('layer4', 128, 3, 1)):
+        for b in range(blocks):
+            p = f'{prefix}{name}.{b}'
+            convbn(p + '.conv1.0', inpl if b == 0 else planes, planes, 3)
+            convbn(p + '.conv2', planes, planes, 3)
+            if b == 0 and (stride != 1 or inpl != planes):
+                shapes[p + '.downsample.0.weight'] = (planes, inpl, 1, 1)
+                bn(p + '.downsample.1', planes)
+        inpl = planes
+    for br in ('branch1', 'branch2', 'branch3', 'branch4'):
+        convbn(f'{prefix}{br}.1', 128, 32, 1)
+    convbn(prefix + 'lastconv.0', 320, 128, 3)
+    shapes[prefix + 'lastconv.2.weight'] = (32, 128, 1, 1)
+    return shapes
+
+
+# whole-PSMNet cases (image crops through the real feature_extraction + the 3-D stack): the live drop-in call
+# DispRCNN3D._forward_eval makes (disprcnn3d.py:266-284 -> stackhourglass.py:106-174)
+PSM_CASES = {
+    'psm_live': dict(R=2, size=224, mindisp=-48, maxdisp=48, seed=41),
+}
+
+# default-initialisation cases (no calibration, nothing damped): stackhourglass.py:90-104 as is
+RAW_CASES = {
+    'raw_tiny': dict(B=2, C=32, Hf=16, Wf=16, mindisp=-16, maxdisp=16, seed=51),
+    'raw_live': dict(B=1, C=32, Hf=56, Wf=56, mindisp=-48, maxdisp=48, seed=52),
+}
 
 CASES = {
     # name: B, C, Hf, Wf, mindisp, maxdisp, seed

@@ -131,7 +131,7 @@ sys.path.insert(0, %r); sys.path.insert(1, '/root/reference')
 import disprcnn_b200
 with warnings.catch_warnings(record=True) as w:
     warnings.simplefilter('always')
-    disprcnn_b200.install(inference_only=True)
+    disprcnn_b200.install()
 assert any('inference-only' in str(x.message) for x in w), 'install() must say that it is inference-only'
 disprcnn_b200.install(inference_only=True)
 from disprcnn.layers import (ROIAlign, roi_align, nms, ROIPool, roi_pool, smooth_l1_loss, Conv2d, ConvTranspose2d, interpolate,

@@ -1,0 +1,167 @@
+"""GPU parity tests of the LIVE drop-in call and of the configs round 1 left untested ("untested configs"):
+
+* the call DispRCNN3D._forward_eval makes (disprcnn3d.py:266-284 -> stackhourglass.py:106-174): image crops [R,3,224,224]
+  through feature_extraction AND the 3-D stack, against the disparity the UNMODIFIED reference PSMNet.forward produced;
+* aligned boxes -> fused ROIAlign crops of both views -> PSMNet, end to end against the oracle chain;
+* the host-buffer entry point (the e2e path of bench.py) in the split-precision mode at the live and benchmark shapes;
+* default-initialised weights;
+* N-rank sharded + gathered == unsharded, bit for bit (needs >= 2 GPUs).
+Tolerance everywhere: 1e-3 px abs against the reference's fp32 forward (north_star), unless stated.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import idispnet_oracle as O
+import recipe
+from helpers import load_case, load_psm_case, load_raw_case, make_full_psmnet, make_psmnet
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-3
+
+
+@pytest.fixture(scope='module')
+def lib(built_lib):
+    return built_lib
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    """Any torch/cuDNN op these tests still reach must run in fp32 (PyTorch's conv default is TF32)."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize('prec', ['auto', 'fp32'])
+def test_whole_psmnet_on_image_crops_matches_reference_forward(lib, prec):
+    case, g, sd, L, R = load_psm_case('psm_live')
+    m = make_full_psmnet(case, sd, prec)
+    assert m.effective_precision(56, 56) == ('fp16x2' if prec == 'auto' else 'fp32')
+    with torch.no_grad():
+        pred = m({'left': L.cuda(), 'right': R.cuda()})          # as DispRCNN3D calls it (disprcnn3d.py:273)
+        pred_seq = m((L.cuda(), R.cuda()))                        # 2-sequence form (stackhourglass.py:110-111)
+        fl = m.feature_extraction(L.cuda())
+    assert tuple(pred.shape) == (case['R'], case['size'], case['size']) and torch.equal(pred, pred_seq)
+    e = np.abs(pred.cpu().numpy() - g['pred'])
+    ef = np.abs(fl.cpu().numpy() - g['fea_left']).max()
+    e64 = np.abs(pred.cpu().numpy() - g['pred_f64']).max()
+    print(f'\n[psm_live] {prec}: |disp - ref_fp32| max {e.max():.3e} mean {e.mean():.3e}; vs float64 arbiter {e64:.3e} '
+          f'(reference itself {float(g["ref_f32_vs_f64_maxabs"][0]):.3e}); |features - ref| max {ef:.3e}')
+    assert e.max() < TOL
+    assert ef < 1e-3
+
+
+def test_boxes_to_disparity_end_to_end_vs_oracle(lib):
+    """disprcnn3d.py:113-159 + :266-284: boxes of a padded 2-image batch -> aligned crop rectangles -> ROIAlign + normalise of
+    both views -> PSMNet.  Product: crop_stereo_rois + PSMNet('auto').  Checker: the oracle's chain on the CPU."""
+    from disprcnn_b200.layers.roi_align import crop_stereo_rois
+    case, g, sd, _, _ = load_psm_case('psm_live')
+    Hd, Wd = 120, 400
+    base = recipe.make_images(2, Hd, Wd + 16, 77)
+    base = torch.nn.functional.avg_pool2d(base, 5, 1, 2)
+    iml, imr = base[..., 8:8 + Wd].contiguous(), base[..., 0:Wd].contiguous()     # right view = left shifted by 8 px
+    lbs = [[[30.2, 10.7, 150.9, 100.1]], [[200.5, 5.0, 395.2, 118.9]]]
+    rbs = [[[22.4, 10.7, 140.0, 100.1]], [[190.1, 5.0, 380.7, 118.9]]]
+    sizes = [(Wd, Hd), (Wd - 20, Hd - 6)]                                           # second image smaller than the padded tensor
+    want_l, want_r = O.align_stereo_boxes(lbs, rbs, [s[0] for s in sizes], [s[1] for s in sizes])
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    with torch.no_grad():
+        cl = torch.from_numpy(O.crop_and_transform_roi_img(iml.numpy(), np.asarray(want_l, np.float32), 224))
+        cr = torch.from_numpy(O.crop_and_transform_roi_img(imr.numpy(), np.asarray(want_r, np.float32), 224))
+        want = O.psmnet_forward(cl, cr, sd, case['mindisp'], case['maxdisp']).numpy()
+    m = make_full_psmnet(case, sd, 'auto')
+    LB = torch.tensor([b for im in lbs for b in im]).cuda()
+    RB = torch.tensor([b for im in rbs for b in im]).cuda()
+    IDX = torch.tensor([0, 1]).cuda()
+    with torch.no_grad():
+        gl, gr, x1s, x1ps, x2s, x2ps = crop_stereo_rois(iml.cuda(), imr.cuda(), LB, RB, IDX, 224, image_sizes=sizes)
+        got = m({'left': gl, 'right': gr}).cpu().numpy()
+    assert np.array_equal(gl.cpu().numpy(), cl.numpy()) and np.array_equal(gr.cpu().numpy(), cr.numpy())   # crops bit-exact
+    assert x2s.tolist() == [r[3] for r in want_l] and x1ps.tolist() == [r[1] for r in want_r]
+    e = np.abs(got - want)
+    print(f'\n[boxes -> disparity] max |d| {e.max():.3e} mean {e.mean():.3e} (disp range {want.min():.1f}..{want.max():.1f})')
+    assert e.max() < TOL
+
+
+@pytest.mark.parametrize('name,prec', [('live', 'fp16x2'), ('full', 'fp16x2'), ('live', 'fp32')])
+def test_host_buffer_entry_point_parity(lib, name, prec):
+    """idisp_plan_forward_host -- the call bench.py's e2e number goes through -- against the reference's own output, and
+    bit-identical to the device-pointer entry."""
+    from disprcnn_b200 import _lib
+    case, g, sd, L, R = load_case(name)
+    m = make_psmnet(case, sd, prec)
+    B, Hf, Wf = case['B'], case['Hf'], case['Wf']
+    with torch.no_grad():
+        dev = m.forward_features(L.cuda(), R.cuda()).cpu()
+    Lp, Rp = L.pin_memory(), R.pin_memory()
+    out = torch.full((B, 4 * Hf, 4 * Wf), float('nan')).pin_memory()
+    for _ in range(2):   # second call reuses the plan-owned staging
+        _lib.check(lib.idisp_plan_forward_host(m._plan, _lib.ptr(Lp), _lib.ptr(Rp), B, Hf, Wf, 4 * Hf, 4 * Wf, _lib.ptr(out), _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        assert torch.equal(out, dev)
+    e = np.abs(out.numpy() - g['pred_up']).max()
+    print(f'\n[{name}] {prec} through idisp_plan_forward_host: max |disp - ref_fp32| {e:.3e}')
+    assert e < TOL
+
+
+@pytest.mark.parametrize('name', ['raw_tiny', 'raw_live'])
+def test_default_initialised_weights(lib, name):
+    """Raw default initialisation (stackhourglass.py:90-104): logits of std ~15, where the reference's OWN fp32 forward is
+    up to 2.5e-3 px from its float64 twin.  Bar: no further from the float64 arbiter than the reference is, plus 1e-3."""
+    case, g, sd, L, R = load_raw_case(name)
+    ref64 = float(g['ref_f32_vs_f64_maxabs'][0])
+    for prec in ('fp32', 'fp16x2', 'auto'):
+        m = make_psmnet(case, sd, prec)
+        with torch.no_grad():
+            up = m.forward_features(L.cuda(), R.cuda()).cpu().numpy()
+            gen = m((L.cuda(), R.cuda())).cpu().numpy()
+        e32, e64 = np.abs(up - g['pred_up']).max(), np.abs(up - g['pred_up_f64']).max()
+        eg = np.abs(gen - g['pred_genuine_f64']).max()
+        print(f'\n[{name}] {prec}: |disp - ref_fp32| {e32:.3e}, |disp - ref_fp64| {e64:.3e} (genuine {eg:.3e}); reference fp32-vs-fp64 {ref64:.3e}')
+        assert e64 < ref64 + TOL and eg < ref64 + TOL
+        assert e32 < 2 * ref64 + TOL
+
+
+_SHARD_SCRIPT = r'''
+import os, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, 'tests')); sys.path.insert(0, os.path.join(%(root)r, 'tests', 'golden'))
+import torch, torch.distributed as dist
+from helpers import load_case, make_psmnet
+from disprcnn_b200.parallel import sharded_forward
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+torch.cuda.set_device(rank)
+dist.init_process_group('nccl', device_id=torch.device('cuda', rank))
+case, g, sd, L, R = load_case('live')
+L, R = torch.cat([L, L.flip(0), L * 0.5]), torch.cat([R, R.flip(0), R * 0.5])      # B = 6 (B = 5 below: ragged shards)
+for prec in ('fp16x2', 'fp32'):
+    m = make_psmnet(case, sd, prec, device=f'cuda:{rank}')
+    for B in (6, 5):
+        Ld, Rd = L[:B].cuda(), R[:B].cuda()
+        with torch.no_grad():
+            whole = m.forward_features(Ld, Rd)                 # unsharded, on this rank
+            got = sharded_forward(m, Ld, Rd)                   # this rank's shard + all-gather
+        assert got.shape == whole.shape, (got.shape, whole.shape)
+        assert torch.equal(got, whole), f'rank {rank} {prec} B={B}: sharded != unsharded, max |d| {(got - whole).abs().max().item()}'
+dist.barrier()
+if rank == 0:
+    print('SHARD_OK')
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.skipif(torch.cuda.is_available() and torch.cuda.device_count() < 2, reason='needs >= 2 GPUs')
+def test_two_rank_sharded_forward_equals_unsharded_bit_for_bit(lib, tmp_path):
+    """parallel.sharded_forward over 2 NCCL ranks (equal and ragged shards) == the unsharded forward on every rank."""
+    script = tmp_path / 'shard_check.py'
+    script.write_text(_SHARD_SCRIPT % {'root': ROOT})
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
+                        '--master-port', '29731', str(script)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and 'SHARD_OK' in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -8,7 +8,7 @@ import torch
 
 import idispnet_oracle as O
 import recipe
-from helpers import GOLDEN, load_case
+from helpers import GOLDEN, load_case, load_psm_case, load_raw_case
 
 ORACLE_DIR = os.path.dirname(os.path.abspath(O.__file__))
 
@@ -50,6 +50,32 @@ def test_disparityregression_and_full_entry():
     p = torch.softmax(torch.randn(2, 32, 3, 5), 1)
     ref = sum(p[:, d] * float(-16 + d) for d in range(32))
     assert torch.allclose(O.disparityregression(p, 16, -16), ref, atol=1e-5)
+
+
+def test_feature_extraction_and_whole_psmnet_match_reference():
+    """The live drop-in call: image crops through the extractor restatement (submodule.py:60-139) and the rest of the path,
+    against the features and the disparity the UNMODIFIED reference PSMNet.forward produced (tests/golden/psm_live.npz)."""
+    case, g, sd, L, R = load_psm_case('psm_live')
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        fl = O.feature_extraction(L, sd)
+        fr = O.feature_extraction(R, sd)
+        pred = O.idispnet_from_features(fl, fr, sd, case['mindisp'], case['maxdisp'], case['size'], case['size'])
+    assert np.abs(fl.numpy() - g['fea_left']).max() < 2e-5 and np.abs(fr.numpy() - g['fea_right']).max() < 2e-5
+    assert np.abs(pred.numpy() - g['pred']).max() < 5e-5
+    assert float(g['ref_f32_vs_f64_maxabs'][0]) < 1e-3
+
+
+@pytest.mark.parametrize('name', ['raw_tiny', 'raw_live'])
+def test_default_initialised_stack_matches_reference(name):
+    """the raw default-init fixture next to the trained-like ones (logit std ~15: the reference's own fp32
+    forward is up to 2.5e-3 px from its float64 twin there -- stored in the fixture)."""
+    case, g, sd, L, R = load_raw_case(name)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        up = O.idispnet_from_features(L, R, sd, case['mindisp'], case['maxdisp'])
+    assert np.abs(up.numpy() - g['pred_up']).max() < 2e-4
+    assert float(g['logits_std'][0]) > 10
 
 
 def _roi_inputs(rc):
