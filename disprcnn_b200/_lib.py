@@ -17,8 +17,9 @@ LIB_DIR = os.path.join(_HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libidisp.so')
 INCLUDE = os.path.join(os.path.dirname(_HERE), 'include')
 
-NVCC_FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
-              '-Xcompiler', '-fPIC', '-shared']
+NVCC_COMPILE_FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a', '-Xcompiler', '-fPIC']
+NVCC_LINK_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-Xcompiler', '-fPIC', '-shared']
+NVCC_FLAGS = NVCC_COMPILE_FLAGS + ['-shared']
 
 PREC_FP32, PREC_BF16, PREC_FP16, PREC_FP16X2 = 0, 1, 2, 3
 CONV_S1, CONV_S2, DECONV_S2 = 0, 1, 2
@@ -30,26 +31,46 @@ def _sources():
     return sorted(glob.glob(os.path.join(CSRC, '*.cu')))
 
 
+def _headers():
+    return glob.glob(os.path.join(CSRC, '*.cuh')) + glob.glob(os.path.join(INCLUDE, '*.h'))
+
+
 def _stale():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = _sources() + glob.glob(os.path.join(CSRC, '*.cuh')) + glob.glob(os.path.join(INCLUDE, '*.h'))
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in _sources() + _headers())
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/*.cu for sm_100a into disprcnn_b200/lib/libidisp.so (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/*.cu for sm_100a into disprcnn_b200/lib/libidisp.so (nvcc cross-compiles without a GPU).
+
+    One object per source (lib/obj/*.o, compiled in parallel, only the stale ones), then one link."""
     if not force and not _stale():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
+    from concurrent.futures import ThreadPoolExecutor
+    obj_dir = os.path.join(LIB_DIR, 'obj')
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB_PATH] + _sources()
-    if verbose:
-        print(' '.join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    hdr_t = max([os.path.getmtime(h) for h in _headers()] + [os.path.getmtime(os.path.abspath(__file__))])
+    jobs, objs = [], []
+    for src in _sources():
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + '.o')
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
+            jobs.append([nvcc] + NVCC_COMPILE_FLAGS + ['-c', src, '-o', obj])
+
+    def run(cmd):
+        if verbose:
+            print(' '.join(cmd))
+        return subprocess.run(cmd, capture_output=True, text=True)
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+        for r in ex.map(run, jobs):
+            if r.returncode != 0:
+                raise RuntimeError('nvcc failed:\n' + r.stdout + r.stderr)
+    r = run([nvcc] + NVCC_LINK_FLAGS + ['-o', LIB_PATH] + objs)
     if r.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + r.stdout + r.stderr)
+        raise RuntimeError('nvcc (link) failed:\n' + r.stdout + r.stderr)
     return LIB_PATH
 
 
@@ -76,6 +97,7 @@ PROTOTYPES = {
     'idisp_plan_forward_host': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     'idisp_plan_get_logits': (_i, [_vp, _vp, _vp]),
     'idisp_plan_launches_per_forward': (_i, [_vp]),
+    'idisp_plan_graph_stats': (_i, [_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     'idisp_plan_enable_timing': (_i, [_vp, _i]),
     'idisp_plan_get_timing': (_i, [_vp, _vp, _vp, _i]),
     'idisp_debug_fused_cost_volume': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
@@ -104,9 +126,13 @@ def last_error():
     return load().idisp_last_error().decode()
 
 
+class Unsupported(RuntimeError):
+    """IDISP_ERR_UNSUPPORTED (status 3): the selected precision mode does not cover this shape."""
+
+
 def check(rc):
     if rc != 0:
-        raise RuntimeError(f'libidisp: {last_error()} (status {rc})')
+        raise (Unsupported if rc == 3 else RuntimeError)(f'libidisp: {last_error()} (status {rc})')
 
 
 def ptr(t):

@@ -1118,9 +1118,12 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   if (MODE == tc::M_DEC) { p.Dout = 2 * D; p.Ho = 2 * H; p.Wo = 2 * W; p.Hr = H; p.Wr = W; }
   p.tiles_h = ceil_div(p.Hr, tc::TH); p.tiles_w = ceil_div(p.Wr, tc::TW); p.nh = (Cout + NT - 1) / NT;
   const int ncols = B * p.tiles_h * p.tiles_w;
-  int dev = 0, sms = 148;
+  int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static int sm_count[64];  // per device, queried once
+  if (dev < 0 || dev >= 64) { set_error("tc_conv3d: device ordinal %d out of range", dev); return IDISP_ERR_INVALID; }
+  if (!sm_count[dev]) cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count[dev] > 0 ? sm_count[dev] : 148;
   int per_slice = sms * OCC / p.nh;
   if (per_slice > ncols) per_slice = ncols;
   const int grid = per_slice * p.nh;
@@ -1138,7 +1141,11 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
     } else {
       using CX = tc::Cfg<CIN, MODE, OCC, NT, (FMT < 2 ? 0 : (FMT == 2 ? 3 : FMT - 2))>;
       auto kern = tc::conv3d_tc_kernel<CIN, MODE, OCC, CVK, NT, FMT>;
-      IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CX::SMEM));
+      static bool smem_opt_in[64];  // per kernel instantiation and device: the opt-in is sticky, set it once
+      if (!smem_opt_in[dev]) {
+        IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CX::SMEM));
+        smem_opt_in[dev] = true;
+      }
       if constexpr (CVK) kern<<<grid, CX::NTHREADS, CX::SMEM, s>>>(map, rmap, cvmaps, p);
       else kern<<<grid, CX::NTHREADS, CX::SMEM, s>>>(map, rmap, tc::CvMaps<false>{}, p);
       return IDISP_OK;

@@ -108,6 +108,16 @@ struct idisp_plan {
   bool timing = false;
   std::vector<cudaEvent_t> ev;
   std::vector<int> ev_layer;  // launch slot -> layer index (-1 cost volume, -2 soft-argmin, 25..27 the 32->1 convs)
+  // switches read ONCE at plan creation (tests flip them between plans): IDISP_NO_FUSED_SPLIT / IDISP_NO_FUSED_CV /
+  // IDISP_X2_SIMT_HEADS / IDISP_NO_GRAPH
+  bool no_fused_split = false, no_fused_cv = false, x2_simt_heads = false, no_graph = false;
+  // CUDA-graph replay of the conv section (everything between the input conversion and the soft-argmin touches only the
+  // workspace, so its ~45 launches -- each with a host-side tensor-map encode -- are captured once per
+  // (B, Hf, Wf, workspace) and replayed with ONE cudaGraphLaunch)
+  struct GraphEntry { int B, Hf, Wf; void *ws; cudaGraphExec_t exec; int launches; unsigned long long stamp; };
+  std::vector<GraphEntry> graphs;
+  unsigned long long graph_clock = 0;
+  int graph_hits = 0, graph_captures = 0;
 };
 
 extern "C" int idisp_version(void) { return IDISP_VERSION; }
@@ -127,6 +137,10 @@ extern "C" int idisp_plan_create(int C, int mindisp, int maxdisp, int precision,
   p->C = C; p->mindisp = mindisp; p->maxdisp = maxdisp; p->precision = precision; p->f16 = precision == IDISP_PREC_FP16 || precision == IDISP_PREC_FP16X2; p->x2 = precision == IDISP_PREC_FP16X2;
   p->D = (maxdisp - mindisp) / 4;
   p->layers = make_layers(C);
+  p->no_fused_split = getenv("IDISP_NO_FUSED_SPLIT") != nullptr;
+  p->no_fused_cv = getenv("IDISP_NO_FUSED_CV") != nullptr;
+  p->x2_simt_heads = getenv("IDISP_X2_SIMT_HEADS") != nullptr;
+  p->no_graph = getenv("IDISP_NO_GRAPH") != nullptr;
   *plan = p;
   return IDISP_OK;
 }
@@ -136,6 +150,7 @@ extern "C" void idisp_plan_destroy(idisp_plan_t *p)
   if (!p) return;
   for (auto &d : p->dev) { tc_weights_free(d.tc); tc_split_weights_free(d.sp); }
   for (auto e : p->ev) cudaEventDestroy(e);
+  for (auto &g : p->graphs) cudaGraphExecDestroy(g.exec);
   if (p->blob) cudaFree(p->blob);
   if (p->range_flag) cudaFree(p->range_flag);
   if (p->stage) cudaFree(p->stage);
@@ -205,6 +220,8 @@ extern "C" int idisp_plan_finalize(idisp_plan_t *p, void *stream)
     total += (wt[i].size() + 63) / 64 * 64 + (bs[i].size() + 63) / 64 * 64;
   }
   for (auto &d : p->dev) { tc_weights_free(d.tc); tc_split_weights_free(d.sp); }
+  for (auto &g : p->graphs) cudaGraphExecDestroy(g.exec);  // captured launches hold the old weight pointers
+  p->graphs.clear();
   if (p->blob) { cudaFree(p->blob); p->blob = nullptr; }
   IDISP_CUDA(cudaMalloc(&p->blob, total * sizeof(float)));
   p->dev.assign(nl, LayerDev());
@@ -344,11 +361,11 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
   // the fused parity-split hand-off needs every layer of the chain on the tensor-core path
   const bool fuse_split = std::is_same<T, __nv_bfloat16>::value && D % 4 == 0 && Hf % 4 == 0 && Wf % 4 == 0 &&
                           tc_supported(IDISP_CONV_S2, 32, 64, D, Hf, Wf) && tc_supported(IDISP_DECONV_S2, 64, 32, D / 2, Hf / 2, Wf / 2) &&
-                          tc_supported(IDISP_CONV_S1, 32, 32, D, Hf, Wf) && !getenv("IDISP_NO_FUSED_SPLIT");
+                          tc_supported(IDISP_CONV_S1, 32, 32, D, Hf, Wf) && !p->no_fused_split;
 #define RUN(expr) do { if ((rc = (expr)) != IDISP_OK) return rc; } while (0)
   // cost volume (stackhourglass.py:115-128)
   const bool fuse_cv = std::is_same<T, __nv_bfloat16>::value && tc_supported(IDISP_CONV_S1, 2 * C, 32, D, Hf, Wf) && C % 8 == 0 && D <= 64 &&
-                       !getenv("IDISP_NO_FUSED_CV");
+                       !p->no_fused_cv;
   if (fuse_cv) {
     // the [B,2C,D,H,W] volume is never written: dres0.0's TMA producer assembles each plane from the two feature maps
     mark(-1);
@@ -359,6 +376,14 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
       RUN(launch_ncdhw_to_blocked_h(left, (__nv_bfloat16 *)b.feaL, B, C, (int64_t)Hf * Wf, p->f16, s)); ++launches;
       RUN(launch_ncdhw_to_blocked_h(right, (__nv_bfloat16 *)b.feaR, B, C, (int64_t)Hf * Wf, p->f16, s)); ++launches;
     }
+  } else {
+    if (p->f16) { set_error("plan_forward: fp16 mode needs the fused cost volume (C in {16,32}, D <= 64)"); return IDISP_ERR_UNSUPPORTED; }
+    mark(-1);
+    RUN(launch_cost_volume_blocked<T>(left, right, B, C, Hf, Wf, p->mindisp, D, (T *)b.cv, s)); ++launches;
+  }
+  // ---- the conv section: reads/writes only the workspace -> one CUDA graph per (B, Hf, Wf, workspace) ----
+  auto conv_section = [&]() -> int {
+  if (fuse_cv) {
     TcCostVolume cvd;
     cvd.left = (const __nv_bfloat16 *)b.feaL; cvd.right = (const __nv_bfloat16 *)b.feaR;
     cvd.shift0 = p->mindisp >= 0 ? p->mindisp / 4 : -((-p->mindisp + 3) / 4);
@@ -366,9 +391,6 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
     ++launches;
     RUN(tc_layer(p, 0, nullptr, 0, &cvd, B, D, Hf, Wf, nullptr, 1, (__nv_bfloat16 *)b.a, nullptr, 0, nullptr, nullptr, b.split, b.part, s, launches));
   } else {
-    if (p->f16) { set_error("plan_forward: fp16 mode needs the fused cost volume (C in {16,32}, D <= 64)"); return IDISP_ERR_UNSUPPORTED; }
-    mark(-1);
-    RUN(launch_cost_volume_blocked<T>(left, right, B, C, Hf, Wf, p->mindisp, D, (T *)b.cv, s)); ++launches;
     RUN(conv(0, b.cv, D, Hf, Wf, nullptr, 1, b.a));
   }
   // dres0 (second conv), dres1 (:130-131)
@@ -402,8 +424,7 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
     float *dst = (k == 1) ? b.costY : b.costX;
     const float *prev = k == 0 ? nullptr : (k == 1 ? b.costX : b.costY);
     mark(25 + k);
-    static const int x2_simt_heads = getenv("IDISP_X2_SIMT_HEADS") ? 1 : 0;  // A/B switch
-    if (p->x2 && x2_simt_heads)
+    if (p->x2 && p->x2_simt_heads)  // A/B switch
       // split precision, 1-channel head on the CUDA cores straight from the hi|lo words (f32 weights and FMAs).  Measured at
       // B=32: 3.8 ms against 1.36 ms for the tensor-core form (w_lo in output column 1) -- kept only as a cross-check.
       RUN(launch_conv3d_to1_x2((const __nv_bfloat16 *)b.c, B, 32, D, Hf, Wf, p->dev[25 + k].w_tap, prev, dst, s));
@@ -414,6 +435,54 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
     else
       RUN(launch_conv3d_to1<T>((const T *)b.c, B, 32, D, Hf, Wf, p->dev[25 + k].w_tap, prev, dst, s));
     ++launches;
+  }
+  return IDISP_OK;
+  };  // conv_section
+  {
+    cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+    const bool graph_ok = !p->no_graph && !p->timing && std::is_same<T, __nv_bfloat16>::value &&
+                          cudaStreamIsCapturing(s, &cst) == cudaSuccess && cst == cudaStreamCaptureStatusNone;
+    if (!graph_ok) {
+      RUN(conv_section());
+    } else {
+      idisp_plan::GraphEntry *hit = nullptr;
+      for (auto &g : p->graphs)
+        if (g.B == B && g.Hf == Hf && g.Wf == Wf && g.ws == workspace) { hit = &g; break; }
+      if (!hit) {
+        const int before = launches;
+        cudaGraph_t graph = nullptr;
+        IDISP_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const int crc = conv_section();
+        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (crc != IDISP_OK) { if (graph) cudaGraphDestroy(graph); return crc; }
+        if (ce != cudaSuccess || !graph) { cudaGetLastError(); p->no_graph = true; launches = before; RUN(conv_section()); }
+        else {
+          cudaGraphExec_t exec = nullptr;
+          const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+          cudaGraphDestroy(graph);
+          if (ie != cudaSuccess) { cudaGetLastError(); p->no_graph = true; launches = before; RUN(conv_section()); }
+          else {
+            if (p->graphs.size() >= 48) {  // least recently used out
+              size_t lru = 0;
+              for (size_t i = 1; i < p->graphs.size(); ++i) if (p->graphs[i].stamp < p->graphs[lru].stamp) lru = i;
+              cudaGraphExecDestroy(p->graphs[lru].exec);
+              p->graphs.erase(p->graphs.begin() + lru);
+            }
+            p->graphs.push_back({B, Hf, Wf, workspace, exec, launches - before, 0ull});
+            hit = &p->graphs.back();
+            ++p->graph_captures;
+            launches = before;
+          }
+        }
+      } else {
+        ++p->graph_hits;
+      }
+      if (hit) {
+        hit->stamp = ++p->graph_clock;
+        IDISP_CUDA(cudaGraphLaunch(hit->exec, s));
+        launches += hit->launches;
+      }
+    }
   }
   // upsample + softmax + regression (:169-174)
   mark(-2);
@@ -491,6 +560,14 @@ extern "C" int idisp_plan_get_logits(idisp_plan_t *p, float *logits, void *strea
 }
 
 extern "C" int idisp_plan_launches_per_forward(const idisp_plan_t *p) { return p ? p->launches : 0; }
+
+extern "C" int idisp_plan_graph_stats(const idisp_plan_t *p, int *captures, int *replays)
+{
+  IDISP_REQUIRE(p != nullptr, "plan_graph_stats: NULL plan");
+  if (captures) *captures = p->graph_captures;
+  if (replays) *replays = p->graph_hits;
+  return IDISP_OK;
+}
 
 extern "C" int idisp_plan_enable_timing(idisp_plan_t *p, int on)
 {

@@ -72,10 +72,35 @@ class PSMNet(nn.Module):
         self.dres2, self.dres3, self.dres4 = hourglass(32), hourglass(32), hourglass(32)
         self.classif1, self.classif2, self.classif3 = _classifier(), _classifier(), _classifier()
         self._init_like_reference()
-        self.check_range = True   # 'auto' only: ask the plan whether the fp16 range was left (one 4-byte D2H + sync per call)
-        self._plans = {}      # effective precision -> [plan handle, weights key]
-        self._plan = None     # the plan of the most recent forward
-        self._workspace = None
+        # 'auto' only: ask the plan whether the fp16 range was left.  True = before returning (one 4-byte D2H + stream sync per
+        # call: the result handed back is always parity-grade); 'deferred' = no sync -- the flag of call N is read at call N+1
+        # (or by range_exceeded()); if it was set, a warning names the affected call and the module switches to fp32 for good;
+        # False = never.
+        self.check_range = True
+        self._reset_runtime_state()
+
+    def _reset_runtime_state(self):
+        """Everything that is NOT a parameter: native plan handles, workspaces, caches (dropped by pickling / deepcopy)."""
+        self._plans = {}        # effective precision -> [plan handle, weights key]
+        self._plan = None       # the plan of the most recent forward
+        self._workspaces = {}   # (device index, stream handle) -> uint8 arena; one per stream, so two streams never share scratch
+        self._workspace = None  # the arena of the most recent forward
+        self._stack_tensors = None
+        self._pending_range = None   # 'deferred' range check: (plan, call number) of a forward whose flag has not been read
+        self._calls = 0
+        self._sticky_fp32 = False
+
+    def __getstate__(self):
+        # ctypes plan handles cannot be pickled / deep-copied (and a copied handle would be destroyed twice): a copy starts
+        # without native state and builds its own plan on first use
+        state = dict(self.__dict__)
+        for k in ('_plans', '_plan', '_workspaces', '_workspace', '_stack_tensors', '_pending_range'):
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._reset_runtime_state()
 
     def _init_like_reference(self):
         # stackhourglass.py:90-104: He-normal for Conv2d/Conv3d (not the transposed convs), BN -> (1, 0)
@@ -89,8 +114,28 @@ class PSMNet(nn.Module):
 
     # ---- plan management ------------------------------------------------------------------
     def _stack_items(self):
-        return [(k, v) for k, v in self.state_dict().items()
-                if not k.startswith('feature_extraction.') and not k.endswith('num_batches_tracked')]
+        """(key, tensor) of every 3-D-stack parameter / buffer the plan consumes.  The list of tensor OBJECTS is cached (a
+        state_dict() walk over 514 entries costs ~2.5 ms of host time per forward); `_weights_key` notices both in-place
+        edits (`_version`) and re-assignment / .to() (`data_ptr`, identity)."""
+        cur = self._stack_tensors
+        if cur is not None:
+            ok = True
+            for (k, owner, name, t) in cur:
+                if getattr(owner, name) is not t:   # parameter object replaced (load_state_dict(assign=True), .to(), ...)
+                    ok = False
+                    break
+            if ok:
+                return [(k, t) for (k, _, _, t) in cur]
+        items = []
+        for mod_name, mod in self.named_modules():
+            if mod_name.startswith('feature_extraction'):
+                continue
+            for name, t in list(mod._parameters.items()) + list(mod._buffers.items()):
+                if t is None or name == 'num_batches_tracked':
+                    continue
+                items.append(((mod_name + '.' if mod_name else '') + name, mod, name, t))
+        self._stack_tensors = items
+        return [(k, t) for (k, _, _, t) in items]
 
     def effective_precision(self, Hf, Wf):
         """The mode a forward at this feature size runs in: ``precision`` itself, or for 'auto' the split-precision
@@ -105,7 +150,7 @@ class PSMNet(nn.Module):
     def _ensure_plan(self, device, precision=None):
         precision = precision or (self.precision if self.precision != 'auto' else 'fp32')
         items = self._stack_items()
-        key = (str(device), tuple((k, v._version, v.data_ptr()) for k, v in items))
+        key = (str(device), tuple((v._version, v.data_ptr()) for _, v in items))
         slot = self._plans.setdefault(precision, [None, None])
         if slot[0] is not None and key == slot[1]:
             self._plan = slot[0]
@@ -158,29 +203,61 @@ class PSMNet(nn.Module):
         def run(precision):
             plan = self._ensure_plan(left_fea.device, precision)
             need = lib.idisp_plan_workspace_bytes(plan, B, Hf, Wf)
-            ws = self._workspace
-            if ws is None or ws.numel() < need or ws.device != left_fea.device:
-                self._workspace = None
-                ws = self._workspace = torch.empty(need, dtype=torch.uint8, device=left_fea.device)
+            wkey = (left_fea.device.index, torch.cuda.current_stream().cuda_stream)
+            ws = self._workspaces.get(wkey)
+            if ws is None or ws.numel() < need:
+                self._workspaces.pop(wkey, None)
+                ws = self._workspaces[wkey] = torch.empty(need, dtype=torch.uint8, device=left_fea.device)
+            self._workspace = ws
             _lib.check(lib.idisp_plan_forward(plan, _lib.ptr(left_fea), _lib.ptr(right_fea), B, Hf, Wf, H, W,
                                               _lib.ptr(ws), ws.numel(), _lib.ptr(out), _lib.stream_ptr()))
 
         with torch.cuda.device(left_fea.device):
+            self._calls += 1
+            if self._pending_range is not None:   # 'deferred' check of the previous call (its work is long finished)
+                self._read_pending_range()
             precision = self.effective_precision(Hf, Wf)
-            run(precision)
-            if self.precision == 'auto' and precision == 'fp16x2' and self.check_range and self.range_exceeded():
-                # the hi words are IEEE halves: an activation beyond 65504 overflows them (and ReLU turns the resulting NaN
-                # into 0: finite but wrong).  Not seen with BatchNorm-ed iDispNet weights, but 'auto' promises a parity-grade
-                # answer, so such a batch is redone by the fp32 FFMA kernels.
-                warnings.warn('PSMNet: activations left the fp16 range of the split-precision mode; batch recomputed in fp32')
+            if self.precision == 'auto' and self._sticky_fp32:
+                precision = 'fp32'
+            try:
+                run(precision)
+            except _lib.Unsupported:
+                # the C side knows more than effective_precision() (tensor-map limits, IDISP_TC_DISABLE, ...): 'auto' promised
+                # a parity-grade answer, so a shape the tensor-core mode rejects goes to the fp32 FFMA kernels
+                if self.precision != 'auto' or precision == 'fp32':
+                    raise
+                precision = 'fp32'
                 run('fp32')
+            if self.precision == 'auto' and precision == 'fp16x2' and self.check_range:
+                if self.check_range == 'deferred':
+                    self._pending_range = (self._plan, self._calls)
+                elif self.range_exceeded():
+                    # the hi words are IEEE halves: an activation beyond 65504 overflows them (and ReLU turns the resulting NaN
+                    # into 0: finite but wrong).  Not seen with BatchNorm-ed iDispNet weights, but 'auto' promises a parity-grade
+                    # answer, so such a batch is redone by the fp32 FFMA kernels.
+                    warnings.warn('PSMNet: activations left the fp16 range of the split-precision mode; batch recomputed in fp32')
+                    run('fp32')
         return out
+
+    def _read_pending_range(self):
+        plan, call = self._pending_range
+        self._pending_range = None
+        flag = ctypes.c_int(0)
+        _lib.check(_lib.load().idisp_plan_range_exceeded(plan, ctypes.byref(flag), _lib.stream_ptr()))
+        if flag.value:
+            self._sticky_fp32 = True
+            warnings.warn(f'PSMNet: forward call #{call} left the fp16 range of the split-precision mode (its result is not '
+                          f"parity-grade); check_range='deferred' switches this module to the fp32 kernels from now on")
+        return bool(flag.value)
 
     def range_exceeded(self):
         """fp16-word modes: did the most recent forward see a value outside the IEEE-half range (idisp_plan_range_exceeded)?
         Synchronises the current stream."""
         if self._plan is None:
             return False
+        if self._pending_range is not None:
+            with torch.cuda.device(self._workspace.device):
+                return self._read_pending_range()
         flag = ctypes.c_int(0)
         with torch.cuda.device(self._workspace.device):
             _lib.check(_lib.load().idisp_plan_range_exceeded(self._plan, ctypes.byref(flag), _lib.stream_ptr()))

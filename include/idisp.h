@@ -152,6 +152,11 @@ int idisp_plan_forward_host(idisp_plan_t *plan, const float *left_host, const fl
 int idisp_plan_get_logits(idisp_plan_t *plan, float *logits, void *stream);
 /* Number of kernel launches one idisp_plan_forward enqueues (for bench bookkeeping). */
 int idisp_plan_launches_per_forward(const idisp_plan_t *plan);
+/* The tensor-core modes capture the conv section of a forward (every launch between the input conversion and the soft-argmin:
+ * it touches only the workspace) into a CUDA graph the first time a (B, Hf, Wf, workspace) combination is seen and replay it
+ * with one cudaGraphLaunch afterwards (disabled by IDISP_NO_GRAPH=1, while per-launch timing is on, and inside a caller's own
+ * stream capture).  Writes how many graphs this plan has captured / how many forwards replayed one (either may be NULL). */
+int idisp_plan_graph_stats(const idisp_plan_t *plan, int *captures, int *replays);
 /* Per-launch device timing of idisp_plan_forward (CUDA events on the forward's stream between
  * consecutive launches).  After a forward with timing enabled, get_timing writes, for each of the
  * launches_per_forward launches, its duration in ms and the layer it ran (0..27 = SURVEY.md

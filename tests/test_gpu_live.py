@@ -165,3 +165,85 @@ def test_two_rank_sharded_forward_equals_unsharded_bit_for_bit(lib, tmp_path):
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
                         '--master-port', '29731', str(script)], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and 'SHARD_OK' in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def _graph_stats(m):
+    import ctypes
+    from disprcnn_b200 import _lib
+    c, r = ctypes.c_int(0), ctypes.c_int(0)
+    _lib.check(_lib.load().idisp_plan_graph_stats(m._plan, ctypes.byref(c), ctypes.byref(r)))
+    return c.value, r.value
+
+
+def test_cuda_graph_replay_is_bit_identical_to_eager_launches(lib, monkeypatch):
+    """The conv section is captured once per (B, Hf, Wf, workspace) and replayed: same bits as the eager launch sequence,
+    for a second batch size as well, and again after the weights change (the captured launches hold weight pointers)."""
+    case, g, sd, L, R = load_case('tiny')
+    monkeypatch.setenv('IDISP_NO_GRAPH', '1')
+    eager = make_psmnet(case, sd, 'fp16x2')
+    monkeypatch.delenv('IDISP_NO_GRAPH')
+    m = make_psmnet(case, sd, 'fp16x2')
+    Lc, Rc = L.cuda(), R.cuda()
+    with torch.no_grad():
+        want2, want1 = eager.forward_features(Lc, Rc), eager.forward_features(Lc[:1], Rc[:1])
+        assert _graph_stats(eager) == (0, 0)
+        a = m.forward_features(Lc, Rc)           # captures
+        b = m.forward_features(Lc, Rc)           # replays
+        c = m.forward_features(Lc[:1], Rc[:1])   # second shape: its own graph
+        d = m.forward_features(Lc, Rc)
+    assert torch.equal(a, want2) and torch.equal(b, want2) and torch.equal(d, want2) and torch.equal(c, want1)
+    caps, reps = _graph_stats(m)
+    assert caps == 2 and reps == 2, (caps, reps)
+    with torch.no_grad():
+        m.classif3[2].weight.mul_(0.5)           # in-place edit -> plan re-finalised -> graphs dropped
+        eager.classif3[2].weight.mul_(0.5)
+        e = m.forward_features(Lc, Rc)
+        assert torch.equal(e, eager.forward_features(Lc, Rc)) and not torch.equal(e, want2)
+
+
+def test_module_survives_deepcopy_and_pickle_after_a_forward(lib, tmp_path):
+    import copy
+    case, g, sd, L, R = load_case('tiny')
+    m = make_psmnet(case, sd, 'auto')
+    with torch.no_grad():
+        want = m.forward_features(L.cuda(), R.cuda())
+        m2 = copy.deepcopy(m)
+        torch.save(m, tmp_path / 'm.pth')
+        m3 = torch.load(tmp_path / 'm.pth', weights_only=False)
+        assert m2._plan is None and m3._plans == {}
+        assert torch.equal(m2.forward_features(L.cuda(), R.cuda()), want)
+        assert torch.equal(m3.forward_features(L.cuda(), R.cuda()), want)
+    del m, m2, m3   # three independent plans, each destroyed once
+
+
+def test_two_streams_do_not_share_a_workspace(lib):
+    case, g, sd, L, R = load_case('tiny')
+    m = make_psmnet(case, sd, 'fp16x2')
+    Lc, Rc = L.cuda(), R.cuda()
+    with torch.no_grad():
+        want = m.forward_features(Lc, Rc)
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        torch.cuda.synchronize()
+        outs = []
+        for _ in range(3):
+            for s in (s1, s2):
+                with torch.cuda.stream(s):
+                    outs.append(m.forward_features(Lc, Rc))
+        torch.cuda.synchronize()
+    assert len(m._workspaces) == 3 and all(torch.equal(o, want) for o in outs)
+
+
+def test_deferred_range_check_reports_at_the_next_call(lib):
+    case, g, sd, L, R = load_case('tiny')
+    m = make_psmnet(case, sd, 'auto')
+    m.check_range = 'deferred'
+    f32 = make_psmnet(case, sd, 'fp32')
+    Lb, Rb = (L * 3e5).cuda(), (R * 3e5).cuda()   # beyond the IEEE-half range
+    with torch.no_grad():
+        ok = m.forward_features(L.cuda(), R.cuda())
+        assert not m.range_exceeded()
+        m.forward_features(Lb, Rb)                  # no sync, no warning yet
+        with pytest.warns(UserWarning, match='call #2'):
+            again = m.forward_features(L.cuda(), R.cuda())
+        assert m._sticky_fp32 and torch.equal(again, f32.forward_features(L.cuda(), R.cuda()))
+    assert (ok - again).abs().max().item() < TOL
