@@ -27,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 C, HF, WF, MIND, MAXD, B_PER_GPU = 32, 112, 112, -96, 96, 32
+GATHER_CHUNKS = int(os.environ.get('IDISP_GATHER_CHUNKS', '1'))
 D = (MAXD - MIND) // 4
 V = D * HF * WF
 H, W = 4 * HF, 4 * WF
@@ -206,6 +207,48 @@ def bench_cost_volume(dev, hbm_gbs, L, R):
             'rois_per_s': n / (ms / 1e3)}
 
 
+def bench_live(dev):
+    """The shape tools/test_net.py really runs (KITTI: R = 1..15 ROI pairs per image, 224x224 crops -> 56x56x32ch, D=24):
+    latency per call through the public API, (a) 3-D stack from features, (b) whole PSMNet.forward from image crops
+    (feature_extraction + stack).  Host-timed with a stream sync per call = what the caller of one image waits for."""
+    import torch
+    import torch.nn as nn
+    from disprcnn_b200.modeling.psmnet.stackhourglass import PSMNet
+    torch.manual_seed(0)
+    m = PSMNet(48, -48)   # precision='auto' -> fp16x2
+    with torch.no_grad():
+        for c in (m.classif1, m.classif2, m.classif3):
+            c[2].weight.mul_(0.1)
+    m = m.to(dev).eval()
+    out = {'workload': 'R ROI pairs, 224x224 crops -> 56x56x32ch features, D=24 (mindisp -48, maxdisp 48) -> 224x224; precision auto (fp16x2)',
+           'stack_ms': {}, 'psmnet_ms': {}, 'psmnet_rois_per_s': {}}
+    g = torch.Generator().manual_seed(5)
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False   # whatever still runs through torch must be fp32-grade
+    with torch.no_grad():
+        for R in (1, 4, 8, 15):
+            fl = torch.randn(R, 32, 56, 56, generator=g).to(dev)
+            fr = torch.randn(R, 32, 56, 56, generator=g).to(dev)
+            il = torch.randn(R, 3, 224, 224, generator=g).to(dev)
+            ir = torch.randn(R, 3, 224, 224, generator=g).to(dev)
+            for name, fn in (('stack_ms', lambda: m.forward_features(fl, fr)), ('psmnet_ms', lambda: m({'left': il, 'right': ir}))):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                ts = []
+                for _ in range(10):
+                    t0 = time.perf_counter()
+                    fn()
+                    torch.cuda.synchronize()
+                    ts.append((time.perf_counter() - t0) * 1e3)
+                ts.sort()
+                out[name][str(R)] = round(ts[len(ts) // 2], 4)
+            out['psmnet_rois_per_s'][str(R)] = round(R / (out['psmnet_ms'][str(R)] / 1e3), 1)
+    torch.backends.cudnn.allow_tf32 = old_tf32
+    out['extractor'] = type(m.feature_extraction).__module__ + ('.native' if getattr(m.feature_extraction, 'native', False) else ' (torch modules)')
+    return out
+
+
 def make_model(precision, device):
     import torch
     import torch.nn as nn
@@ -264,7 +307,7 @@ def main():
     import torch
     import torch.distributed as dist
     from disprcnn_b200 import _lib
-    from disprcnn_b200.parallel import gather_disparity
+    from disprcnn_b200.parallel import gather_disparity, sharded_forward_async
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
     lib = _lib.load()
     torch.cuda.set_device(local_rank)
@@ -280,9 +323,21 @@ def main():
     L, R = L_host.to(dev), R_host.to(dev)
     stream = torch.cuda.current_stream()
 
+    pending = []  # N > 1: all-gathers in flight on NCCL's own stream (each overlaps the next step's kernels)
+
     def step_device():
-        local = m.forward_features(L, R)
-        return gather_disparity(local, Bg) if world > 1 else local
+        if world == 1:
+            return m.forward_features(L, R)
+        pending.append(sharded_forward_async(m, L, R, presharded=True, chunks=GATHER_CHUNKS))
+        if len(pending) > 2:  # at most two result buffers (2 x Bg x H x W f32) alive: step i-2 must have landed
+            return pending.pop(0).wait()
+        return None
+
+    def drain():
+        out = None
+        while pending:
+            out = pending.pop(0).wait()
+        return out
 
     def barrier():
         if world > 1:
@@ -303,39 +358,78 @@ def main():
             dist.barrier()
         return ms.item()
 
+    gather_info = None
     with torch.no_grad():
         for _ in range(warm):
             out = step_device()
+        if world > 1:
+            out = drain()
+            # sharded + gathered == unsharded, checked once before timing: this rank recomputes the NEXT rank's shard from that
+            # rank's seeded inputs and compares it bit for bit with what the gather delivered (ROIs are independent, kernels
+            # deterministic, so the per-shard result is the unsharded result restricted to the shard)
+            nxt = (rank + 1) % world
+            gn = torch.Generator().manual_seed(1234 + nxt)
+            Ln = torch.randn(B_PER_GPU, C, HF, WF, generator=gn).relu().to(dev)
+            Rn = torch.randn(B_PER_GPU, C, HF, WF, generator=gn).relu().to(dev)
+            mine = m.forward_features(Ln, Rn)
+            same = torch.equal(mine, out[nxt * B_PER_GPU:(nxt + 1) * B_PER_GPU])
+            flag = torch.tensor([0 if same else 1], device=dev)
+            dist.all_reduce(flag)
+            assert flag.item() == 0, f'rank {rank}: gathered shard of rank {nxt} differs from its recomputation'
+            del Ln, Rn, mine
+            # the collective alone: one all_gather_into_tensor of [B_PER_GPU, H, W] f32 per rank, CUDA events on this stream
+            local = out[rank * B_PER_GPU:(rank + 1) * B_PER_GPU].clone()
+            buf = torch.empty_like(out)
+            for _ in range(2):
+                dist.all_gather_into_tensor(buf, local)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            for _ in range(5):
+                dist.all_gather_into_tensor(buf, local)
+            g1.record(stream)
+            torch.cuda.synchronize()
+            gms = torch.tensor([g0.elapsed_time(g1) / 5], device=dev)
+            dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+            nbytes = local.numel() * 4
+            gather_info = {'allgather_ms': gms.item(), 'bytes_per_rank': nbytes, 'algbw_gbs': nbytes * world / gms.item() / 1e6,
+                           'busbw_gbs': nbytes * (world - 1) / gms.item() / 1e6, 'sharded_equals_unsharded': True,
+                           'overlap': f'async_op all-gather on NCCL\'s stream in {GATHER_CHUNKS} ROI sub-chunk(s); the gather of step i '
+                                      'overlaps the kernels of step i+1; every gather completes inside the timed region'}
+            del buf, local
         assert os.environ.get('IDISP_TC_DBG') or torch.isfinite(out).all(), 'non-finite disparity in warm-up'
         plan = m._plan
-        # ---- value: device-resident inputs, per-launch events on (roofline leg) ----
-        _lib.check(lib.idisp_plan_enable_timing(plan, 1))
+        # ---- value: device-resident inputs; K steps enqueued back to back, no host sync inside the timed region ----
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
-        layer_ms = {}
-        ms_total = 0.0
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        per_step = []
         for _ in range(args.steps):
             step_device()
-            n = lib.idisp_plan_launches_per_forward(plan)
-            ms = (ctypes.c_float * n)()
-            ly = (ctypes.c_int * n)(*([-100] * n))
-            # reading the events waits for this step only; the next step is enqueued right after
-            _lib.check(lib.idisp_plan_get_timing(plan, ms, ly, n))
-            per_step.append((list(ms), list(ly)))
+        drain()  # N > 1: the current stream waits for every gather still in flight
         e1.record(stream)
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = t.item()
+        launches_per_step = lib.idisp_plan_launches_per_forward(plan) + (GATHER_CHUNKS if world > 1 else 0)
+        # ---- roofline leg: the same K steps again with CUDA events between the launches (on the launching stream; the plan
+        # then launches eagerly instead of replaying its CUDA graph).  Only the per-kernel durations come from here. ----
+        _lib.check(lib.idisp_plan_enable_timing(plan, 1))
+        per_step = []
+        for _ in range(args.steps):
+            m.forward_features(L, R)
+            n = lib.idisp_plan_launches_per_forward(plan)
+            ms = (ctypes.c_float * n)()
+            ly = (ctypes.c_int * n)(*([-100] * n))
+            _lib.check(lib.idisp_plan_get_timing(plan, ms, ly, n))
+            per_step.append((list(ms), list(ly)))
+        torch.cuda.synchronize()
         clocks = sampler.stop() if rank == 0 else None
         _lib.check(lib.idisp_plan_enable_timing(plan, 0))
-        launches_per_step = lib.idisp_plan_launches_per_forward(plan) + (1 if world > 1 else 0)
         conv_ms = sum(v for msl, lyl in per_step for v, l in zip(msl, lyl) if 0 <= l <= 27)
         other_ms = sum(v for msl, lyl in per_step for v, l in zip(msl, lyl) if -100 < l < 0)
         by_layer = {}
@@ -374,7 +468,7 @@ def main():
             'scaling': 'weak', 'vs_baseline': None,
             'dtype': {'fp32': 'f32', 'fp16x2': 'fp16x2 (operands and activations as hi+lo IEEE-half word pairs, fp32 accumulate: fp32-grade)'}.get(
                 args.precision, f'{args.precision} (fp32 accumulate)'), 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'global_batch': Bg, 'parallelism': f'dp{world} (ROI shards, one all-gather of disparity maps)',
+            'config': {'workload': WORKLOAD, 'global_batch': Bg, 'parallelism': f'dp{world} (ROI shards, one all-gather of disparity maps' + (', overlapped with the next step on NCCL\'s stream)' if world > 1 else ')'),
                        'precision_mode': args.precision,
                        'l2': 'no explicit flush: each step streams >10 GB of activations per GPU, far beyond the 126 MB L2'},
             'e2e': {'value': e2e, 'unit': 'ROIs/s', 'h2d_bytes_per_step': 2 * B_PER_GPU * C * HF * WF * 4 * world,
@@ -393,6 +487,8 @@ def main():
             'ms_by_layer': {str(k): round(v, 4) for k, v in sorted(by_layer.items())},
             'clocks': clocks,
         }
+        if gather_info:
+            result['allgather'] = gather_info
         if world == 1 and args.precision != 'fp32' and not os.environ.get('IDISP_TC_DBG'):
             # the parity (fp32 FFMA) mode on the same inputs and weights: its throughput, and how far the bf16 tensor-core
             # mode's disparities sit from it (fp32 mode itself is 2-7e-5 px from the reference, tests/test_gpu_parity.py)
@@ -435,6 +531,35 @@ def main():
         if world == 1:
             result['roi_align'] = bench_roi_align(dev, hbm)
             result['cost_volume'] = bench_cost_volume(dev, hbm, L, R)
+            if not os.environ.get('IDISP_BENCH_SKIP_LIVE'):
+                result['live_shape'] = bench_live(dev)
+        if world == 1 and not os.environ.get('IDISP_BENCH_SKIP_REFGPU') and not os.environ.get('IDISP_TC_DBG'):
+            # north_star's ">= 4x over the reference GPU path": the same stack in eager PyTorch + cuDNN on THIS GPU, outside the timed
+            # region, with its own clock record (tools/ref_gpu_timing.py: torch.nn restatement of SURVEY.md Appendix A, random weights)
+            del m
+            torch.cuda.empty_cache()
+            sys.path.insert(0, os.path.join(ROOT, 'tools'))
+            import ref_gpu_timing
+            rs = ClockSampler(local_rank)
+            rs.start()
+            best = None
+            for chunk in (8, 32):   # give the reference its best batch split
+                try:
+                    r = ref_gpu_timing.measure(B_PER_GPU, chunk, 2, as_written=False, device=dev)
+                except RuntimeError as e:   # (out of memory at the larger split)
+                    r = None
+                    torch.cuda.empty_cache()
+                if r and (best is None or r['tf32_rois_per_s'] > best['tf32_rois_per_s']):
+                    best = r
+            rc = rs.stop()
+            if best:
+                result['reference_gpu'] = {
+                    'what': 'eager PyTorch + cuDNN restatement of the 3-D stack (incl. device-side cost volume, upsample, softmax, regression) on this GPU',
+                    'workload': best['workload'], 'tf32_rois_per_s': best['tf32_rois_per_s'], 'fp32_rois_per_s': best['fp32_rois_per_s'],
+                    'tf32_note': 'allow_tf32=True is PyTorch\'s default for convolutions, i.e. what tools/test_net.py executes',
+                    'tf32_disparity_vs_fp32_px': best['variants']['tf32 convs (PyTorch default allow_tf32=True), device-side cost volume']['disparity_vs_fp32_px'],
+                    'speedup_vs_tf32': value / best['tf32_rois_per_s'], 'speedup_vs_fp32': value / best['fp32_rois_per_s'],
+                    'e2e_speedup_vs_tf32': e2e / best['tf32_rois_per_s'], 'clocks': rc}
         if world == 1 and not args.no_cpu_baseline:
             sd = {k: v for k, v in m.state_dict().items() if not k.startswith('feature_extraction')}
             val, dt, cores, sample = cpu_port_rois_per_s(sd, 1, 1, budget_s=45.0)  # 1 warm-up: oneDNN primitive creation is per shape

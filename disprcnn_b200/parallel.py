@@ -50,15 +50,72 @@ def gather_disparity(local, B, group=None):
     return torch.cat(parts, 0)
 
 
-def sharded_forward(model, left_fea, right_fea, H=None, W=None, group=None, gather=True):
+class PendingGather:
+    """An all-gather in flight on the collective's own (side) stream.  ``wait()`` makes the CURRENT stream wait for it and
+    returns the gathered [B,H,W] tensor; until then the current stream is free to run the next batch's kernels."""
+
+    def __init__(self, works, bufs, B, world, chunk_sizes, shard):
+        self._works, self._bufs, self._B, self._world, self._chunks, self._shard = works, bufs, B, world, chunk_sizes, shard
+        self._out = None
+
+    def wait(self):
+        if self._out is not None:
+            return self._out
+        for w in self._works:
+            w.wait()   # stream-level wait (no host block): current stream <- the NCCL stream's completion event
+        if len(self._bufs) == 1:
+            self._out = self._bufs[0].view(self._B, *self._bufs[0].shape[2:])
+        else:
+            # chunk c of rank r sits at bufs[c][r]; the full batch is rank-major: [r][c0 | c1 | ...]
+            self._out = torch.cat([torch.cat([b[r] for b in self._bufs], 0) for r in range(self._world)], 0)
+        return self._out
+
+
+def sharded_forward_async(model, left_fea, right_fea, H=None, W=None, group=None, chunks=1, presharded=False):
+    """Shard, compute, and START the gather without blocking the compute stream ("issue on a side stream in
+    >= 2 sub-chunks to overlap with the tail ROIs' compute").
+
+    The local shard is processed in ``chunks`` ROI sub-chunks; as soon as a sub-chunk's soft-argmin is enqueued its
+    ``all_gather_into_tensor`` is issued with ``async_op=True`` -- NCCL runs it on its own stream behind an event, so the
+    gather of sub-chunk c overlaps the kernels of sub-chunk c+1 (and, when the caller defers ``wait()``, of the next batch).
+    Requires equal shards (B a multiple of the world size; pad the batch otherwise -- ``sharded_forward`` handles ragged
+    batches with the blocking path).  Returns a ``PendingGather``.
+    """
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if presharded:
+        B = left_fea.shape[0] * world
+        lo, hi = 0, left_fea.shape[0]
+    else:
+        B = left_fea.shape[0]
+        lo, hi = shard_range(B, rank, world)
+    if B % world:
+        raise RuntimeError(f'sharded_forward_async: batch {B} is not a multiple of the world size {world}')
+    per = B // world
+    chunks = max(1, min(int(chunks), per))
+    sizes = [per // chunks + (1 if c < per % chunks else 0) for c in range(chunks)]
+    works, bufs, a = [], [], lo
+    for n in sizes:
+        local = model.forward_features(left_fea[a:a + n], right_fea[a:a + n], H, W).contiguous()
+        buf = torch.empty((world, n) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        works.append(dist.all_gather_into_tensor(buf.view(world * n, *local.shape[1:]), local, group=group, async_op=True))
+        bufs.append(buf)
+        a += n
+    return PendingGather(works, bufs, B, world, sizes, (lo, hi))
+
+
+def sharded_forward(model, left_fea, right_fea, H=None, W=None, group=None, gather=True, chunks=1):
     """Run `model.forward_features` on this rank's shard of the (replicated or pre-sharded) batch.
 
     left_fea/right_fea: the FULL [B,C,Hf,Wf] batch (each rank slices its own chunk).  Returns the
-    gathered [B,H,W] disparity (or the local block when gather=False).
+    gathered [B,H,W] disparity (or the local block when gather=False).  ``chunks`` > 1 (equal shards only) overlaps the
+    gather of each ROI sub-chunk with the next sub-chunk's kernels (see ``sharded_forward_async``).
     """
     B = left_fea.shape[0]
     if dist.is_available() and dist.is_initialized():
-        lo, hi = shard_range(B, dist.get_rank(group), dist.get_world_size(group))
+        world = dist.get_world_size(group)
+        lo, hi = shard_range(B, dist.get_rank(group), world)
+        if gather and chunks > 1 and B % world == 0:
+            return sharded_forward_async(model, left_fea, right_fea, H, W, group, chunks).wait()
     else:
         lo, hi = 0, B
     local = model.forward_features(left_fea[lo:hi], right_fea[lo:hi], H, W)

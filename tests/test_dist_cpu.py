@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from disprcnn_b200.parallel import gather_disparity, shard_range, sharded_forward
+from disprcnn_b200.parallel import gather_disparity, shard_range, sharded_forward, sharded_forward_async
 
 
 def test_shard_range_partitions():
@@ -47,6 +47,14 @@ def _worker(rank, world, port, B, q):
         lo, hi = shard_range(B, rank, world)
         local = sharded_forward(_FakeModel(), L, R, gather=False)
         ok = torch.equal(full, want) and torch.equal(local, want[lo:hi]) and full.shape[0] == B
+        if B % world == 0:  # the overlapped form: sub-chunked async gathers, two batches in flight before the first wait()
+            for chunks in (1, 2, 3):
+                ok = ok and torch.equal(sharded_forward(_FakeModel(), L, R, chunks=chunks), want)
+            p1 = sharded_forward_async(_FakeModel(), L, R, chunks=2)
+            p2 = sharded_forward_async(_FakeModel(), L * 2, R * 2, chunks=2)
+            ok = ok and torch.equal(p1.wait(), want) and torch.equal(p2.wait(), want * 2) and p1.wait() is p1.wait()
+            p3 = sharded_forward_async(_FakeModel(), L[lo:hi], R[lo:hi], chunks=2, presharded=True)
+            ok = ok and torch.equal(p3.wait(), want)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

@@ -92,7 +92,17 @@ def main():
     ap.add_argument('--chunk', type=int, default=8, help='ROIs per forward (the eager path materialises 3 x 154 MB per ROI at the output)')
     ap.add_argument('--steps', type=int, default=3)
     a = ap.parse_args()
-    dev = torch.device('cuda:0')
+    print(json.dumps(measure(a.batch, a.chunk, a.steps), indent=1))
+
+
+def measure(batch=32, chunk=8, steps=3, as_written=True, device=None):
+    """Time the eager torch + cuDNN stack on `device`; returns the dict this tool prints (bench.py calls this for its
+    `reference_gpu` entry)."""
+    class _A:
+        pass
+    a = _A()
+    a.batch, a.chunk, a.steps = batch, chunk, steps
+    dev = torch.device('cuda:0') if device is None else device
     torch.manual_seed(0)
     C, Hf, Wf, mind, maxd = 32, 112, 112, -96, 96
     m = Stack(C, mind, maxd)
@@ -140,10 +150,13 @@ def main():
     out['variants']['tf32 convs (PyTorch default allow_tf32=True), device-side cost volume'] = {
         'ms_per_batch': ms, 'rois_per_s': a.batch / ms * 1e3, 'wall_ms': wall,
         'disparity_vs_fp32_px': {'max': diff.max().item(), 'mean': diff.mean().item()}}
-    _, ms, wall = run(True, True)
-    out['variants']['tf32 convs, cost volume as written (CPU zeros + H2D, stackhourglass.py:117)'] = {
-        'ms_per_batch': ms, 'rois_per_s': a.batch / wall * 1e3, 'wall_ms': wall, 'note': 'rois_per_s from wall clock (host work inside)'}
-    print(json.dumps(out, indent=1))
+    if as_written:
+        _, ms, wall = run(True, True)
+        out['variants']['tf32 convs, cost volume as written (CPU zeros + H2D, stackhourglass.py:117)'] = {
+            'ms_per_batch': ms, 'rois_per_s': a.batch / wall * 1e3, 'wall_ms': wall, 'note': 'rois_per_s from wall clock (host work inside)'}
+    out['fp32_rois_per_s'] = out['variants']['fp32 (allow_tf32=False), device-side cost volume']['rois_per_s']
+    out['tf32_rois_per_s'] = out['variants']['tf32 convs (PyTorch default allow_tf32=True), device-side cost volume']['rois_per_s']
+    return out
 
 
 if __name__ == '__main__':
