@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(LIB_DIR, 'libidisp.so')
 INCLUDE = os.path.join(os.path.dirname(_HERE), 'include')
 
 NVCC_COMPILE_FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a', '-Xcompiler', '-fPIC']
+NVCC_COMPILE_FLAGS += os.environ.get('IDISP_NVCC_EXTRA', '').split()   # e.g. -DIDISP_MRG=0 for an A/B build
 NVCC_LINK_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-Xcompiler', '-fPIC', '-shared']
 NVCC_FLAGS = NVCC_COMPILE_FLAGS + ['-shared']
 

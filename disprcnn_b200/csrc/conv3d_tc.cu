@@ -52,6 +52,9 @@ namespace idisp {
 #ifndef IDISP_TRI
 #define IDISP_TRI 1  // per-step accumulator triples in the stride-1 split-precision kernels (see Cfg::TRI); 0: banked plane ring
 #endif
+#ifndef IDISP_MRG
+#define IDISP_MRG 1  // TRI kernels with both weight words resident: x_hi feeds [w_hi | w_lo] in ONE N=192 MMA (see Cfg::MRG)
+#endif
 #ifndef IDISP_NMAIN
 #define IDISP_NMAIN 3  // accumulator banks of the main term in the split-precision kernels (see Cfg)
 #endif
@@ -95,6 +98,12 @@ template <int CIN, int MODE, int OCC, int NT, int XM = 0> struct Cfg {
   // epilogue drains the triple after every step and carries the two open planes' sums in registers (fp32 round-to-nearest).
   // Each column then sees only 9*KS truncating adds, and the correction terms get a triple of their own.
   static constexpr bool TRI = IDISP_TRI && XM != 0 && MODE == M_S1 && (NT == 32 || NT == 16) && OCC == 1;
+  // MRG (TRI, both weight words resident, 32-wide blocks): the two terms that share x_hi are ONE MMA with B = [w_hi | w_lo]
+  // (N = 192: 96 tensor cycles, where two N = 96 MMAs cost 2 x 56 cycles of the 128 B/clk shared-memory port -- the A tile
+  // is read once instead of twice); its D is the step's main triple followed by its correction triple, and the x_lo * w_hi
+  // MMA (N = 96, the hi rows of the same B chunk) adds into the correction triple.  Edge planes compute all three kd blocks:
+  // the epilogue never reads the block of a plane outside the volume.
+  static constexpr bool MRG = IDISP_MRG && TRI && XM == 1 && NT == 32;
   static constexpr int NMAIN = (!TRI && XM != 0 && MODE != M_DEC && NT <= 32 && OCC == 1) ? IDISP_NMAIN : 1;
   static constexpr int NB = NMAIN + ((NMAIN > 1 && XP) ? 1 : 0);
   static constexpr int AW = XP ? 2 : 1;        // activation words per stage
@@ -115,7 +124,8 @@ template <int CIN, int MODE, int OCC, int NT, int XM = 0> struct Cfg {
   static constexpr int KSM = XP == 1 ? 3 * KS : (XP == 2 ? 2 * KS : KS);  // MMAs per tap
   static constexpr int WBYTES = 27 * KSW * NT * 32;               // 27 taps x Cin (x words) x NT couts x 16 bit
   static constexpr int NSLOT = TRI ? 2 : TCOLS / (ACC_COLS * NB);   // TRI: two step-triples (MMA fills one while the other drains)
-  static constexpr int TRI_SMALL = 2 * 3 * NT;                    // TRI: column offset of the correction terms' triples
+  static constexpr int TRI_STRIDE = MRG ? 6 * NT : 3 * NT;        // TRI: TMEM columns between the two step buffers
+  static constexpr int TRI_SMALL = MRG ? 3 * NT : 2 * 3 * NT;     // TRI: column offset of a step's correction triple from its main triple
   static constexpr int BANK_COLS = NSLOT * ACC_COLS;              // TMEM column distance between accumulator banks
   static_assert(TRI || NSLOT >= 4, "the accumulator ring needs four slots");
   static constexpr int STAGES_FIT = (228 * 1024 / OCC - 1024 - WBYTES - 1024) / STAGE_BYTES;
@@ -336,13 +346,29 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           ptx::tc_fence_after();
           const uint32_t s = q % C::STAGES, t = q % NSLOT;
           const int plo = z > 0 ? z - 1 : 0, phi = z + 1 < Dout ? z + 1 : Dout - 1;  // output planes this input plane feeds
-          const int j0 = plo - (z - 1), nblk = phi - plo + 1;                           // first block / blocks of [kd=2|kd=1|kd=0]
-          const uint32_t dm = tmem_base + t * 3 * NT + j0 * NT, ds = dm + C::TRI_SMALL;
+          const int j0 = C::MRG ? 0 : plo - (z - 1), nblk = C::MRG ? 3 : phi - plo + 1;   // first block / blocks of [kd=2|kd=1|kd=0]
+          const uint32_t dm = tmem_base + t * C::TRI_STRIDE + j0 * NT, ds = dm + C::TRI_SMALL;
           const uint32_t id1 = ptx::make_idesc_h<F16>(128, NT * nblk);
           const uint64_t a0 = desc_add(a_desc0, s * C::STAGE_BYTES);
-          const uint64_t b1 = ptx::make_smem_desc(w_addr + j0 * NT * 16, 3 * NT * 16, 128);
           int ncol = col, nz = z + 1;
           if (nz == Din) { nz = 0; ncol += ncta; }
+          if constexpr (C::MRG) {
+            // B chunk of (tap, k-step): [2 kcores][hi: 3 x NT rows | lo: 3 x NT rows][8]
+            const uint32_t id2 = ptx::make_idesc_h<F16>(128, 2 * 3 * NT);
+            const uint64_t bm = ptx::make_smem_desc(w_addr, 6 * NT * 16, 128);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              if (tap == 5) waits(ncol, q + 1);
+#pragma unroll
+              for (int ks = 0; ks < C::KS; ++ks) {
+                const uint32_t a_tap = ((tap / 3) * MC::SUB_W + (tap % 3)) * 16;
+                const uint32_t boff = (tap * C::KS + ks) * 2 * C::WCHUNK;
+                mma(dm, desc_add(a0, a_tap + A_KOFF(ks)), desc_add(bm, boff), id2);           // x_hi * [w_hi | w_lo] -> [main | corr]
+                mma(ds, desc_add(a0, a_tap + A_KOFF(C::KS + ks)), desc_add(bm, boff), id1);   // x_lo * w_hi -> corr
+              }
+            }
+          } else {
+          const uint64_t b1 = ptx::make_smem_desc(w_addr + j0 * NT * 16, 3 * NT * 16, 128);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             if (tap == 5) waits(ncol, q + 1);
@@ -351,6 +377,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               const uint32_t aoff = ((tap / 3) * MC::SUB_W + (tap % 3)) * 16 + A_KOFF(ks);
               mma((XP != 0 && ks >= C::KS) ? ds : dm, desc_add(a0, aoff), desc_add(b1, (tap * C::KSW + B_KS(ks)) * C::WCHUNK), id1);
             }
+          }
           }
           commit(empty_bar(s));
           commit(accf_bar(t));
@@ -608,7 +635,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           ptx::tc_fence_after();
           uint32_t b0[16], b1[16], b2[16];
           if (owner) {
-            const uint32_t tb = tmem_base + lane_addr + t * 3 * NT + cbase;
+            const uint32_t tb = tmem_base + lane_addr + t * C::TRI_STRIDE + cbase;
             ptx::tmem_ld_32x16(tb, b0);
             ptx::tmem_ld_32x16(tb + NT, b1);
             ptx::tmem_ld_32x16(tb + 2 * NT, b2);
@@ -958,6 +985,8 @@ int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16,
   if (!tc_supported(kind, cin, cout, 4, 16, 16)) return IDISP_OK;  // layer stays on the SIMT kernel
   const int NT = nt > 0 ? nt : tc::nt_of(kind, cin, cout);
   out.nt = NT;
+  // Cfg::MRG layout (two-word stride-1 weights, 32-wide blocks): per (tap, k-step) ONE chunk [2 kcores][hi 3*NT | lo 3*NT][8]
+  const bool mrg = IDISP_MRG && IDISP_TRI && words == 2 && kind == IDISP_CONV_S1 && NT == 32 && cin == 32;
   const int KS = words * cin / 16, NH = (cout + NT - 1) / NT;  // k-steps per tap: the lo word's follow the hi word's
   const size_t per_nh = (size_t)27 * KS * NT * 16;  // bf16 elements
   // 16-bit storage words (bf16 or IEEE half, same size): convert through cvt()
@@ -988,9 +1017,13 @@ int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16,
         for (int ks = 0; ks < KS; ++ks)
           for (int kc = 0; kc < 2; ++kc)
             for (int n = 0; n < 3 * NT; ++n)
-              for (int e = 0; e < 8; ++e)
-                base[((((size_t)t2 * KS + ks) * 2 + kc) * 3 * NT + n) * 8 + e] =
-                    cvt(wv(kdj[n / NT], t2 / 3, t2 % 3, ks * 16 + kc * 8 + e, nh * NT + n % NT));
+              for (int e = 0; e < 8; ++e) {
+                // (ks >= cin/16: the lo word's k-steps; wv() turns channel index cin + c into the lo word of channel c)
+                const int ksw = mrg ? ks % (cin / 16) : ks, word = mrg ? ks / (cin / 16) : 0;
+                const size_t dst = mrg ? ((((size_t)t2 * (cin / 16) + ksw) * 2 + kc) * 6 * NT + word * 3 * NT + n) * 8 + e
+                                       : ((((size_t)t2 * KS + ks) * 2 + kc) * 3 * NT + n) * 8 + e;
+                base[dst] = cvt(wv(kdj[n / NT], t2 / 3, t2 % 3, ks * 16 + kc * 8 + e, nh * NT + n % NT));
+              }
     } else {
       // DECONV: [kd][ks][2 kcores][9*NT rows][8]; rows = entries e0..e4 (tc::dec_*), blocks = output classes
       //   class = pw*2+ph; per axis: p=0 -> k=1 (shift 0); p=1 -> k=2 (shift 0), k=0 (shift 1)

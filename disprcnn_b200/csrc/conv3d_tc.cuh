@@ -54,6 +54,17 @@ int tc_conv3d_split(const TcSplitWeights &w, const __nv_bfloat16 *x, int B, int 
                     void *scratch, int flags, __nv_bfloat16 *y_split, const TcCostVolume *cv, float *part, cudaStream_t s,
                     int *launches = nullptr, int *range_flag = nullptr);
 
+// The 32 -> 1 classifier convolutions as "all 27 taps in N" GEMM + shifted sum (head_tc.cu); f16 / x2 as above.
+struct TcHeadWeights {
+  void *dev = nullptr;
+  int f16 = 0, x2 = 0;
+};
+int tc_head_weights_prepare(const float *w_tap, int cin, int f16, int x2, TcHeadWeights &out, cudaStream_t s);
+void tc_head_weights_free(TcHeadWeights &w);
+bool tc_head_supported(const TcHeadWeights &w, int D, int H, int W);
+// x: blocked 16-bit [B][(x2 ? 2 : 1) * 4][D][H][W][8]; y1 = conv(x) (+ res1), both [B][D][H][W] f32
+int tc_head_conv(const TcHeadWeights &w, const __nv_bfloat16 *x, int B, int D, int H, int W, const float *res1, float *y1, cudaStream_t s);
+
 // whether the tensor-core kernel covers this layer shape (otherwise the SIMT kernel runs it)
 bool tc_supported(int kind, int cin, int cout, int D, int H, int W);
 // device scratch the layer needs (stride-2 convs re-lay their input into parity sub-volumes)

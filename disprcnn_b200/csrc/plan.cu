@@ -46,6 +46,7 @@ struct LayerDev {
   float *bias = nullptr;   // [cout] f32 (nullptr for the bare 32->1 convs)
   TcWeights tc;            // 16-bit re-lay for the tcgen05 kernel (tensor-core precisions)
   TcSplitWeights sp;       // split precision: hi / lo / two-word packings
+  TcHeadWeights head;      // 32 -> 1 layers: the taps-in-N packing of head_tc.cu
 };
 
 static std::vector<LayerSpec> make_layers(int C)
@@ -148,7 +149,7 @@ extern "C" int idisp_plan_create(int C, int mindisp, int maxdisp, int precision,
 extern "C" void idisp_plan_destroy(idisp_plan_t *p)
 {
   if (!p) return;
-  for (auto &d : p->dev) { tc_weights_free(d.tc); tc_split_weights_free(d.sp); }
+  for (auto &d : p->dev) { tc_weights_free(d.tc); tc_split_weights_free(d.sp); tc_head_weights_free(d.head); }
   for (auto e : p->ev) cudaEventDestroy(e);
   for (auto &g : p->graphs) cudaGraphExecDestroy(g.exec);
   if (p->blob) cudaFree(p->blob);
@@ -219,7 +220,7 @@ extern "C" int idisp_plan_finalize(idisp_plan_t *p, void *stream)
     relayout_taps(w, L.kind, L.cin, L.cout, L.bn ? scale.data() : nullptr, wt[i]);
     total += (wt[i].size() + 63) / 64 * 64 + (bs[i].size() + 63) / 64 * 64;
   }
-  for (auto &d : p->dev) { tc_weights_free(d.tc); tc_split_weights_free(d.sp); }
+  for (auto &d : p->dev) { tc_weights_free(d.tc); tc_split_weights_free(d.sp); tc_head_weights_free(d.head); }
   for (auto &g : p->graphs) cudaGraphExecDestroy(g.exec);  // captured launches hold the old weight pointers
   p->graphs.clear();
   if (p->blob) { cudaFree(p->blob); p->blob = nullptr; }
@@ -240,6 +241,7 @@ extern "C" int idisp_plan_finalize(idisp_plan_t *p, void *stream)
       int rc = p->x2 ? tc_split_weights_prepare(wt[i].data(), L.kind, L.cin, L.cout, p->dev[i].sp, s)
                      : tc_weights_prepare(wt[i].data(), L.kind, L.cin, L.cout, p->f16, p->dev[i].tc, s);
       if (rc) return rc;
+      if (L.cout == 1 && (rc = tc_head_weights_prepare(wt[i].data(), L.cin, p->f16, p->x2, p->dev[i].head, s))) return rc;
     }
   }
   IDISP_CUDA(cudaStreamSynchronize(s));  // host vectors go out of scope
@@ -428,6 +430,8 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
       // split precision, 1-channel head on the CUDA cores straight from the hi|lo words (f32 weights and FMAs).  Measured at
       // B=32: 3.8 ms against 1.36 ms for the tensor-core form (w_lo in output column 1) -- kept only as a cross-check.
       RUN(launch_conv3d_to1_x2((const __nv_bfloat16 *)b.c, B, 32, D, Hf, Wf, p->dev[25 + k].w_tap, prev, dst, s));
+    else if (std::is_same<T, __nv_bfloat16>::value && tc_head_supported(p->dev[25 + k].head, D, Hf, Wf))
+      RUN(tc_head_conv(p->dev[25 + k].head, (const __nv_bfloat16 *)b.c, B, D, Hf, Wf, prev, dst, s));
     else if (std::is_same<T, __nv_bfloat16>::value && tc_supported(IDISP_CONV_S1, 32, 1, D, Hf, Wf))
       RUN(tc_layer(p, 25 + k, (const __nv_bfloat16 *)b.c, 0, nullptr, B, D, Hf, Wf, nullptr, 0, nullptr, nullptr, 0, prev, dst, b.split, b.part, s,
                    launches));
@@ -621,6 +625,20 @@ static int conv3d_hook(const float *x, int B, int Cin, int D, int H, int W, cons
   if (sizeof(T) == 2) HR(launch_ncdhw_to_blocked_h(x, (__nv_bfloat16 *)xb, B, Cin, Vi, f16, s));
   else HR(launch_ncdhw_to_blocked<T>(x, xb, B, Cin, Vi, s));
   if (Cout == 1) {
+    TcHeadWeights hw;
+    if (tcp && Cin == 32) {
+      rc = tc_head_weights_prepare(w_tap.data(), Cin, f16, 0, hw, s);
+      if (rc == IDISP_OK && tc_head_supported(hw, D, H, W)) {
+        rc = tc_head_conv(hw, (const __nv_bfloat16 *)xb, B, D, H, W, residual, y, s);
+        cudaStreamSynchronize(s);
+        tc_head_weights_free(hw);
+        if (rc) { cleanup(); return rc; }
+        cleanup();
+        return IDISP_OK;
+      }
+      tc_head_weights_free(hw);
+      if (rc) { cleanup(); return rc; }
+    }
     if (tcp) {
       HR(tc_weights_prepare(w_tap.data(), kind, Cin, Cout, f16, tcw, s));
       HR(tc_conv3d(tcw, (const __nv_bfloat16 *)xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, residual, y, nullptr, 0, nullptr, nullptr, s));
@@ -679,7 +697,18 @@ static int conv3d_hook_x2(const float *x, int B, int Cin, int D, int H, int W, c
   const size_t sb = 2 * tc_scratch_bytes(kind, B, Cin, D, H, W);
   if (sb) HK(cudaMalloc(&scratch, sb));
   if (Cout == 1) {
-    HR(tc_conv3d_split(sw, xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, residual, y, scratch, 0, nullptr, nullptr, nullptr, s));
+    TcHeadWeights hw;
+    rc = Cin == 32 ? tc_head_weights_prepare(w_tap.data(), Cin, 1, 1, hw, s) : IDISP_OK;
+    if (rc == IDISP_OK && tc_head_supported(hw, D, H, W)) {
+      rc = tc_head_conv(hw, xb, B, D, H, W, residual, y, s);
+      cudaStreamSynchronize(s);
+      tc_head_weights_free(hw);
+      if (rc) { cleanup(); return rc; }
+    } else {
+      tc_head_weights_free(hw);
+      if (rc) { cleanup(); return rc; }
+      HR(tc_conv3d_split(sw, xb, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, residual, y, scratch, 0, nullptr, nullptr, nullptr, s));
+    }
   } else {
     HK(cudaMalloc(&yb, (size_t)B * Cout * Vo * 4));
     HK(cudaMalloc(&part, (size_t)B * Cout * Vo * 4));
