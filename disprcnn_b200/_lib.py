@@ -101,6 +101,13 @@ PROTOTYPES = {
     'idisp_plan_graph_stats': (_i, [_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     'idisp_plan_enable_timing': (_i, [_vp, _i]),
     'idisp_plan_get_timing': (_i, [_vp, _vp, _vp, _i]),
+    'idisp_extractor_create': (_i, [ctypes.POINTER(_vp)]),
+    'idisp_extractor_destroy': (None, [_vp]),
+    'idisp_extractor_set_tensor': (_i, [_vp, ctypes.c_char_p, _vp, _sz]),
+    'idisp_extractor_finalize': (_i, [_vp, _vp]),
+    'idisp_extractor_workspace_bytes': (_sz, [_vp, _i, _i, _i]),
+    'idisp_extractor_forward': (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, _vp, _vp]),
+    'idisp_extractor_launches_per_forward': (_i, [_vp]),
     'idisp_debug_fused_cost_volume': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 

@@ -1,0 +1,465 @@
+// feature2d.cu -- the 2-D feature extractor of iDispNet (disprcnn/modeling/psmnet/submodule.py:60-139: firstconv, layer1-4 of
+// BasicBlocks (:25-48), four SPP branches (avg-pool -> 1x1 convbn -> ReLU -> bilinear align_corners upsample), concat,
+// lastconv) on the CUDA cores in fp32 -- SURVEY.md section 8(f) row 1.  In the live call (stackhourglass.py:112-113) it runs once
+// per view before the cost volume; with it the whole PSMNet.forward executes inside libidisp (no cuDNN / ATen kernels).
+//
+// Layout: plain NCHW f32 (the layout of the image crops that come in and of the [B,32,H/4,W/4] features the 3-D stack's
+// entry point takes).  BatchNorm2d (eval, eps 1e-5) is folded in float64 into the kernel (per-Cout scale) and a bias, like the
+// 3-D layers (plan.cu).  One generic direct-convolution kernel covers every conv of the extractor:
+//   k in {1, 3}, stride in {1, 2}, dilation in {1, 2} (padding = dilation for k = 3, 0 for k = 1: submodule.py:13-16,
+//   downsample :103-105), fused bias (+ residual) (+ ReLU), input / output addressed with their own batch strides so that
+//   `raw` and `skip` live INSIDE the 320-channel concat tensor (no copy for torch.cat, submodule.py:134-135).
+// Tiling: a CTA computes 32 x 8 output pixels x COB output channels; a thread owns 4 neighbouring pixels x COB/4 channels
+// (64 or 32 accumulators); input patch and weight slice of 8 input channels are staged in shared memory per step.
+// Roofline: fp32 FFMA (CUDA cores; ~75 TFLOP/s peak): 22.19 GFLOP per 224 x 224 crop.
+#include <map>
+#include <string>
+#include <vector>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace idisp {
+namespace f2d {
+
+constexpr int TW = 32, TH = 8, CI = 8, PXT = 4;   // output tile, input channels per step, pixels per thread
+
+struct ConvParams {
+  const float *x, *w, *bias, *res;
+  float *y;
+  int Cin, Cout, H, W, Ho, Wo, stride, dil, pad, relu;
+  long long xbs, ybs, rbs;   // batch strides (elements) of input, output, residual
+  int tiles_w, tiles_h;
+};
+
+// w: [Cin][K*K][Cout] f32 (BN scale folded in)
+template <int K, int COB>
+__global__ void __launch_bounds__(256) conv2d_kernel(const ConvParams p)
+{
+  constexpr int CPT = COB / 4;                       // output channels per thread
+  extern __shared__ float smem[];
+  const int PH = (TH - 1) * p.stride + (K - 1) * p.dil + 1, PW = (TW - 1) * p.stride + (K - 1) * p.dil + 1;
+  const int PWp = PW | 1;                            // odd row pitch: fewer bank conflicts for the stride-2 reads
+  float *s_in = smem;                                // [CI][PH][PWp]
+  float *s_w = smem + CI * PH * PWp;                 // [CI][K*K][COB]
+  const int tid = threadIdx.x;
+  const int pg = tid & 63, cg = tid >> 6;
+  const int px0 = (pg & 7) * PXT, py = pg >> 3;
+  const int tile = blockIdx.x, tw = tile % p.tiles_w, th = tile / p.tiles_w;
+  const int cb = blockIdx.y * COB;                   // first output channel of this CTA
+  const int n = blockIdx.z;
+  const int ox0 = tw * TW, oy0 = th * TH;
+  const int ix0 = ox0 * p.stride - p.pad, iy0 = oy0 * p.stride - p.pad;
+  const float *xn = p.x + (long long)n * p.xbs;
+  float acc[PXT][CPT];
+#pragma unroll
+  for (int i = 0; i < PXT; ++i)
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) acc[i][c] = 0.f;
+
+  for (int c0 = 0; c0 < p.Cin; c0 += CI) {
+    const int nci = min(CI, p.Cin - c0);
+    __syncthreads();
+    // input patch (zero outside the image = conv padding; zero for the channels beyond Cin)
+    for (int i = tid; i < CI * PH * PW; i += 256) {
+      const int xx = i % PW, yy = (i / PW) % PH, ci = i / (PW * PH);
+      const int gx = ix0 + xx, gy = iy0 + yy;
+      float v = 0.f;
+      if (ci < nci && gx >= 0 && gx < p.W && gy >= 0 && gy < p.H) v = __ldg(xn + ((long long)(c0 + ci) * p.H + gy) * p.W + gx);
+      s_in[(ci * PH + yy) * PWp + xx] = v;
+    }
+    for (int i = tid; i < CI * K * K * COB; i += 256) {
+      const int co = i % COB, t = (i / COB) % (K * K), ci = i / (COB * K * K);
+      float v = 0.f;
+      if (ci < nci && cb + co < p.Cout) v = __ldg(p.w + ((long long)(c0 + ci) * K * K + t) * p.Cout + cb + co);
+      s_w[i] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ci = 0; ci < CI; ++ci) {
+#pragma unroll
+      for (int kh = 0; kh < K; ++kh) {
+        const float *row = s_in + (ci * PH + py * p.stride + kh * p.dil) * PWp + px0 * p.stride;
+#pragma unroll
+        for (int kw = 0; kw < K; ++kw) {
+          float xv[PXT];
+#pragma unroll
+          for (int i = 0; i < PXT; ++i) xv[i] = row[i * p.stride + kw * p.dil];
+          const float4 *wp = reinterpret_cast<const float4 *>(s_w + (ci * K * K + kh * K + kw) * COB + cg * CPT);
+#pragma unroll
+          for (int c4 = 0; c4 < CPT / 4; ++c4) {
+            const float4 wv = wp[c4];
+#pragma unroll
+            for (int i = 0; i < PXT; ++i) {
+              acc[i][c4 * 4 + 0] = fmaf(xv[i], wv.x, acc[i][c4 * 4 + 0]);
+              acc[i][c4 * 4 + 1] = fmaf(xv[i], wv.y, acc[i][c4 * 4 + 1]);
+              acc[i][c4 * 4 + 2] = fmaf(xv[i], wv.z, acc[i][c4 * 4 + 2]);
+              acc[i][c4 * 4 + 3] = fmaf(xv[i], wv.w, acc[i][c4 * 4 + 3]);
+            }
+          }
+        }
+      }
+    }
+  }
+  const int oy = oy0 + py;
+  if (oy >= p.Ho) return;
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    const int co = cb + cg * CPT + c;
+    if (co >= p.Cout) continue;
+    const float b = p.bias ? __ldg(p.bias + co) : 0.f;
+#pragma unroll
+    for (int i = 0; i < PXT; ++i) {
+      const int ox = ox0 + px0 + i;
+      if (ox >= p.Wo) continue;
+      const long long o = ((long long)co * p.Ho + oy) * p.Wo + ox;
+      float v = acc[i][c] + b;
+      if (p.res) v += __ldg(p.res + (long long)n * p.rbs + o);
+      if (p.relu) v = fmaxf(v, 0.f);
+      p.y[(long long)n * p.ybs + o] = v;
+    }
+  }
+}
+
+// AvgPool2d(k, stride k) (submodule.py:78-92: kernel = stride, no padding, floor): one thread per output element
+__global__ void avgpool_kernel(const float *__restrict__ x, long long xbs, int C, int H, int W, int k, int Ho, int Wo, float *__restrict__ y)
+{
+  const long long total = (long long)gridDim.y * C * Ho * Wo;
+  (void)total;
+  const int n = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C * Ho * Wo; i += gridDim.x * blockDim.x) {
+    const int ox = i % Wo, oy = (i / Wo) % Ho, c = i / (Wo * Ho);
+    const float *src = x + (long long)n * xbs + ((long long)c * H + oy * k) * W + ox * k;
+    float s = 0.f;
+    for (int yy = 0; yy < k; ++yy)
+      for (int xx = 0; xx < k; ++xx) s += __ldg(src + (long long)yy * W + xx);
+    y[((long long)n * C + c) * Ho * Wo + oy * Wo + ox] = s / (float)(k * k);
+  }
+}
+
+// F.interpolate(mode='bilinear', align_corners=True) (submodule.py:115-132) of [B,C,Hi,Wi] into channels [c_off, c_off+C) of
+// the concat tensor [B,Ctot,Ho,Wo].  ATen's index math: scale = (in-1)/(out-1) (0 when out == 1), src = scale*o,
+// i0 = (int)src, i1 = i0 + (i0 < in-1), l1 = src - i0.
+__global__ void upsample_bilinear_kernel(const float *__restrict__ x, int C, int Hi, int Wi, int Ho, int Wo, float *__restrict__ y, long long ybs,
+                                         int c_off)
+{
+  const int n = blockIdx.y;
+  const float sh = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f, sw = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C * Ho * Wo; i += gridDim.x * blockDim.x) {
+    const int ox = i % Wo, oy = (i / Wo) % Ho, c = i / (Wo * Ho);
+    const float fy = sh * oy, fx = sw * ox;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+    const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    const float *src = x + ((long long)n * C + c) * Hi * Wi;
+    const float v = hy * (hx * __ldg(src + y0 * Wi + x0) + lx * __ldg(src + y0 * Wi + x1)) +
+                    ly * (hx * __ldg(src + y1 * Wi + x0) + lx * __ldg(src + y1 * Wi + x1));
+    y[(long long)n * ybs + ((long long)(c_off + c) * Ho + oy) * Wo + ox] = v;
+  }
+}
+
+}  // namespace f2d
+
+// ---------------------------------------------------------------------------------------
+// host side: the layer table, BN folding, the forward schedule
+// ---------------------------------------------------------------------------------------
+struct F2dLayer {
+  std::string prefix;   // state_dict prefix relative to feature_extraction ("" prefix handled by the caller)
+  int cin, cout, k, stride, dil;
+  bool bn;              // prefix.0.weight + prefix.1.* (convbn) / downsample: prefix.0.weight + prefix.1.* too / bare conv: prefix.weight
+  float *w = nullptr, *bias = nullptr;   // device: [Cin][k*k][Cout], [Cout]
+};
+
+}  // namespace idisp
+
+using namespace idisp;
+
+struct idisp_extractor {
+  std::vector<F2dLayer> layers;
+  std::map<std::string, int> index;                  // prefix -> layer
+  std::map<std::string, std::vector<float>> host;    // reference-keyed tensors
+  float *blob = nullptr;
+  bool finalized = false;
+  int launches = 0;
+};
+
+static void f2d_add(idisp_extractor *e, const std::string &prefix, int cin, int cout, int k, int stride, int dil, bool bn)
+{
+  F2dLayer L;
+  L.prefix = prefix; L.cin = cin; L.cout = cout; L.k = k; L.stride = stride; L.dil = dil; L.bn = bn;
+  e->index[prefix] = (int)e->layers.size();
+  e->layers.push_back(L);
+}
+
+extern "C" int idisp_extractor_create(idisp_extractor_t **out)
+{
+  IDISP_REQUIRE(out != nullptr, "extractor_create: NULL out pointer");
+  idisp_extractor *e = new idisp_extractor();
+  // submodule.py:63-68
+  f2d_add(e, "firstconv.0", 3, 32, 3, 2, 1, true);
+  f2d_add(e, "firstconv.2", 32, 32, 3, 1, 1, true);
+  f2d_add(e, "firstconv.4", 32, 32, 3, 1, 1, true);
+  // :70-73 _make_layer(BasicBlock, planes, blocks, stride, pad, dilation)
+  struct Stage { const char *name; int planes, blocks, stride, dil; };
+  const Stage stages[4] = {{"layer1", 32, 3, 1, 1}, {"layer2", 64, 16, 2, 1}, {"layer3", 128, 3, 1, 1}, {"layer4", 128, 3, 1, 2}};
+  int inpl = 32;
+  for (const Stage &s : stages) {
+    for (int b = 0; b < s.blocks; ++b) {
+      const std::string p = std::string(s.name) + "." + std::to_string(b);
+      const int cin = b == 0 ? inpl : s.planes, st = b == 0 ? s.stride : 1;
+      f2d_add(e, p + ".conv1.0", cin, s.planes, 3, st, s.dil, true);
+      f2d_add(e, p + ".conv2", s.planes, s.planes, 3, 1, s.dil, true);
+      if (b == 0 && (s.stride != 1 || inpl != s.planes)) f2d_add(e, p + ".downsample", inpl, s.planes, 1, s.stride, 1, true);
+    }
+    inpl = s.planes;
+  }
+  for (const char *br : {"branch1", "branch2", "branch3", "branch4"}) f2d_add(e, std::string(br) + ".1", 128, 32, 1, 1, 1, true);
+  f2d_add(e, "lastconv.0", 320, 128, 3, 1, 1, true);
+  f2d_add(e, "lastconv.2", 128, 32, 1, 1, 1, false);
+  *out = e;
+  return IDISP_OK;
+}
+
+extern "C" void idisp_extractor_destroy(idisp_extractor_t *e)
+{
+  if (!e) return;
+  if (e->blob) cudaFree(e->blob);
+  delete e;
+}
+
+extern "C" int idisp_extractor_set_tensor(idisp_extractor_t *e, const char *key, const float *data, size_t numel)
+{
+  IDISP_REQUIRE(e && key && (data || numel == 0), "extractor_set_tensor: NULL argument");
+  const std::string k = key;
+  if (k.size() >= 19 && k.compare(k.size() - 19, 19, "num_batches_tracked") == 0) return IDISP_OK;
+  e->host[k].assign(data, data + numel);
+  e->finalized = false;
+  return IDISP_OK;
+}
+
+static int f2d_need(idisp_extractor *e, const std::string &key, size_t numel, const float **out)
+{
+  auto it = e->host.find(key);
+  if (it == e->host.end()) { set_error("extractor_finalize: missing state_dict entry '%s'", key.c_str()); return IDISP_ERR_STATE; }
+  if (it->second.size() != numel) {
+    set_error("extractor_finalize: '%s' has %zu elements, expected %zu", key.c_str(), it->second.size(), numel);
+    return IDISP_ERR_STATE;
+  }
+  *out = it->second.data();
+  return IDISP_OK;
+}
+
+extern "C" int idisp_extractor_finalize(idisp_extractor_t *e, void *stream)
+{
+  IDISP_REQUIRE(e != nullptr, "extractor_finalize: NULL extractor");
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<std::vector<float>> wt(e->layers.size()), bs(e->layers.size());
+  size_t total = 0;
+  for (size_t i = 0; i < e->layers.size(); ++i) {
+    F2dLayer &L = e->layers[i];
+    const int kk = L.k * L.k;
+    const float *w = nullptr;
+    int rc;
+    std::vector<double> scale(L.cout, 1.0);
+    if (L.bn) {
+      const float *g, *b, *m, *v;
+      if ((rc = f2d_need(e, L.prefix + ".0.weight", (size_t)L.cout * L.cin * kk, &w))) return rc;
+      if ((rc = f2d_need(e, L.prefix + ".1.weight", L.cout, &g))) return rc;
+      if ((rc = f2d_need(e, L.prefix + ".1.bias", L.cout, &b))) return rc;
+      if ((rc = f2d_need(e, L.prefix + ".1.running_mean", L.cout, &m))) return rc;
+      if ((rc = f2d_need(e, L.prefix + ".1.running_var", L.cout, &v))) return rc;
+      bs[i].resize(L.cout);
+      for (int c = 0; c < L.cout; ++c) {
+        scale[c] = (double)g[c] / std::sqrt((double)v[c] + 1e-5);
+        bs[i][c] = (float)((double)b[c] - (double)m[c] * scale[c]);
+      }
+    } else {
+      if ((rc = f2d_need(e, L.prefix + ".weight", (size_t)L.cout * L.cin * kk, &w))) return rc;
+    }
+    wt[i].assign((size_t)L.cin * kk * L.cout, 0.f);   // [Cout][Cin][k][k] -> [Cin][k*k][Cout]
+    for (int co = 0; co < L.cout; ++co)
+      for (int ci = 0; ci < L.cin; ++ci)
+        for (int t = 0; t < kk; ++t)
+          wt[i][((size_t)ci * kk + t) * L.cout + co] = (float)((double)w[((size_t)co * L.cin + ci) * kk + t] * scale[co]);
+    total += (wt[i].size() + 63) / 64 * 64 + (bs[i].size() + 63) / 64 * 64;
+  }
+  if (e->blob) { cudaFree(e->blob); e->blob = nullptr; }
+  IDISP_CUDA(cudaMalloc(&e->blob, total * sizeof(float)));
+  size_t off = 0;
+  for (size_t i = 0; i < e->layers.size(); ++i) {
+    F2dLayer &L = e->layers[i];
+    L.w = e->blob + off;
+    IDISP_CUDA(cudaMemcpyAsync(L.w, wt[i].data(), wt[i].size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    off += (wt[i].size() + 63) / 64 * 64;
+    L.bias = nullptr;
+    if (!bs[i].empty()) {
+      L.bias = e->blob + off;
+      IDISP_CUDA(cudaMemcpyAsync(L.bias, bs[i].data(), bs[i].size() * sizeof(float), cudaMemcpyHostToDevice, s));
+      off += (bs[i].size() + 63) / 64 * 64;
+    }
+  }
+  IDISP_CUDA(cudaStreamSynchronize(s));
+  e->finalized = true;
+  return IDISP_OK;
+}
+
+namespace {
+struct F2dDims { int H2, W2, H4, W4; };
+inline F2dDims f2d_dims(int H, int W)
+{
+  F2dDims d;
+  d.H2 = (H - 1) / 2 + 1; d.W2 = (W - 1) / 2 + 1;      // k3 s2 p1
+  d.H4 = (d.H2 - 1) / 2 + 1; d.W4 = (d.W2 - 1) / 2 + 1;
+  return d;
+}
+inline size_t up256(size_t x) { return (x + 255) / 256 * 256; }
+}  // namespace
+
+// buffers: two half-resolution 32-channel tensors + a temp (firstconv / layer1), three quarter-resolution 128-channel tensors
+// (layer2-4 ping-pong + temp), the 320-channel concat tensor, pooled / branch temporaries, lastconv.0's 128-channel output
+extern "C" size_t idisp_extractor_workspace_bytes(const idisp_extractor_t *e, int B, int H, int W)
+{
+  if (!e || B <= 0 || H <= 0 || W <= 0) return 0;
+  const F2dDims d = f2d_dims(H, W);
+  const size_t half = up256((size_t)B * 32 * d.H2 * d.W2 * 4), quart = up256((size_t)B * 128 * d.H4 * d.W4 * 4);
+  const size_t cat = up256((size_t)B * 320 * d.H4 * d.W4 * 4), pool = up256((size_t)B * 128 * d.H4 * d.W4 / 64 * 4 + 4096);
+  return 3 * half + 4 * quart + cat + 2 * pool;
+}
+
+static int f2d_conv(idisp_extractor *e, const std::string &prefix, const float *x, long long xbs, int B, int H, int W, const float *res, long long rbs,
+                    int relu, float *y, long long ybs, int *Ho_out, int *Wo_out, cudaStream_t s)
+{
+  auto it = e->index.find(prefix);
+  if (it == e->index.end()) { set_error("extractor: unknown layer '%s'", prefix.c_str()); return IDISP_ERR_INVALID; }
+  const F2dLayer &L = e->layers[it->second];
+  f2d::ConvParams p;
+  p.x = x; p.w = L.w; p.bias = L.bias; p.res = res; p.y = y;
+  p.Cin = L.cin; p.Cout = L.cout; p.H = H; p.W = W; p.stride = L.stride; p.dil = L.dil; p.relu = relu;
+  p.pad = L.k == 3 ? L.dil : 0;
+  p.Ho = (H + 2 * p.pad - L.dil * (L.k - 1) - 1) / L.stride + 1;
+  p.Wo = (W + 2 * p.pad - L.dil * (L.k - 1) - 1) / L.stride + 1;
+  p.xbs = xbs; p.ybs = ybs > 0 ? ybs : (long long)L.cout * p.Ho * p.Wo; p.rbs = rbs > 0 ? rbs : (long long)L.cout * p.Ho * p.Wo;
+  p.tiles_w = ceil_div(p.Wo, f2d::TW); p.tiles_h = ceil_div(p.Ho, f2d::TH);
+  if (Ho_out) *Ho_out = p.Ho;
+  if (Wo_out) *Wo_out = p.Wo;
+  const int cob = L.cout >= 64 ? 64 : 32;
+  const int PH = (f2d::TH - 1) * L.stride + (L.k - 1) * L.dil + 1, PW = ((f2d::TW - 1) * L.stride + (L.k - 1) * L.dil + 1) | 1;
+  const size_t smem = (size_t)(f2d::CI * PH * PW + f2d::CI * L.k * L.k * cob) * sizeof(float);
+  dim3 grid(p.tiles_w * p.tiles_h, ceil_div(L.cout, cob), B);
+  auto go = [&](auto kern, bool *opted) -> int {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) { set_error("extractor: device ordinal %d out of range", dev); return IDISP_ERR_INVALID; }
+    if (!opted[dev]) { IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); opted[dev] = true; }
+    kern<<<grid, 256, smem, s>>>(p);
+    IDISP_LAUNCH_CHECK();
+    return IDISP_OK;
+  };
+  static bool o0[64], o1[64], o2[64], o3[64];
+  ++e->launches;
+  if (L.k == 3) return cob == 64 ? go(f2d::conv2d_kernel<3, 64>, o0) : go(f2d::conv2d_kernel<3, 32>, o1);
+  return cob == 64 ? go(f2d::conv2d_kernel<1, 64>, o2) : go(f2d::conv2d_kernel<1, 32>, o3);
+}
+
+// images [B,3,H,W] f32 NCHW -> features [B,32,H/4,W/4] f32 NCHW (submodule.py:112-139)
+extern "C" int idisp_extractor_forward(idisp_extractor_t *e, const float *images, int B, int H, int W, void *workspace, size_t workspace_bytes,
+                                       float *features, void *stream)
+{
+  IDISP_REQUIRE(e != nullptr, "extractor_forward: NULL extractor");
+  if (!e->finalized) { set_error("extractor_forward: not finalised (call idisp_extractor_finalize after loading weights)"); return IDISP_ERR_STATE; }
+  IDISP_REQUIRE(B >= 0 && H > 0 && W > 0, "extractor_forward: bad shape B=%d H=%d W=%d", B, H, W);
+  if (B == 0) return IDISP_OK;
+  const F2dDims d = f2d_dims(H, W);
+  IDISP_REQUIRE(d.H4 >= 56 && d.W4 >= 56, "extractor_forward: %dx%d input gives a %dx%d feature map, smaller than branch1's 56x56 average pool "
+                "(submodule.py:78)", H, W, d.H4, d.W4);
+  IDISP_REQUIRE(images && features && workspace, "extractor_forward: NULL pointer");
+  IDISP_REQUIRE(workspace_bytes >= idisp_extractor_workspace_bytes(e, B, H, W), "extractor_forward: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  e->launches = 0;
+  char *base = (char *)workspace;
+  const size_t half = up256((size_t)B * 32 * d.H2 * d.W2 * 4), quart = up256((size_t)B * 128 * d.H4 * d.W4 * 4);
+  const size_t catb = up256((size_t)B * 320 * d.H4 * d.W4 * 4), poolb = up256((size_t)B * 128 * d.H4 * d.W4 / 64 * 4 + 4096);
+  float *h0 = (float *)base, *h1 = (float *)(base + half), *h2 = (float *)(base + 2 * half);
+  float *q0 = (float *)(base + 3 * half), *q1 = (float *)(base + 3 * half + quart), *q2 = (float *)(base + 3 * half + 2 * quart),
+        *q3 = (float *)(base + 3 * half + 3 * quart);
+  float *cat = (float *)(base + 3 * half + 4 * quart);
+  float *pool = (float *)(base + 3 * half + 4 * quart + catb), *brt = (float *)(base + 3 * half + 4 * quart + catb + poolb);
+  int rc, Ho, Wo;
+#define FR(expr) do { if ((rc = (expr)) != IDISP_OK) return rc; } while (0)
+  const long long hw4 = (long long)d.H4 * d.W4, cat_bs = 320 * hw4;
+  // firstconv (:63-68)
+  FR(f2d_conv(e, "firstconv.0", images, (long long)3 * H * W, B, H, W, nullptr, 0, 1, h0, 0, &Ho, &Wo, s));
+  FR(f2d_conv(e, "firstconv.2", h0, (long long)32 * Ho * Wo, B, Ho, Wo, nullptr, 0, 1, h1, 0, nullptr, nullptr, s));
+  FR(f2d_conv(e, "firstconv.4", h1, (long long)32 * Ho * Wo, B, Ho, Wo, nullptr, 0, 1, h0, 0, nullptr, nullptr, s));
+  // layer1: three BasicBlocks at half resolution (:25-48: conv1+ReLU, conv2, += x, no ReLU after the add)
+  float *cur = h0, *tmp = h1, *nxt = h2;
+  const long long hbs = (long long)32 * Ho * Wo;
+  for (int b = 0; b < 3; ++b) {
+    const std::string p = "layer1." + std::to_string(b);
+    FR(f2d_conv(e, p + ".conv1.0", cur, hbs, B, Ho, Wo, nullptr, 0, 1, tmp, 0, nullptr, nullptr, s));
+    FR(f2d_conv(e, p + ".conv2", tmp, hbs, B, Ho, Wo, cur, hbs, 0, nxt, 0, nullptr, nullptr, s));
+    float *t = cur; cur = nxt; nxt = t;
+  }
+  // layer2: 16 blocks, first one stride 2 with a 1x1 stride-2 downsample of the input; the LAST block writes `raw` into
+  // channels [0,64) of the concat tensor
+  const int H2 = Ho, W2 = Wo;
+  float *qc = q0, *qt = q1, *qn = q2;
+  long long qc_bs = 64 * hw4;
+  for (int b = 0; b < 16; ++b) {
+    const std::string p = "layer2." + std::to_string(b);
+    if (b == 0) {
+      FR(f2d_conv(e, p + ".conv1.0", cur, hbs, B, H2, W2, nullptr, 0, 1, qt, 0, &Ho, &Wo, s));
+      FR(f2d_conv(e, p + ".downsample", cur, hbs, B, H2, W2, nullptr, 0, 0, q3, 0, nullptr, nullptr, s));
+      FR(f2d_conv(e, p + ".conv2", qt, 64 * hw4, B, Ho, Wo, q3, 64 * hw4, 0, qc, 0, nullptr, nullptr, s));
+    } else {
+      float *dst = b == 15 ? cat : qn;
+      const long long dbs = b == 15 ? cat_bs : 64 * hw4;
+      FR(f2d_conv(e, p + ".conv1.0", qc, qc_bs, B, Ho, Wo, nullptr, 0, 1, qt, 0, nullptr, nullptr, s));
+      FR(f2d_conv(e, p + ".conv2", qt, 64 * hw4, B, Ho, Wo, qc, qc_bs, 0, dst, dbs, nullptr, nullptr, s));
+      if (b < 15) { float *t = qc; qc = qn; qn = t; }
+      else { qc = cat; qc_bs = cat_bs; }
+    }
+  }
+  // layer3 (64 -> 128, 1x1 downsample of `raw` in block 0), layer4 (dilation 2); the last block writes `skip` into channels [64,192)
+  float *raw = cat;
+  float *sc = q0, *st = q1, *sn = q2;
+  long long sc_bs = 128 * hw4;
+  for (int li = 3; li <= 4; ++li)
+    for (int b = 0; b < 3; ++b) {
+      const std::string p = "layer" + std::to_string(li) + "." + std::to_string(b);
+      const bool last = li == 4 && b == 2;
+      float *dst = last ? cat + 64 * hw4 : sn;
+      const long long dbs = last ? cat_bs : 128 * hw4;
+      if (li == 3 && b == 0) {
+        FR(f2d_conv(e, p + ".conv1.0", raw, cat_bs, B, Ho, Wo, nullptr, 0, 1, st, 0, nullptr, nullptr, s));
+        FR(f2d_conv(e, p + ".downsample", raw, cat_bs, B, Ho, Wo, nullptr, 0, 0, q3, 0, nullptr, nullptr, s));
+        FR(f2d_conv(e, p + ".conv2", st, 128 * hw4, B, Ho, Wo, q3, 128 * hw4, 0, sc, 0, nullptr, nullptr, s));
+        continue;
+      }
+      FR(f2d_conv(e, p + ".conv1.0", sc, sc_bs, B, Ho, Wo, nullptr, 0, 1, st, 0, nullptr, nullptr, s));
+      FR(f2d_conv(e, p + ".conv2", st, 128 * hw4, B, Ho, Wo, sc, sc_bs, 0, dst, dbs, nullptr, nullptr, s));
+      if (!last) { float *t = sc; sc = sn; sn = t; }
+    }
+  const float *skip = cat + 64 * hw4;
+  // SPP branches (:78-92, :115-132); concat order raw, skip, branch4, branch3, branch2, branch1 (:134-135)
+  const int ks[4] = {56, 32, 16, 8};
+  const int c_off[4] = {288, 256, 224, 192};  // branch1 .. branch4
+  for (int bi = 0; bi < 4; ++bi) {
+    const int k = ks[bi], Hp = (Ho - k) / k + 1, Wp = (Wo - k) / k + 1;
+    const int n_el = 128 * Hp * Wp;
+    f2d::avgpool_kernel<<<dim3(ceil_div(n_el, 256), B), 256, 0, s>>>(skip, cat_bs, 128, Ho, Wo, k, Hp, Wp, pool);
+    IDISP_LAUNCH_CHECK();
+    FR(f2d_conv(e, "branch" + std::to_string(bi + 1) + ".1", pool, (long long)128 * Hp * Wp, B, Hp, Wp, nullptr, 0, 1, brt, 0, nullptr, nullptr, s));
+    f2d::upsample_bilinear_kernel<<<dim3(ceil_div(32 * Ho * Wo, 256), B), 256, 0, s>>>(brt, 32, Hp, Wp, Ho, Wo, cat, cat_bs, c_off[bi]);
+    IDISP_LAUNCH_CHECK();
+    e->launches += 2;
+  }
+  // lastconv (:94-96)
+  FR(f2d_conv(e, "lastconv.0", cat, cat_bs, B, Ho, Wo, nullptr, 0, 1, q0, 0, nullptr, nullptr, s));
+  FR(f2d_conv(e, "lastconv.2", q0, 128 * hw4, B, Ho, Wo, nullptr, 0, 0, features, 0, nullptr, nullptr, s));
+#undef FR
+  return IDISP_OK;
+}
+
+extern "C" int idisp_extractor_launches_per_forward(const idisp_extractor_t *e) { return e ? e->launches : 0; }

@@ -119,6 +119,7 @@ struct idisp_plan {
   std::vector<GraphEntry> graphs;
   unsigned long long graph_clock = 0;
   int graph_hits = 0, graph_captures = 0;
+  cudaStream_t cap_stream = nullptr;  // capture happens here: the caller's stream may be the legacy default stream, which cannot capture
 };
 
 extern "C" int idisp_version(void) { return IDISP_VERSION; }
@@ -152,6 +153,7 @@ extern "C" void idisp_plan_destroy(idisp_plan_t *p)
   for (auto &d : p->dev) { tc_weights_free(d.tc); tc_split_weights_free(d.sp); tc_head_weights_free(d.head); }
   for (auto e : p->ev) cudaEventDestroy(e);
   for (auto &g : p->graphs) cudaGraphExecDestroy(g.exec);
+  if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
   if (p->blob) cudaFree(p->blob);
   if (p->range_flag) cudaFree(p->range_flag);
   if (p->stage) cudaFree(p->stage);
@@ -453,30 +455,39 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
       for (auto &g : p->graphs)
         if (g.B == B && g.Hf == Hf && g.Wf == Wf && g.ws == workspace) { hit = &g; break; }
       if (!hit) {
+        // Capture on the plan's own stream (nothing executes there; the caller's stream may be the legacy default stream, on
+        // which capture is not permitted); the instantiated graph is then launched into the caller's stream.
         const int before = launches;
         cudaGraph_t graph = nullptr;
-        IDISP_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        const int crc = conv_section();
-        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
-        if (crc != IDISP_OK) { if (graph) cudaGraphDestroy(graph); return crc; }
-        if (ce != cudaSuccess || !graph) { cudaGetLastError(); p->no_graph = true; launches = before; RUN(conv_section()); }
-        else {
-          cudaGraphExec_t exec = nullptr;
-          const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
-          cudaGraphDestroy(graph);
-          if (ie != cudaSuccess) { cudaGetLastError(); p->no_graph = true; launches = before; RUN(conv_section()); }
-          else {
-            if (p->graphs.size() >= 48) {  // least recently used out
-              size_t lru = 0;
-              for (size_t i = 1; i < p->graphs.size(); ++i) if (p->graphs[i].stamp < p->graphs[lru].stamp) lru = i;
-              cudaGraphExecDestroy(p->graphs[lru].exec);
-              p->graphs.erase(p->graphs.begin() + lru);
-            }
-            p->graphs.push_back({B, Hf, Wf, workspace, exec, launches - before, 0ull});
-            hit = &p->graphs.back();
-            ++p->graph_captures;
-            launches = before;
+        cudaGraphExec_t exec = nullptr;
+        bool ok = p->cap_stream || cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+          cudaStream_t user = s;
+          s = p->cap_stream;
+          const int crc = conv_section();
+          s = user;
+          const cudaError_t ce = cudaStreamEndCapture(p->cap_stream, &graph);
+          if (crc != IDISP_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return crc; }
+          ok = ce == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+          if (graph) cudaGraphDestroy(graph);
+        }
+        if (!ok) {  // no graphs on this driver / in this context: launch eagerly from now on
+          cudaGetLastError();
+          p->no_graph = true;
+          launches = before;
+          RUN(conv_section());
+        } else {
+          if (p->graphs.size() >= 48) {  // least recently used out
+            size_t lru = 0;
+            for (size_t i = 1; i < p->graphs.size(); ++i) if (p->graphs[i].stamp < p->graphs[lru].stamp) lru = i;
+            cudaGraphExecDestroy(p->graphs[lru].exec);
+            p->graphs.erase(p->graphs.begin() + lru);
           }
+          p->graphs.push_back({B, Hf, Wf, workspace, exec, launches - before, 0ull});
+          hit = &p->graphs.back();
+          ++p->graph_captures;
+          launches = before;
         }
       } else {
         ++p->graph_hits;

@@ -282,4 +282,9 @@ class PSMNet(nn.Module):
         _, _, H, W = left.shape
         if isinstance(self.feature_extraction, nn.Identity):  # feature-input configs (BASELINE configs 1-3)
             return self.forward_features(left, right, H, W)
+        if not self.training and getattr(self.feature_extraction, 'native', False) and left.shape == right.shape:
+            # both views in ONE extractor pass (weights are shared, stackhourglass.py:112-113): twice the parallelism per launch
+            fea = self.feature_extraction(torch.cat([left, right], 0))
+            nb = left.shape[0]
+            return self.forward_features(fea[:nb], fea[nb:], H, W)
         return self.forward_features(self.feature_extraction(left), self.feature_extraction(right), H, W)

@@ -1,13 +1,16 @@
 """Building blocks of iDispNet -- API mirror of disprcnn/modeling/psmnet/submodule.py.
 
 ``convbn_3d`` (submodule.py:19-22) and ``disparityregression`` (:51-57) are the hot-path names;
-``feature_extraction`` (:60-139) is the adjacent 2-D extractor ("next" row):
-it is kept as plain torch modules with the reference's parameter names so reference
-checkpoints load, and runs through torch until its own kernels land.
+``feature_extraction`` (:60-139) is the adjacent 2-D extractor: a module tree with
+the reference's parameter names so reference checkpoints load; in eval mode on a GPU its forward runs inside
+libidisp (csrc/feature2d.cu through ``idisp_extractor_forward``: no cuDNN / ATen kernels), in training mode the
+torch modules run (training is outside the B200 path).
 
 The 3-D modules built here are PARAMETER HOLDERS with the reference's ``state_dict`` layout; in
 eval mode on a GPU their arithmetic is executed by libidisp (see stackhourglass.PSMNet).
 """
+import ctypes
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -86,6 +89,86 @@ class feature_extraction(nn.Module):
             setattr(self, name, nn.Sequential(nn.AvgPool2d((k, k), stride=(k, k)), convbn(128, 32, 1, 1, 0, 1), relu()))
         self.lastconv = nn.Sequential(convbn(320, 128, 3, 1, 1, 1), relu(),
                                       nn.Conv2d(128, 32, kernel_size=1, padding=0, stride=1, bias=False))
+        self.native = True   # eval + CUDA: run inside libidisp (False: the torch modules, e.g. for A/B timing against cuDNN)
+        self._reset_runtime_state()
+
+    def _reset_runtime_state(self):
+        self._handle = None     # idisp_extractor_t*
+        self._key = None        # weights the handle was finalised with
+        self._tensors = None
+        self._workspaces = {}   # (device index, stream) -> uint8 arena
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        for k in ('_handle', '_key', '_tensors', '_workspaces'):
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._reset_runtime_state()
+
+    def __del__(self):
+        try:
+            if getattr(self, '_handle', None) is not None:
+                _lib.load().idisp_extractor_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    def _items(self):
+        cur = self._tensors
+        if cur is not None and all(getattr(owner, name) is t for (_, owner, name, t) in cur):
+            return cur
+        items = []
+        for mod_name, mod in self.named_modules():
+            for name, t in list(mod._parameters.items()) + list(mod._buffers.items()):
+                if t is None or name == 'num_batches_tracked':
+                    continue
+                items.append(((mod_name + '.' if mod_name else '') + name, mod, name, t))
+        self._tensors = items
+        return items
+
+    def _ensure_handle(self, device):
+        items = self._items()
+        key = (str(device), tuple((t._version, t.data_ptr()) for (_, _, _, t) in items))
+        if self._handle is not None and key == self._key:
+            return self._handle
+        lib = _lib.load()
+        if self._handle is None:
+            h = ctypes.c_void_p()
+            _lib.check(lib.idisp_extractor_create(ctypes.byref(h)))
+            self._handle = h
+        for k, _, _, t in items:
+            host = t.detach().to('cpu', torch.float32).contiguous()
+            _lib.check(lib.idisp_extractor_set_tensor(self._handle, k.encode(), _lib.ptr(host), host.numel()))
+        with torch.cuda.device(device):
+            _lib.check(lib.idisp_extractor_finalize(self._handle, _lib.stream_ptr()))
+        self._key = key
+        return self._handle
+
+    def forward_native(self, x):
+        """submodule.py:112-139 inside libidisp: [B,3,H,W] f32 CUDA -> [B,32,H/4,W/4]."""
+        _lib.require_cuda(x)
+        x = x.contiguous().float()
+        B, C, H, W = x.shape
+        if C != 3:
+            raise RuntimeError(f'feature_extraction: 3-channel images expected, got {C}')
+        Hq, Wq = ((H - 1) // 2 + 1 - 1) // 2 + 1, ((W - 1) // 2 + 1 - 1) // 2 + 1
+        out = torch.empty((B, 32, Hq, Wq), dtype=torch.float32, device=x.device)
+        if B == 0:
+            return out
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            h = self._ensure_handle(x.device)
+            need = lib.idisp_extractor_workspace_bytes(h, B, H, W)
+            wkey = (x.device.index, torch.cuda.current_stream().cuda_stream)
+            ws = self._workspaces.get(wkey)
+            if ws is None or ws.numel() < need:
+                self._workspaces.pop(wkey, None)
+                ws = self._workspaces[wkey] = torch.empty(need, dtype=torch.uint8, device=x.device)
+            _lib.check(lib.idisp_extractor_forward(h, _lib.ptr(x), B, H, W, _lib.ptr(ws), ws.numel(), _lib.ptr(out), _lib.stream_ptr()))
+        return out
 
     def _stage(self, planes, blocks, stride, pad, dilation):
         down = None
@@ -98,6 +181,8 @@ class feature_extraction(nn.Module):
         return nn.Sequential(*mods)
 
     def forward(self, x):
+        if not self.training and self.native:
+            return self.forward_native(x)   # raises for CPU tensors: no CPU path in eval mode
         raw = self.layer2(self.layer1(self.firstconv(x)))
         skip = self.layer4(self.layer3(raw))
         size = skip.shape[-2:]

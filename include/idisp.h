@@ -65,6 +65,7 @@ enum {
 };
 
 typedef struct idisp_plan idisp_plan_t;
+typedef struct idisp_extractor idisp_extractor_t;
 
 int idisp_version(void);
 /* Thread-local description of the last failing call ("" if none). Never NULL. */
@@ -163,6 +164,22 @@ int idisp_plan_graph_stats(const idisp_plan_t *plan, int *captures, int *replays
  * Appendix A order minus one; -1 = cost volume, -2 = soft-argmin).  capacity = array lengths. */
 int idisp_plan_enable_timing(idisp_plan_t *plan, int on);
 int idisp_plan_get_timing(idisp_plan_t *plan, float *ms, int *layer, int capacity);
+
+/* ---- the 2-D feature extractor that precedes the cost volume in the live call -------------------
+ * disprcnn/modeling/psmnet/submodule.py:60-139 (feature_extraction: firstconv, layer1-4 of BasicBlocks :25-48, four SPP
+ * branches, concat, lastconv), applied to each view at stackhourglass.py:112-113.  Same pattern as the plan: hand over the
+ * reference's state_dict entries by key (relative to the module: "firstconv.0.0.weight", "layer2.0.downsample.1.running_var",
+ * "lastconv.2.weight", ...; *.num_batches_tracked is ignored), finalize (BatchNorm2d folded in float64), forward.
+ * images [B,3,H,W] f32 NCHW device -> features [B,32,H/4,W/4] f32 NCHW device (H/4 = ((H-1)/2+1-1)/2+1: two k3 s2 p1 convs);
+ * H/4 and W/4 must be at least 56 (branch1's 56x56 average pool, submodule.py:78).  fp32 FFMA kernels, no CPU path. */
+int idisp_extractor_create(idisp_extractor_t **extractor);
+void idisp_extractor_destroy(idisp_extractor_t *extractor);
+int idisp_extractor_set_tensor(idisp_extractor_t *extractor, const char *key, const float *data, size_t numel);
+int idisp_extractor_finalize(idisp_extractor_t *extractor, void *stream);
+size_t idisp_extractor_workspace_bytes(const idisp_extractor_t *extractor, int B, int H, int W);
+int idisp_extractor_forward(idisp_extractor_t *extractor, const float *images, int B, int H, int W, void *workspace,
+                            size_t workspace_bytes, float *features, void *stream);
+int idisp_extractor_launches_per_forward(const idisp_extractor_t *extractor);
 
 /* Test hook: the cost volume exactly as the tensor-core path assembles it inside dres0.0's TMA loader (never
  * materialised in the product path): bf16-rounded values, NCDHW f32 out [B,2C,D,Hf,Wf].  C in {16, 32}. */

@@ -247,3 +247,38 @@ def test_deferred_range_check_reports_at_the_next_call(lib):
             again = m.forward_features(L.cuda(), R.cuda())
         assert m._sticky_fp32 and torch.equal(again, f32.forward_features(L.cuda(), R.cuda()))
     assert (ok - again).abs().max().item() < TOL
+
+
+def test_feature_extraction_native_kernels_match_reference(lib):
+    """submodule.py:60-139 inside libidisp (csrc/feature2d.cu) against the features the UNMODIFIED reference produced for the
+    same crops (psm_live golden), against the oracle at a non-square size, and -- as a cross-check -- the torch modules."""
+    case, g, sd, L, R = load_psm_case('psm_live')
+    m = make_full_psmnet(case, sd, 'auto')
+    fe = m.feature_extraction
+    assert fe.native
+    with torch.no_grad():
+        fl, fr = fe(L.cuda()), fe(R.cuda())
+        both = fe(torch.cat([L, R]).cuda())
+    el, er = np.abs(fl.cpu().numpy() - g['fea_left']).max(), np.abs(fr.cpu().numpy() - g['fea_right']).max()
+    e64 = np.abs(fl.cpu().numpy() - g['fea_left_f64']).max()
+    print(f'\n[extractor] |features - ref_fp32| max {el:.3e} / {er:.3e} (|ref| max {np.abs(g["fea_left"]).max():.2f}); vs float64 {e64:.3e}')
+    assert el < 2e-4 and er < 2e-4
+    assert torch.equal(both[:2], fl) and torch.equal(both[2:], fr)          # images are independent
+    # other sizes: H/4 x W/4 = 58 x 66 -> SPP pools 1x1, 1x2, 3x4, 7x8 (floor), bilinear upsample from each
+    g2 = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 3, 232, 264, generator=g2)
+    fsd = {k[len('feature_extraction.'):]: v for k, v in sd.items() if k.startswith('feature_extraction.')}
+    with torch.no_grad():
+        want = O.feature_extraction(x, fsd, prefix='').numpy()
+        got = fe(x.cuda()).cpu().numpy()
+    assert got.shape == (1, 32, 58, 66) and np.abs(got - want).max() < 2e-4, np.abs(got - want).max()
+    fe.native = False
+    with torch.no_grad():
+        via_torch = fe(x.cuda()).cpu().numpy()
+    fe.native = True
+    assert np.abs(via_torch - want).max() < 2e-4
+    with pytest.raises(RuntimeError, match='56x56'):
+        fe(torch.zeros(1, 3, 128, 128).cuda())                             # feature map smaller than branch1's pool
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        fe(torch.zeros(1, 3, 224, 224))
+    assert fe(torch.zeros(0, 3, 224, 224).cuda()).shape == (0, 32, 56, 56)
