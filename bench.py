@@ -528,6 +528,7 @@ def main():
                                                 'note': 'fails the 1e-3 parity bar; not the headline'}
                 del m16
             del m32
+        model_sd = None
         if world == 1:
             result['roi_align'] = bench_roi_align(dev, hbm)
             result['cost_volume'] = bench_cost_volume(dev, hbm, L, R)
@@ -536,6 +537,7 @@ def main():
         if world == 1 and not os.environ.get('IDISP_BENCH_SKIP_REFGPU') and not os.environ.get('IDISP_TC_DBG'):
             # north_star's ">= 4x over the reference GPU path": the same stack in eager PyTorch + cuDNN on THIS GPU, outside the timed
             # region, with its own clock record (tools/ref_gpu_timing.py: torch.nn restatement of SURVEY.md Appendix A, random weights)
+            model_sd = {k: v.detach().cpu() for k, v in m.state_dict().items() if not k.startswith('feature_extraction')}
             del m
             torch.cuda.empty_cache()
             sys.path.insert(0, os.path.join(ROOT, 'tools'))
@@ -561,8 +563,9 @@ def main():
                     'speedup_vs_tf32': value / best['tf32_rois_per_s'], 'speedup_vs_fp32': value / best['fp32_rois_per_s'],
                     'e2e_speedup_vs_tf32': e2e / best['tf32_rois_per_s'], 'clocks': rc}
         if world == 1 and not args.no_cpu_baseline:
-            sd = {k: v for k, v in m.state_dict().items() if not k.startswith('feature_extraction')}
-            val, dt, cores, sample = cpu_port_rois_per_s(sd, 1, 1, budget_s=45.0)  # 1 warm-up: oneDNN primitive creation is per shape
+            if model_sd is None:
+                model_sd = {k: v.detach().cpu() for k, v in m.state_dict().items() if not k.startswith('feature_extraction')}
+            val, dt, cores, sample = cpu_port_rois_per_s(model_sd, 1, 1, budget_s=45.0)  # 1 warm-up: oneDNN primitive creation is per shape
             result['cpu_baseline'] = {'value': val, 'unit': 'ROIs/s', 'cores': cores, 'kind': 'port', 'sample': sample}
         print(json.dumps(result))
     if world > 1:

@@ -157,7 +157,7 @@ struct Params {
   int B, Din, Dout, Ho, Wo, Hr, Wr, Cout, relu;  // (Hr,Wr): row grid the 8x16 tiles cover
   int tiles_h, tiles_w, nh;
   int cv_shift0;                  // mindisp/4: plane k <-> right-view shift i = k + cv_shift0
-  int dbg;                        // timing experiments only (IDISP_TC_DBG): 1 no MMAs, 2 no TMA loads, 4 no global stores, 8 no tcgen05.ld, 16 no tcgen05.st
+  int dbg;                        // timing experiments only (IDISP_TC_DBG): 1 no MMAs, 2 no TMA loads, 4 no global stores, 8 no tcgen05.ld, 16 no tcgen05.st, 32 TRI epilogue = handshake only
 };
 
 // DECONV stacking table: per kd, five MMAs (entries) that share an input shift
@@ -633,6 +633,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           }
           ptx::mbar_wait(accf_bar(t), (tq / NSLOT) & 1);
           ptx::tc_fence_after();
+          if (p.dbg & 32) {  // timing experiment: handshake only (no TMEM traffic, no arithmetic, no global memory)
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(acce_bar(t));
+            continue;
+          }
           uint32_t b0[16], b1[16], b2[16];
           if (owner) {
             const uint32_t tb = tmem_base + lane_addr + t * C::TRI_STRIDE + cbase;

@@ -82,9 +82,18 @@ def make_stereo_crops(R, size, seed, max_shift=12):
     pixels plus a little independent noise, so the network sees a real correspondence problem."""
     g = _gen(seed, 'crops')
     pad = 2 * max_shift
-    base = torch.rand(R, 3, size + 8, size + pad + 8, generator=g)
-    base = torch.nn.functional.avg_pool2d(base, 5, 1, 2) * 0.6 + torch.nn.functional.avg_pool2d(base, 9, 1, 4) * 0.4
-    base = (base - base.mean()) / base.std() * 0.25 + 0.45
+    Hb, Wb = size + 8, size + pad + 8
+    noise_src = torch.rand(R, 3, Hb + 8, Wb + 8, generator=g)
+
+    def box_blur(x, k):   # explicit shifted adds in a fixed order: bit-reproducible on any CPU (a pooling kernel's summation order is not)
+        acc = torch.zeros(R, 3, Hb, Wb)
+        o = 4 - k // 2
+        for dy in range(k):
+            for dx in range(k):
+                acc = acc + x[:, :, o + dy:o + dy + Hb, o + dx:o + dx + Wb]
+        return acc / float(k * k)
+    base = box_blur(noise_src, 5) * 0.6 + box_blur(noise_src, 9) * 0.4
+    base = (base - 0.5) * 2.5 + 0.45   # fixed affine stretch (no data-dependent statistics)
     noise = torch.randn(R, 3, size, size, generator=g) * 0.01
     shifts = torch.randint(-max_shift, max_shift + 1, (R,), generator=g)
     left = torch.stack([base[r, :, 4:4 + size, 4 + max_shift:4 + max_shift + size] for r in range(R)])

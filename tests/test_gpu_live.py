@@ -179,13 +179,14 @@ def test_cuda_graph_replay_is_bit_identical_to_eager_launches(lib, monkeypatch):
     """The conv section is captured once per (B, Hf, Wf, workspace) and replayed: same bits as the eager launch sequence,
     for a second batch size as well, and again after the weights change (the captured launches hold weight pointers)."""
     case, g, sd, L, R = load_case('tiny')
-    monkeypatch.setenv('IDISP_NO_GRAPH', '1')
-    eager = make_psmnet(case, sd, 'fp16x2')
-    monkeypatch.delenv('IDISP_NO_GRAPH')
-    m = make_psmnet(case, sd, 'fp16x2')
     Lc, Rc = L.cuda(), R.cuda()
+    monkeypatch.setenv('IDISP_NO_GRAPH', '1')     # read when a plan is created, i.e. at a model's first forward
+    eager = make_psmnet(case, sd, 'fp16x2')
     with torch.no_grad():
         want2, want1 = eager.forward_features(Lc, Rc), eager.forward_features(Lc[:1], Rc[:1])
+    monkeypatch.delenv('IDISP_NO_GRAPH')
+    m = make_psmnet(case, sd, 'fp16x2')
+    with torch.no_grad():
         assert _graph_stats(eager) == (0, 0)
         a = m.forward_features(Lc, Rc)           # captures
         b = m.forward_features(Lc, Rc)           # replays
