@@ -328,7 +328,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     {
       const bool lead = ptx::elect_one();
       const bool do_mma = lead && !(p.dbg & 1);
-      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id) { if (do_mma) ptx::umma_bf16_ss(d, a, b, id, 1u); };
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc = 1u) { if (do_mma) ptx::umma_bf16_ss(d, a, b, id, acc); };
       auto commit = [&](uint32_t bar) { if (lead) ptx::umma_commit(bar); };
       const uint64_t a_desc0 = ptx::make_smem_desc(stage_addr0, C::PLANE_BYTES, C::ROW_BYTES);
       auto wait_acc_empty = [&](uint32_t g) { ptx::mbar_wait(acce_bar(g % NSLOT), ((g / NSLOT) & 1) ^ 1); };
@@ -363,8 +363,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               for (int ks = 0; ks < C::KS; ++ks) {
                 const uint32_t a_tap = ((tap / 3) * MC::SUB_W + (tap % 3)) * 16;
                 const uint32_t boff = (tap * C::KS + ks) * 2 * C::WCHUNK;
-                mma(dm, desc_add(a0, a_tap + A_KOFF(ks)), desc_add(bm, boff), id2);           // x_hi * [w_hi | w_lo] -> [main | corr]
-                mma(ds, desc_add(a0, a_tap + A_KOFF(C::KS + ks)), desc_add(bm, boff), id1);   // x_lo * w_hi -> corr
+                // (the step's triples are fresh: the very first MMA overwrites them, nothing is zeroed on drain)
+                mma(dm, desc_add(a0, a_tap + A_KOFF(ks)), desc_add(bm, boff), id2, (tap | ks) ? 1u : 0u);   // x_hi * [w_hi | w_lo] -> [main | corr]
+                mma(ds, desc_add(a0, a_tap + A_KOFF(C::KS + ks)), desc_add(bm, boff), id1);                 // x_lo * w_hi -> corr
               }
             }
           } else {
@@ -375,7 +376,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
             for (int ks = 0; ks < C::KSM; ++ks) {
               const uint32_t aoff = ((tap / 3) * MC::SUB_W + (tap % 3)) * 16 + A_KOFF(ks);
-              mma((XP != 0 && ks >= C::KS) ? ds : dm, desc_add(a0, aoff), desc_add(b1, (tap * C::KSW + B_KS(ks)) * C::WCHUNK), id1);
+              // first MMA into the main triple (tap 0, k-step 0) and into the correction triple (tap 0, k-step KS) overwrite
+              mma((XP != 0 && ks >= C::KS) ? ds : dm, desc_add(a0, aoff), desc_add(b1, (tap * C::KSW + B_KS(ks)) * C::WCHUNK), id1,
+                  (tap == 0 && (ks == 0 || ks == C::KS)) ? 0u : 1u);
             }
           }
           }
@@ -612,7 +615,172 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           if (p.y_split) *reinterpret_cast<uint4 *>(p.y_split + ospl + (int64_t)cblk_out * 8 * sub * 8) = lo;
         }
       };
-      if constexpr (C::TRI) {
+      if constexpr (C::TRI && NT == 32) {
+        // ---- per-step triples, 32-wide blocks (every stride-1 split-precision layer) ----
+        // Both epilogue groups drain EVERY step's triple; group `egroup` owns output channels [16*egroup, 16*egroup+16) = channel
+        // blocks cbg0, cbg0+1.  Measured (IDISP_TC_DBG=32/28): with the epilogue reduced to its barrier handshake a 32->32 layer
+        // runs at the MMA stream's 1.54 ms, with it at 2.2 ms, and neither the TMEM traffic nor the global stores matter -- the
+        // epilogue's INSTRUCTION count is the limiter.  So: all per-column addressing is hoisted out of the step loop (plane
+        // strides are added to running offsets), nothing is zeroed on drain (the first MMA of a step overwrites), the half-range
+        // test works on the packed words.
+        const int cbg0 = nh * 4 + egroup * 2;
+        const int64_t blk_elems = Vo * 8;                                   // one channel block, either layout (8 * sub = Vo)
+        const int64_t lo_off = (int64_t)cblk_out * blk_elems;               // hi word -> lo word
+        const int64_t col_blk = ((int64_t)n * out_blocks + cbg0) * blk_elems;
+        const int64_t plane_nat = (int64_t)p.Ho * p.Wo * 8, plane_spl = (int64_t)(p.Ho / 2) * (p.Wo / 2) * 8;
+        const int64_t nat0 = col_blk + ((int64_t)hr * p.Wo + wr) * 8;       // natural layout, plane 0
+        const int64_t spl0 = col_blk + ((int64_t)((hr & 1) * 2 + (wr & 1)) * sub + (int64_t)(hr >> 1) * (p.Wo / 2) + (wr >> 1)) * 8;  // parity layout, plane 0
+        const int64_t part0 = (((int64_t)n * cblk_out + cbg0) * Vo + (int64_t)hr * p.Wo + wr) * 8;   // fp32 partial (natural), plane 0
+        const bool has_res = p.residual != nullptr, has_part = p.part_in != nullptr, out_x2 = p.x2 != 0;
+        float P0[16], P1[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { P0[i] = 0.f; P1[i] = 0.f; }
+        bool bad = false;
+        // element offset of plane q inside a channel block
+        auto nat_of = [&](int q) { return nat0 + (int64_t)q * plane_nat; };
+        auto spl_of = [&](int q) { return spl0 + (int64_t)(q & 1) * 4 * sub * 8 + (int64_t)(q >> 1) * plane_spl; };
+        auto emit = [&](int q, const float (&sum)[16], const XPre (&xq)[2]) {
+          const int64_t onat = nat_of(q), ospl = spl_of(q);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            float a[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) a[c] = sum[i * 8 + c];
+            if (has_part) {
+              a[0] += xq[i].p0.x; a[1] += xq[i].p0.y; a[2] += xq[i].p0.z; a[3] += xq[i].p0.w;
+              a[4] += xq[i].p1.x; a[5] += xq[i].p1.y; a[6] += xq[i].p1.z; a[7] += xq[i].p1.w;
+            }
+            if (p.part_out) {
+              float4 *po = reinterpret_cast<float4 *>(p.part_out + part0 + (int64_t)q * plane_nat + (int64_t)i * blk_elems);
+              po[0] = make_float4(a[0], a[1], a[2], a[3]);
+              po[1] = make_float4(a[4], a[5], a[6], a[7]);
+              continue;
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) a[c] += bias_s[egroup * 16 + i * 8 + c];
+            if (has_res) {
+              const F8 rh = unpack8h<F16>(xq[i].rh);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) a[c] += rh.v[c];
+              if (out_x2) {
+                const F8 rl = unpack8h<F16>(xq[i].rl);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) a[c] += rl.v[c];
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) a[c] = fmaxf(a[c], 0.f);
+            }
+            F8 f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) f.v[c] = a[c];
+            const uint4 hi = pack8h<F16>(f);
+            if (F16) {  // a half whose exponent field is all ones: the value left the IEEE-half range (or was NaN)
+              const uint32_t m = ((hi.x & 0x7fff7fffu) + 0x04000400u) | ((hi.y & 0x7fff7fffu) + 0x04000400u) |
+                                 ((hi.z & 0x7fff7fffu) + 0x04000400u) | ((hi.w & 0x7fff7fffu) + 0x04000400u);
+              bad |= (m & 0x80008000u) != 0;
+            }
+            const int64_t bo = (int64_t)i * blk_elems;
+            if (!p.skip_y) *reinterpret_cast<uint4 *>(p.y + onat + bo) = hi;
+            if (p.y_split) *reinterpret_cast<uint4 *>(p.y_split + ospl + bo) = hi;
+            if (out_x2) {  // second word: what the first one rounded away
+              const F8 h = unpack8h<F16>(hi);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) f.v[c] -= h.v[c];
+              const uint4 lo = pack8h<F16>(f);
+              if (!p.skip_y) *reinterpret_cast<uint4 *>(p.y + onat + bo + lo_off) = lo;
+              if (p.y_split) *reinterpret_cast<uint4 *>(p.y_split + ospl + bo + lo_off) = lo;
+            }
+          }
+        };
+        auto xload2 = [&](XPre (&xq)[2], int q) {
+          if (has_part) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float4 *pp = reinterpret_cast<const float4 *>(p.part_in + part0 + (int64_t)q * plane_nat + (int64_t)i * blk_elems);
+              xq[i].p0 = __ldg(pp); xq[i].p1 = __ldg(pp + 1);
+            }
+          }
+          if (has_res) {
+            const int64_t ro = p.residual_is_split ? spl_of(q) : nat_of(q);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              xq[i].rh = __ldg(reinterpret_cast<const uint4 *>(p.residual + ro + (int64_t)i * blk_elems));
+              xq[i].rl = out_x2 ? __ldg(reinterpret_cast<const uint4 *>(p.residual + ro + (int64_t)i * blk_elems + lo_off)) : make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+        };
+        for (int z = 0; z < Dout; ++z, ++tq) {
+          const uint32_t t = tq % NSLOT;
+          XPre xq[2];
+          if (valid && z >= 1) xload2(xq, z - 1);      // operands of the plane this step completes: requested before the wait
+          ptx::mbar_wait(accf_bar(t), (tq / NSLOT) & 1);
+          ptx::tc_fence_after();
+          if (p.dbg & 32) {  // timing experiment: handshake only (no TMEM traffic, no arithmetic, no global memory)
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(acce_bar(t));
+            continue;
+          }
+          const uint32_t tb = tmem_base + lane_addr + t * C::TRI_STRIDE + egroup * 16;
+          // plane z-1 = P0 + block 0 (complete);  plane z: P1 + block 1;  plane z+1: block 2 (first contribution).
+          // Two TMEM round trips (blocks 0+1, then block 2) keep the live registers under the 168-register cap; the
+          // correction triple (x_lo*w_hi + x_hi*w_lo) is summed with the main one in fp32 round-to-nearest.
+          float N0[16];   // next step's P0 = plane z so far
+          {
+            uint32_t b0[16], b1[16];
+            ptx::tmem_ld_32x16(tb, b0);
+            ptx::tmem_ld_32x16(tb + NT, b1);
+            if (XP != 0) {
+              uint32_t u0[16], u1[16];
+              ptx::tmem_ld_32x16(tb + C::TRI_SMALL, u0);
+              ptx::tmem_ld_32x16(tb + C::TRI_SMALL + NT, u1);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                P0[i] += __uint_as_float(b0[i]) + __uint_as_float(u0[i]);
+                N0[i] = P1[i] + (__uint_as_float(b1[i]) + __uint_as_float(u1[i]));
+              }
+            } else {
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { P0[i] += __uint_as_float(b0[i]); N0[i] = P1[i] + __uint_as_float(b1[i]); }
+            }
+          }
+          {
+            uint32_t b2[16];
+            ptx::tmem_ld_32x16(tb + 2 * NT, b2);
+            if (XP != 0) {
+              uint32_t u2[16];
+              ptx::tmem_ld_32x16(tb + C::TRI_SMALL + 2 * NT, u2);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) P1[i] = __uint_as_float(b2[i]) + __uint_as_float(u2[i]);
+            } else {
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) P1[i] = __uint_as_float(b2[i]);
+            }
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(acce_bar(t));   // the MMA warp may overwrite this buffer (first MMA of a step: accumulate = 0)
+          if (z >= 1 && valid) emit(z - 1, P0, xq);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) P0[i] = N0[i];
+          if (z == Dout - 1) {  // no step z+1: plane z is complete as well
+            if (valid) {
+              xload2(xq, z);
+              emit(z, P0, xq);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { P0[i] = 0.f; P1[i] = 0.f; }
+          }
+        }
+        if (bad && p.range_flag) *p.range_flag = 1;
+      } else if constexpr (C::TRI) {
+        // (16-wide blocks: the 1-channel head in its generic-kernel form, kept as a cross-check of head_tc.cu -- IDISP_OLD_HEAD=1)
         // Both epilogue groups drain EVERY step's triple; group `egroup` owns output channels [16*egroup, 16*egroup+16) of the
         // CTA's 32 (16-wide blocks, i.e. the 1-channel head: group 0 owns all of them, group 1 only keeps the barrier count).
         // P0 / P1: running sums of the two open planes (z and z+1 after step z).

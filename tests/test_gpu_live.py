@@ -277,7 +277,7 @@ def test_feature_extraction_native_kernels_match_reference(lib):
     with torch.no_grad():
         via_torch = fe(x.cuda()).cpu().numpy()
     fe.native = True
-    assert np.abs(via_torch - want).max() < 2e-4
+    assert np.abs(via_torch - want).max() < 1e-3   # (cuDNN picks its own algorithms: Winograd variants sit a few 1e-4 from the direct sum)
     with pytest.raises(RuntimeError, match='56x56'):
         fe(torch.zeros(1, 3, 128, 128).cuda())                             # feature map smaller than branch1's pool
     with pytest.raises(RuntimeError, match='no CPU path'):
