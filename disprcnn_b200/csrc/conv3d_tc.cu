@@ -55,6 +55,9 @@ namespace idisp {
 #ifndef IDISP_MRG
 #define IDISP_MRG 1  // TRI kernels with both weight words resident: x_hi feeds [w_hi | w_lo] in ONE N=192 MMA (see Cfg::MRG)
 #endif
+#ifndef IDISP_TRI_EG
+#define IDISP_TRI_EG 4  // epilogue groups (of 4 warps) of the per-step-triple kernels with 32-wide blocks: 4 x 8 channels or 2 x 16
+#endif
 #ifndef IDISP_NMAIN
 #define IDISP_NMAIN 3  // accumulator banks of the main term in the split-precision kernels (see Cfg)
 #endif
@@ -111,7 +114,11 @@ template <int CIN, int MODE, int OCC, int NT, int XM = 0> struct Cfg {
   static constexpr int ACC_COLS = MC::ACC_BLOCKS * NT;   // TMEM columns of one output plane
   static constexpr int WCHUNK = 2 * 3 * NT * 16;          // B operand of one (kh,kw,kstep): [2 kcores][3 blocks x NT rows][8] bf16
   static_assert(MODE != M_DEC || NT == 32 || NT == 16, "the transposed-conv stacking table scales from 32-wide blocks");
-  static constexpr int EGROUPS = OCC == 2 ? 1 : 2;        // epilogue groups of 4 warps (alternate output planes)
+  // epilogue groups of 4 warps.  Plane-ring kernels: the groups take alternate output planes.  Per-step-triple kernels: every
+  // group drains every step and owns 32/EGROUPS of the block's channels -- four groups, because the epilogue of a step is a
+  // dependent instruction chain per warp (TMEM loads -> sums -> pack -> stores) that must stay shorter than the step's MMA
+  // stream (measured: 2 groups x 16 channels 1.85 ms per 32->32 layer against 1.50 ms for the MMA stream alone)
+  static constexpr int EGROUPS = OCC == 2 ? 1 : ((TRI && NT == 32) ? IDISP_TRI_EG : 2);
   static constexpr int NTHREADS = 128 + 128 * EGROUPS;    // warps 0-3: TMA producer / MMA issuer / TMEM allocator / idle
   static constexpr int TCOLS = 512 / OCC;                 // TMEM columns of this CTA
   static constexpr int KS = CIN / 16;    // K=16 MMAs per tap
@@ -206,7 +213,7 @@ __device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t byte_off) { re
 
 // FMT: 0 bf16, 1 IEEE half, 2 IEEE half split-precision pass (plain K), 3 / 4 the same with in-launch K concatenation XP = 1 / 2
 template <int CIN, int MODE, int OCC, bool CV, int NT, int FMT>
-__global__ void __launch_bounds__((Cfg<CIN, MODE, OCC, NT>::NTHREADS), OCC)
+__global__ void __launch_bounds__((Cfg<CIN, MODE, OCC, NT, (FMT < 2 ? 0 : (FMT == 2 ? 3 : FMT - 2))>::NTHREADS), OCC)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap rmap,
                  const __grid_constant__ CvMaps<CV> lmaps, const Params p)
 {
@@ -617,13 +624,14 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       };
       if constexpr (C::TRI && NT == 32) {
         // ---- per-step triples, 32-wide blocks (every stride-1 split-precision layer) ----
-        // Both epilogue groups drain EVERY step's triple; group `egroup` owns output channels [16*egroup, 16*egroup+16) = channel
-        // blocks cbg0, cbg0+1.  Measured (IDISP_TC_DBG=32/28): with the epilogue reduced to its barrier handshake a 32->32 layer
+        // All EGROUPS epilogue groups drain EVERY step's triple; group `egroup` owns CPG = 32/EGROUPS output channels = NCBG channel
+        // blocks starting at cbg0.  Measured (IDISP_TC_DBG=32/28): with the epilogue reduced to its barrier handshake a 32->32 layer
         // runs at the MMA stream's 1.54 ms, with it at 2.2 ms, and neither the TMEM traffic nor the global stores matter -- the
         // epilogue's INSTRUCTION count is the limiter.  So: all per-column addressing is hoisted out of the step loop (plane
         // strides are added to running offsets), nothing is zeroed on drain (the first MMA of a step overwrites), the half-range
         // test works on the packed words.
-        const int cbg0 = nh * 4 + egroup * 2;
+        constexpr int CPG = 32 / C::EGROUPS, NCBG = CPG / 8;   // channels / channel blocks per epilogue group
+        const int cbg0 = nh * 4 + egroup * NCBG;
         const int64_t blk_elems = Vo * 8;                                   // one channel block, either layout (8 * sub = Vo)
         const int64_t lo_off = (int64_t)cblk_out * blk_elems;               // hi word -> lo word
         const int64_t col_blk = ((int64_t)n * out_blocks + cbg0) * blk_elems;
@@ -632,17 +640,17 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         const int64_t spl0 = col_blk + ((int64_t)((hr & 1) * 2 + (wr & 1)) * sub + (int64_t)(hr >> 1) * (p.Wo / 2) + (wr >> 1)) * 8;  // parity layout, plane 0
         const int64_t part0 = (((int64_t)n * cblk_out + cbg0) * Vo + (int64_t)hr * p.Wo + wr) * 8;   // fp32 partial (natural), plane 0
         const bool has_res = p.residual != nullptr, has_part = p.part_in != nullptr, out_x2 = p.x2 != 0;
-        float P0[16], P1[16];
+        float P0[CPG], P1[CPG];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { P0[i] = 0.f; P1[i] = 0.f; }
+        for (int i = 0; i < CPG; ++i) { P0[i] = 0.f; P1[i] = 0.f; }
         bool bad = false;
         // element offset of plane q inside a channel block
         auto nat_of = [&](int q) { return nat0 + (int64_t)q * plane_nat; };
         auto spl_of = [&](int q) { return spl0 + (int64_t)(q & 1) * 4 * sub * 8 + (int64_t)(q >> 1) * plane_spl; };
-        auto emit = [&](int q, const float (&sum)[16], const XPre (&xq)[2]) {
+        auto emit = [&](int q, const float (&sum)[CPG], const XPre (&xq)[NCBG]) {
           const int64_t onat = nat_of(q), ospl = spl_of(q);
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
+          for (int i = 0; i < NCBG; ++i) {
             float a[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) a[c] = sum[i * 8 + c];
@@ -657,7 +665,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               continue;
             }
 #pragma unroll
-            for (int c = 0; c < 8; ++c) a[c] += bias_s[egroup * 16 + i * 8 + c];
+            for (int c = 0; c < 8; ++c) a[c] += bias_s[egroup * CPG + i * 8 + c];
             if (has_res) {
               const F8 rh = unpack8h<F16>(xq[i].rh);
 #pragma unroll
@@ -694,10 +702,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             }
           }
         };
-        auto xload2 = [&](XPre (&xq)[2], int q) {
+        auto xload2 = [&](XPre (&xq)[NCBG], int q) {
           if (has_part) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < NCBG; ++i) {
               const float4 *pp = reinterpret_cast<const float4 *>(p.part_in + part0 + (int64_t)q * plane_nat + (int64_t)i * blk_elems);
               xq[i].p0 = __ldg(pp); xq[i].p1 = __ldg(pp + 1);
             }
@@ -705,7 +713,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           if (has_res) {
             const int64_t ro = p.residual_is_split ? spl_of(q) : nat_of(q);
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < NCBG; ++i) {
               xq[i].rh = __ldg(reinterpret_cast<const uint4 *>(p.residual + ro + (int64_t)i * blk_elems));
               xq[i].rl = out_x2 ? __ldg(reinterpret_cast<const uint4 *>(p.residual + ro + (int64_t)i * blk_elems + lo_off)) : make_uint4(0u, 0u, 0u, 0u);
             }
@@ -713,7 +721,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         };
         for (int z = 0; z < Dout; ++z, ++tq) {
           const uint32_t t = tq % NSLOT;
-          XPre xq[2];
+          XPre xq[NCBG];
           if (valid && z >= 1) xload2(xq, z - 1);      // operands of the plane this step completes: requested before the wait
           ptx::mbar_wait(accf_bar(t), (tq / NSLOT) & 1);
           ptx::tc_fence_after();
@@ -723,44 +731,44 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             if (lane == 0) ptx::mbar_arrive(acce_bar(t));
             continue;
           }
-          const uint32_t tb = tmem_base + lane_addr + t * C::TRI_STRIDE + egroup * 16;
+          const uint32_t tb = tmem_base + lane_addr + t * C::TRI_STRIDE + egroup * CPG;
           // plane z-1 = P0 + block 0 (complete);  plane z: P1 + block 1;  plane z+1: block 2 (first contribution).
           // Two TMEM round trips (blocks 0+1, then block 2) keep the live registers under the 168-register cap; the
           // correction triple (x_lo*w_hi + x_hi*w_lo) is summed with the main one in fp32 round-to-nearest.
-          float N0[16];   // next step's P0 = plane z so far
+          float N0[CPG];   // next step's P0 = plane z so far
           {
-            uint32_t b0[16], b1[16];
-            ptx::tmem_ld_32x16(tb, b0);
-            ptx::tmem_ld_32x16(tb + NT, b1);
+            uint32_t b0[CPG], b1[CPG];
+            ptx::tmem_ld_cols(tb, b0);
+            ptx::tmem_ld_cols(tb + NT, b1);
             if (XP != 0) {
-              uint32_t u0[16], u1[16];
-              ptx::tmem_ld_32x16(tb + C::TRI_SMALL, u0);
-              ptx::tmem_ld_32x16(tb + C::TRI_SMALL + NT, u1);
+              uint32_t u0[CPG], u1[CPG];
+              ptx::tmem_ld_cols(tb + C::TRI_SMALL, u0);
+              ptx::tmem_ld_cols(tb + C::TRI_SMALL + NT, u1);
               ptx::tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
+              for (int i = 0; i < CPG; ++i) {
                 P0[i] += __uint_as_float(b0[i]) + __uint_as_float(u0[i]);
                 N0[i] = P1[i] + (__uint_as_float(b1[i]) + __uint_as_float(u1[i]));
               }
             } else {
               ptx::tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) { P0[i] += __uint_as_float(b0[i]); N0[i] = P1[i] + __uint_as_float(b1[i]); }
+              for (int i = 0; i < CPG; ++i) { P0[i] += __uint_as_float(b0[i]); N0[i] = P1[i] + __uint_as_float(b1[i]); }
             }
           }
           {
-            uint32_t b2[16];
-            ptx::tmem_ld_32x16(tb + 2 * NT, b2);
+            uint32_t b2[CPG];
+            ptx::tmem_ld_cols(tb + 2 * NT, b2);
             if (XP != 0) {
-              uint32_t u2[16];
-              ptx::tmem_ld_32x16(tb + C::TRI_SMALL + 2 * NT, u2);
+              uint32_t u2[CPG];
+              ptx::tmem_ld_cols(tb + C::TRI_SMALL + 2 * NT, u2);
               ptx::tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) P1[i] = __uint_as_float(b2[i]) + __uint_as_float(u2[i]);
+              for (int i = 0; i < CPG; ++i) P1[i] = __uint_as_float(b2[i]) + __uint_as_float(u2[i]);
             } else {
               ptx::tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) P1[i] = __uint_as_float(b2[i]);
+              for (int i = 0; i < CPG; ++i) P1[i] = __uint_as_float(b2[i]);
             }
           }
           ptx::tc_fence_before();
@@ -768,14 +776,14 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           if (lane == 0) ptx::mbar_arrive(acce_bar(t));   // the MMA warp may overwrite this buffer (first MMA of a step: accumulate = 0)
           if (z >= 1 && valid) emit(z - 1, P0, xq);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) P0[i] = N0[i];
+          for (int i = 0; i < CPG; ++i) P0[i] = N0[i];
           if (z == Dout - 1) {  // no step z+1: plane z is complete as well
             if (valid) {
               xload2(xq, z);
               emit(z, P0, xq);
             }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { P0[i] = 0.f; P1[i] = 0.f; }
+            for (int i = 0; i < CPG; ++i) { P0[i] = 0.f; P1[i] = 0.f; }
           }
         }
         if (bad && p.range_flag) *p.range_flag = 1;
@@ -921,7 +929,109 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         }
         ptx::mbar_wait(accf_bar(r), (g / NSLOT) & 1);
         ptx::tc_fence_after();
-        if (MODE == M_DEC && X2) {
+        if constexpr (MODE == M_DEC && X2 && NT == 16) {
+          // Split-precision transposed conv (16-wide blocks): the whole output plane (4 parity classes x 16 channels) is drained
+          // and the slot released in ONE TMEM round trip; addressing is hoisted (per column / per plane), the per-voxel work is
+          // the lean fin2 (IDISP_TC_DBG ablations: this epilogue, not the MMA stream, bounded the layer: 2.1 ms without any MMA).
+          uint32_t v[64];
+          {
+            const uint32_t t0 = tmem_base + lane_addr + r * C::ACC_COLS;
+            uint32_t a16[16];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {   // column block of class (ph, pw) = pw*2 + ph
+              ptx::tmem_ld_32x16(t0 + c4 * NT, a16);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[c4 * 16 + i] = a16[i];
+              ptx::tmem_st_32x16(t0 + c4 * NT, zero);
+            }
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(acce_bar(r));
+          }
+          if (valid && !(p.dbg & 4)) {
+            const int64_t blk_elems = Vo * 8, lo_off = (int64_t)cblk_out * blk_elems;
+            const int64_t col_blk = ((int64_t)n * out_blocks + nh * 2) * blk_elems;
+            const int64_t natq = col_blk + (((int64_t)qo * p.Ho + 2 * hr) * p.Wo + 2 * wr) * 8;
+            const int64_t splq = col_blk + ((int64_t)(qo & 1) * 4 * sub + ((int64_t)(qo >> 1) * (p.Ho / 2) + hr) * (p.Wo / 2) + wr) * 8;
+            const int64_t partq = (((int64_t)n * cblk_out + nh * 2) * Vo + ((int64_t)qo * p.Ho + 2 * hr) * p.Wo + 2 * wr) * 8;
+            const bool has_res = p.residual != nullptr, has_part = p.part_in != nullptr, out_x2 = p.x2 != 0;
+            bool bad = false;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const int ph = c4 >> 1, pw = c4 & 1, cblock = pw * 2 + ph;
+              const int64_t onat = natq + ((int64_t)ph * p.Wo + pw) * 8, ospl = splq + (int64_t)(ph * 2 + pw) * sub * 8;
+              const int64_t opart = partq + ((int64_t)ph * p.Wo + pw) * 8;
+              XPre dq[2];
+#pragma unroll
+              for (int cb = 0; cb < 2; ++cb) {
+                if (has_part) {
+                  const float4 *pp = reinterpret_cast<const float4 *>(p.part_in + opart + (int64_t)cb * blk_elems);
+                  dq[cb].p0 = __ldg(pp); dq[cb].p1 = __ldg(pp + 1);
+                }
+                if (has_res) {
+                  const int64_t ro = (p.residual_is_split ? ospl : onat) + (int64_t)cb * blk_elems;
+                  dq[cb].rh = __ldg(reinterpret_cast<const uint4 *>(p.residual + ro));
+                  dq[cb].rl = out_x2 ? __ldg(reinterpret_cast<const uint4 *>(p.residual + ro + lo_off)) : make_uint4(0u, 0u, 0u, 0u);
+                }
+              }
+#pragma unroll
+              for (int cb = 0; cb < 2; ++cb) {
+                float a[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) a[c] = __uint_as_float(v[cblock * 16 + cb * 8 + c]);
+                if (has_part) {
+                  a[0] += dq[cb].p0.x; a[1] += dq[cb].p0.y; a[2] += dq[cb].p0.z; a[3] += dq[cb].p0.w;
+                  a[4] += dq[cb].p1.x; a[5] += dq[cb].p1.y; a[6] += dq[cb].p1.z; a[7] += dq[cb].p1.w;
+                }
+                if (p.part_out) {
+                  float4 *po = reinterpret_cast<float4 *>(p.part_out + opart + (int64_t)cb * blk_elems);
+                  po[0] = make_float4(a[0], a[1], a[2], a[3]);
+                  po[1] = make_float4(a[4], a[5], a[6], a[7]);
+                  continue;
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) a[c] += bias_s[cb * 8 + c];
+                if (has_res) {
+                  const F8 rh = unpack8h<F16>(dq[cb].rh);
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) a[c] += rh.v[c];
+                  if (out_x2) {
+                    const F8 rl = unpack8h<F16>(dq[cb].rl);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) a[c] += rl.v[c];
+                  }
+                }
+                if (p.relu) {
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) a[c] = fmaxf(a[c], 0.f);
+                }
+                F8 f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) f.v[c] = a[c];
+                const uint4 hi = pack8h<F16>(f);
+                {  // a half whose exponent field is all ones: the value left the IEEE-half range (or was NaN)
+                  const uint32_t mm = ((hi.x & 0x7fff7fffu) + 0x04000400u) | ((hi.y & 0x7fff7fffu) + 0x04000400u) |
+                                      ((hi.z & 0x7fff7fffu) + 0x04000400u) | ((hi.w & 0x7fff7fffu) + 0x04000400u);
+                  bad |= (mm & 0x80008000u) != 0;
+                }
+                const int64_t bo = (int64_t)cb * blk_elems;
+                if (!p.skip_y) *reinterpret_cast<uint4 *>(p.y + onat + bo) = hi;
+                if (p.y_split) *reinterpret_cast<uint4 *>(p.y_split + ospl + bo) = hi;
+                if (out_x2) {
+                  const F8 h = unpack8h<F16>(hi);
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) f.v[c] -= h.v[c];
+                  const uint4 lo = pack8h<F16>(f);
+                  if (!p.skip_y) *reinterpret_cast<uint4 *>(p.y + onat + bo + lo_off) = lo;
+                  if (p.y_split) *reinterpret_cast<uint4 *>(p.y_split + ospl + bo + lo_off) = lo;
+                }
+              }
+            }
+            if (bad && p.range_flag) *p.range_flag = 1;
+          }
+        } else if (MODE == M_DEC && X2) {
           // split-precision pass: one parity class (32 accumulator columns, column block = pw*2 + ph) at a time; its
           // partial / residual operands are requested as one batch before the TMEM read
 #pragma unroll
