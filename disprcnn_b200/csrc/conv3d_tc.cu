@@ -56,7 +56,7 @@ namespace idisp {
 #define IDISP_MRG 1  // TRI kernels with both weight words resident: x_hi feeds [w_hi | w_lo] in ONE N=192 MMA (see Cfg::MRG)
 #endif
 #ifndef IDISP_TRI_EG
-#define IDISP_TRI_EG 4  // epilogue groups (of 4 warps) of the per-step-triple kernels with 32-wide blocks: 4 x 8 channels or 2 x 16
+#define IDISP_TRI_EG 2  // epilogue groups (of 4 warps) of the per-step-triple kernels with 32-wide blocks: 4 x 8 channels or 2 x 16
 #endif
 #ifndef IDISP_NMAIN
 #define IDISP_NMAIN 3  // accumulator banks of the main term in the split-precision kernels (see Cfg)
@@ -116,8 +116,9 @@ template <int CIN, int MODE, int OCC, int NT, int XM = 0> struct Cfg {
   static_assert(MODE != M_DEC || NT == 32 || NT == 16, "the transposed-conv stacking table scales from 32-wide blocks");
   // epilogue groups of 4 warps.  Plane-ring kernels: the groups take alternate output planes.  Per-step-triple kernels: every
   // group drains every step and owns 32/EGROUPS of the block's channels -- four groups, because the epilogue of a step is a
-  // dependent instruction chain per warp (TMEM loads -> sums -> pack -> stores) that must stay shorter than the step's MMA
-  // stream (measured: 2 groups x 16 channels 1.85 ms per 32->32 layer against 1.50 ms for the MMA stream alone)
+  // dependent instruction chain per warp (TMEM loads -> sums -> pack -> stores).  Measured per 32->32 layer: 2 groups x 16
+  // channels 1.87 ms, 4 groups x 8 channels 2.07 ms (MMA stream alone: 1.50 ms) -- more epilogue warps take issue slots from
+  // the MMA warp's scheduler, so two groups it is
   static constexpr int EGROUPS = OCC == 2 ? 1 : ((TRI && NT == 32) ? IDISP_TRI_EG : 2);
   static constexpr int NTHREADS = 128 + 128 * EGROUPS;    // warps 0-3: TMA producer / MMA issuer / TMEM allocator / idle
   static constexpr int TCOLS = 512 / OCC;                 // TMEM columns of this CTA
@@ -164,7 +165,7 @@ struct Params {
   int B, Din, Dout, Ho, Wo, Hr, Wr, Cout, relu;  // (Hr,Wr): row grid the 8x16 tiles cover
   int tiles_h, tiles_w, nh;
   int cv_shift0;                  // mindisp/4: plane k <-> right-view shift i = k + cv_shift0
-  int dbg;                        // timing experiments only (IDISP_TC_DBG): 1 no MMAs, 2 no TMA loads, 4 no global stores, 8 no tcgen05.ld, 16 no tcgen05.st, 32 TRI epilogue = handshake only
+  int dbg;                        // timing experiments only (IDISP_TC_DBG): 1 no MMAs, 2 no TMA loads, 4 no global stores, 8 no tcgen05.ld, 16 no tcgen05.st, 32 TRI epilogue = handshake only, 64 TRI epilogue without the per-voxel work, 128 TRI epilogue without TMEM reads
 };
 
 // DECONV stacking table: per kd, five MMAs (entries) that share an input shift
@@ -732,6 +733,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             continue;
           }
           const uint32_t tb = tmem_base + lane_addr + t * C::TRI_STRIDE + egroup * CPG;
+          if (p.dbg & 128) {  // timing experiment: no TMEM reads, the arithmetic and the stores run on whatever the registers hold
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(acce_bar(t));
+            if (z >= 1 && valid) emit(z - 1, P0, xq);
+            continue;
+          }
           // plane z-1 = P0 + block 0 (complete);  plane z: P1 + block 1;  plane z+1: block 2 (first contribution).
           // Two TMEM round trips (blocks 0+1, then block 2) keep the live registers under the 168-register cap; the
           // correction triple (x_lo*w_hi + x_hi*w_lo) is summed with the main one in fp32 round-to-nearest.
@@ -774,7 +782,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(acce_bar(t));   // the MMA warp may overwrite this buffer (first MMA of a step: accumulate = 0)
-          if (z >= 1 && valid) emit(z - 1, P0, xq);
+          if (z >= 1 && valid && !(p.dbg & 64)) emit(z - 1, P0, xq);   // (64: timing experiment without the per-voxel work)
 #pragma unroll
           for (int i = 0; i < CPG; ++i) P0[i] = N0[i];
           if (z == Dout - 1) {  // no step z+1: plane z is complete as well

@@ -9,8 +9,10 @@
 //     out[z, y, x] = sum_{kd,kh,kw} P[(z + kd - 1, y + kh - 1, x + kw - 1), (kd, kh, kw)]
 // i.e. every input voxel is multiplied with all 27 taps at once (4 MMAs per k-step pair instead of 36) and the epilogue adds
 // each product to the output voxel it belongs to: in-plane through shared memory, across planes through three rolling
-// register sums.  Split precision (fp16x2): x_hi feeds [w_hi | w_lo] in one N = 64 MMA, x_lo feeds w_hi (N = 32); the three
-// partial products land in separate TMEM column groups (two adds per column) and are summed in fp32 round-to-nearest.
+// register sums.  Split precision (fp16x2): x_hi feeds [w_hi | w_lo] in one N = 64 MMA, x_lo feeds w_hi (N = 32, added into the
+// x_hi*w_lo columns: both are 2^-11-sized correction terms, four adds per column); main and correction columns are summed in
+// fp32 round-to-nearest.  The epilogue is bounded by the TMEM read port (64 B/clk: /opt/skills/guides/B300_MICROARCH.md), so it
+// reads as few columns as it can: 64 per M half, and the warps whose rows lie beyond the 180 haloed voxels read nothing.
 //
 // Tiling: a CTA walks one (n, 16-row, 8-column) output tile through all D planes.  Its haloed input tile is 18 x 10 = 180
 // voxels = GEMM rows 0..179, i.e. two M = 128 MMAs per operand pair (rows >= 180 read whatever follows in shared memory and
@@ -35,7 +37,7 @@ constexpr int SROW = 184;                                   // padded row length
 template <bool X2> struct Cfg {
   static constexpr int AW = X2 ? 2 : 1;                     // activation words
   static constexpr int NB = X2 ? 64 : 32;                   // B rows (taps, hi | lo)
-  static constexpr int GCOLS = X2 ? 96 : 32;                // TMEM columns of one M half: [main 32 | x_hi*w_lo 32 | x_lo*w_hi 32]
+  static constexpr int GCOLS = X2 ? 64 : 32;                // TMEM columns of one M half: [main 32 | corrections (x_hi*w_lo + x_lo*w_hi) 32]
   static constexpr int PCOLS = 2 * GCOLS;                   // one plane buffer (two M halves)
   static constexpr int WBYTES = 2 * 2 * NB * 16;            // [2 k-steps][2 kcores][NB rows][8] 16-bit
   static constexpr int STAGE_BYTES = AW * 4 * PLANE_BYTES;  // 4 channel blocks per word
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(256, 1) head_tc_kernel(const __grid_constant__
             if (lead) ptx::umma_bf16_ss(d, a_hi, b, idm, ks);                      // x_hi * [w_hi | w_lo]
             if (X2) {
               const uint64_t a_lo = a0 + (uint64_t)(((4 + 2 * ks) * PLANE_BYTES + h * 2048) >> 4);
-              if (lead) ptx::umma_bf16_ss(d + 64, a_lo, b, ids, ks);               // x_lo * w_hi
+              if (lead) ptx::umma_bf16_ss(d + 32, a_lo, b, ids, 1u);               // x_lo * w_hi, into the correction columns
             }
           }
         }
@@ -161,20 +163,20 @@ __global__ void __launch_bounds__(256, 1) head_tc_kernel(const __grid_constant__
         asm volatile("bar.sync 1, 128;" ::: "memory");     // everyone is done reading S of the previous plane
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+          const int vox = h * 128 + et;
+          if (h * 128 + (warp & 3) * 32 >= NVOX) continue;   // (warp-uniform) this warp's 32 rows lie beyond the haloed tile: nothing to read
           const uint32_t ta = tmem_base + lane_addr + t * C::PCOLS + h * C::GCOLS;
           uint32_t v[32];
           ptx::tmem_ld_32x32(ta, v);
           if (X2) {
-            uint32_t u[32], x[32];
+            uint32_t u[32];
             ptx::tmem_ld_32x32(ta + 32, u);
-            ptx::tmem_ld_32x32(ta + 64, x);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 27; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + (__uint_as_float(u[j]) + __uint_as_float(x[j])));
+            for (int j = 0; j < 27; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
           } else {
             ptx::tmem_ld_wait();
           }
-          const int vox = h * 128 + et;
           if (vox < NVOX) {
 #pragma unroll
             for (int j = 0; j < 27; ++j) S[j * SROW + vox] = __uint_as_float(v[j]);
