@@ -85,6 +85,8 @@ PROTOTYPES = {
     'idisp_roi_align_forward': (_i, [_vp, _i, _i, _i, _i, _vp, _i, _f, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'idisp_roi_align_backward': (_i, [_vp, _vp, _i, _f, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     'idisp_stereo_rois': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    'idisp_roi_disparity_paste': (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp]),
+    'idisp_roi_depth_paste': (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     'idisp_cost_volume': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     'idisp_conv3d': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     'idisp_softargmin': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),

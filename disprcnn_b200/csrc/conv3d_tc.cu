@@ -905,7 +905,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
           for (int cb = 0; cb < NXQ; ++cb) xload(xq[cb], cb, pos, (qo & 1) * 4 + (hr & 1) * 2 + (wr & 1), sidx);
         }
-        if (MODE == M_DEC && X2 && valid && (p.part_in || p.residual)) {
+        constexpr bool DEC_LEAN = MODE == M_DEC && X2 && NT == 16;   // (this form loads its operands itself, before the wait: below)
+        if (MODE == M_DEC && X2 && !DEC_LEAN && valid && (p.part_in || p.residual)) {
           // the plane's 16 voxel blocks per thread are consumed class by class below; ask L2 for all of them now
 #pragma unroll
           for (int i = 0; i < 4 * (NT / 8); ++i) {
@@ -935,29 +936,16 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             resv[i] = __ldg(reinterpret_cast<const uint4 *>(p.residual + ro));
           }
         }
-        ptx::mbar_wait(accf_bar(r), (g / NSLOT) & 1);
-        ptx::tc_fence_after();
-        if constexpr (MODE == M_DEC && X2 && NT == 16) {
-          // Split-precision transposed conv (16-wide blocks): the whole output plane (4 parity classes x 16 channels) is drained
-          // and the slot released in ONE TMEM round trip; addressing is hoisted (per column / per plane), the per-voxel work is
-          // the lean fin2 (IDISP_TC_DBG ablations: this epilogue, not the MMA stream, bounded the layer: 2.1 ms without any MMA).
-          uint32_t v[64];
-          {
-            const uint32_t t0 = tmem_base + lane_addr + r * C::ACC_COLS;
-            uint32_t a16[16];
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {   // column block of class (ph, pw) = pw*2 + ph
-              ptx::tmem_ld_32x16(t0 + c4 * NT, a16);
-              ptx::tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[c4 * 16 + i] = a16[i];
-              ptx::tmem_st_32x16(t0 + c4 * NT, zero);
-            }
-            ptx::tmem_st_wait();
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(acce_bar(r));
-          }
+        if constexpr (!DEC_LEAN) {
+          ptx::mbar_wait(accf_bar(r), (g / NSLOT) & 1);
+          ptx::tc_fence_after();
+        }
+        if constexpr (DEC_LEAN) {
+          // Split-precision transposed conv (16-wide blocks).  The epilogue, not the MMA stream, bounds this layer (2.1 ms without
+          // any MMA against 1.5 ms for the MMA stream alone, IDISP_TC_DBG ablations), and inside it the chain "load the residual
+          // words of a parity class -> wait -> finish -> next class" was serialised on L2 / DRAM latency.  So: the operands of ALL
+          // four classes (16 x 16 B per thread) are requested before the accumulator is even waited for (see below the wait),
+          // addressing is hoisted, the per-voxel work is the lean form.
           if (valid && !(p.dbg & 4)) {
             const int64_t blk_elems = Vo * 8, lo_off = (int64_t)cblk_out * blk_elems;
             const int64_t col_blk = ((int64_t)n * out_blocks + nh * 2) * blk_elems;
@@ -966,32 +954,47 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             const int64_t partq = (((int64_t)n * cblk_out + nh * 2) * Vo + ((int64_t)qo * p.Ho + 2 * hr) * p.Wo + 2 * wr) * 8;
             const bool has_res = p.residual != nullptr, has_part = p.part_in != nullptr, out_x2 = p.x2 != 0;
             bool bad = false;
+            uint4 rh[4][2], rl[4][2];   // residual words of the 4 classes x 2 channel blocks
+            if (has_res) {
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              const int ph = c4 >> 1, pw = c4 & 1, cblock = pw * 2 + ph;
-              const int64_t onat = natq + ((int64_t)ph * p.Wo + pw) * 8, ospl = splq + (int64_t)(ph * 2 + pw) * sub * 8;
-              const int64_t opart = partq + ((int64_t)ph * p.Wo + pw) * 8;
-              XPre dq[2];
+              for (int c4 = 0; c4 < 4; ++c4) {
+                const int ph = c4 >> 1, pw = c4 & 1;
+                const int64_t ro = p.residual_is_split ? splq + (int64_t)(ph * 2 + pw) * sub * 8 : natq + ((int64_t)ph * p.Wo + pw) * 8;
 #pragma unroll
-              for (int cb = 0; cb < 2; ++cb) {
-                if (has_part) {
-                  const float4 *pp = reinterpret_cast<const float4 *>(p.part_in + opart + (int64_t)cb * blk_elems);
-                  dq[cb].p0 = __ldg(pp); dq[cb].p1 = __ldg(pp + 1);
-                }
-                if (has_res) {
-                  const int64_t ro = (p.residual_is_split ? ospl : onat) + (int64_t)cb * blk_elems;
-                  dq[cb].rh = __ldg(reinterpret_cast<const uint4 *>(p.residual + ro));
-                  dq[cb].rl = out_x2 ? __ldg(reinterpret_cast<const uint4 *>(p.residual + ro + lo_off)) : make_uint4(0u, 0u, 0u, 0u);
+                for (int cb = 0; cb < 2; ++cb) {
+                  rh[c4][cb] = __ldg(reinterpret_cast<const uint4 *>(p.residual + ro + (int64_t)cb * blk_elems));
+                  rl[c4][cb] = out_x2 ? __ldg(reinterpret_cast<const uint4 *>(p.residual + ro + (int64_t)cb * blk_elems + lo_off)) : make_uint4(0u, 0u, 0u, 0u);
                 }
               }
+            }
+            ptx::mbar_wait(accf_bar(r), (g / NSLOT) & 1);
+            ptx::tc_fence_after();
+            const uint32_t t0 = tmem_base + lane_addr + r * C::ACC_COLS;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const int ph = c4 >> 1, pw = c4 & 1, cblock = pw * 2 + ph;   // accumulator column block of class (ph, pw)
+              uint32_t v[16];
+              ptx::tmem_ld_32x16(t0 + cblock * NT, v);
+              ptx::tmem_ld_wait();
+              ptx::tmem_st_32x16(t0 + cblock * NT, zero);
+              if (c4 == 3) {
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(acce_bar(r));
+              }
+              const int64_t onat = natq + ((int64_t)ph * p.Wo + pw) * 8, ospl = splq + (int64_t)(ph * 2 + pw) * sub * 8;
+              const int64_t opart = partq + ((int64_t)ph * p.Wo + pw) * 8;
 #pragma unroll
               for (int cb = 0; cb < 2; ++cb) {
                 float a[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) a[c] = __uint_as_float(v[cblock * 16 + cb * 8 + c]);
+                for (int c = 0; c < 8; ++c) a[c] = __uint_as_float(v[cb * 8 + c]);
                 if (has_part) {
-                  a[0] += dq[cb].p0.x; a[1] += dq[cb].p0.y; a[2] += dq[cb].p0.z; a[3] += dq[cb].p0.w;
-                  a[4] += dq[cb].p1.x; a[5] += dq[cb].p1.y; a[6] += dq[cb].p1.z; a[7] += dq[cb].p1.w;
+                  const float4 *pp = reinterpret_cast<const float4 *>(p.part_in + opart + (int64_t)cb * blk_elems);
+                  const float4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+                  a[0] += p0.x; a[1] += p0.y; a[2] += p0.z; a[3] += p0.w;
+                  a[4] += p1.x; a[5] += p1.y; a[6] += p1.z; a[7] += p1.w;
                 }
                 if (p.part_out) {
                   float4 *po = reinterpret_cast<float4 *>(p.part_out + opart + (int64_t)cb * blk_elems);
@@ -1002,13 +1005,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
                 for (int c = 0; c < 8; ++c) a[c] += bias_s[cb * 8 + c];
                 if (has_res) {
-                  const F8 rh = unpack8h<F16>(dq[cb].rh);
+                  const F8 r0 = unpack8h<F16>(rh[c4][cb]);
 #pragma unroll
-                  for (int c = 0; c < 8; ++c) a[c] += rh.v[c];
+                  for (int c = 0; c < 8; ++c) a[c] += r0.v[c];
                   if (out_x2) {
-                    const F8 rl = unpack8h<F16>(dq[cb].rl);
+                    const F8 r1 = unpack8h<F16>(rl[c4][cb]);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) a[c] += rl.v[c];
+                    for (int c = 0; c < 8; ++c) a[c] += r1.v[c];
                   }
                 }
                 if (p.relu) {
@@ -1038,6 +1041,16 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               }
             }
             if (bad && p.range_flag) *p.range_flag = 1;
+          } else {   // rows outside the volume (or the no-store timing experiment): drain and release only
+            ptx::mbar_wait(accf_bar(r), (g / NSLOT) & 1);
+            ptx::tc_fence_after();
+            const uint32_t t0 = tmem_base + lane_addr + r * C::ACC_COLS;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) ptx::tmem_st_32x16(t0 + c4 * NT, zero);
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(acce_bar(r));
           }
         } else if (MODE == M_DEC && X2) {
           // split-precision pass: one parity class (32 accumulator columns, column block = pw*2 + ph) at a time; its

@@ -84,6 +84,21 @@ int idisp_stereo_rois(const float *left_boxes, const float *right_boxes, const i
                       const int *image_wh, int n_images, float *rois_left, float *rois_right, long long *x1_x1p_x2_x2p,
                       void *stream);
 
+/* Hand-off of the per-ROI disparity maps iDispNet returns.  roi_disp [R,S,S] f32; left_boxes / right_boxes
+ * [R,4] f32 -- device pointers; boxes are expanded to integers like utils/stereo_utils.py:219-229 and must lie inside the image.
+ * Per ROI (disprcnn/structures/disparity.py:39-78 DisparityMap.resize / crop as called at disprcnn3d.py:173-175): bilinear
+ * align_corners=True resize of its map to (y2-y1, max(x2-x1, x2p-x1p)), value / S * width, crop to x2-x1 columns, + (x1 - x1p).
+ *   idisp_roi_disparity_paste (DispRCNN3D.roi_disp_postprocess, disprcnn3d.py:161-190): clamp at 0, multiply by the ROI's mask
+ *     (masks: [R,H,W] uint8 0/1 or NULL), out [N,H,W] = maximum over the image's ROIs (0 where there is none);
+ *     roi_start: device int32 [N+1], ROIs roi_start[n] .. roi_start[n+1]-1 belong to image n.
+ *   idisp_roi_depth_paste (PointRCNN.process_input, modeling/pointnet_module/point_rcnn/lib/net/point_rcnn.py:113-136):
+ *     out [R,H,W] = fu_baseline[r] / (disp + 1e-6) inside the ROI's box, 0 elsewhere.
+ * Agreement with the reference: fp32 rounding of the interpolation (tests: 2e-5 abs / 1e-5 rel). */
+int idisp_roi_disparity_paste(const float *roi_disp, int R, int S, const float *left_boxes, const float *right_boxes,
+                              const int *roi_start, int N, const unsigned char *masks, int H, int W, float *out, void *stream);
+int idisp_roi_depth_paste(const float *roi_disp, int R, int S, const float *left_boxes, const float *right_boxes,
+                          const float *fu_baseline, int H, int W, float *out, void *stream);
+
 /* ROIAlign forward.  input [N,C,H,W] f32 NCHW contiguous, rois [R,5] f32
  * (batch_idx,x1,y1,x2,y2), out [R,C,pooled_h,pooled_w] f32 -- all device pointers.
  * mean/inv_std: optional device pointers to C floats; when non-NULL the kernel writes

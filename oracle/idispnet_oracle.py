@@ -28,6 +28,8 @@ Reference locations restated here (paths relative to the reference root):
   ROIAlign (CPU kernel) .. disprcnn/csrc/cpu/ROIAlign_cpu.cpp:18-219
   crop + normalise ....... disprcnn/modeling/detector/disprcnn3d.py:44-50
   ROI box alignment ...... disprcnn3d.py:126-146, utils/stereo_utils.py:219-229
+  ROI disparity hand-off . disprcnn3d.py:161-190 (roi_disp_postprocess), structures/disparity.py:39-78 (resize / crop),
+                           modeling/pointnet_module/point_rcnn/lib/net/point_rcnn.py:113-136 (depth maps)
 
 The arithmetic that the reference delegates to PyTorch (Conv3d,
 ConvTranspose3d, BatchNorm3d in eval mode, F.interpolate, F.softmax) is
@@ -340,3 +342,51 @@ def align_stereo_boxes(left_boxes, right_boxes, width, height):
             rl.append([i, x1, y1, x1 + mw, y2])
             rr.append([i, x1p, y1, x1p + mw, y2])
     return rl, rr
+
+
+# ----------------------------------------------------------------------------
+# hand-off of the per-ROI disparity maps (disprcnn3d.py:161-190, point_rcnn.py:113-136, structures/disparity.py:39-78)
+# ----------------------------------------------------------------------------
+def _resize_crop_shift(disp_roi, lb, rb):
+    """DisparityMap(out[i]).resize((max(x2-x1, x2p-x1p), y2-y1)).crop((0, 0, x2-x1, y2-y1)).data
+    (disprcnn3d.py:171-175 / point_rcnn.py:124-129; resize / crop: structures/disparity.py:39-78); the shift by x1 - x1p is
+    written differently at the two call sites (one float add at disprcnn3d.py:178, two at point_rcnn.py:130) and stays there."""
+    x1, y1, x2, y2 = math.floor(lb[0]), math.floor(lb[1]), math.ceil(lb[2]), math.ceil(lb[3])
+    x1p, x2p = math.floor(rb[0]), math.ceil(rb[2])
+    dst_w, dst_h = max(x2 - x1, x2p - x1p), y2 - y1
+    src_w = disp_roi.shape[1]
+    t = F.interpolate(disp_roi[None, None], (dst_h, dst_w), mode='bilinear', align_corners=True)[0, 0]
+    t = t / src_w * dst_w                       # disparity.py:60
+    t = t[:y2 - y1, :x2 - x1]                   # crop (the resized map is at least that large)
+    return t, (x1, y1, x2, y2), x1p
+
+
+def roi_disp_postprocess(roi_disp, left_boxes, right_boxes, masks, height, width):
+    """disprcnn3d.py:161-190.  roi_disp [R,S,S]; left_boxes / right_boxes: lists (per image) of box lists; masks [R,H,W] (0/1) or
+    None.  Returns [N,H,W]."""
+    outs, r = [], 0
+    for lbs, rbs in zip(left_boxes, right_boxes):
+        per_img = []
+        for lb, rb in zip(lbs, rbs):
+            d, (x1, y1, x2, y2), x1p = _resize_crop_shift(roi_disp[r], lb, rb)
+            m = torch.zeros((height, width))
+            m[y1:y1 + d.shape[0], x1:x1 + d.shape[1]] = d + (x1 - x1p)          # disprcnn3d.py:178
+            m = m.clamp(min=0)
+            if masks is not None:
+                m = m * masks[r].float()
+            per_img.append(m)
+            r += 1
+        outs.append(torch.stack(per_img).max(dim=0)[0] if per_img else torch.zeros((height, width)))
+    return torch.stack(outs) if outs else torch.zeros((0, height, width))
+
+
+def roi_depth_maps(roi_disp, left_boxes, right_boxes, fu_baseline, height, width):
+    """point_rcnn.py:124-134: per-ROI image-sized depth maps, fu*baseline / (disp + 1e-6) inside the box."""
+    outs = []
+    for r, (lb, rb) in enumerate(zip(left_boxes, right_boxes)):
+        d, (x1, y1, x2, y2), x1p = _resize_crop_shift(roi_disp[r], lb, rb)
+        d = d + x1 - x1p                                                         # point_rcnn.py:130: (disp + x1) - x1p
+        m = torch.zeros((height, width))
+        m[y1:y2, x1:x2] = float(fu_baseline[r]) / (d + 1e-6)
+        outs.append(m)
+    return torch.stack(outs) if outs else torch.zeros((0, height, width))

@@ -17,6 +17,8 @@ What is executed:
   * The live drop-in call (``psm_*``): ``PSMNet.forward`` UNMODIFIED -- real ``feature_extraction`` on [R,3,224,224] crop pairs
     (what ``DispRCNN3D._forward_eval`` does, disprcnn3d.py:266-284) -- plus the reference's own per-view features.
   * ``raw_*``: the 3-D stack with the reference's DEFAULT initialisation (stackhourglass.py:90-104), uncalibrated.
+  * ``paste_*``: the reference's ``DisparityMap.resize / crop`` (structures/disparity.py:39-78) executed inside restatements of its two
+    call-site loops (disprcnn3d.py:161-190, point_rcnn.py:113-136).
   * ROIAlign: the reference CPU kernel compiled from its own source.
 BatchNorm running statistics are calibrated by two train-mode passes of the reference
 and stored in the fixture (weights themselves are regenerated from tests/golden/recipe.py).
@@ -33,7 +35,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-sys.path.insert(0, '/root/reference')
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, ROOT)
 
 import recipe  # noqa: E402
 from disprcnn.modeling.psmnet.stackhourglass import PSMNet  # noqa: E402  (the reference)
@@ -229,6 +232,48 @@ def gen_raw(name, case):
     np.savez_compressed(os.path.join(HERE, f'{name}.npz'), **out)
 
 
+def gen_paste(name, case):
+    """the per-ROI disparity hand-off, produced by EXECUTING the reference's own ``DisparityMap.resize`` /
+    ``.crop`` (disprcnn/structures/disparity.py:39-78; importable once disprcnn_b200.install() has put the ``disprcnn._C`` shim in
+    place -- ``disprcnn.layers`` is what it imports) inside the two loops that call it, restated here line by line:
+    ``DispRCNN3D.roi_disp_postprocess`` (disprcnn3d.py:161-190) and the depth part of ``PointRCNN.process_input``
+    (point_rcnn.py:113-136)."""
+    import warnings
+    import disprcnn_b200
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        disprcnn_b200.install(inference_only=True)
+    from disprcnn.structures.disparity import DisparityMap   # the reference class
+    from disprcnn.utils.stereo_utils import expand_box_to_integer
+    disp, lbs, rbs, masks, fub = recipe.make_paste_inputs(case)
+    H, W = case['H'], case['W']
+    maps, depths, r = [], [], 0
+    for lb_img, rb_img in zip(lbs, rbs):
+        roi_disps_per_img = []
+        for leftbox, rightbox in zip(lb_img, rb_img):
+            x1, y1, x2, y2 = expand_box_to_integer(leftbox)
+            x1p, _, x2p, _ = expand_box_to_integer(rightbox)
+            roi_disp = DisparityMap(disp[r]).resize((max(x2 - x1, x2p - x1p), y2 - y1)).crop((0, 0, x2 - x1, y2 - y1))     # disprcnn3d.py:173-175
+            disparity_map_per_roi = torch.zeros((H, W))
+            disparity_map_per_roi[int(y1):int(y1) + roi_disp.height, int(x1):int(x1) + roi_disp.width] = roi_disp.data + (x1 - x1p)
+            disparity_map_per_roi = disparity_map_per_roi.clone().clamp(min=0)
+            disparity_map_per_roi = disparity_map_per_roi * masks[r].float()
+            roi_disps_per_img.append(disparity_map_per_roi)
+            # point_rcnn.py:124-134
+            depth_map_per_roi = torch.zeros((H, W))
+            disp_roi = DisparityMap(disp[r]).resize((max(x2 - x1, x2p - x1p), y2 - y1)).crop((0, 0, x2 - x1, y2 - y1)).data
+            disp_roi = disp_roi + x1 - x1p
+            depth_roi = float(fub[r]) / (disp_roi + 1e-6)
+            depth_map_per_roi[y1:y2, x1:x2] = depth_roi
+            depths.append(depth_map_per_roi)
+            r += 1
+        maps.append(torch.stack(roi_disps_per_img).max(dim=0)[0] if roi_disps_per_img else torch.zeros((H, W)))
+    out = dict(disparity_maps=torch.stack(maps).numpy(), depth_maps=torch.stack(depths).numpy(), disp_crc=recipe.checksum(disp),
+               mask_crc=recipe.checksum(masks))
+    print(f'{name}: {len(depths)} ROIs on {len(maps)} images {H}x{W}; disparity map max {float(torch.stack(maps).max()):.2f}')
+    np.savez_compressed(os.path.join(HERE, f'{name}.npz'), **out)
+
+
 def gen_roi():
     import build_ref
     ref = build_ref.build()
@@ -243,7 +288,7 @@ def gen_roi():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or list(recipe.CASES) + list(recipe.PSM_CASES) + list(recipe.RAW_CASES) + ['roi']
+    which = sys.argv[1:] or list(recipe.CASES) + list(recipe.PSM_CASES) + list(recipe.RAW_CASES) + list(recipe.PASTE_CASES) + ['roi']
     for name in which:
         if name == 'roi':
             gen_roi()
@@ -251,5 +296,7 @@ if __name__ == '__main__':
             gen_psm(name, recipe.PSM_CASES[name])
         elif name in recipe.RAW_CASES:
             gen_raw(name, recipe.RAW_CASES[name])
+        elif name in recipe.PASTE_CASES:
+            gen_paste(name, recipe.PASTE_CASES[name])
         else:
             gen_case(name, recipe.CASES[name])

@@ -210,3 +210,27 @@ ROI_CASES = {
     'border': dict(N=1, C=4, H=33, W=47, ph=14, pw=9, scale=0.5, sr=0, seed=23, rois=[
         [0, 0, 0, 93, 65], [0, 80, 50, 120, 90], [0, 92, 64, 94, 66], [0, -10, -10, 4, 4]]),
 }
+
+
+# per-ROI disparity hand-off (disprcnn3d.py:161-190, point_rcnn.py:113-136): integer-expanded boxes inside the image (the
+# detector clips its boxes, structures/bounding_box.py clip_to_image), S x S ROI maps, binary masks, fu*baseline per ROI
+PASTE_CASES = {
+    'paste_small': dict(H=96, W=310, S=32, seed=61, boxes=[
+        # per image: (left box, right box)
+        [([10.3, 5.2, 70.8, 60.1], [2.1, 5.2, 60.0, 60.1]), ([100.0, 20.0, 289.5, 92.7], [80.4, 20.0, 275.0, 92.7]),
+         ([40.2, 30.9, 120.4, 80.0], [30.0, 30.9, 118.9, 80.0])],
+        [([0.0, 0.0, 309.0, 95.0], [0.0, 0.0, 300.2, 95.0]), ([200.6, 40.1, 256.3, 68.8], [190.2, 40.1, 250.0, 68.8])],
+        [],
+    ]),
+}
+
+
+def make_paste_inputs(case):
+    g = _gen(case['seed'], 'paste')
+    lbs = [[list(b[0]) for b in img] for img in case['boxes']]
+    rbs = [[list(b[1]) for b in img] for img in case['boxes']]
+    R = sum(len(i) for i in lbs)
+    disp = (torch.randn(R, case['S'], case['S'], generator=g) * 6.0 + 4.0).contiguous()
+    masks = (torch.rand(R, case['H'], case['W'], generator=g) > 0.3).to(torch.uint8).contiguous()
+    fub = (300.0 + 200.0 * torch.rand(R, generator=g)).contiguous()
+    return disp, lbs, rbs, masks, fub

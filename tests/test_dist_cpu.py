@@ -77,3 +77,52 @@ def test_gather_world2_gloo(B):
 def test_gather_without_process_group_is_identity():
     x = torch.randn(3, 4, 5)
     assert gather_disparity(x, 3) is x
+
+
+def _pred_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from disprcnn_b200.parallel import gather_predictions
+
+        def make(img):
+            g = torch.Generator().manual_seed(100 + img)
+            n = img % 3   # some images have no detections
+            return {'bbox': torch.rand(n, 4, generator=g) * 300, 'scores': torch.rand(n, generator=g), 'labels': torch.randint(0, 4, (n,), generator=g),
+                    'disparity': torch.rand(5 + img, 7, generator=g), 'keep': torch.rand(n, generator=g) > 0.5,
+                    'mask': (torch.rand(n, 3, 3, generator=g) * 255).to(torch.uint8)}
+        mine = {img: make(img) for img in range(7) if img % world == rank}     # images dealt round-robin, like the eval sampler
+        every = gather_predictions(mine)
+        only0 = gather_predictions(mine, dst=0)
+        ok = list(every) == list(range(7)) and (only0 is None) == (rank != 0)
+        for img in range(7):
+            want = make(img)
+            for k, v in want.items():
+                got = every[img][k]
+                ok = ok and got.dtype == v.dtype and tuple(got.shape) == tuple(v.shape) and torch.equal(got, v)
+        empty = gather_predictions({} if rank == 1 else {3: make(3)})            # a rank with nothing to contribute
+        ok = ok and list(empty) == [3]
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_typed_prediction_gather_world2_gloo():
+    """per-image prediction fields travel as typed raw bytes in one padded all-gather (no pickling)."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pred_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_typed_prediction_gather_without_process_group():
+    from disprcnn_b200.parallel import gather_predictions
+    p = {4: {'a': torch.ones(2)}, 1: {'a': torch.zeros(3)}}
+    out = gather_predictions(p)
+    assert list(out) == [1, 4] and out[4]['a'] is p[4]['a']

@@ -283,3 +283,47 @@ def test_feature_extraction_native_kernels_match_reference(lib):
     with pytest.raises(RuntimeError, match='no CPU path'):
         fe(torch.zeros(1, 3, 224, 224))
     assert fe(torch.zeros(0, 3, 224, 224).cuda()).shape == (0, 32, 56, 56)
+
+
+def test_roi_disparity_handoff_kernels(lib):
+    """csrc/roi_paste.cu against the reference-executed fixture and the oracle (disprcnn3d.py:161-190, point_rcnn.py:113-136).
+    Floating point (bilinear weights, one division): 2e-5 abs on disparities of magnitude ~30, 1e-5 relative on depths."""
+    from disprcnn_b200.layers.roi_disparity import paste_roi_disparity, roi_depth_maps
+    case = recipe.PASTE_CASES['paste_small']
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'paste_small.npz'))
+    disp, lbs, rbs, masks, fub = recipe.make_paste_inputs(case)
+    H, W = case['H'], case['W']
+    LB = torch.tensor([b for im in lbs for b in im]).cuda()
+    RB = torch.tensor([b for im in rbs for b in im]).cuda()
+    counts = [len(im) for im in lbs]
+    got = paste_roi_disparity(disp.cuda(), LB, RB, counts, H, W, masks.cuda()).cpu().numpy()
+    e = np.abs(got - g['disparity_maps']).max()
+    depth = roi_depth_maps(disp.cuda(), LB, RB, fub.cuda(), H, W).cpu().numpy()
+    rel = np.abs(depth - g['depth_maps']) / np.maximum(np.abs(g['depth_maps']), 1e-3)
+    print(f'\n[paste] disparity maps max |d| {e:.3e} (max {g["disparity_maps"].max():.1f}); depth maps max rel {rel.max():.3e}')
+    assert got.shape == g['disparity_maps'].shape and e < 2e-5
+    assert (depth == 0).sum() == (g['depth_maps'] == 0).sum() and rel.max() < 1e-5
+    # no masks; bool masks; one image without ROIs; nothing at all
+    nomask = paste_roi_disparity(disp.cuda(), LB, RB, counts, H, W).cpu()
+    want = O.roi_disp_postprocess(disp, lbs, rbs, None, H, W)
+    assert (nomask - want).abs().max().item() < 2e-5
+    assert torch.equal(paste_roi_disparity(disp.cuda(), LB, RB, counts, H, W, masks.bool().cuda()).cpu(), torch.from_numpy(got))
+    assert paste_roi_disparity(disp[:0].cuda(), LB[:0], RB[:0], [], H, W).shape == (0, H, W)
+    assert float(paste_roi_disparity(disp[:0].cuda(), LB[:0], RB[:0], [0, 0], H, W).abs().max()) == 0.0
+    assert roi_depth_maps(disp[:0].cuda(), LB[:0], RB[:0], fub[:0].cuda(), H, W).shape == (0, H, W)
+    with pytest.raises(RuntimeError):
+        paste_roi_disparity(disp.cuda(), LB, RB, [1, 1], H, W)
+    # random boxes at the KITTI image size with the live 224 x 224 ROI maps
+    gen = torch.Generator().manual_seed(9)
+    H2, W2, R2 = 375, 1242, 7
+    x1 = torch.rand(R2, generator=gen) * 900; y1 = torch.rand(R2, generator=gen) * 200
+    w = 20 + torch.rand(R2, generator=gen) * 300; h = 20 + torch.rand(R2, generator=gen) * 150
+    off = torch.rand(R2, generator=gen) * 60
+    lb = torch.stack([x1, y1, (x1 + w).clamp(max=W2 - 1), (y1 + h).clamp(max=H2 - 1)], 1)
+    rb = torch.stack([(x1 - off).clamp(min=0), y1, (x1 - off + w * 1.1).clamp(max=W2 - 1), (y1 + h).clamp(max=H2 - 1)], 1)
+    d2 = torch.randn(R2, 224, 224, generator=gen) * 10
+    m2 = (torch.rand(R2, H2, W2, generator=gen) > 0.5)
+    counts2 = [3, 4]
+    want2 = O.roi_disp_postprocess(d2, [lb[:3].tolist(), lb[3:].tolist()], [rb[:3].tolist(), rb[3:].tolist()], m2, H2, W2)
+    got2 = paste_roi_disparity(d2.cuda(), lb.cuda(), rb.cuda(), counts2, H2, W2, m2.cuda()).cpu()
+    assert (got2 - want2).abs().max().item() < 1e-4

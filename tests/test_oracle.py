@@ -139,3 +139,18 @@ def test_crop_normalise_and_box_alignment():
     m = np.asarray(O.IMAGENET_MEAN, np.float32)[None, :, None, None]
     s = np.asarray(O.IMAGENET_STD, np.float32)[None, :, None, None]
     assert np.array_equal(out, (raw - m) / s)
+
+
+def test_roi_disparity_handoff_matches_reference():
+    """resize / crop / shift / clamp / mask / max of the per-ROI disparity maps and the depth maps, against the
+    fixture made by executing the reference's DisparityMap inside its two call-site loops (tests/golden/paste_small.npz)."""
+    case = recipe.PASTE_CASES['paste_small']
+    g = np.load(os.path.join(GOLDEN, 'paste_small.npz'))
+    disp, lbs, rbs, masks, fub = recipe.make_paste_inputs(case)
+    assert int(recipe.checksum(disp)[0]) == int(g['disp_crc'][0]) and int(recipe.checksum(masks)[0]) == int(g['mask_crc'][0])
+    maps = O.roi_disp_postprocess(disp, lbs, rbs, masks, case['H'], case['W'])
+    flat_l, flat_r = [b for im in lbs for b in im], [b for im in rbs for b in im]
+    depth = O.roi_depth_maps(disp, flat_l, flat_r, fub, case['H'], case['W'])
+    assert np.array_equal(maps.numpy(), g['disparity_maps'])     # same torch CPU ops in the same order
+    assert np.array_equal(depth.numpy(), g['depth_maps'])
+    assert maps.shape == (3, case['H'], case['W']) and float(maps[2].abs().max()) == 0.0   # image without ROIs -> zero map
