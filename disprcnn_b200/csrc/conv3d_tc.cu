@@ -58,6 +58,9 @@ namespace idisp {
 #ifndef IDISP_TRI_EG
 #define IDISP_TRI_EG 2  // epilogue groups (of 4 warps) of the per-step-triple kernels with 32-wide blocks: 4 x 8 channels or 2 x 16
 #endif
+#ifndef IDISP_S2T
+#define IDISP_S2T 1  // stride-2 32->64 split-precision conv with per-step accumulator pairs (see Cfg::S2T); 0: banked plane ring
+#endif
 #ifndef IDISP_NMAIN
 #define IDISP_NMAIN 3  // accumulator banks of the main term in the split-precision kernels (see Cfg)
 #endif
@@ -107,7 +110,16 @@ template <int CIN, int MODE, int OCC, int NT, int XM = 0> struct Cfg {
   // MMA (N = 96, the hi rows of the same B chunk) adds into the correction triple.  Edge planes compute all three kd blocks:
   // the epilogue never reads the block of a plane outside the volume.
   static constexpr bool MRG = IDISP_MRG && TRI && XM == 1 && NT == 32;
-  static constexpr int NMAIN = (!TRI && XM != 0 && MODE != M_DEC && NT <= 32 && OCC == 1) ? IDISP_NMAIN : 1;
+  // S2T (stride 2, Cin 32, both weight words resident, 32-wide blocks): the stride-2 twin of TRI + MRG.  A step = one PAIR of
+  // input planes (2p, 2p+1); its accumulators are a fresh pair of blocks [plane p | plane p+1] in three column groups,
+  // laid out [C0 | M0 | M1 | C1 | X0 | X1] (M = x_hi*w_hi, C = x_hi*w_lo, X = x_lo*w_hi) so that every MMA's D is contiguous:
+  //   even plane (kd 1 -> block 0):  x_hi * [w_lo | w_hi](kd1)                     N =  64 -> [C0 | M0];  x_lo * w_hi(kd1)  N = 32 -> X0
+  //   odd plane (kd 2 -> block 0, kd 0 -> block 1): x_hi * [lo2 | hi2 | hi0 | lo0]  N = 128 -> [C0 M0 M1 C1];  x_lo * [hi2 | hi0]  N = 64 -> [X0 X1]
+  // The epilogue drains the pair after every step: plane p = carry (block 1 of the previous step) + block 0; carry = block 1.
+  // Against the banked plane ring (N = 32 / 64 MMAs, inline barrier waits): 3 600 instead of 4 752 shared-memory-port cycles
+  // per output plane, waits of the next stage issued inside the current stage's MMA stream.
+  static constexpr bool S2T = IDISP_S2T && IDISP_TRI && XM == 1 && MODE == M_S2 && CIN == 32 && NT == 32 && OCC == 1;
+  static constexpr int NMAIN = (!TRI && !S2T && XM != 0 && MODE != M_DEC && NT <= 32 && OCC == 1) ? IDISP_NMAIN : 1;
   static constexpr int NB = NMAIN + ((NMAIN > 1 && XP) ? 1 : 0);
   static constexpr int AW = XP ? 2 : 1;        // activation words per stage
   static constexpr int BW = XP == 1 ? 2 : 1;   // weight words resident in shared memory
@@ -119,23 +131,27 @@ template <int CIN, int MODE, int OCC, int NT, int XM = 0> struct Cfg {
   // dependent instruction chain per warp (TMEM loads -> sums -> pack -> stores).  Measured per 32->32 layer: 2 groups x 16
   // channels 1.87 ms, 4 groups x 8 channels 2.07 ms (MMA stream alone: 1.50 ms) -- more epilogue warps take issue slots from
   // the MMA warp's scheduler, so two groups it is
-  static constexpr int EGROUPS = OCC == 2 ? 1 : ((TRI && NT == 32) ? IDISP_TRI_EG : 2);
+  static constexpr int EGROUPS = OCC == 2 ? 1 : (((TRI && NT == 32) || S2T) ? IDISP_TRI_EG : 2);
   static constexpr int NTHREADS = 128 + 128 * EGROUPS;    // warps 0-3: TMA producer / MMA issuer / TMEM allocator / idle
   static constexpr int TCOLS = 512 / OCC;                 // TMEM columns of this CTA
   static constexpr int KS = CIN / 16;    // K=16 MMAs per tap
   static constexpr int CBLK = CIN / 8;   // channel blocks
-  static constexpr int PLANE_BYTES = MC::SUB_W * MC::SUB_H * 16;  // one channel block of one sub-tile (LBO of A)
+  // (S2T: 17 rows instead of the 18 ModeCfg pads to -- with two activation words the sub-tile stays a multiple of 128 B -- which buys
+  //  the third pipeline stage next to the 110 KB of weights: with two stages the layer was bound by TMA latency)
+  static constexpr int SUB_H = S2T ? TH + 1 : MC::SUB_H;
+  static constexpr int PLANE_BYTES = MC::SUB_W * SUB_H * 16;  // one channel block of one sub-tile (LBO of A)
   static constexpr int ROW_BYTES = MC::SUB_W * 16;                // one tile row (SBO of A)
   static constexpr int SUB_BYTES = AW * CBLK * PLANE_BYTES;
   static constexpr int STAGE_BYTES = MC::SUBS * SUB_BYTES;
   static constexpr int KSW = BW * KS;                              // weight k-steps per tap
   static constexpr int KSM = XP == 1 ? 3 * KS : (XP == 2 ? 2 * KS : KS);  // MMAs per tap
   static constexpr int WBYTES = 27 * KSW * NT * 32;               // 27 taps x Cin (x words) x NT couts x 16 bit
-  static constexpr int NSLOT = TRI ? 2 : TCOLS / (ACC_COLS * NB);   // TRI: two step-triples (MMA fills one while the other drains)
+  static constexpr int NSLOT = (TRI || S2T) ? 2 : TCOLS / (ACC_COLS * NB);   // TRI: two step-triples (MMA fills one while the other drains)
   static constexpr int TRI_STRIDE = MRG ? 6 * NT : 3 * NT;        // TRI: TMEM columns between the two step buffers
   static constexpr int TRI_SMALL = MRG ? 3 * NT : 2 * 3 * NT;     // TRI: column offset of a step's correction triple from its main triple
   static constexpr int BANK_COLS = NSLOT * ACC_COLS;              // TMEM column distance between accumulator banks
-  static_assert(TRI || NSLOT >= 4, "the accumulator ring needs four slots");
+  static constexpr int S2T_STRIDE = 6 * NT;                       // S2T: TMEM columns of one step buffer
+  static_assert(TRI || S2T || NSLOT >= 4, "the accumulator ring needs four slots");
   static constexpr int STAGES_FIT = (228 * 1024 / OCC - 1024 - WBYTES - 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int BAR_OFF = WBYTES + STAGES * STAGE_BYTES;
@@ -254,7 +270,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     ptx::prefetch_tensormap(&xmap);
     ptx::prefetch_tensormap(&rmap);
     for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-    for (int r = 0; r < NSLOT; ++r) { ptx::mbar_init(accf_bar(r), 1); ptx::mbar_init(acce_bar(r), C::TRI ? 4 * C::EGROUPS : 4); }
+    for (int r = 0; r < NSLOT; ++r) { ptx::mbar_init(accf_bar(r), 1); ptx::mbar_init(acce_bar(r), (C::TRI || C::S2T) ? 4 * C::EGROUPS : 4); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<C::TCOLS>(ptx::smem_u32(tmem_ptr_smem));
@@ -451,7 +467,67 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           col = ncol; z = nz; g0 = ng0; ++q;
         }
       }
-      for (int col = cta; MODE != M_S1 && !C::TRI && col < ncols; col += ncta, g0 += Dout) {
+      if constexpr (C::S2T) {
+        // B chunk of (kh, kw, k-step): [2 kcores][192 rows][8]: rows [lo kd1 | hi kd1 | lo kd2 | hi kd2 | hi kd0 | lo kd0]
+        const uint32_t id_e = ptx::make_idesc_h<F16>(128, 2 * NT), id_o = ptx::make_idesc_h<F16>(128, 4 * NT), id_x = ptx::make_idesc_h<F16>(128, NT);
+        const uint64_t b0 = ptx::make_smem_desc(w_addr, 6 * NT * 16, 128);
+        uint32_t sq = 0;  // stage counter (two stages per input plane), tq: step counter
+        uint32_t tq2 = 0;
+        bool first_wait = true;
+        for (int col = cta; col < ncols; col += ncta) {
+          for (int pz = 0; pz < Dout; ++pz, ++tq2) {
+            const uint32_t t = tq2 % NSLOT;
+            const uint32_t dbase = tmem_base + t * C::S2T_STRIDE;   // [C0 | M0 | M1 | C1 | X0 | X1]
+            ptx::mbar_wait(acce_bar(t), ((tq2 / NSLOT) & 1) ^ 1);
+#pragma unroll
+            for (int odd = 0; odd < 2; ++odd) {
+#pragma unroll
+              for (int ph = 0; ph < 2; ++ph, ++sq) {
+                const uint32_t s = sq % C::STAGES;
+                if (first_wait) { ptx::mbar_wait(full_bar(s), (sq / C::STAGES) & 1); first_wait = false; }
+                ptx::tc_fence_after();
+                const uint64_t a0 = desc_add(a_desc0, s * C::STAGE_BYTES);
+                constexpr int NTAPS_MAX = 6;
+#pragma unroll
+                for (int tt = 0; tt < NTAPS_MAX; ++tt) {
+                  if (ph == 0 && tt >= 3) break;
+                  // ph=0 (even input rows): kh=1, kw=tt.  ph=1 (odd rows): kh = 0 (tt<3) or 2 (tt>=3), kw = tt%3
+                  const int kh = ph == 0 ? 1 : (tt < 3 ? 0 : 2), kw = tt % 3;
+                  const int rh = kh == 0 ? 0 : 1, rw = kw == 0 ? 0 : 1, sub_t = kw != 1 ? 1 : 0;
+                  const uint32_t aoff0 = sub_t * C::SUB_BYTES + (rh * MC::SUB_W + rw) * 16;
+                  if (tt == (ph == 0 ? 1 : 3)) {   // the next stage's TMA data: waited for in the middle of this stage's stream
+                    const uint32_t ns = (sq + 1) % C::STAGES;
+                    const bool more = !(odd == 1 && ph == 1 && pz == Dout - 1 && col + ncta >= ncols);
+                    if (more) ptx::mbar_wait(full_bar(ns), ((sq + 1) / C::STAGES) & 1);
+                  }
+#pragma unroll
+                  for (int ks = 0; ks < C::KS; ++ks) {
+                    const uint32_t boff = ((kh * 3 + kw) * C::KS + ks) * 2 * C::WCHUNK;
+                    const uint64_t a_hi = desc_add(a0, aoff0 + A_KOFF(ks)), a_lo = desc_add(a0, aoff0 + A_KOFF(C::KS + ks));
+                    const bool first = ph == 0 && tt == 0 && ks == 0;   // first MMA of this input plane
+                    if (odd == 0) {
+                      mma(dbase, a_hi, desc_add(b0, boff), id_e, first ? 0u : 1u);                       // -> [C0 | M0]
+                      mma(dbase + 4 * NT, a_lo, desc_add(b0, boff + NT * 16), id_x, first ? 0u : 1u);     // hi kd1 -> X0
+                    } else if (first) {
+                      // block 0 already holds the even plane's sums, block 1 is fresh: the first MMAs of the odd plane are split
+                      mma(dbase, a_hi, desc_add(b0, boff + 2 * NT * 16), id_e, 1u);                       // [lo2 | hi2] -> [C0 | M0]
+                      mma(dbase + 2 * NT, a_hi, desc_add(b0, boff + 4 * NT * 16), id_e, 0u);              // [hi0 | lo0] -> [M1 | C1]
+                      mma(dbase + 4 * NT, a_lo, desc_add(b0, boff + 3 * NT * 16), id_x, 1u);              // hi2 -> X0
+                      mma(dbase + 5 * NT, a_lo, desc_add(b0, boff + 4 * NT * 16), id_x, 0u);              // hi0 -> X1
+                    } else {
+                      mma(dbase, a_hi, desc_add(b0, boff + 2 * NT * 16), id_o);                           // -> [C0 | M0 | M1 | C1]
+                      mma(dbase + 4 * NT, a_lo, desc_add(b0, boff + 3 * NT * 16), id_e);                  // [hi2 | hi0] -> [X0 | X1]
+                    }
+                  }
+                }
+                commit(empty_bar(s));
+              }
+            }
+            commit(accf_bar(t));
+          }
+        }
+      }
+      for (int col = cta; MODE != M_S1 && !C::TRI && !C::S2T && col < ncols; col += ncta, g0 += Dout) {
         for (int z = 0; z < Din; ++z) {
           if (MODE == M_S1) {
           } else if (MODE == M_S2) {
@@ -623,8 +699,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           if (p.y_split) *reinterpret_cast<uint4 *>(p.y_split + ospl + (int64_t)cblk_out * 8 * sub * 8) = lo;
         }
       };
-      if constexpr (C::TRI && NT == 32) {
-        // ---- per-step triples, 32-wide blocks (every stride-1 split-precision layer) ----
+      if constexpr ((C::TRI && NT == 32) || C::S2T) {
+        // ---- per-step triples, 32-wide blocks (every stride-1 split-precision layer; S2T: per-step pairs of the stride-2 conv) ----
         // All EGROUPS epilogue groups drain EVERY step's triple; group `egroup` owns CPG = 32/EGROUPS output channels = NCBG channel
         // blocks starting at cbg0.  Measured (IDISP_TC_DBG=32/28): with the epilogue reduced to its barrier handshake a 32->32 layer
         // runs at the MMA stream's 1.54 ms, with it at 2.2 ms, and neither the TMEM traffic nor the global stores matter -- the
@@ -720,6 +796,45 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             }
           }
         };
+        if constexpr (C::S2T) {
+          float CAR[CPG];   // block 1 of the previous step: what input plane 2p-1 (kd = 0) contributed to output plane p
+#pragma unroll
+          for (int i = 0; i < CPG; ++i) CAR[i] = 0.f;
+          for (int pz = 0; pz < Dout; ++pz, ++tq) {
+            const uint32_t t = tq % NSLOT;
+            XPre xq[NCBG];
+            if (valid) xload2(xq, pz);
+            ptx::mbar_wait(accf_bar(t), (tq / NSLOT) & 1);
+            ptx::tc_fence_after();
+            const uint32_t tb = tmem_base + lane_addr + t * C::S2T_STRIDE + egroup * CPG;   // [C0 | M0 | M1 | C1 | X0 | X1]
+            {
+              uint32_t c0[CPG], m0[CPG], x0[CPG];
+              ptx::tmem_ld_cols(tb, c0);
+              ptx::tmem_ld_cols(tb + NT, m0);
+              ptx::tmem_ld_cols(tb + 4 * NT, x0);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < CPG; ++i) P0[i] = CAR[i] + (__uint_as_float(m0[i]) + (__uint_as_float(c0[i]) + __uint_as_float(x0[i])));
+            }
+            {
+              uint32_t m1[CPG], c1[CPG], x1[CPG];
+              ptx::tmem_ld_cols(tb + 2 * NT, m1);
+              ptx::tmem_ld_cols(tb + 3 * NT, c1);
+              ptx::tmem_ld_cols(tb + 5 * NT, x1);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < CPG; ++i) CAR[i] = __uint_as_float(m1[i]) + (__uint_as_float(c1[i]) + __uint_as_float(x1[i]));
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(acce_bar(t));
+            if (valid && !(p.dbg & 4)) emit(pz, P0, xq);
+            if (pz == Dout - 1) {
+#pragma unroll
+              for (int i = 0; i < CPG; ++i) CAR[i] = 0.f;
+            }
+          }
+        } else
         for (int z = 0; z < Dout; ++z, ++tq) {
           const uint32_t t = tq % NSLOT;
           XPre xq[NCBG];
@@ -890,7 +1005,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           }
         }
       }
-      for (int qo = egroup; !C::TRI && qo < Dout; qo += C::EGROUPS) {
+      for (int qo = egroup; !C::TRI && !C::S2T && qo < Dout; qo += C::EGROUPS) {
         const uint32_t g = g0 + qo, r = g % NSLOT;
         // residual operands do not depend on the accumulator: request them BEFORE waiting for it (single-precision-word
         // modes only; the split-precision passes load at use)
@@ -946,7 +1061,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           // words of a parity class -> wait -> finish -> next class" was serialised on L2 / DRAM latency.  So: the operands of ALL
           // four classes (16 x 16 B per thread) are requested before the accumulator is even waited for (see below the wait),
           // addressing is hoisted, the per-voxel work is the lean form.
-          if (valid && !(p.dbg & 4)) {
+          {
+            // (tcgen05.ld / .st are warp-collective: every lane runs them; only the global-memory work is predicated)
+            const bool live = valid && !(p.dbg & 4);
             const int64_t blk_elems = Vo * 8, lo_off = (int64_t)cblk_out * blk_elems;
             const int64_t col_blk = ((int64_t)n * out_blocks + nh * 2) * blk_elems;
             const int64_t natq = col_blk + (((int64_t)qo * p.Ho + 2 * hr) * p.Wo + 2 * wr) * 8;
@@ -955,7 +1072,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             const bool has_res = p.residual != nullptr, has_part = p.part_in != nullptr, out_x2 = p.x2 != 0;
             bool bad = false;
             uint4 rh[4][2], rl[4][2];   // residual words of the 4 classes x 2 channel blocks
-            if (has_res) {
+            if (has_res && live) {
 #pragma unroll
               for (int c4 = 0; c4 < 4; ++c4) {
                 const int ph = c4 >> 1, pw = c4 & 1;
@@ -983,6 +1100,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(acce_bar(r));
               }
+              if (!live) continue;
               const int64_t onat = natq + ((int64_t)ph * p.Wo + pw) * 8, ospl = splq + (int64_t)(ph * 2 + pw) * sub * 8;
               const int64_t opart = partq + ((int64_t)ph * p.Wo + pw) * 8;
 #pragma unroll
@@ -1041,16 +1159,6 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               }
             }
             if (bad && p.range_flag) *p.range_flag = 1;
-          } else {   // rows outside the volume (or the no-store timing experiment): drain and release only
-            ptx::mbar_wait(accf_bar(r), (g / NSLOT) & 1);
-            ptx::tc_fence_after();
-            const uint32_t t0 = tmem_base + lane_addr + r * C::ACC_COLS;
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) ptx::tmem_st_32x16(t0 + c4 * NT, zero);
-            ptx::tmem_st_wait();
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(acce_bar(r));
           }
         } else if (MODE == M_DEC && X2) {
           // split-precision pass: one parity class (32 accumulator columns, column block = pw*2 + ph) at a time; its
@@ -1292,6 +1400,9 @@ int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16,
   out.nt = NT;
   // Cfg::MRG layout (two-word stride-1 weights, 32-wide blocks): per (tap, k-step) ONE chunk [2 kcores][hi 3*NT | lo 3*NT][8]
   const bool mrg = IDISP_MRG && IDISP_TRI && words == 2 && kind == IDISP_CONV_S1 && NT == 32 && cin == 32;
+  // Cfg::S2T layout (two-word stride-2 weights, Cin 32, 32-wide blocks): per (kh, kw, k-step) ONE chunk of 192 rows
+  // [lo kd1 | hi kd1 | lo kd2 | hi kd2 | hi kd0 | lo kd0]
+  const bool s2t = IDISP_S2T && IDISP_TRI && words == 2 && kind == IDISP_CONV_S2 && NT == 32 && cin == 32;
   const int KS = words * cin / 16, NH = (cout + NT - 1) / NT;  // k-steps per tap: the lo word's follow the hi word's
   const size_t per_nh = (size_t)27 * KS * NT * 16;  // bf16 elements
   // 16-bit storage words (bf16 or IEEE half, same size): convert through cvt()
@@ -1324,9 +1435,14 @@ int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16,
             for (int n = 0; n < 3 * NT; ++n)
               for (int e = 0; e < 8; ++e) {
                 // (ks >= cin/16: the lo word's k-steps; wv() turns channel index cin + c into the lo word of channel c)
-                const int ksw = mrg ? ks % (cin / 16) : ks, word = mrg ? ks / (cin / 16) : 0;
-                const size_t dst = mrg ? ((((size_t)t2 * (cin / 16) + ksw) * 2 + kc) * 6 * NT + word * 3 * NT + n) * 8 + e
-                                       : ((((size_t)t2 * KS + ks) * 2 + kc) * 3 * NT + n) * 8 + e;
+                const int ksw = (mrg || s2t) ? ks % (cin / 16) : ks, word = (mrg || s2t) ? ks / (cin / 16) : 0;
+                size_t dst = mrg ? ((((size_t)t2 * (cin / 16) + ksw) * 2 + kc) * 6 * NT + word * 3 * NT + n) * 8 + e
+                                 : ((((size_t)t2 * KS + ks) * 2 + kc) * 3 * NT + n) * 8 + e;
+                if (s2t) {
+                  const int kd = kdj[n / NT];   // row group of (kd, word): kd1 -> {lo 0, hi 1}; kd2 -> {lo 2, hi 3}; kd0 -> {hi 4, lo 5}
+                  const int grp = kd == 1 ? (word ? 0 : 1) : (kd == 2 ? (word ? 2 : 3) : (word ? 5 : 4));
+                  dst = ((((size_t)t2 * (cin / 16) + ksw) * 2 + kc) * 6 * NT + grp * NT + n % NT) * 8 + e;
+                }
                 base[dst] = cvt(wv(kdj[n / NT], t2 / 3, t2 % 3, ks * 16 + kc * 8 + e, nh * NT + n % NT));
               }
     } else {
@@ -1392,6 +1508,9 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   tc::EncodeTiledFn enc = tc::get_encode();
   if (!enc) { set_error("tc_conv3d: cuTensorMapEncodeTiled not available from the driver"); return IDISP_ERR_CUDA; }
   CUtensorMap map, rmap;
+  const int fmt = !w.f16 ? 0 : (opts.xp ? 2 + opts.xp : ((opts.x2 || opts.part_in || opts.part_out) ? 2 : 1));
+  // rows of a sub-tile box: Cfg::SUB_H of the kernel variant this launch selects (the S2T form reads 17 rows, see Cfg)
+  const int sub_h = (IDISP_S2T && IDISP_TRI && MODE == tc::M_S2 && CIN == 32 && NT == 32 && OCC == 1 && fmt == 3) ? tc::TH + 1 : MC::SUB_H;
   static thread_local tc::CvMaps<true> cvmaps;  // ~8 KB of kernel parameters, encoded per launch (host-only work)
   CUresult r;
   const void *src = x;
@@ -1409,7 +1528,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
     const int D2 = D / 2, H2 = H / 2, W2 = W / 2;
     const cuuint64_t dims[5] = {(cuuint64_t)W2 * 8, (cuuint64_t)H2, (cuuint64_t)D2, 8, (cuuint64_t)B * blk_stride};
     const cuuint64_t strides[4] = {(cuuint64_t)W2 * 16, (cuuint64_t)H2 * W2 * 16, (cuuint64_t)D2 * H2 * W2 * 16, (cuuint64_t)8 * D2 * H2 * W2 * 16};
-    const cuuint32_t box[5] = {8 * MC::SUB_W, MC::SUB_H, 1, 1, (cuuint32_t)(aw * C::CBLK)};
+    const cuuint32_t box[5] = {8 * MC::SUB_W, (cuuint32_t)sub_h, 1, 1, (cuuint32_t)(aw * C::CBLK)};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1465,7 +1584,6 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   int per_slice = sms * OCC / p.nh;
   if (per_slice > ncols) per_slice = ncols;
   const int grid = per_slice * p.nh;
-  const int fmt = !w.f16 ? 0 : (opts.xp ? 2 + opts.xp : ((opts.x2 || opts.part_in || opts.part_out) ? 2 : 1));
   auto go = [&](auto fmt_c, auto cv_c) -> int {
     constexpr int FMT = decltype(fmt_c)::value;
     constexpr bool CVK = decltype(cv_c)::value;
