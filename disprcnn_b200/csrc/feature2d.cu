@@ -23,7 +23,7 @@
 namespace idisp {
 namespace f2d {
 
-constexpr int TW = 32, TH = 8, CI = 8, PXT = 4;   // output tile, input channels per step, pixels per thread
+constexpr int TW = 32, TH = 8, CI = 16, PXT = 4;   // output tile, input channels per step, pixels per thread
 
 struct ConvParams {
   const float *x, *w, *bias, *res;
@@ -35,7 +35,7 @@ struct ConvParams {
 
 // w: [Cin][K*K][Cout] f32 (BN scale folded in)
 template <int K, int COB>
-__global__ void __launch_bounds__(256) conv2d_kernel(const ConvParams p)
+__global__ void __launch_bounds__(256, 2) conv2d_kernel(const ConvParams p)
 {
   constexpr int CPT = COB / 4;                       // output channels per thread
   extern __shared__ float smem[];
@@ -61,13 +61,18 @@ __global__ void __launch_bounds__(256) conv2d_kernel(const ConvParams p)
   for (int c0 = 0; c0 < p.Cin; c0 += CI) {
     const int nci = min(CI, p.Cin - c0);
     __syncthreads();
-    // input patch (zero outside the image = conv padding; zero for the channels beyond Cin)
-    for (int i = tid; i < CI * PH * PW; i += 256) {
-      const int xx = i % PW, yy = (i / PW) % PH, ci = i / (PW * PH);
-      const int gx = ix0 + xx, gy = iy0 + yy;
-      float v = 0.f;
-      if (ci < nci && gx >= 0 && gx < p.W && gy >= 0 && gy < p.H) v = __ldg(xn + ((long long)(c0 + ci) * p.H + gy) * p.W + gx);
-      s_in[(ci * PH + yy) * PWp + xx] = v;
+    // input patch (zero outside the image = conv padding; zero for the channels beyond Cin): one warp per (channel, row),
+    // lanes along the row -- coalesced, and no integer division per element
+    for (int rowi = tid >> 5; rowi < CI * PH; rowi += 8) {
+      const int ci = rowi / PH, yy = rowi - ci * PH;
+      const int gy = iy0 + yy;
+      const bool rok = ci < nci && gy >= 0 && gy < p.H;
+      const float *src = xn + ((long long)(c0 + ci) * p.H + gy) * p.W;
+      float *dst = s_in + rowi * PWp;
+      for (int xx = tid & 31; xx < PW; xx += 32) {
+        const int gx = ix0 + xx;
+        dst[xx] = (rok && gx >= 0 && gx < p.W) ? __ldg(src + gx) : 0.f;
+      }
     }
     for (int i = tid; i < CI * K * K * COB; i += 256) {
       const int co = i % COB, t = (i / COB) % (K * K), ci = i / (COB * K * K);
@@ -343,7 +348,10 @@ static int f2d_conv(idisp_extractor *e, const std::string &prefix, const float *
   p.tiles_w = ceil_div(p.Wo, f2d::TW); p.tiles_h = ceil_div(p.Ho, f2d::TH);
   if (Ho_out) *Ho_out = p.Ho;
   if (Wo_out) *Wo_out = p.Wo;
-  const int cob = L.cout >= 64 ? 64 : 32;
+  // 64 output channels per CTA when that still fills the machine (two CTAs per SM), else 32: small ROI batches (R = 1..4 on
+  // the live path) otherwise leave most SMs idle
+  int cob = L.cout >= 64 ? 64 : 32;
+  if (cob == 64 && (long long)p.tiles_w * p.tiles_h * ceil_div(L.cout, 64) * B < 2 * 148) cob = 32;
   const int PH = (f2d::TH - 1) * L.stride + (L.k - 1) * L.dil + 1, PW = ((f2d::TW - 1) * L.stride + (L.k - 1) * L.dil + 1) | 1;
   const size_t smem = (size_t)(f2d::CI * PH * PW + f2d::CI * L.k * L.k * cob) * sizeof(float);
   dim3 grid(p.tiles_w * p.tiles_h, ceil_div(L.cout, cob), B);
@@ -351,7 +359,7 @@ static int f2d_conv(idisp_extractor *e, const std::string &prefix, const float *
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) { set_error("extractor: device ordinal %d out of range", dev); return IDISP_ERR_INVALID; }
-    if (!opted[dev]) { IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); opted[dev] = true; }
+    if (!opted[dev]) { IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); opted[dev] = true; }
     kern<<<grid, 256, smem, s>>>(p);
     IDISP_LAUNCH_CHECK();
     return IDISP_OK;

@@ -18,7 +18,9 @@
 // voxels = GEMM rows 0..179, i.e. two M = 128 MMAs per operand pair (rows >= 180 read whatever follows in shared memory and
 // are never used).  One TMA box per plane lands [blocks][18][10][8 ch] = consecutive 16-byte rows: exactly the no-swizzle
 // K-major A layout (SBO = 128 B, LBO = one channel-block plane), zero fill outside the volume = the conv padding.
-// Roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue.  Accumulators are
+// Roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue group A (TMEM -> tap-major products in
+// shared memory), warps 8-11 epilogue group B (shifted sums -> logits); A and B hand two product buffers back and forth through
+// named barriers, so a plane's extraction overlaps the previous plane's gather.  Accumulators are
 // double-buffered (2 x 192 TMEM columns); no zero-on-drain: the first k-step of a plane overwrites (accumulate = 0).
 // Roofline: HBM (reads the 32-channel activation once: 2.47 GB per 32 ROIs at configs[1] = 0.38 ms), not tensor.
 #include "conv3d_tc.cuh"
@@ -43,11 +45,11 @@ template <bool X2> struct Cfg {
   static constexpr int STAGE_BYTES = AW * 4 * PLANE_BYTES;  // 4 channel blocks per word
   static constexpr int STAGES = 4;
   static constexpr int RING_PAD = 2048;                     // rows 128..255 of the last block read past the stage
-  static constexpr int S_BYTES = 27 * SROW * 4;             // product buffer [27 taps][SROW] f32
+  static constexpr int S_BYTES = 2 * 27 * SROW * 4;         // two product buffers [27 taps][SROW] f32 (group A fills one while B reads the other)
   static constexpr int S_OFF = WBYTES + STAGES * STAGE_BYTES + RING_PAD;
   static constexpr int BAR_OFF = S_OFF + S_BYTES;
   static constexpr int SMEM = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
-  static constexpr int NTHREADS = 256;
+  static constexpr int NTHREADS = 384;
   static_assert(WBYTES % 128 == 0 && STAGE_BYTES % 128 == 0 && S_OFF % 16 == 0 && BAR_OFF % 8 == 0, "alignment");
 };
 
@@ -59,7 +61,7 @@ struct Params {
 };
 
 template <bool X2, bool F16>
-__global__ void __launch_bounds__(256, 1) head_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
+__global__ void __launch_bounds__(384, 1) head_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
 {
   using C = Cfg<X2>;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -140,27 +142,19 @@ __global__ void __launch_bounds__(256, 1) head_tc_kernel(const __grid_constant__
         if (lead) { ptx::umma_commit(empty_bar(s)); ptx::umma_commit(accf_bar(t)); }
       }
     }
-  } else if (warp >= 4) {
-    // ================= epilogue: products -> shared memory -> shifted sums =================
+  } else if (warp >= 4 && warp < 8) {
+    // ================= epilogue group A: products TMEM -> shared memory (tap-major) =================
+    // Named barriers: 1 + b = "S[b] full" (A arrives, B waits), 3 + b = "S[b] free" (B arrives, A waits); 256 = both groups.
     const int et = threadIdx.x - 128;                       // 0..127 = TMEM lane = GEMM row inside an M half
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    const int wl = et & 7, hl = et >> 3;                    // output position inside the 8 x 16 tile
-    const int64_t HW = (int64_t)p.H * p.W;
     uint32_t q = 0;
     for (int col = blockIdx.x; col < ncols; col += gridDim.x) {
-      const int tw = col % p.tiles_w, th = (col / p.tiles_w) % p.tiles_h, n = col / (p.tiles_w * p.tiles_h);
-      const int hr = th * TH + hl, wr = tw * TW + wl;
-      const bool valid = hr < p.H && wr < p.W;
-      const int64_t obase = (int64_t)n * D * HW + (int64_t)hr * p.W + wr;
-      float r_prev = 0.f, r_cur = 0.f;                      // running sums of output planes z-1 and z
       for (int z = 0; z < D; ++z, ++q) {
         const uint32_t t = q & 1;
-        // the residual (earlier heads' logits) of the plane this step completes: request it before waiting
-        float res = 0.f;
-        if (valid && p.res1 && z >= 1) res = __ldg(p.res1 + obase + (int64_t)(z - 1) * HW);
+        float *Sb = S + (q & 1) * (27 * SROW);
         ptx::mbar_wait(accf_bar(t), (q >> 1) & 1);
         ptx::tc_fence_after();
-        asm volatile("bar.sync 1, 128;" ::: "memory");     // everyone is done reading S of the previous plane
+        if (q & 1) asm volatile("bar.sync 4, 256;" ::: "memory"); else asm volatile("bar.sync 3, 256;" ::: "memory");   // S[b] free
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int vox = h * 128 + et;
@@ -179,21 +173,44 @@ __global__ void __launch_bounds__(256, 1) head_tc_kernel(const __grid_constant__
           }
           if (vox < NVOX) {
 #pragma unroll
-            for (int j = 0; j < 27; ++j) S[j * SROW + vox] = __uint_as_float(v[j]);
+            for (int j = 0; j < 27; ++j) Sb[j * SROW + vox] = __uint_as_float(v[j]);
           }
         }
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(acce_bar(t));       // TMEM buffer t may be overwritten
-        asm volatile("bar.sync 1, 128;" ::: "memory");     // S complete
+        if (q & 1) asm volatile("bar.arrive 2, 256;" ::: "memory"); else asm volatile("bar.arrive 1, 256;" ::: "memory");   // S[b] full
+      }
+    }
+  } else if (warp >= 8) {
+    // ================= epilogue group B: shifted sums shared memory -> logits =================
+    const int et = threadIdx.x - 256;
+    const int wl = et & 7, hl = et >> 3;                    // output position inside the 8 x 16 tile
+    const int64_t HW = (int64_t)p.H * p.W;
+    asm volatile("bar.arrive 3, 256;" ::: "memory");       // both product buffers start free
+    asm volatile("bar.arrive 4, 256;" ::: "memory");
+    uint32_t q = 0;
+    for (int col = blockIdx.x; col < ncols; col += gridDim.x) {
+      const int tw = col % p.tiles_w, th = (col / p.tiles_w) % p.tiles_h, n = col / (p.tiles_w * p.tiles_h);
+      const int hr = th * TH + hl, wr = tw * TW + wl;
+      const bool valid = hr < p.H && wr < p.W;
+      const int64_t obase = (int64_t)n * D * HW + (int64_t)hr * p.W + wr;
+      float r_prev = 0.f, r_cur = 0.f;                      // running sums of output planes z-1 and z
+      for (int z = 0; z < D; ++z, ++q) {
+        const float *Sb = S + (q & 1) * (27 * SROW);
+        // the residual (earlier heads' logits) of the plane this step completes: request it before waiting
+        float res = 0.f;
+        if (valid && p.res1 && z >= 1) res = __ldg(p.res1 + obase + (int64_t)(z - 1) * HW);
+        if (q & 1) asm volatile("bar.sync 2, 256;" ::: "memory"); else asm volatile("bar.sync 1, 256;" ::: "memory");   // S[b] full
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;                 // kd = 0, 1, 2 contributions of input plane z
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
           const int off = (hl + k / 3) * SW + wl + k % 3;
-          a0 += S[k * SROW + off];
-          a1 += S[(9 + k) * SROW + off];
-          a2 += S[(18 + k) * SROW + off];
+          a0 += Sb[k * SROW + off];
+          a1 += Sb[(9 + k) * SROW + off];
+          a2 += Sb[(18 + k) * SROW + off];
         }
+        if (q & 1) asm volatile("bar.arrive 4, 256;" ::: "memory"); else asm volatile("bar.arrive 3, 256;" ::: "memory");   // S[b] free
         // out[q] = sum_kd w[kd] . in[q + kd - 1]: input plane z feeds q = z+1 (kd 0), z (kd 1), z-1 (kd 2)
         if (z >= 1 && valid) p.y1[obase + (int64_t)(z - 1) * HW] = r_prev + a2 + res;
         r_prev = r_cur + a1;
@@ -308,7 +325,7 @@ int tc_head_conv(const TcHeadWeights &w, const __nv_bfloat16 *x, int B, int D, i
       IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
       opted[dev] = true;
     }
-    kern<<<grid, 256, smem_bytes, s>>>(map, p);
+    kern<<<grid, 384, smem_bytes, s>>>(map, p);
     IDISP_LAUNCH_CHECK();
     return IDISP_OK;
   };
