@@ -110,6 +110,8 @@ PROTOTYPES = {
     'idisp_extractor_workspace_bytes': (_sz, [_vp, _i, _i, _i]),
     'idisp_extractor_forward': (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, _vp, _vp]),
     'idisp_extractor_launches_per_forward': (_i, [_vp]),
+    'idisp_extractor_set_precision': (_i, [_vp, _i]),
+    'idisp_extractor_range_exceeded': (_i, [_vp, ctypes.POINTER(ctypes.c_int), _vp]),
     'idisp_debug_fused_cost_volume': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 

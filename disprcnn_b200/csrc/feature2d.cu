@@ -19,6 +19,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "conv2d_tc.cuh"
 
 namespace idisp {
 namespace f2d {
@@ -174,6 +175,7 @@ struct F2dLayer {
   int cin, cout, k, stride, dil;
   bool bn;              // prefix.0.weight + prefix.1.* (convbn) / downsample: prefix.0.weight + prefix.1.* too / bare conv: prefix.weight
   float *w = nullptr, *bias = nullptr;   // device: [Cin][k*k][Cout], [Cout]
+  C2dWeights tc;                         // tensor-core packing (3x3 stride-1 layers with Cin a multiple of 32, precision fp16x2)
 };
 
 }  // namespace idisp
@@ -187,6 +189,10 @@ struct idisp_extractor {
   float *blob = nullptr;
   bool finalized = false;
   int launches = 0;
+  // IDISP_PREC_FP16X2 (default): the 53 stride-1 3x3 convs run on tcgen05 in split precision (conv2d_tc.cu), the rest on the
+  // fp32 FFMA kernels below; IDISP_PREC_FP32: everything on the FFMA kernels
+  int precision = IDISP_PREC_FP16X2;
+  int *range_flag = nullptr;   // device int: a value left the IEEE-half range in the last fp16x2 forward
 };
 
 static void f2d_add(idisp_extractor *e, const std::string &prefix, int cin, int cout, int k, int stride, int dil, bool bn)
@@ -229,8 +235,30 @@ extern "C" int idisp_extractor_create(idisp_extractor_t **out)
 extern "C" void idisp_extractor_destroy(idisp_extractor_t *e)
 {
   if (!e) return;
+  for (auto &L : e->layers) c2d_weights_free(L.tc);
   if (e->blob) cudaFree(e->blob);
+  if (e->range_flag) cudaFree(e->range_flag);
   delete e;
+}
+
+extern "C" int idisp_extractor_set_precision(idisp_extractor_t *e, int precision)
+{
+  IDISP_REQUIRE(e != nullptr, "extractor_set_precision: NULL extractor");
+  IDISP_REQUIRE(precision == IDISP_PREC_FP32 || precision == IDISP_PREC_FP16X2, "extractor_set_precision: IDISP_PREC_FP32 or IDISP_PREC_FP16X2 expected, got %d",
+                precision);
+  if (precision != e->precision) e->finalized = false;   // the tensor-core packing is made at finalize
+  e->precision = precision;
+  return IDISP_OK;
+}
+
+extern "C" int idisp_extractor_range_exceeded(idisp_extractor_t *e, int *exceeded, void *stream)
+{
+  IDISP_REQUIRE(e != nullptr && exceeded != nullptr, "extractor_range_exceeded: NULL argument");
+  *exceeded = 0;
+  if (!e->range_flag) return IDISP_OK;
+  IDISP_CUDA(cudaMemcpyAsync(exceeded, e->range_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  IDISP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return IDISP_OK;
 }
 
 extern "C" int idisp_extractor_set_tensor(idisp_extractor_t *e, const char *key, const float *data, size_t numel)
@@ -304,6 +332,14 @@ extern "C" int idisp_extractor_finalize(idisp_extractor_t *e, void *stream)
       off += (bs[i].size() + 63) / 64 * 64;
     }
   }
+  for (size_t i = 0; i < e->layers.size(); ++i) {
+    F2dLayer &L = e->layers[i];
+    c2d_weights_free(L.tc);
+    if (e->precision == IDISP_PREC_FP16X2 && L.k == 3 && L.stride == 1 && L.cin % 32 == 0 && L.cout % 32 == 0) {
+      const int rc = c2d_weights_prepare(wt[i].data(), L.cin, L.cout, L.tc, s);
+      if (rc) return rc;
+    }
+  }
   IDISP_CUDA(cudaStreamSynchronize(s));
   e->finalized = true;
   return IDISP_OK;
@@ -329,7 +365,9 @@ extern "C" size_t idisp_extractor_workspace_bytes(const idisp_extractor_t *e, in
   const F2dDims d = f2d_dims(H, W);
   const size_t half = up256((size_t)B * 32 * d.H2 * d.W2 * 4), quart = up256((size_t)B * 128 * d.H4 * d.W4 * 4);
   const size_t cat = up256((size_t)B * 320 * d.H4 * d.W4 * 4), pool = up256((size_t)B * 128 * d.H4 * d.W4 / 64 * 4 + 4096);
-  return 3 * half + 4 * quart + cat + 2 * pool;
+  // + tensor-core path: three half-resolution and six quarter-resolution blocked split-precision tensors (same bytes as their
+  // f32 twins), the blocked concat tensor, one more NCHW staging tensor at each resolution, the fp32 partial of lastconv.0
+  return 3 * half + 4 * quart + cat + 2 * pool + (3 * half + 6 * quart + cat) + (half + 2 * quart) + quart;
 }
 
 static int f2d_conv(idisp_extractor *e, const std::string &prefix, const float *x, long long xbs, int B, int H, int W, const float *res, long long rbs,
@@ -396,6 +434,131 @@ extern "C" int idisp_extractor_forward(idisp_extractor_t *e, const float *images
   int rc, Ho, Wo;
 #define FR(expr) do { if ((rc = (expr)) != IDISP_OK) return rc; } while (0)
   const long long hw4 = (long long)d.H4 * d.W4, cat_bs = 320 * hw4;
+  if (e->precision == IDISP_PREC_FP16X2) {
+    // ---------------- tensor-core path: the 53 stride-1 3x3 convs on tcgen05 in split precision (conv2d_tc.cu) ----------------
+    // Blocked split-precision tensors ("x2": [N][hi C/8 | lo C/8][H][W][8] halves) carry the activations between those layers;
+    // the few layers that stay on the FFMA kernels (the two stride-2 3x3 convs, the 1x1 convs, pooling, upsampling) read and
+    // write NCHW f32 through the converters.  `raw`, `skip` and the four SPP branches live inside the blocked 320-channel concat
+    // tensor (torch.cat of submodule.py:134-135 is never executed).
+    char *tb = base + 3 * half + 4 * quart + catb + 2 * poolb;
+    __nv_bfloat16 *X[3], *Y[6];
+    for (int i = 0; i < 3; ++i) X[i] = (__nv_bfloat16 *)(tb + i * half);
+    for (int i = 0; i < 6; ++i) Y[i] = (__nv_bfloat16 *)(tb + 3 * half + i * quart);
+    __nv_bfloat16 *CATX = (__nv_bfloat16 *)(tb + 3 * half + 6 * quart);
+    float *nh1 = (float *)(tb + 3 * half + 6 * quart + catb);                 // NCHW staging, half resolution (32 ch)
+    float *nq4 = (float *)(tb + 3 * half + 6 * quart + catb + half);           // NCHW staging, quarter resolution (128 ch) x 2
+    float *nq5 = (float *)(tb + 3 * half + 6 * quart + catb + half + quart);
+    float *part = (float *)(tb + 3 * half + 6 * quart + catb + half + 2 * quart);
+    if (!e->range_flag) IDISP_CUDA(cudaMalloc(&e->range_flag, sizeof(int)));
+    IDISP_CUDA(cudaMemsetAsync(e->range_flag, 0, sizeof(int), s));
+    auto T = [](__nv_bfloat16 *p, int C) { C2dTensor t; t.p = p; t.blocks = 2 * C / 8; t.blk0 = 0; t.lo = C / 8; return t; };
+    auto sub = [](C2dTensor t, int c_off) { t.blk0 += c_off / 8; return t; };
+    auto layer = [&](const std::string &prefix) -> const F2dLayer * {
+      auto it = e->index.find(prefix);
+      return it == e->index.end() ? nullptr : &e->layers[it->second];
+    };
+    // one tensor-core conv layer; Cin > 128 runs as chunk groups of <= 4 chained through the fp32 partial
+    auto tc = [&](const std::string &prefix, const C2dTensor &x, int Hc, int Wc, const C2dTensor *res, int relu, const C2dTensor &y) -> int {
+      const F2dLayer *L = layer(prefix);
+      if (!L || !L->tc.dev) { set_error("extractor: layer '%s' has no tensor-core packing", prefix.c_str()); return IDISP_ERR_STATE; }
+      const int nch = L->cin / 32;
+      for (int c0 = 0; c0 < nch; c0 += 4) {
+        const int n = nch - c0 < 4 ? nch - c0 : 4;
+        const bool first = c0 == 0, last = c0 + n == nch;
+        const int r = c2d_conv(L->tc, L->dil, x, c0, n, B, Hc, Wc, last ? L->bias : nullptr, last ? res : nullptr, last ? relu : 0, y,
+                               first ? nullptr : part, last ? nullptr : part, e->range_flag, s);
+        if (r) return r;
+        ++e->launches;
+      }
+      return IDISP_OK;
+    };
+    auto to_x2 = [&](const float *src, int C, long long HWc, const C2dTensor &dst) -> int {
+      ++e->launches;
+      return c2d_nchw_to_x2(src, (long long)C * HWc, dst.p, dst.blocks, dst.blk0, dst.lo, B, C, HWc, e->range_flag, s);
+    };
+    auto to_nchw = [&](const C2dTensor &src, int C, long long HWc, float *dst) -> int {
+      ++e->launches;
+      return c2d_x2_to_nchw(src.p, src.blocks, src.blk0, src.lo, dst, (long long)C * HWc, B, C, HWc, s);
+    };
+    // firstconv (:63-68): the stride-2 3 -> 32 conv on the FFMA kernel, then two tensor-core convs
+    FR(f2d_conv(e, "firstconv.0", images, (long long)3 * H * W, B, H, W, nullptr, 0, 1, h0, 0, &Ho, &Wo, s));
+    const int H2 = Ho, W2 = Wo;
+    const long long hw2 = (long long)H2 * W2;
+    FR(to_x2(h0, 32, hw2, T(X[0], 32)));
+    FR(tc("firstconv.2", T(X[0], 32), H2, W2, nullptr, 1, T(X[1], 32)));
+    FR(tc("firstconv.4", T(X[1], 32), H2, W2, nullptr, 1, T(X[0], 32)));
+    int cur = 0, tmp = 1, nxt = 2;
+    for (int b = 0; b < 3; ++b) {   // layer1 (:25-48: conv1 + ReLU, conv2, += x)
+      const std::string p = "layer1." + std::to_string(b);
+      const C2dTensor xc = T(X[cur], 32), xt = T(X[tmp], 32), xn = T(X[nxt], 32);
+      FR(tc(p + ".conv1.0", xc, H2, W2, nullptr, 1, xt));
+      FR(tc(p + ".conv2", xt, H2, W2, &xc, 0, xn));
+      const int t = cur; cur = nxt; nxt = t;
+    }
+    // layer2.0: stride-2 conv1 and the 1x1 stride-2 downsample on the FFMA kernels (NCHW), conv2 on the tensor cores
+    FR(to_nchw(T(X[cur], 32), 32, hw2, nh1));
+    FR(f2d_conv(e, "layer2.0.conv1.0", nh1, 32 * hw2, B, H2, W2, nullptr, 0, 1, nq4, 0, &Ho, &Wo, s));
+    FR(f2d_conv(e, "layer2.0.downsample", nh1, 32 * hw2, B, H2, W2, nullptr, 0, 0, nq5, 0, nullptr, nullptr, s));
+    FR(to_x2(nq4, 64, hw4, T(Y[0], 64)));
+    FR(to_x2(nq5, 64, hw4, T(Y[1], 64)));
+    {
+      const C2dTensor a = T(Y[0], 64), dsm = T(Y[1], 64);
+      FR(tc("layer2.0.conv2", a, Ho, Wo, &dsm, 0, T(Y[2], 64)));
+    }
+    const C2dTensor CAT = T(CATX, 320);
+    int qc = 2, qt = 0, qn = 1;
+    for (int b = 1; b < 16; ++b) {   // layer2.1 .. 15; the last block writes `raw` = channels [0, 64) of the concat tensor
+      const std::string p = "layer2." + std::to_string(b);
+      const C2dTensor xc = T(Y[qc], 64), xt = T(Y[qt], 64);
+      const C2dTensor xn = b == 15 ? sub(CAT, 0) : T(Y[qn], 64);
+      FR(tc(p + ".conv1.0", xc, Ho, Wo, nullptr, 1, xt));
+      FR(tc(p + ".conv2", xt, Ho, Wo, &xc, 0, xn));
+      const int t = qc; qc = qn; qn = t;
+    }
+    // layer3.0: conv1 64 -> 128 on the tensor cores (reads `raw` in place), 1x1 downsample on the FFMA kernel
+    const C2dTensor raw = sub(CAT, 0);
+    FR(tc("layer3.0.conv1.0", raw, Ho, Wo, nullptr, 1, T(Y[0], 128)));
+    FR(to_nchw(raw, 64, hw4, nq4));
+    FR(f2d_conv(e, "layer3.0.downsample", nq4, 64 * hw4, B, Ho, Wo, nullptr, 0, 0, nq5, 0, nullptr, nullptr, s));
+    FR(to_x2(nq5, 128, hw4, T(Y[1], 128)));
+    {
+      const C2dTensor a = T(Y[0], 128), dsm = T(Y[1], 128);
+      FR(tc("layer3.0.conv2", a, Ho, Wo, &dsm, 0, T(Y[2], 128)));
+    }
+    int sc = 2, st = 0, sn = 1;
+    for (int li = 3; li <= 4; ++li)
+      for (int b = (li == 3 ? 1 : 0); b < 3; ++b) {   // layer3.1, .2, layer4.0 .. 2 (dilation 2); the last one writes `skip`
+        const std::string p = "layer" + std::to_string(li) + "." + std::to_string(b);
+        const bool lastb = li == 4 && b == 2;
+        const C2dTensor xc = T(Y[sc], 128), xt = T(Y[st], 128);
+        const C2dTensor xn = lastb ? sub(CAT, 64) : T(Y[sn], 128);
+        FR(tc(p + ".conv1.0", xc, Ho, Wo, nullptr, 1, xt));
+        FR(tc(p + ".conv2", xt, Ho, Wo, &xc, 0, xn));
+        const int t = sc; sc = sn; sn = t;
+      }
+    // SPP branches (:78-92, :115-132) on the FFMA kernels from an NCHW copy of `skip`; their upsampled outputs are collected in
+    // concat order (branch4, branch3, branch2, branch1) and converted into channels [192, 320) of the concat tensor in one go
+    FR(to_nchw(sub(CAT, 64), 128, hw4, nq4));
+    {
+      const int ks[4] = {56, 32, 16, 8};
+      const int c_off[4] = {96, 64, 32, 0};  // branch1 .. branch4 inside the 128-channel staging tensor
+      for (int bi = 0; bi < 4; ++bi) {
+        const int k = ks[bi], Hp = (Ho - k) / k + 1, Wp = (Wo - k) / k + 1;
+        f2d::avgpool_kernel<<<dim3(ceil_div(128 * Hp * Wp, 256), B), 256, 0, s>>>(nq4, 128 * hw4, 128, Ho, Wo, k, Hp, Wp, pool);
+        IDISP_LAUNCH_CHECK();
+        FR(f2d_conv(e, "branch" + std::to_string(bi + 1) + ".1", pool, (long long)128 * Hp * Wp, B, Hp, Wp, nullptr, 0, 1, brt, 0, nullptr, nullptr, s));
+        f2d::upsample_bilinear_kernel<<<dim3(ceil_div(32 * Ho * Wo, 256), B), 256, 0, s>>>(brt, 32, Hp, Wp, Ho, Wo, nq5, 128 * hw4, c_off[bi]);
+        IDISP_LAUNCH_CHECK();
+        e->launches += 2;
+      }
+    }
+    FR(to_x2(nq5, 128, hw4, sub(CAT, 192)));
+    // lastconv (:94-96): 320 -> 128 on the tensor cores (three chunk groups), the final 1x1 on the FFMA kernel
+    FR(tc("lastconv.0", CAT, Ho, Wo, nullptr, 1, T(Y[0], 128)));
+    FR(to_nchw(T(Y[0], 128), 128, hw4, nq4));
+    FR(f2d_conv(e, "lastconv.2", nq4, 128 * hw4, B, Ho, Wo, nullptr, 0, 0, features, 0, nullptr, nullptr, s));
+    return IDISP_OK;
+  }
   // firstconv (:63-68)
   FR(f2d_conv(e, "firstconv.0", images, (long long)3 * H * W, B, H, W, nullptr, 0, 1, h0, 0, &Ho, &Wo, s));
   FR(f2d_conv(e, "firstconv.2", h0, (long long)32 * Ho * Wo, B, Ho, Wo, nullptr, 0, 1, h1, 0, nullptr, nullptr, s));

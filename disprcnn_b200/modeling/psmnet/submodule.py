@@ -90,17 +90,21 @@ class feature_extraction(nn.Module):
         self.lastconv = nn.Sequential(convbn(320, 128, 3, 1, 1, 1), relu(),
                                       nn.Conv2d(128, 32, kernel_size=1, padding=0, stride=1, bias=False))
         self.native = True   # eval + CUDA: run inside libidisp (False: the torch modules, e.g. for A/B timing against cuDNN)
+        # 'auto' (default): the stride-1 3x3 convs on the tensor cores in split precision ('fp16x2', fp32-grade); a batch whose
+        # activations leave the IEEE-half range is redone by the fp32 FFMA kernels ('fp32' selects those outright)
+        self.precision = 'auto'
+        self.check_range = True
         self._reset_runtime_state()
 
     def _reset_runtime_state(self):
-        self._handle = None     # idisp_extractor_t*
-        self._key = None        # weights the handle was finalised with
+        self._handles = {}      # precision -> [idisp_extractor_t*, weights key it was finalised with]
+        self._handle = None     # handle of the most recent forward
         self._tensors = None
         self._workspaces = {}   # (device index, stream) -> uint8 arena
 
     def __getstate__(self):
         state = dict(self.__dict__)
-        for k in ('_handle', '_key', '_tensors', '_workspaces'):
+        for k in ('_handles', '_handle', '_tensors', '_workspaces'):
             state.pop(k, None)
         return state
 
@@ -110,9 +114,11 @@ class feature_extraction(nn.Module):
 
     def __del__(self):
         try:
-            if getattr(self, '_handle', None) is not None:
-                _lib.load().idisp_extractor_destroy(self._handle)
-                self._handle = None
+            for slot in getattr(self, '_handles', {}).values():
+                if slot[0] is not None:
+                    _lib.load().idisp_extractor_destroy(slot[0])
+                    slot[0] = None
+            self._handle = None
         except Exception:
             pass
 
@@ -129,23 +135,27 @@ class feature_extraction(nn.Module):
         self._tensors = items
         return items
 
-    def _ensure_handle(self, device):
+    def _ensure_handle(self, device, precision):
         items = self._items()
         key = (str(device), tuple((t._version, t.data_ptr()) for (_, _, _, t) in items))
-        if self._handle is not None and key == self._key:
-            return self._handle
+        slot = self._handles.setdefault(precision, [None, None])
+        if slot[0] is not None and key == slot[1]:
+            self._handle = slot[0]
+            return slot[0]
         lib = _lib.load()
-        if self._handle is None:
+        if slot[0] is None:
             h = ctypes.c_void_p()
             _lib.check(lib.idisp_extractor_create(ctypes.byref(h)))
-            self._handle = h
+            _lib.check(lib.idisp_extractor_set_precision(h, _lib.PREC_FP16X2 if precision == 'fp16x2' else _lib.PREC_FP32))
+            slot[0] = h
         for k, _, _, t in items:
             host = t.detach().to('cpu', torch.float32).contiguous()
-            _lib.check(lib.idisp_extractor_set_tensor(self._handle, k.encode(), _lib.ptr(host), host.numel()))
+            _lib.check(lib.idisp_extractor_set_tensor(slot[0], k.encode(), _lib.ptr(host), host.numel()))
         with torch.cuda.device(device):
-            _lib.check(lib.idisp_extractor_finalize(self._handle, _lib.stream_ptr()))
-        self._key = key
-        return self._handle
+            _lib.check(lib.idisp_extractor_finalize(slot[0], _lib.stream_ptr()))
+        slot[1] = key
+        self._handle = slot[0]
+        return slot[0]
 
     def forward_native(self, x):
         """submodule.py:112-139 inside libidisp: [B,3,H,W] f32 CUDA -> [B,32,H/4,W/4]."""
@@ -158,9 +168,12 @@ class feature_extraction(nn.Module):
         out = torch.empty((B, 32, Hq, Wq), dtype=torch.float32, device=x.device)
         if B == 0:
             return out
+        if self.precision not in ('auto', 'fp16x2', 'fp32'):
+            raise ValueError("feature_extraction.precision must be 'auto', 'fp16x2' or 'fp32'")
         lib = _lib.load()
-        with torch.cuda.device(x.device):
-            h = self._ensure_handle(x.device)
+
+        def run(precision):
+            h = self._ensure_handle(x.device, precision)
             need = lib.idisp_extractor_workspace_bytes(h, B, H, W)
             wkey = (x.device.index, torch.cuda.current_stream().cuda_stream)
             ws = self._workspaces.get(wkey)
@@ -168,6 +181,17 @@ class feature_extraction(nn.Module):
                 self._workspaces.pop(wkey, None)
                 ws = self._workspaces[wkey] = torch.empty(need, dtype=torch.uint8, device=x.device)
             _lib.check(lib.idisp_extractor_forward(h, _lib.ptr(x), B, H, W, _lib.ptr(ws), ws.numel(), _lib.ptr(out), _lib.stream_ptr()))
+            return h
+
+        with torch.cuda.device(x.device):
+            h = run('fp32' if self.precision == 'fp32' else 'fp16x2')
+            if self.precision == 'auto' and self.check_range:
+                flag = ctypes.c_int(0)
+                _lib.check(lib.idisp_extractor_range_exceeded(h, ctypes.byref(flag), _lib.stream_ptr()))
+                if flag.value:
+                    import warnings
+                    warnings.warn('feature_extraction: activations left the fp16 range of the split-precision mode; batch recomputed in fp32')
+                    run('fp32')
         return out
 
     def _stage(self, planes, blocks, stride, pad, dilation):

@@ -195,6 +195,13 @@ size_t idisp_extractor_workspace_bytes(const idisp_extractor_t *extractor, int B
 int idisp_extractor_forward(idisp_extractor_t *extractor, const float *images, int B, int H, int W, void *workspace,
                             size_t workspace_bytes, float *features, void *stream);
 int idisp_extractor_launches_per_forward(const idisp_extractor_t *extractor);
+/* Arithmetic of the 53 stride-1 3x3 convolutions (99 % of the extractor's FLOPs): IDISP_PREC_FP16X2 (default) = tcgen05 tensor
+ * cores in split precision (two IEEE-half words per value, three MMAs per product, fp32 accumulate: fp32-grade, csrc/conv2d_tc.cu);
+ * IDISP_PREC_FP32 = the fp32 FFMA kernels for every layer.  Call before idisp_extractor_finalize (a change un-finalises). */
+int idisp_extractor_set_precision(idisp_extractor_t *extractor, int precision);
+/* IDISP_PREC_FP16X2 only: did the most recent forward see a value outside the IEEE-half range (see idisp_plan_range_exceeded)?
+ * Writes 0/1 to *exceeded (host pointer); synchronises `stream`. */
+int idisp_extractor_range_exceeded(idisp_extractor_t *extractor, int *exceeded, void *stream);
 
 /* Test hook: the cost volume exactly as the tensor-core path assembles it inside dres0.0's TMA loader (never
  * materialised in the product path): bf16-rounded values, NCDHW f32 out [B,2C,D,Hf,Wf].  C in {16, 32}. */

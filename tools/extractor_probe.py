@@ -20,7 +20,16 @@ with torch.no_grad():
     for _ in range(5):
         fe(x)
     torch.cuda.synchronize()
-    print(f'native extractor, {R} images: {(time.perf_counter() - t0) / 5 * 1e3:.3f} ms per call')
+    print(f'native extractor (tensor-core split precision), {R} images: {(time.perf_counter() - t0) / 5 * 1e3:.3f} ms per call')
+    fe.precision = 'fp32'
+    for _ in range(2):
+        fe(x)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        fe(x)
+    torch.cuda.synchronize()
+    print(f'native extractor (fp32 FFMA kernels), {R} images: {(time.perf_counter() - t0) / 5 * 1e3:.3f} ms per call')
     fe.native = False
     torch.backends.cudnn.allow_tf32 = False
     for _ in range(3):
