@@ -9,14 +9,17 @@
 // shared memory; the nine taps are the same bytes read through descriptors shifted by (kh*d*row + kw*d) * 16 B.
 // Weight-stationary: a CTA keeps ALL taps of its 32 output channels for up to 128 input channels resident in shared memory
 // (36 KB per 32-channel chunk: [9 taps][2 k-steps][2 kcores][lo 32 rows | hi 32 rows][8]) and streams tiles past them, so B
-// is read from L2 once per CTA instead of once per tile.  MMAs: x_hi * [w_lo | w_hi] is ONE N = 64 MMA into [C | M] (corrections
-// | main), x_lo * w_hi an N = 32 MMA into C.  tcgen05.mma adds into the fp32 accumulator by truncation, so every
-// 32-channel chunk gets its own [C | M] column bank (18 adds per main column, like the 3-D kernels' per-step triples) and the
-// epilogue sums the banks in fp32 round-to-nearest.  Cin = 320 (lastconv.0) runs as three launches chained through an fp32 partial.
+// is read from L2 once per CTA instead of once per tile.  MMAs: x_hi * [w_hi | w_lo] is ONE N = 64 MMA (main | corrections), x_lo *
+// w_hi an N = 32 MMA into the corrections.  tcgen05.mma adds into the fp32 accumulator by TRUNCATION: a bias towards
+// zero that grows with the number of adds a column collects, and through 53 chained layers it showed (18 adds per main column: features
+// 5e-6 relative too small, disparity 1.1e-3 px).  So every 32-channel chunk gets a bank of THREE column blocks [M0 | C | M1]: the main
+// products of k-step 0 go to M0 and those of k-step 1 to M1 (9 adds each), both k-steps share the correction block between them
+// (B rows are packed [hi | lo] for k-step 0 and [lo | hi] for k-step 1, so each merged MMA's D stays contiguous); the epilogue sums
+// blocks and banks in fp32 round-to-nearest.  Cin = 320 (lastconv.0) runs as three launches chained through an fp32 partial.
 // Epilogue: + bias (+ residual hi + lo) (ReLU) -> hi = half(v), lo = half(v - hi) -> 16-byte stores, channel-block offsets on
 // input / output / residual so that `raw`, `skip` and the SPP branches live inside the 320-channel concat tensor.
-// Roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue; accumulators double-
-// buffered (2 x 256 TMEM columns).  Roofline: tensor (3 half-precision MMAs per algorithmic product) / shared-memory port.
+// Roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue; accumulators are
+// double-buffered where two sets of banks fit the 512 TMEM columns (up to 64 input channels per launch).  Roofline: tensor (3 half-precision MMAs per algorithmic product) / shared-memory port.
 #include "conv2d_tc.cuh"
 #include "sm100_ptx.cuh"
 
@@ -44,7 +47,7 @@ struct Params {
   const float *part_in;
   float *part_out;
   int *range_flag;
-  int B, H, W, relu, nchunks, stages;
+  int B, H, W, relu, nchunks, stages, nbuf;
   int in_blocks, in_blk0, in_lo;
   int out_blocks, out_blk0, out_lo;
   int res_blocks, res_blk0, res_lo;
@@ -114,15 +117,16 @@ __global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant
     const uint64_t a_desc0 = ptx::make_smem_desc(stage0, G::PLANE, G::SUB_W * 16);
     const uint64_t b_desc0 = ptx::make_smem_desc(w_addr, 64 * 16, 128);
     const uint32_t id64 = ptx::make_idesc_h<true>(128, 64), id32 = ptx::make_idesc_h<true>(128, 32);
+    const uint32_t nbuf = (uint32_t)p.nbuf, bufcols = (uint32_t)p.nchunks * 96;
     uint32_t q = 0, it = 0;
     for (int tile = cta; tile < ntiles; tile += ncta, ++it) {
-      const uint32_t t = it & 1;
-      ptx::mbar_wait(acce_bar(t), ((it >> 1) & 1) ^ 1);
+      const uint32_t t = it % nbuf;
+      ptx::mbar_wait(acce_bar(t), ((it / nbuf) & 1) ^ 1);
       for (int c = 0; c < p.nchunks; ++c, ++q) {
         const uint32_t s = q % S;
         ptx::mbar_wait(full_bar(s), (q / S) & 1);
         ptx::tc_fence_after();
-        const uint32_t d = tmem_base + t * 256 + c * 64;                  // this chunk's [C | M] bank
+        const uint32_t d = tmem_base + t * bufcols + c * 96;               // this chunk's bank [M0 | C | M1]
         const uint64_t a0 = a_desc0 + (uint64_t)((s * G::STAGE) >> 4);
         const uint64_t b0 = b_desc0 + (uint64_t)(((uint32_t)c * CHUNK_W_BYTES) >> 4);
 #pragma unroll
@@ -134,8 +138,18 @@ __global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant
             const uint64_t a_lo = a0 + (uint64_t)(((4 + 2 * ks) * G::PLANE + shift) >> 4);
             const uint64_t b = b0 + (uint64_t)(((tap * 2 + ks) * 2048) >> 4);
             if (lead) {
-              ptx::umma_bf16_ss(d, a_hi, b, id64, (tap | ks) ? 1u : 0u);          // x_hi * [w_lo | w_hi] -> [C | M]
-              ptx::umma_bf16_ss(d, a_lo, b + (uint64_t)((32 * 16) >> 4), id32, 1u);   // x_lo * w_hi -> C
+              if (ks == 0) {   // B rows [hi | lo] -> D = [M0 | C]; the very first MMA of the tile overwrites both blocks
+                ptx::umma_bf16_ss(d, a_hi, b, id64, tap ? 1u : 0u);
+                ptx::umma_bf16_ss(d + 32, a_lo, b, id32, 1u);                                     // x_lo * w_hi (rows 0..31) -> C
+              } else {         // B rows [lo | hi] -> D = [C | M1]; M1's first MMA must overwrite it, C must be kept: split once
+                if (tap == 0) {
+                  ptx::umma_bf16_ss(d + 32, a_hi, b, id32, 1u);                                   // x_hi * w_lo -> C
+                  ptx::umma_bf16_ss(d + 64, a_hi, b + (uint64_t)((32 * 16) >> 4), id32, 0u);      // x_hi * w_hi -> M1 (overwrite)
+                } else {
+                  ptx::umma_bf16_ss(d + 32, a_hi, b, id64, 1u);
+                }
+                ptx::umma_bf16_ss(d + 32, a_lo, b + (uint64_t)((32 * 16) >> 4), id32, 1u);        // x_lo * w_hi (rows 32..63) -> C
+              }
             }
           }
         }
@@ -150,9 +164,10 @@ __global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     const int64_t HW = (int64_t)p.H * p.W;
     bool bad = false;
+    const uint32_t nbuf = (uint32_t)p.nbuf, bufcols = (uint32_t)p.nchunks * 96;
     uint32_t it = 0;
     for (int tile = cta; tile < ntiles; tile += ncta, ++it) {
-      const uint32_t t = it & 1;
+      const uint32_t t = it % nbuf;
       const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
       const int hr = th * TH + hl, wr = tw * TW + wl;
       const bool valid = hr < p.H && wr < p.W;
@@ -167,21 +182,28 @@ __global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant
           rl[cb] = __ldg(reinterpret_cast<const uint4 *>(p.res + (rb + (int64_t)(cb + p.res_lo) * HW) * 8));
         }
       }
-      ptx::mbar_wait(accf_bar(t), (it >> 1) & 1);
+      ptx::mbar_wait(accf_bar(t), (it / nbuf) & 1);
       ptx::tc_fence_after();
       float acc[32];
       for (int c = 0; c < p.nchunks; ++c) {                 // (warp-uniform trip count: tcgen05.ld is warp-collective)
-        const uint32_t ta = tmem_base + lane_addr + t * 256 + c * 64;
-        uint32_t u[32], v[32];
-        ptx::tmem_ld_32x32(ta, u);
-        ptx::tmem_ld_32x32(ta + 32, v);
+        const uint32_t ta = tmem_base + lane_addr + t * bufcols + c * 96;   // [M0 | C | M1]
+        uint32_t m0[32], cc[32];
+        ptx::tmem_ld_32x32(ta, m0);
+        ptx::tmem_ld_32x32(ta + 32, cc);
         ptx::tmem_ld_wait();
+        float bank[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bank[i] = __uint_as_float(m0[i]) + __uint_as_float(cc[i]);
+        ptx::tmem_ld_32x32(ta + 64, m0);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bank[i] += __uint_as_float(m0[i]);
         if (c == 0) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(v[i]) + __uint_as_float(u[i]);
+          for (int i = 0; i < 32; ++i) acc[i] = bank[i];
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(v[i]) + __uint_as_float(u[i]);
+          for (int i = 0; i < 32; ++i) acc[i] += bank[i];
         }
       }
       ptx::tc_fence_before();
@@ -309,7 +331,7 @@ void c2d_weights_free(C2dWeights &w)
 }
 
 // w: HOST [Cin][9][Cout] f32 (tap = kh*3+kw, BN scale folded in) -> [Cout/32 slices][Cin/32 chunks][9 taps][2 k-steps][2 kcores][64 rows][8]:
-// rows 0..31 = half(w - half(w)) of output channel slice*32 + row, rows 32..63 = half(w) of output channel slice*32 + row - 32
+// k-step 0: rows 0..31 = half(w) (hi), rows 32..63 = half(w - half(w)) (lo) of output channel slice*32 + row % 32; k-step 1: [lo | hi]
 int c2d_weights_prepare(const float *w, int cin, int cout, C2dWeights &out, cudaStream_t s)
 {
   c2d_weights_free(out);
@@ -327,7 +349,8 @@ int c2d_weights_prepare(const float *w, int cin, int cout, C2dWeights &out, cuda
                 const int ci = ch * 32 + ks * 16 + kc * 8 + e, co = sl * 32 + row % 32;
                 const float v = w[((size_t)ci * 9 + tap) * cout + co];
                 const __half hi = __float2half_rn(v);
-                const __half val = row >= 32 ? hi : __float2half_rn(v - __half2float(hi));
+                const bool is_hi = ks == 0 ? row < 32 : row >= 32;
+                const __half val = is_hi ? hi : __float2half_rn(v - __half2float(hi));
                 h[((((((size_t)sl * nch + ch) * 9 + tap) * 2 + ks) * 2 + kc) * 64 + row) * 8 + e] = val;
               }
   IDISP_CUDA(cudaMalloc(&out.dev, h.size() * 2));
@@ -391,6 +414,7 @@ int c2d_conv(const C2dWeights &w, int dil, const C2dTensor &x, int chunk0, int n
   p.w_slice_bytes = nch_total * c2d::CHUNK_W_BYTES;
   p.bias = bias; p.res = res ? res->p : nullptr; p.y = y.p; p.part_in = part_in; p.part_out = part_out; p.range_flag = range_flag;
   p.B = B; p.H = H; p.W = W; p.relu = relu; p.nchunks = nchunks; p.stages = stages;
+  p.nbuf = 2 * nchunks * 96 <= 512 ? 2 : 1;   // two sets of accumulator banks where they fit the 512 TMEM columns
   p.in_blocks = x.blocks; p.in_blk0 = x.blk0 + chunk0 * 4; p.in_lo = x.lo;
   p.out_blocks = y.blocks; p.out_blk0 = y.blk0; p.out_lo = y.lo;
   p.res_blocks = res ? res->blocks : 0; p.res_blk0 = res ? res->blk0 : 0; p.res_lo = res ? res->lo : 0;
