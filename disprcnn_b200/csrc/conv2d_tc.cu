@@ -30,9 +30,11 @@ namespace idisp {
 namespace c2d {
 
 constexpr int TW = 8, TH = 16;
-constexpr int CHUNK_W_BYTES = 9 * 2 * 2 * 64 * 16;   // weights of one 32-input-channel chunk for 32 output channels
 
+// DIL = 0 selects the 1x1 convolution (one tap, no halo); DIL = 1 / 2 the 3x3 convolution with that dilation (padding = dilation)
 template <int DIL> struct Geo {
+  static constexpr int TAPS = DIL == 0 ? 1 : 9;
+  static constexpr int CHUNK_W = TAPS * 2 * 2 * 64 * 16;   // weights of one 32-input-channel chunk for 32 output channels
   static constexpr int SUB_W = TW + 2 * DIL, SUB_H = TH + 2 * DIL;
   static constexpr int PLANE = SUB_W * SUB_H * 16;      // one channel block of the haloed tile
   static constexpr int STAGE = 8 * PLANE;               // [hi: 4 blocks | lo: 4 blocks]
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant
   using G = Geo<DIL>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = ptx::smem_u32(smem);
-  const uint32_t wbytes = (uint32_t)p.nchunks * CHUNK_W_BYTES;
+  const uint32_t wbytes = (uint32_t)p.nchunks * G::CHUNK_W;
   const uint32_t w_addr = smem_base, stage0 = smem_base + wbytes, bar0 = stage0 + (uint32_t)p.stages * G::STAGE;
   const uint32_t S = (uint32_t)p.stages;
   auto full_bar = [&](uint32_t s) { return bar0 + 8u * s; };
@@ -128,9 +130,9 @@ __global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant
         ptx::tc_fence_after();
         const uint32_t d = tmem_base + t * bufcols + c * 96;               // this chunk's bank [M0 | C | M1]
         const uint64_t a0 = a_desc0 + (uint64_t)((s * G::STAGE) >> 4);
-        const uint64_t b0 = b_desc0 + (uint64_t)(((uint32_t)c * CHUNK_W_BYTES) >> 4);
+        const uint64_t b0 = b_desc0 + (uint64_t)(((uint32_t)c * G::CHUNK_W) >> 4);
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int tap = 0; tap < G::TAPS; ++tap) {
           const uint32_t shift = ((tap / 3) * DIL * G::SUB_W + (tap % 3) * DIL) * 16;
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
@@ -332,26 +334,27 @@ void c2d_weights_free(C2dWeights &w)
 
 // w: HOST [Cin][9][Cout] f32 (tap = kh*3+kw, BN scale folded in) -> [Cout/32 slices][Cin/32 chunks][9 taps][2 k-steps][2 kcores][64 rows][8]:
 // k-step 0: rows 0..31 = half(w) (hi), rows 32..63 = half(w - half(w)) (lo) of output channel slice*32 + row % 32; k-step 1: [lo | hi]
-int c2d_weights_prepare(const float *w, int cin, int cout, C2dWeights &out, cudaStream_t s)
+int c2d_weights_prepare(const float *w, int cin, int cout, int taps, C2dWeights &out, cudaStream_t s)
 {
   c2d_weights_free(out);
-  out.cin = cin; out.cout = cout;
+  out.cin = cin; out.cout = cout; out.taps = taps;
+  if (taps != 1 && taps != 9) { set_error("c2d_weights_prepare: 1 or 9 taps expected, got %d", taps); return IDISP_ERR_INVALID; }
   if (cin % 32 || cout % 32) { set_error("c2d_weights_prepare: Cin=%d / Cout=%d must be multiples of 32", cin, cout); return IDISP_ERR_INVALID; }
   const int nsl = cout / 32, nch = cin / 32;
-  std::vector<__half> h((size_t)nsl * nch * 9 * 2 * 2 * 64 * 8);
+  std::vector<__half> h((size_t)nsl * nch * taps * 2 * 2 * 64 * 8);
   for (int sl = 0; sl < nsl; ++sl)
     for (int ch = 0; ch < nch; ++ch)
-      for (int tap = 0; tap < 9; ++tap)
+      for (int tap = 0; tap < taps; ++tap)
         for (int ks = 0; ks < 2; ++ks)
           for (int kc = 0; kc < 2; ++kc)
             for (int row = 0; row < 64; ++row)
               for (int e = 0; e < 8; ++e) {
                 const int ci = ch * 32 + ks * 16 + kc * 8 + e, co = sl * 32 + row % 32;
-                const float v = w[((size_t)ci * 9 + tap) * cout + co];
+                const float v = w[((size_t)ci * taps + tap) * cout + co];
                 const __half hi = __float2half_rn(v);
                 const bool is_hi = ks == 0 ? row < 32 : row >= 32;
                 const __half val = is_hi ? hi : __float2half_rn(v - __half2float(hi));
-                h[((((((size_t)sl * nch + ch) * 9 + tap) * 2 + ks) * 2 + kc) * 64 + row) * 8 + e] = val;
+                h[((((((size_t)sl * nch + ch) * taps + tap) * 2 + ks) * 2 + kc) * 64 + row) * 8 + e] = val;
               }
   IDISP_CUDA(cudaMalloc(&out.dev, h.size() * 2));
   IDISP_CUDA(cudaMemcpyAsync(out.dev, h.data(), h.size() * 2, cudaMemcpyHostToDevice, s));
@@ -388,7 +391,7 @@ int c2d_conv(const C2dWeights &w, int dil, const C2dTensor &x, int chunk0, int n
              int relu, const C2dTensor &y, const float *part_in, float *part_out, int *range_flag, cudaStream_t s)
 {
   if (B == 0) return IDISP_OK;
-  if (!w.dev || (dil != 1 && dil != 2) || nchunks < 1 || nchunks > 4 || (chunk0 + nchunks) * 32 > w.cin) {
+  if (!w.dev || dil < 0 || dil > 2 || w.taps != (dil == 0 ? 1 : 9) || nchunks < 1 || nchunks > 4 || (chunk0 + nchunks) * 32 > w.cin) {
     set_error("c2d_conv: bad arguments (dil=%d chunks [%d,%d) of Cin=%d)", dil, chunk0, chunk0 + nchunks, w.cin);
     return IDISP_ERR_INVALID;
   }
@@ -396,7 +399,8 @@ int c2d_conv(const C2dWeights &w, int dil, const C2dTensor &x, int chunk0, int n
   if (!enc) { set_error("c2d_conv: cuTensorMapEncodeTiled not available from the driver"); return IDISP_ERR_CUDA; }
   const int sub_w = c2d::TW + 2 * dil, sub_h = c2d::TH + 2 * dil;
   const int stage = 8 * sub_w * sub_h * 16;
-  const int wbytes = nchunks * c2d::CHUNK_W_BYTES;
+  const int chunk_w = w.taps * 2 * 2 * 64 * 16;
+  const int wbytes = nchunks * chunk_w;
   int stages = (232448 - 2048 - wbytes) / stage;
   if (stages > 6) stages = 6;
   if (stages < 2) { set_error("c2d_conv: shared memory does not hold two input stages next to %d weight chunks", nchunks); return IDISP_ERR_INVALID; }
@@ -410,8 +414,8 @@ int c2d_conv(const C2dWeights &w, int dil, const C2dTensor &x, int chunk0, int n
   if (r != CUDA_SUCCESS) { set_error("c2d_conv: cuTensorMapEncodeTiled failed (%d) for W=%d H=%d blocks=%d", (int)r, W, H, B * x.blocks); return IDISP_ERR_CUDA; }
   c2d::Params p;
   const int nch_total = w.cin / 32;
-  p.w = (const __nv_bfloat16 *)w.dev + (size_t)chunk0 * (c2d::CHUNK_W_BYTES / 2);   // [slice][chunk][...]: this launch's chunks of slice 0
-  p.w_slice_bytes = nch_total * c2d::CHUNK_W_BYTES;
+  p.w = (const __nv_bfloat16 *)w.dev + (size_t)chunk0 * (chunk_w / 2);   // [slice][chunk][...]: this launch's chunks of slice 0
+  p.w_slice_bytes = nch_total * chunk_w;
   p.bias = bias; p.res = res ? res->p : nullptr; p.y = y.p; p.part_in = part_in; p.part_out = part_out; p.range_flag = range_flag;
   p.B = B; p.H = H; p.W = W; p.relu = relu; p.nchunks = nchunks; p.stages = stages;
   p.nbuf = 2 * nchunks * 96 <= 512 ? 2 : 1;   // two sets of accumulator banks where they fit the 512 TMEM columns
@@ -431,8 +435,11 @@ int c2d_conv(const C2dWeights &w, int dil, const C2dTensor &x, int chunk0, int n
   if (per_slice > ntiles) per_slice = ntiles;
   const int grid = per_slice * p.nslices;
   const int smem = wbytes + stages * stage + (2 * stages + 4) * 8 + 16;
-  static bool o1[64], o2[64];
-  if (dil == 1) {
+  static bool o0[64], o1[64], o2[64];
+  if (dil == 0) {
+    if (!o0[dev]) { IDISP_CUDA(cudaFuncSetAttribute(c2d::conv2d_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)); o0[dev] = true; }
+    c2d::conv2d_tc_kernel<0><<<grid, 256, smem, s>>>(map, p);
+  } else if (dil == 1) {
     if (!o1[dev]) { IDISP_CUDA(cudaFuncSetAttribute(c2d::conv2d_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)); o1[dev] = true; }
     c2d::conv2d_tc_kernel<1><<<grid, 256, smem, s>>>(map, p);
   } else {

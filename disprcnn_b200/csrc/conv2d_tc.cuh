@@ -7,7 +7,7 @@ namespace idisp {
 // packed B operand of one 3x3 conv layer (see c2d_weights_prepare)
 struct C2dWeights {
   void *dev = nullptr;
-  int cin = 0, cout = 0;
+  int cin = 0, cout = 0, taps = 9;
 };
 
 // a blocked split-precision activation tensor [N][blocks][H][W][8] (IEEE-half words), or a channel range inside one:
@@ -19,7 +19,8 @@ struct C2dTensor {
   int lo = 0;       // hi -> lo block distance (= C_total / 8)
 };
 
-int c2d_weights_prepare(const float *w /* HOST [Cin][9][Cout] f32 */, int cin, int cout, C2dWeights &out, cudaStream_t s);
+int c2d_weights_prepare(const float *w /* HOST [Cin][taps][Cout] f32, taps = 9 (3x3) or 1 (1x1) */, int cin, int cout, int taps, C2dWeights &out,
+                        cudaStream_t s);
 void c2d_weights_free(C2dWeights &w);
 int c2d_nchw_to_x2(const float *src, long long src_bs, __nv_bfloat16 *dst, int blocks, int blk0, int lo_off, int B, int C, long long HW, int *range_flag,
                    cudaStream_t s);

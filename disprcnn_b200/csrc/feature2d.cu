@@ -128,19 +128,36 @@ __global__ void __launch_bounds__(256, 2) conv2d_kernel(const ConvParams p)
   }
 }
 
-// AvgPool2d(k, stride k) (submodule.py:78-92: kernel = stride, no padding, floor): one thread per output element
+// AvgPool2d(k, stride k) (submodule.py:78-92: kernel = stride, no padding, floor): one WARP per output element (the 56 x 56
+// window of branch1 is 3136 elements), lanes stride over the window, shuffle reduction
 __global__ void avgpool_kernel(const float *__restrict__ x, long long xbs, int C, int H, int W, int k, int Ho, int Wo, float *__restrict__ y)
 {
-  const long long total = (long long)gridDim.y * C * Ho * Wo;
-  (void)total;
-  const int n = blockIdx.y;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C * Ho * Wo; i += gridDim.x * blockDim.x) {
+  const int n = blockIdx.y, lane = threadIdx.x & 31;
+  const int nwarp = gridDim.x * (blockDim.x >> 5);
+  for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < C * Ho * Wo; i += nwarp) {
     const int ox = i % Wo, oy = (i / Wo) % Ho, c = i / (Wo * Ho);
     const float *src = x + (long long)n * xbs + ((long long)c * H + oy * k) * W + ox * k;
     float s = 0.f;
-    for (int yy = 0; yy < k; ++yy)
-      for (int xx = 0; xx < k; ++xx) s += __ldg(src + (long long)yy * W + xx);
-    y[((long long)n * C + c) * Ho * Wo + oy * Wo + ox] = s / (float)(k * k);
+    for (int e = lane; e < k * k; e += 32) s += __ldg(src + (long long)(e / k) * W + e % k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) y[((long long)n * C + c) * Ho * Wo + oy * Wo + ox] = s / (float)(k * k);
+  }
+}
+
+// 1x1 conv + bias (+ ReLU) on a handful of pixels (the SPP branches: 128 -> 32 channels on 1 .. 49 pixels per image): one thread
+// per output element, weights [Cin][Cout] read coalesced across the output channels
+__global__ void pointwise_small_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias, int Cin, int Cout,
+                                       int HW, int relu, float *__restrict__ y)
+{
+  const int n = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Cout * HW; i += gridDim.x * blockDim.x) {
+    const int co = i % Cout, pos = i / Cout;
+    const float *xp = x + (long long)n * Cin * HW + pos;
+    float a = 0.f;
+    for (int ci = 0; ci < Cin; ++ci) a = fmaf(__ldg(xp + (long long)ci * HW), __ldg(w + (long long)ci * Cout + co), a);
+    a += bias ? __ldg(bias + co) : 0.f;
+    y[((long long)n * Cout + co) * HW + pos] = relu ? fmaxf(a, 0.f) : a;
   }
 }
 
@@ -335,8 +352,8 @@ extern "C" int idisp_extractor_finalize(idisp_extractor_t *e, void *stream)
   for (size_t i = 0; i < e->layers.size(); ++i) {
     F2dLayer &L = e->layers[i];
     c2d_weights_free(L.tc);
-    if (e->precision == IDISP_PREC_FP16X2 && L.k == 3 && L.stride == 1 && L.cin % 32 == 0 && L.cout % 32 == 0) {
-      const int rc = c2d_weights_prepare(wt[i].data(), L.cin, L.cout, L.tc, s);
+    if (e->precision == IDISP_PREC_FP16X2 && L.stride == 1 && L.cin % 32 == 0 && L.cout % 32 == 0 && L.prefix.compare(0, 6, "branch") != 0) {
+      const int rc = c2d_weights_prepare(wt[i].data(), L.cin, L.cout, L.k * L.k, L.tc, s);
       if (rc) return rc;
     }
   }
@@ -408,6 +425,17 @@ static int f2d_conv(idisp_extractor *e, const std::string &prefix, const float *
   return cob == 64 ? go(f2d::conv2d_kernel<1, 64>, o2) : go(f2d::conv2d_kernel<1, 32>, o3);
 }
 
+static int f2d_pointwise_small(idisp_extractor *e, const std::string &prefix, const float *x, int B, int HW, int relu, float *y, cudaStream_t s)
+{
+  auto it = e->index.find(prefix);
+  if (it == e->index.end()) { set_error("extractor: unknown layer '%s'", prefix.c_str()); return IDISP_ERR_INVALID; }
+  const F2dLayer &L = e->layers[it->second];
+  f2d::pointwise_small_kernel<<<dim3(ceil_div(L.cout * HW, 128), B), 128, 0, s>>>(x, L.w, L.bias, L.cin, L.cout, HW, relu, y);
+  IDISP_LAUNCH_CHECK();
+  ++e->launches;
+  return IDISP_OK;
+}
+
 // images [B,3,H,W] f32 NCHW -> features [B,32,H/4,W/4] f32 NCHW (submodule.py:112-139)
 extern "C" int idisp_extractor_forward(idisp_extractor_t *e, const float *images, int B, int H, int W, void *workspace, size_t workspace_bytes,
                                        float *features, void *stream)
@@ -465,7 +493,7 @@ extern "C" int idisp_extractor_forward(idisp_extractor_t *e, const float *images
       for (int c0 = 0; c0 < nch; c0 += 4) {
         const int n = nch - c0 < 4 ? nch - c0 : 4;
         const bool first = c0 == 0, last = c0 + n == nch;
-        const int r = c2d_conv(L->tc, L->dil, x, c0, n, B, Hc, Wc, last ? L->bias : nullptr, last ? res : nullptr, last ? relu : 0, y,
+        const int r = c2d_conv(L->tc, L->k == 1 ? 0 : L->dil, x, c0, n, B, Hc, Wc, last ? L->bias : nullptr, last ? res : nullptr, last ? relu : 0, y,
                                first ? nullptr : part, last ? nullptr : part, e->range_flag, s);
         if (r) return r;
         ++e->launches;
@@ -515,12 +543,10 @@ extern "C" int idisp_extractor_forward(idisp_extractor_t *e, const float *images
       FR(tc(p + ".conv2", xt, Ho, Wo, &xc, 0, xn));
       const int t = qc; qc = qn; qn = t;
     }
-    // layer3.0: conv1 64 -> 128 on the tensor cores (reads `raw` in place), 1x1 downsample on the FFMA kernel
+    // layer3.0: conv1 64 -> 128 and the 1x1 downsample on the tensor cores (both read `raw` in place)
     const C2dTensor raw = sub(CAT, 0);
     FR(tc("layer3.0.conv1.0", raw, Ho, Wo, nullptr, 1, T(Y[0], 128)));
-    FR(to_nchw(raw, 64, hw4, nq4));
-    FR(f2d_conv(e, "layer3.0.downsample", nq4, 64 * hw4, B, Ho, Wo, nullptr, 0, 0, nq5, 0, nullptr, nullptr, s));
-    FR(to_x2(nq5, 128, hw4, T(Y[1], 128)));
+    FR(tc("layer3.0.downsample", raw, Ho, Wo, nullptr, 0, T(Y[1], 128)));   // 1x1 (stride 1) 64 -> 128 + BN: one-tap tensor-core conv
     {
       const C2dTensor a = T(Y[0], 128), dsm = T(Y[1], 128);
       FR(tc("layer3.0.conv2", a, Ho, Wo, &dsm, 0, T(Y[2], 128)));
@@ -544,19 +570,19 @@ extern "C" int idisp_extractor_forward(idisp_extractor_t *e, const float *images
       const int c_off[4] = {96, 64, 32, 0};  // branch1 .. branch4 inside the 128-channel staging tensor
       for (int bi = 0; bi < 4; ++bi) {
         const int k = ks[bi], Hp = (Ho - k) / k + 1, Wp = (Wo - k) / k + 1;
-        f2d::avgpool_kernel<<<dim3(ceil_div(128 * Hp * Wp, 256), B), 256, 0, s>>>(nq4, 128 * hw4, 128, Ho, Wo, k, Hp, Wp, pool);
+        f2d::avgpool_kernel<<<dim3(ceil_div(128 * Hp * Wp, 8), B), 256, 0, s>>>(nq4, 128 * hw4, 128, Ho, Wo, k, Hp, Wp, pool);
         IDISP_LAUNCH_CHECK();
-        FR(f2d_conv(e, "branch" + std::to_string(bi + 1) + ".1", pool, (long long)128 * Hp * Wp, B, Hp, Wp, nullptr, 0, 1, brt, 0, nullptr, nullptr, s));
+        FR(f2d_pointwise_small(e, "branch" + std::to_string(bi + 1) + ".1", pool, B, Hp * Wp, 1, brt, s));
         f2d::upsample_bilinear_kernel<<<dim3(ceil_div(32 * Ho * Wo, 256), B), 256, 0, s>>>(brt, 32, Hp, Wp, Ho, Wo, nq5, 128 * hw4, c_off[bi]);
         IDISP_LAUNCH_CHECK();
         e->launches += 2;
       }
     }
     FR(to_x2(nq5, 128, hw4, sub(CAT, 192)));
-    // lastconv (:94-96): 320 -> 128 on the tensor cores (three chunk groups), the final 1x1 on the FFMA kernel
+    // lastconv (:94-96): 320 -> 128 (three chunk groups) and the final 1x1 on the tensor cores, then NCHW f32 for the 3-D stack
     FR(tc("lastconv.0", CAT, Ho, Wo, nullptr, 1, T(Y[0], 128)));
-    FR(to_nchw(T(Y[0], 128), 128, hw4, nq4));
-    FR(f2d_conv(e, "lastconv.2", nq4, 128 * hw4, B, Ho, Wo, nullptr, 0, 0, features, 0, nullptr, nullptr, s));
+    FR(tc("lastconv.2", T(Y[0], 128), Ho, Wo, nullptr, 0, T(Y[1], 32)));    // 1x1 128 -> 32, no BN, no bias
+    FR(to_nchw(T(Y[1], 32), 32, hw4, features));
     return IDISP_OK;
   }
   // firstconv (:63-68)
@@ -619,9 +645,9 @@ extern "C" int idisp_extractor_forward(idisp_extractor_t *e, const float *images
   for (int bi = 0; bi < 4; ++bi) {
     const int k = ks[bi], Hp = (Ho - k) / k + 1, Wp = (Wo - k) / k + 1;
     const int n_el = 128 * Hp * Wp;
-    f2d::avgpool_kernel<<<dim3(ceil_div(n_el, 256), B), 256, 0, s>>>(skip, cat_bs, 128, Ho, Wo, k, Hp, Wp, pool);
+    f2d::avgpool_kernel<<<dim3(ceil_div(n_el, 8), B), 256, 0, s>>>(skip, cat_bs, 128, Ho, Wo, k, Hp, Wp, pool);
     IDISP_LAUNCH_CHECK();
-    FR(f2d_conv(e, "branch" + std::to_string(bi + 1) + ".1", pool, (long long)128 * Hp * Wp, B, Hp, Wp, nullptr, 0, 1, brt, 0, nullptr, nullptr, s));
+    FR(f2d_pointwise_small(e, "branch" + std::to_string(bi + 1) + ".1", pool, B, Hp * Wp, 1, brt, s));
     f2d::upsample_bilinear_kernel<<<dim3(ceil_div(32 * Ho * Wo, 256), B), 256, 0, s>>>(brt, 32, Hp, Wp, Ho, Wo, cat, cat_bs, c_off[bi]);
     IDISP_LAUNCH_CHECK();
     e->launches += 2;
