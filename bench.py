@@ -219,19 +219,37 @@ def bench_live(dev):
     with torch.no_grad():
         for c in (m.classif1, m.classif2, m.classif3):
             c[2].weight.mul_(0.1)
-    m = m.to(dev).eval()
+    m = m.to(dev)
+    # random-init BatchNorm statistics are (0, 1): calibrate the extractor's on synthetic crops (two train-mode passes through the
+    # torch modules, as tests/golden does) and scale its output to unit variance, so that activations stay in the range trained
+    # weights produce -- otherwise the fp16 words of the split-precision mode overflow and 'auto' (correctly) reruns in fp32
+    gcal = torch.Generator().manual_seed(7)
+    fe = m.feature_extraction
+    for mod in fe.modules():
+        if isinstance(mod, nn.BatchNorm2d):
+            mod.momentum = None
+    fe.train()
+    with torch.no_grad():
+        for _ in range(2):
+            f = fe(torch.randn(4, 3, 224, 224, generator=gcal).to(dev))
+        fe.lastconv[2].weight.mul_(1.0 / float(f.std()))
+    m = m.eval()
+    import warnings
     out = {'workload': 'R ROI pairs, 224x224 crops -> 56x56x32ch features, D=24 (mindisp -48, maxdisp 48) -> 224x224; precision auto (fp16x2)',
-           'stack_ms': {}, 'psmnet_ms': {}, 'psmnet_rois_per_s': {}}
+           'stack_ms': {}, 'psmnet_ms': {}, 'extractor_ms': {}, 'psmnet_rois_per_s': {}}
     g = torch.Generator().manual_seed(5)
     old_tf32 = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False   # whatever still runs through torch must be fp32-grade
-    with torch.no_grad():
+    with torch.no_grad(), warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter('always')
         for R in (1, 4, 8, 15):
             fl = torch.randn(R, 32, 56, 56, generator=g).to(dev)
             fr = torch.randn(R, 32, 56, 56, generator=g).to(dev)
             il = torch.randn(R, 3, 224, 224, generator=g).to(dev)
             ir = torch.randn(R, 3, 224, 224, generator=g).to(dev)
-            for name, fn in (('stack_ms', lambda: m.forward_features(fl, fr)), ('psmnet_ms', lambda: m({'left': il, 'right': ir}))):
+            both = torch.cat([il, ir])
+            for name, fn in (('stack_ms', lambda: m.forward_features(fl, fr)), ('psmnet_ms', lambda: m({'left': il, 'right': ir})),
+                             ('extractor_ms', lambda: m.feature_extraction(both))):
                 for _ in range(3):
                     fn()
                 torch.cuda.synchronize()
@@ -245,6 +263,7 @@ def bench_live(dev):
                 out[name][str(R)] = round(ts[len(ts) // 2], 4)
             out['psmnet_rois_per_s'][str(R)] = round(R / (out['psmnet_ms'][str(R)] / 1e3), 1)
     torch.backends.cudnn.allow_tf32 = old_tf32
+    out['fp32_fallbacks'] = sum('fp16 range' in str(w.message) for w in caught)   # must be 0 for the numbers above to be the fp16x2 path
     out['extractor'] = type(m.feature_extraction).__module__ + ('.native' if getattr(m.feature_extraction, 'native', False) else ' (torch modules)')
     return out
 
