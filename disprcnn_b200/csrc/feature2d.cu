@@ -210,6 +210,14 @@ struct idisp_extractor {
   // fp32 FFMA kernels below; IDISP_PREC_FP32: everything on the FFMA kernels
   int precision = IDISP_PREC_FP16X2;
   int *range_flag = nullptr;   // device int: a value left the IEEE-half range in the last fp16x2 forward
+  // CUDA-graph replay of the tensor-core path's middle section (everything between the first conv, which reads the caller's
+  // images, and the last converter, which writes the caller's features, touches only the workspace): ~90 launches, each with a
+  // host-side tensor-map encode, become one cudaGraphLaunch per (B, H, W, workspace)
+  struct GraphEntry { int B, H, W; void *ws; cudaGraphExec_t exec; int launches; unsigned long long stamp; };
+  std::vector<GraphEntry> graphs;
+  unsigned long long graph_clock = 0;
+  cudaStream_t cap_stream = nullptr;
+  bool no_graph = false;
 };
 
 static void f2d_add(idisp_extractor *e, const std::string &prefix, int cin, int cout, int k, int stride, int dil, bool bn)
@@ -245,6 +253,7 @@ extern "C" int idisp_extractor_create(idisp_extractor_t **out)
   for (const char *br : {"branch1", "branch2", "branch3", "branch4"}) f2d_add(e, std::string(br) + ".1", 128, 32, 1, 1, 1, true);
   f2d_add(e, "lastconv.0", 320, 128, 3, 1, 1, true);
   f2d_add(e, "lastconv.2", 128, 32, 1, 1, 1, false);
+  e->no_graph = getenv("IDISP_NO_GRAPH") != nullptr;
   *out = e;
   return IDISP_OK;
 }
@@ -253,6 +262,8 @@ extern "C" void idisp_extractor_destroy(idisp_extractor_t *e)
 {
   if (!e) return;
   for (auto &L : e->layers) c2d_weights_free(L.tc);
+  for (auto &g : e->graphs) cudaGraphExecDestroy(g.exec);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   if (e->blob) cudaFree(e->blob);
   if (e->range_flag) cudaFree(e->range_flag);
   delete e;
@@ -349,6 +360,8 @@ extern "C" int idisp_extractor_finalize(idisp_extractor_t *e, void *stream)
       off += (bs[i].size() + 63) / 64 * 64;
     }
   }
+  for (auto &g : e->graphs) cudaGraphExecDestroy(g.exec);   // captured launches hold the old weight pointers
+  e->graphs.clear();
   for (size_t i = 0; i < e->layers.size(); ++i) {
     F2dLayer &L = e->layers[i];
     c2d_weights_free(L.tc);
@@ -512,6 +525,8 @@ extern "C" int idisp_extractor_forward(idisp_extractor_t *e, const float *images
     FR(f2d_conv(e, "firstconv.0", images, (long long)3 * H * W, B, H, W, nullptr, 0, 1, h0, 0, &Ho, &Wo, s));
     const int H2 = Ho, W2 = Wo;
     const long long hw2 = (long long)H2 * W2;
+    Ho = (H2 - 1) / 2 + 1; Wo = (W2 - 1) / 2 + 1;   // quarter resolution (layer2.0's stride-2 conv)
+    auto middle = [&]() -> int {
     FR(to_x2(h0, 32, hw2, T(X[0], 32)));
     FR(tc("firstconv.2", T(X[0], 32), H2, W2, nullptr, 1, T(X[1], 32)));
     FR(tc("firstconv.4", T(X[1], 32), H2, W2, nullptr, 1, T(X[0], 32)));
@@ -525,7 +540,7 @@ extern "C" int idisp_extractor_forward(idisp_extractor_t *e, const float *images
     }
     // layer2.0: stride-2 conv1 and the 1x1 stride-2 downsample on the FFMA kernels (NCHW), conv2 on the tensor cores
     FR(to_nchw(T(X[cur], 32), 32, hw2, nh1));
-    FR(f2d_conv(e, "layer2.0.conv1.0", nh1, 32 * hw2, B, H2, W2, nullptr, 0, 1, nq4, 0, &Ho, &Wo, s));
+    FR(f2d_conv(e, "layer2.0.conv1.0", nh1, 32 * hw2, B, H2, W2, nullptr, 0, 1, nq4, 0, nullptr, nullptr, s));
     FR(f2d_conv(e, "layer2.0.downsample", nh1, 32 * hw2, B, H2, W2, nullptr, 0, 0, nq5, 0, nullptr, nullptr, s));
     FR(to_x2(nq4, 64, hw4, T(Y[0], 64)));
     FR(to_x2(nq5, 64, hw4, T(Y[1], 64)));
@@ -582,6 +597,52 @@ extern "C" int idisp_extractor_forward(idisp_extractor_t *e, const float *images
     // lastconv (:94-96): 320 -> 128 (three chunk groups) and the final 1x1 on the tensor cores, then NCHW f32 for the 3-D stack
     FR(tc("lastconv.0", CAT, Ho, Wo, nullptr, 1, T(Y[0], 128)));
     FR(tc("lastconv.2", T(Y[0], 128), Ho, Wo, nullptr, 0, T(Y[1], 32)));    // 1x1 128 -> 32, no BN, no bias
+    return IDISP_OK;
+    };  // middle
+    {
+      cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+      const bool graph_ok = !e->no_graph && cudaStreamIsCapturing(s, &cst) == cudaSuccess && cst == cudaStreamCaptureStatusNone;
+      idisp_extractor::GraphEntry *hit = nullptr;
+      if (graph_ok)
+        for (auto &g : e->graphs)
+          if (g.B == B && g.H == H && g.W == W && g.ws == workspace) { hit = &g; break; }
+      if (graph_ok && !hit) {
+        const int before = e->launches;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        bool ok = e->cap_stream || cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+          cudaStream_t user = s;
+          s = e->cap_stream;
+          const int crc = middle();
+          s = user;
+          const cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+          if (crc != IDISP_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return crc; }
+          ok = ce == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+          if (graph) cudaGraphDestroy(graph);
+        }
+        if (!ok) { cudaGetLastError(); e->no_graph = true; e->launches = before; }
+        else {
+          if (e->graphs.size() >= 32) {
+            size_t lru = 0;
+            for (size_t i = 1; i < e->graphs.size(); ++i) if (e->graphs[i].stamp < e->graphs[lru].stamp) lru = i;
+            cudaGraphExecDestroy(e->graphs[lru].exec);
+            e->graphs.erase(e->graphs.begin() + lru);
+          }
+          e->graphs.push_back({B, H, W, workspace, exec, e->launches - before, 0ull});
+          hit = &e->graphs.back();
+          e->launches = before;
+        }
+      }
+      if (hit) {
+        hit->stamp = ++e->graph_clock;
+        IDISP_CUDA(cudaGraphLaunch(hit->exec, s));
+        e->launches += hit->launches;
+      } else {
+        FR(middle());
+      }
+    }
     FR(to_nchw(T(Y[1], 32), 32, hw4, features));
     return IDISP_OK;
   }
