@@ -25,7 +25,7 @@ def main(path, note):
     rd = wr = t = 0.0
     n = 0
     for r in rows[2:]:
-        if 'conv3d_tc_kernel' not in r[ni] and 'conv3d_simt' not in r[ni] and 'conv3d_to1' not in r[ni] and 'space_to_depth' not in r[ni]:
+        if not any(k in r[ni] for k in ('conv3d_tc_kernel', 'head_tc_kernel', 'conv3d_simt', 'conv3d_to1', 'space_to_depth')):
             continue
         rd += gb(r[ri], units[ri]); wr += gb(r[wi], units[wi]); t += ms(r[ti], units[ti]); n += 1
     print(json.dumps({'source': note, 'conv_launches': n, 'dram_read_gb_per_step': round(rd, 3), 'dram_write_gb_per_step': round(wr, 3),
