@@ -61,6 +61,9 @@ namespace idisp {
 #ifndef IDISP_S2T
 #define IDISP_S2T 1  // stride-2 32->64 split-precision conv with per-step accumulator pairs (see Cfg::S2T); 0: banked plane ring
 #endif
+#ifndef IDISP_DTR
+#define IDISP_DTR 1  // transposed split-precision conv with per-step accumulators and kd-stacked, class-major MMAs (see Cfg::DTR)
+#endif
 #ifndef IDISP_NMAIN
 #define IDISP_NMAIN 3  // accumulator banks of the main term in the split-precision kernels (see Cfg)
 #endif
@@ -119,6 +122,16 @@ template <int CIN, int MODE, int OCC, int NT, int XM = 0> struct Cfg {
   // Against the banked plane ring (N = 32 / 64 MMAs, inline barrier waits): 3 600 instead of 4 752 shared-memory-port cycles
   // per output plane, waits of the next stage issued inside the current stage's MMA stream.
   static constexpr bool S2T = IDISP_S2T && IDISP_TRI && XM == 1 && MODE == M_S2 && CIN == 32 && NT == 32 && OCC == 1;
+  // DTR (transposed conv, both weight words resident, 16-wide blocks): the transposed twin of TRI.  A step = one INPUT plane z; its
+  // accumulators are a fresh 12-block buffer laid out CLASS-major, [c00 | c10 | c11 | c01] (class = (ph, pw) of the output voxel
+  // (2h+ph, 2w+pw)), each class holding the three output planes the input plane feeds, [2z-1 (kd 0) | 2z (kd 1) | 2z+1 (kd 2)].
+  // In that order the classes an input shift feeds are adjacent, and the three kd are stacked in N:
+  //   shift (0,0) -> all four classes, N = 12*NT;  (0,1) -> [c11 | c01], N = 6*NT;  (1,0) -> [c10 | c11], N = 6*NT;  (1,1) -> c11, N = 3*NT
+  // i.e. 4 MMAs per k-step (252 shared-memory-port cycles) where the plane-ring form issues 3 x 5 of N = 64 / 32 / 16 (588 cycles):
+  // with 16-wide blocks every MMA paid the 4 KB A read for 16-64 columns of work.  The epilogue drains a buffer after every step:
+  // plane 2z-1 = carry + block 0, plane 2z = block 1, carry = block 2 (fp32 round-to-nearest, carried in registers).
+  static constexpr bool DTR = IDISP_DTR && XM == 1 && MODE == M_DEC && NT == 16 && OCC == 1;
+  static constexpr int DTR_STRIDE = 12 * NT;                      // DTR: TMEM columns of one step buffer
   static constexpr int NMAIN = (!TRI && !S2T && XM != 0 && MODE != M_DEC && NT <= 32 && OCC == 1) ? IDISP_NMAIN : 1;
   static constexpr int NB = NMAIN + ((NMAIN > 1 && XP) ? 1 : 0);
   static constexpr int AW = XP ? 2 : 1;        // activation words per stage
@@ -146,12 +159,12 @@ template <int CIN, int MODE, int OCC, int NT, int XM = 0> struct Cfg {
   static constexpr int KSW = BW * KS;                              // weight k-steps per tap
   static constexpr int KSM = XP == 1 ? 3 * KS : (XP == 2 ? 2 * KS : KS);  // MMAs per tap
   static constexpr int WBYTES = 27 * KSW * NT * 32;               // 27 taps x Cin (x words) x NT couts x 16 bit
-  static constexpr int NSLOT = (TRI || S2T) ? 2 : TCOLS / (ACC_COLS * NB);   // TRI: two step-triples (MMA fills one while the other drains)
+  static constexpr int NSLOT = (TRI || S2T || DTR) ? 2 : TCOLS / (ACC_COLS * NB);   // TRI: two step-triples (MMA fills one while the other drains)
   static constexpr int TRI_STRIDE = MRG ? 6 * NT : 3 * NT;        // TRI: TMEM columns between the two step buffers
   static constexpr int TRI_SMALL = MRG ? 3 * NT : 2 * 3 * NT;     // TRI: column offset of a step's correction triple from its main triple
   static constexpr int BANK_COLS = NSLOT * ACC_COLS;              // TMEM column distance between accumulator banks
   static constexpr int S2T_STRIDE = 6 * NT;                       // S2T: TMEM columns of one step buffer
-  static_assert(TRI || S2T || NSLOT >= 4, "the accumulator ring needs four slots");
+  static_assert(TRI || S2T || DTR || NSLOT >= 4, "the accumulator ring needs four slots");
   static constexpr int STAGES_FIT = (228 * 1024 / OCC - 1024 - WBYTES - 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int BAR_OFF = WBYTES + STAGES * STAGE_BYTES;
@@ -171,6 +184,7 @@ struct Params {
   __nv_bfloat16 *y_split;         // optional second copy of y in the 8-parity-sub-volume layout a stride-2 consumer reads
   int residual_is_split;          // transposed conv only: `residual` is stored in that parity layout (of the OUTPUT grid)
   int skip_y;                     // write only y_split (the natural copy has no reader)
+  int res_map;                    // Cfg::DTR: the second tensor map covers `residual` (boxes of one output plane tile x 2 channel blocks)
   // split-precision ("x2") passes: a product of (hi+lo) operands is three launches whose accumulators are chained through an
   // fp32 partial; the last pass applies the epilogue and stores the result as two 16-bit words (hi blocks, then lo blocks)
   const float *part_in;           // fp32 partial sums of the earlier pass(es), blocked [B][Cout/8][V][8], or nullptr
@@ -181,7 +195,7 @@ struct Params {
   int B, Din, Dout, Ho, Wo, Hr, Wr, Cout, relu;  // (Hr,Wr): row grid the 8x16 tiles cover
   int tiles_h, tiles_w, nh;
   int cv_shift0;                  // mindisp/4: plane k <-> right-view shift i = k + cv_shift0
-  int dbg;                        // timing experiments only (IDISP_TC_DBG): 1 no MMAs, 2 no TMA loads, 4 no global stores, 8 no tcgen05.ld, 16 no tcgen05.st, 32 TRI epilogue = handshake only, 64 TRI epilogue without the per-voxel work, 128 TRI epilogue without TMEM reads
+  int dbg;                        // timing experiments only (IDISP_TC_DBG): 1 no MMAs, 2 no TMA loads, 4 no global stores, 8 no tcgen05.ld, 16 no tcgen05.st, 32 TRI epilogue = handshake only, 64 TRI epilogue without the per-voxel work, 128 TRI epilogue without TMEM reads, 256 DTR without the residual L2 prefetch, 512 DTR without residual loads
 };
 
 // DECONV stacking table: per kd, five MMAs (entries) that share an input shift
@@ -270,7 +284,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     ptx::prefetch_tensormap(&xmap);
     ptx::prefetch_tensormap(&rmap);
     for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
-    for (int r = 0; r < NSLOT; ++r) { ptx::mbar_init(accf_bar(r), 1); ptx::mbar_init(acce_bar(r), (C::TRI || C::S2T) ? 4 * C::EGROUPS : 4); }
+    for (int r = 0; r < NSLOT; ++r) { ptx::mbar_init(accf_bar(r), 1); ptx::mbar_init(acce_bar(r), (C::TRI || C::S2T || C::DTR) ? 4 * C::EGROUPS : 4); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<C::TCOLS>(ptx::smem_u32(tmem_ptr_smem));
@@ -338,6 +352,21 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             } else if (lead) {
               ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
               ptx::tma_load_4d(stage_addr0 + s * C::STAGE_BYTES, &xmap, full_bar(s), (tw * TW - halo) * 8, th * TH - halo, z, n * p.in_blk_stride + p.in_blk_off);
+            }
+            if constexpr (C::DTR) {
+              // The epilogue adds a residual tensor of the output's size; its loads were the layer's critical path (DRAM latency in a
+              // dependent chain per output plane).  The producer runs two to four steps ahead of the epilogue: it asks L2 for the
+              // residual boxes of the two output planes (2z, 2z+1) this input plane completes / opens -- one tiled TMA prefetch per
+              // plane and precision word (16 KB each), so the epilogue's loads are L2 hits.  (Per-row bulk prefetches, 512 per step,
+              // made the layer 2x SLOWER: the TMA unit is bound by operation count.)
+              if (p.res_map && lead && !(p.dbg & 256)) {
+                const int cblk_out = p.Cout / 8, out_blocks = p.x2 ? 2 * cblk_out : cblk_out;
+                for (int i = 0; i < (p.x2 ? 4 : 2); ++i) {
+                  const int qo = 2 * z + (i & 1), blk = n * out_blocks + nh * 2 + (i >> 1) * cblk_out;
+                  if (p.residual_is_split) ptx::tma_prefetch_5d(&rmap, tw * TW * 8, th * TH, qo >> 1, (qo & 1) * 4, blk);
+                  else ptx::tma_prefetch_4d(&rmap, 2 * tw * TW * 8, 2 * th * TH, qo, blk);
+                }
+              }
             }
             ++q;
           }
@@ -527,7 +556,41 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           }
         }
       }
-      for (int col = cta; MODE != M_S1 && !C::TRI && !C::S2T && col < ncols; col += ncta, g0 += Dout) {
+      if constexpr (C::DTR) {
+        // weights: [k-step][2 kcores][27*NT rows][8]; rows = shift (0,0): 4 classes x 3 kd x NT | (0,1): 2 x 3 x NT | (1,0): 2 x 3 x NT | (1,1): 3 x NT
+        constexpr uint32_t KCH = 2 * 27 * NT * 16;   // bytes of one weight k-step
+        const uint64_t b0 = ptx::make_smem_desc(w_addr, 27 * NT * 16, 128);
+        const uint32_t id12 = ptx::make_idesc_h<F16>(128, 12 * NT), id6 = ptx::make_idesc_h<F16>(128, 6 * NT), id3 = ptx::make_idesc_h<F16>(128, 3 * NT);
+        auto waits = [&](int col_, uint32_t q_) {
+          if (col_ >= ncols) return;
+          ptx::mbar_wait(acce_bar(q_ % NSLOT), ((q_ / NSLOT) & 1) ^ 1);
+          ptx::mbar_wait(full_bar(q_ % C::STAGES), (q_ / C::STAGES) & 1);
+        };
+        int col = cta, z = 0;
+        waits(col, 0);
+        while (col < ncols) {
+          ptx::tc_fence_after();
+          const uint32_t s = q % C::STAGES, t = q % NSLOT;
+          const uint32_t d = tmem_base + t * C::DTR_STRIDE;   // [c00 | c10 | c11 | c01] x [2z-1 | 2z | 2z+1] x NT
+          const uint64_t a0 = desc_add(a_desc0, s * C::STAGE_BYTES);
+          int ncol = col, nz = z + 1;
+          if (nz == Din) { nz = 0; ncol += ncta; }
+#pragma unroll
+          for (int ks = 0; ks < C::KSM; ++ks) {
+            if (ks == C::KSM / 2) waits(ncol, q + 1);
+            const uint32_t ak = A_KOFF(ks), bk = B_KS(ks) * KCH;
+            // (the step's buffer is fresh: the first MMA, which covers all of it, overwrites)
+            mma(d, desc_add(a0, ak), desc_add(b0, bk), id12, ks ? 1u : 0u);                                                  // shift (0,0)
+            mma(d + 6 * NT, desc_add(a0, ak + 16), desc_add(b0, bk + 12 * NT * 16), id6);                                    // shift (0,1) -> [c11 | c01]
+            mma(d + 3 * NT, desc_add(a0, ak + MC::SUB_W * 16), desc_add(b0, bk + 18 * NT * 16), id6);                         // shift (1,0) -> [c10 | c11]
+            mma(d + 6 * NT, desc_add(a0, ak + (MC::SUB_W + 1) * 16), desc_add(b0, bk + 24 * NT * 16), id3);                   // shift (1,1) -> c11
+          }
+          commit(empty_bar(s));
+          commit(accf_bar(t));
+          col = ncol; z = nz; ++q;
+        }
+      }
+      for (int col = cta; MODE != M_S1 && !C::TRI && !C::S2T && !C::DTR && col < ncols; col += ncta, g0 += Dout) {
         for (int z = 0; z < Din; ++z) {
           if (MODE == M_S1) {
           } else if (MODE == M_S2) {
@@ -1004,8 +1067,169 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             for (int i = 0; i < 16; ++i) { P0[i] = 0.f; P1[i] = 0.f; }
           }
         }
+      } else if constexpr (C::DTR) {
+        // ---- per-step buffers of the transposed conv (see Cfg::DTR) ----
+        // Rows are INPUT positions (hr, wr).  Both epilogue groups drain every step: group `egroup` owns the output rows of parity
+        // ph = egroup, i.e. the classes (ph, pw = 0) and (ph, pw = 1) -- the neighbouring output voxels (2wr, 2wr+1) -- and handles
+        // them TOGETHER plane by plane, so every natural-layout access of a thread is one 32-byte sector (256-bit LDG / STG; with one
+        // class at a time each 16-byte store half-filled a sector and the pw = 1 store came 16 stores later).
+        //   plane 2z-1 = carry + block 0, plane 2z = block 1, carry = block 2   (per class; fp32 round-to-nearest, in registers)
+        // The residual words of a plane are requested before its TMEM read (the producer warp prefetched them into L2 earlier).
+        const int ph = egroup;
+        const int ci0 = ph == 0 ? 0 : 1, ci1 = ph == 0 ? 3 : 2;   // column groups of (ph, pw=0), (ph, pw=1): [c00 | c10 | c11 | c01]
+        const bool live = valid && !(p.dbg & 4);
+        const int64_t blk_elems = Vo * 8, lo_off = (int64_t)cblk_out * blk_elems;
+        const int64_t col_blk = ((int64_t)n * out_blocks + nh * 2) * blk_elems;
+        const int64_t plane_nat = (int64_t)p.Ho * p.Wo * 8, plane_spl = (int64_t)(p.Ho / 2) * (p.Wo / 2) * 8;
+        const int64_t nat0 = col_blk + ((int64_t)(2 * hr + ph) * p.Wo + 2 * wr) * 8;                                      // plane 0, pw 0
+        const int64_t spl0 = col_blk + ((int64_t)(ph * 2) * sub + (int64_t)hr * (p.Wo / 2) + wr) * 8;                      // plane 0, pw 0
+        auto nat_of = [&](int q) { return nat0 + (int64_t)q * plane_nat; };                                               // (pw 1: + 8 elements)
+        auto spl_of = [&](int q) { return spl0 + (int64_t)(q & 1) * 4 * sub * 8 + (int64_t)(q >> 1) * plane_spl; };      // (pw 1: + sub * 8)
+        const bool has_res = p.residual != nullptr && !(p.dbg & 512), out_x2 = p.x2 != 0, res_split = p.residual_is_split != 0;
+        struct Res { uint4 h[2][2], l[2][2]; };   // residual words of the voxel pair: [pw][channel block] x (hi, lo)
+        auto rload = [&](Res &r, int q) {
+          if (res_split) {
+            const __nv_bfloat16 *rp = p.residual + spl_of(q);
+#pragma unroll
+            for (int pw = 0; pw < 2; ++pw)
+#pragma unroll
+              for (int cb = 0; cb < 2; ++cb) {
+                r.h[pw][cb] = __ldg(reinterpret_cast<const uint4 *>(rp + (int64_t)pw * sub * 8 + (int64_t)cb * blk_elems));
+                r.l[pw][cb] = out_x2 ? __ldg(reinterpret_cast<const uint4 *>(rp + (int64_t)pw * sub * 8 + (int64_t)cb * blk_elems + lo_off)) : make_uint4(0u, 0u, 0u, 0u);
+              }
+          } else {
+            const __nv_bfloat16 *rp = p.residual + nat_of(q);
+#pragma unroll
+            for (int cb = 0; cb < 2; ++cb) {
+              const ptx::U8 a = ptx::ldg_v8(rp + (int64_t)cb * blk_elems);
+              r.h[0][cb] = a.a; r.h[1][cb] = a.b;
+              if (out_x2) {
+                const ptx::U8 b = ptx::ldg_v8(rp + (int64_t)cb * blk_elems + lo_off);
+                r.l[0][cb] = b.a; r.l[1][cb] = b.b;
+              } else {
+                r.l[0][cb] = make_uint4(0u, 0u, 0u, 0u); r.l[1][cb] = make_uint4(0u, 0u, 0u, 0u);
+              }
+            }
+          }
+        };
+        bool bad = false;
+        // one voxel's 8 channels of one channel block: + bias (+ residual) (ReLU) -> hi / lo words
+        auto cook = [&](const float *v8, int cb, const uint4 &rh, const uint4 &rl, uint4 &hi, uint4 &lo) {
+          F8 f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) f.v[c] = v8[c] + bias_s[cb * 8 + c];
+          if (has_res) {
+            const F8 r0 = unpack8h<F16>(rh);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) f.v[c] += r0.v[c];
+            if (out_x2) {
+              const F8 r1 = unpack8h<F16>(rl);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) f.v[c] += r1.v[c];
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) f.v[c] = fmaxf(f.v[c], 0.f);
+          }
+          hi = pack8h<F16>(f);
+          {  // a half whose exponent field is all ones: the value left the IEEE-half range (or was NaN)
+            const uint32_t mm = ((hi.x & 0x7fff7fffu) + 0x04000400u) | ((hi.y & 0x7fff7fffu) + 0x04000400u) |
+                                ((hi.z & 0x7fff7fffu) + 0x04000400u) | ((hi.w & 0x7fff7fffu) + 0x04000400u);
+            bad |= (mm & 0x80008000u) != 0;
+          }
+          const F8 h = unpack8h<F16>(hi);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) f.v[c] -= h.v[c];
+          lo = pack8h<F16>(f);
+        };
+        auto emit = [&](int q, const float (&v0)[16], const float (&v1)[16], const Res &r) {
+          const int64_t onat = nat_of(q), ospl = spl_of(q);
+#pragma unroll
+          for (int cb = 0; cb < 2; ++cb) {
+            uint4 h0, l0, h1, l1;
+            cook(v0 + cb * 8, cb, r.h[0][cb], r.l[0][cb], h0, l0);
+            cook(v1 + cb * 8, cb, r.h[1][cb], r.l[1][cb], h1, l1);
+            const int64_t bo = (int64_t)cb * blk_elems;
+            if (p.dbg & 1024) {  // A/B: default cache policy
+              if (!p.skip_y) {
+                ptx::stg_v8(p.y + onat + bo, h0, h1);
+                if (out_x2) ptx::stg_v8(p.y + onat + bo + lo_off, l0, l1);
+              }
+              if (p.y_split) {
+                *reinterpret_cast<uint4 *>(p.y_split + ospl + bo) = h0;
+                *reinterpret_cast<uint4 *>(p.y_split + ospl + bo + sub * 8) = h1;
+                if (out_x2) {
+                  *reinterpret_cast<uint4 *>(p.y_split + ospl + bo + lo_off) = l0;
+                  *reinterpret_cast<uint4 *>(p.y_split + ospl + bo + lo_off + sub * 8) = l1;
+                }
+              }
+              continue;
+            }
+            if (!p.skip_y) {
+              ptx::stg_cs_v8(p.y + onat + bo, h0, h1);
+              if (out_x2) ptx::stg_cs_v8(p.y + onat + bo + lo_off, l0, l1);
+            }
+            if (p.y_split) {
+              ptx::stg_cs_v4(p.y_split + ospl + bo, h0);
+              ptx::stg_cs_v4(p.y_split + ospl + bo + sub * 8, h1);
+              if (out_x2) {
+                ptx::stg_cs_v4(p.y_split + ospl + bo + lo_off, l0);
+                ptx::stg_cs_v4(p.y_split + ospl + bo + lo_off + sub * 8, l1);
+              }
+            }
+          }
+        };
+        float CAR0[16], CAR1[16];   // block 2 of the previous step: what input plane z-1 (kd = 2) contributed to output plane 2z-1
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { CAR0[i] = 0.f; CAR1[i] = 0.f; }
+        for (int z = 0; z < Din; ++z, ++tq) {
+          const uint32_t t = tq % NSLOT;
+          const uint32_t tb0 = tmem_base + lane_addr + t * C::DTR_STRIDE + ci0 * 3 * NT, tb1 = tmem_base + lane_addr + t * C::DTR_STRIDE + ci1 * 3 * NT;
+          Res r;
+          if (live && has_res && z >= 1) rload(r, 2 * z - 1);
+          ptx::mbar_wait(accf_bar(t), (tq / NSLOT) & 1);
+          ptx::tc_fence_after();
+          {
+            uint32_t a0[16], a1[16];
+            ptx::tmem_ld_32x16(tb0, a0);
+            ptx::tmem_ld_32x16(tb1, a1);
+            ptx::tmem_ld_wait();
+            if (live && z >= 1) {
+              float v0[16], v1[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { v0[i] = CAR0[i] + __uint_as_float(a0[i]); v1[i] = CAR1[i] + __uint_as_float(a1[i]); }
+              emit(2 * z - 1, v0, v1, r);
+            }
+          }
+          if (live && has_res) rload(r, 2 * z);
+          {
+            uint32_t b0[16], b1[16], c0[16], c1[16];
+            ptx::tmem_ld_32x16(tb0 + NT, b0);
+            ptx::tmem_ld_32x16(tb1 + NT, b1);
+            ptx::tmem_ld_32x16(tb0 + 2 * NT, c0);
+            ptx::tmem_ld_32x16(tb1 + 2 * NT, c1);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(acce_bar(t));   // the MMA warp may overwrite this buffer
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { CAR0[i] = __uint_as_float(c0[i]); CAR1[i] = __uint_as_float(c1[i]); }
+            if (live) {
+              float v0[16], v1[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { v0[i] = __uint_as_float(b0[i]); v1[i] = __uint_as_float(b1[i]); }
+              emit(2 * z, v0, v1, r);
+            }
+          }
+          if (z == Din - 1 && live) {  // no step z+1: plane 2z+1 is complete with its kd = 2 contribution
+            if (has_res) rload(r, 2 * z + 1);
+            emit(2 * z + 1, CAR0, CAR1, r);
+          }
+        }
+        if (bad && p.range_flag) *p.range_flag = 1;
       }
-      for (int qo = egroup; !C::TRI && !C::S2T && qo < Dout; qo += C::EGROUPS) {
+      for (int qo = egroup; !C::TRI && !C::S2T && !C::DTR && qo < Dout; qo += C::EGROUPS) {
         const uint32_t g = g0 + qo, r = g % NSLOT;
         // residual operands do not depend on the accumulator: request them BEFORE waiting for it (single-precision-word
         // modes only; the split-precision passes load at use)
@@ -1403,6 +1627,7 @@ int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16,
   // Cfg::S2T layout (two-word stride-2 weights, Cin 32, 32-wide blocks): per (kh, kw, k-step) ONE chunk of 192 rows
   // [lo kd1 | hi kd1 | lo kd2 | hi kd2 | hi kd0 | lo kd0]
   const bool s2t = IDISP_S2T && IDISP_TRI && words == 2 && kind == IDISP_CONV_S2 && NT == 32 && cin == 32;
+  const bool dtr = IDISP_DTR && words == 2 && kind == IDISP_DECONV_S2 && NT == 16;   // Cfg::DTR layout (two-word transposed conv, 16-wide blocks)
   const int KS = words * cin / 16, NH = (cout + NT - 1) / NT;  // k-steps per tap: the lo word's follow the hi word's
   const size_t per_nh = (size_t)27 * KS * NT * 16;  // bf16 elements
   // 16-bit storage words (bf16 or IEEE half, same size): convert through cvt()
@@ -1455,6 +1680,23 @@ int tc_weights_prepare(const float *w_tap, int kind, int cin, int cout, int f16,
           {0, 1},                          // e2 shift(1,0): class 1       (ph=1 -> kh=0, pw=0 -> kw=1)
           {0, 2},                          // e3 shift(1,0): class 3       (kh=0, pw=1 with shift_w 0 -> kw=2)
           {0, 0}};                         // e4 shift(1,1): class 3
+      if (dtr) {
+        // Cfg::DTR layout: [ks][2 kcores][27*NT rows][8]; rows = (input shift, class, kd, cout) with the classes in the order
+        // c00 | c10 | c11 | c01 ((ph,pw) of the output voxel) and, inside a class, the three kd (output planes 2z-1, 2z, 2z+1)
+        static const Blk dblocks[9] = {
+            {1, 1}, {2, 1}, {2, 2}, {1, 2},  // shift (0,0): c00, c10, c11, c01
+            {2, 0}, {1, 0},                  // shift (0,1): c11, c01  (pw = 1 -> kw = 0 reads in[w+1])
+            {0, 1}, {0, 2},                  // shift (1,0): c10, c11  (ph = 1 -> kh = 0 reads in[h+1])
+            {0, 0}};                         // shift (1,1): c11
+        for (int ks = 0; ks < KS; ++ks)
+          for (int kc = 0; kc < 2; ++kc)
+            for (int row = 0; row < 27 * NT; ++row)
+              for (int e = 0; e < 8; ++e) {
+                const Blk b = dblocks[row / (3 * NT)];
+                const int kd = (row / NT) % 3;
+                base[(((size_t)ks * 2 + kc) * 27 * NT + row) * 8 + e] = cvt(wv(kd, b.kh, b.kw, ks * 16 + kc * 8 + e, nh * NT + row % NT));
+              }
+      } else
       for (int kd = 0; kd < 3; ++kd)
         for (int ks = 0; ks < KS; ++ks)
           for (int kc = 0; kc < 2; ++kc)
@@ -1569,6 +1811,29 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   p.part_in = opts.part_in; p.part_out = opts.part_out; p.x2 = opts.x2; p.in_blk_stride = blk_stride; p.in_blk_off = opts.in_blk_off;
   p.range_flag = opts.range_flag;
   if (!cv) rmap = map;
+  p.res_map = 0;
+  if (MODE == tc::M_DEC && NT == 16 && fmt == 3 && IDISP_DTR && residual) {
+    // Cfg::DTR: a second map over the residual tensor (output-sized, 2 * Cout/8 blocks per sample) for the producer's L2 prefetches:
+    // one box = the output-plane tile of one CTA column (16 x 32 voxels) x this CTA's two channel blocks of one precision word
+    const int Do = 2 * D, Ho = 2 * H, Wo = 2 * W;
+    const cuuint64_t nblk = (cuuint64_t)B * (opts.x2 ? 2 : 1) * (Cout / 8);
+    const cuuint32_t estr5[5] = {1, 1, 1, 1, 1};
+    CUresult rr;
+    if ((x_is_split >> 1) & 1) {  // parity layout [blk][8 classes][Do/2][Ho/2][Wo/2][8]
+      const cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, 8, nblk};
+      const cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16, (cuuint64_t)8 * D * H * W * 16};
+      const cuuint32_t box[5] = {8 * tc::TW, tc::TH, 1, 4, 2};
+      rr = enc(&rmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16 *>(residual), dims, strides, box, estr5, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      const cuuint64_t dims[4] = {(cuuint64_t)Wo * 8, (cuuint64_t)Ho, (cuuint64_t)Do, nblk};
+      const cuuint64_t strides[3] = {(cuuint64_t)Wo * 16, (cuuint64_t)Ho * Wo * 16, (cuuint64_t)Do * Ho * Wo * 16};
+      const cuuint32_t box[4] = {16 * tc::TW, 2 * tc::TH, 1, 2};
+      rr = enc(&rmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16 *>(residual), dims, strides, box, estr5, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (rr == CUDA_SUCCESS) p.res_map = 1; else rmap = map;   // (prefetching is an optimisation: a shape the map cannot express just goes without)
+  }
   { static int dbg = -1; if (dbg < 0) { const char *e = getenv("IDISP_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   if (MODE == tc::M_S1) { p.Dout = D; p.Ho = H; p.Wo = W; p.Hr = H; p.Wr = W; }
   if (MODE == tc::M_S2) { p.Dout = D / 2; p.Ho = H / 2; p.Wo = W / 2; p.Hr = H / 2; p.Wr = W / 2; }

@@ -36,14 +36,17 @@ constexpr int NVOX = SW * SH;                               // 180 haloed voxels
 constexpr int PLANE_BYTES = NVOX * 16;                      // one channel block of the haloed tile
 constexpr int SROW = 184;                                   // padded row length of the tap-major product buffer
 
-template <bool X2> struct Cfg {
+// OCC = CTAs per SM.  The kernel is bound by memory latency (DRAM 46-50 %, tensor pipe 13 % in the ncu capture): with two
+// resident CTAs (two input stages each, half of TMEM each) a second chain of TMA loads / drains fills the first one's bubbles.
+template <bool X2, int OCC = 1> struct Cfg {
   static constexpr int AW = X2 ? 2 : 1;                     // activation words
   static constexpr int NB = X2 ? 64 : 32;                   // B rows (taps, hi | lo)
   static constexpr int GCOLS = X2 ? 64 : 32;                // TMEM columns of one M half: [main 32 | corrections (x_hi*w_lo + x_lo*w_hi) 32]
   static constexpr int PCOLS = 2 * GCOLS;                   // one plane buffer (two M halves)
   static constexpr int WBYTES = 2 * 2 * NB * 16;            // [2 k-steps][2 kcores][NB rows][8] 16-bit
   static constexpr int STAGE_BYTES = AW * 4 * PLANE_BYTES;  // 4 channel blocks per word
-  static constexpr int STAGES = 4;
+  static constexpr int STAGES = OCC == 2 ? 2 : 4;
+  static constexpr int TCOLS = 512 / OCC;                   // TMEM columns of this CTA (two plane buffers = 2 * PCOLS <= 256)
   static constexpr int RING_PAD = 2048;                     // rows 128..255 of the last block read past the stage
   static constexpr int S_BYTES = 2 * 27 * SROW * 4;         // two product buffers [27 taps][SROW] f32 (group A fills one while B reads the other)
   static constexpr int S_OFF = WBYTES + STAGES * STAGE_BYTES + RING_PAD;
@@ -60,10 +63,10 @@ struct Params {
   int B, D, H, W, tiles_h, tiles_w;
 };
 
-template <bool X2, bool F16>
-__global__ void __launch_bounds__(384, 1) head_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
+template <bool X2, bool F16, int OCC>
+__global__ void __launch_bounds__(384, OCC) head_tc_kernel(const __grid_constant__ CUtensorMap xmap, const Params p)
 {
-  using C = Cfg<X2>;
+  using C = Cfg<X2, OCC>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = ptx::smem_u32(smem);
   const uint32_t w_addr = smem_base, stage0 = smem_base + C::WBYTES, bar0 = smem_base + C::BAR_OFF;
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(384, 1) head_tc_kernel(const __grid_constant__
     for (int t = 0; t < 2; ++t) { ptx::mbar_init(accf_bar(t), 1); ptx::mbar_init(acce_bar(t), 4); }
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc<512>(ptx::smem_u32(tmem_ptr_smem));
+  if (warp == 2) ptx::tmem_alloc<C::TCOLS>(ptx::smem_u32(tmem_ptr_smem));
   {
     const uint4 *src = reinterpret_cast<const uint4 *>(p.w);
     uint4 *dst = reinterpret_cast<uint4 *>(smem);
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(384, 1) head_tc_kernel(const __grid_constant__
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
+  if (warp == 2) ptx::tmem_dealloc<C::TCOLS>(tmem_base);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -319,7 +322,10 @@ int tc_head_conv(const TcHeadWeights &w, const __nv_bfloat16 *x, int B, int D, i
   static int sm_count[64];
   if (dev < 0 || dev >= 64) { set_error("tc_head_conv: device ordinal %d out of range", dev); return IDISP_ERR_INVALID; }
   if (!sm_count[dev]) cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
-  const int grid = ncols < sm_count[dev] ? ncols : sm_count[dev];
+  static int occ2 = -1;   // two CTAs per SM (default); IDISP_HEAD_OCC1=1: the one-CTA form (four input stages)
+  if (occ2 < 0) { const char *e = getenv("IDISP_HEAD_OCC1"); occ2 = (e && e[0] == '1') ? 0 : 1; }
+  const int slots = sm_count[dev] * (occ2 ? 2 : 1);
+  const int grid = ncols < slots ? ncols : slots;
   auto go = [&](auto kern, int smem_bytes, bool *opted) -> int {
     if (!opted[dev]) {
       IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -329,10 +335,15 @@ int tc_head_conv(const TcHeadWeights &w, const __nv_bfloat16 *x, int B, int D, i
     IDISP_LAUNCH_CHECK();
     return IDISP_OK;
   };
-  static bool o0[64], o1[64], o2[64];
-  if (w.x2) return go(headtc::head_tc_kernel<true, true>, headtc::Cfg<true>::SMEM, o0);
-  if (w.f16) return go(headtc::head_tc_kernel<false, true>, headtc::Cfg<false>::SMEM, o1);
-  return go(headtc::head_tc_kernel<false, false>, headtc::Cfg<false>::SMEM, o2);
+  static bool o0[64], o1[64], o2[64], o3[64], o4[64], o5[64];
+  if (occ2) {
+    if (w.x2) return go(headtc::head_tc_kernel<true, true, 2>, headtc::Cfg<true, 2>::SMEM, o3);
+    if (w.f16) return go(headtc::head_tc_kernel<false, true, 2>, headtc::Cfg<false, 2>::SMEM, o4);
+    return go(headtc::head_tc_kernel<false, false, 2>, headtc::Cfg<false, 2>::SMEM, o5);
+  }
+  if (w.x2) return go(headtc::head_tc_kernel<true, true, 1>, headtc::Cfg<true, 1>::SMEM, o0);
+  if (w.f16) return go(headtc::head_tc_kernel<false, true, 1>, headtc::Cfg<false, 1>::SMEM, o1);
+  return go(headtc::head_tc_kernel<false, false, 1>, headtc::Cfg<false, 1>::SMEM, o2);
 }
 
 }  // namespace idisp

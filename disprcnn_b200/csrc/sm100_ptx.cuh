@@ -70,6 +70,51 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uin
 
 // ---------------- TMA (cp.async.bulk.tensor, tiled mode) ----------------
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// `bytes` (multiple of 16, 16 B aligned) of global memory -> L2, asynchronously, no register or shared-memory destination
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// tiled TMA prefetch: the box at the given coordinates -> L2 (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *m, int c0, int c1, int c2, int c3)
+{
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap *m, int c0, int c1, int c2, int c3, int c4)
+{
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+// 256-bit global accesses (sm_100: LDG / STG .256), 32-byte aligned
+struct __align__(32) U8 { uint4 a, b; };
+__device__ __forceinline__ U8 ldg_v8(const void *p)
+{
+  U8 r;
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_v8(void *p, const uint4 &a, const uint4 &b)
+{
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+               "r"(b.z), "r"(b.w)
+               : "memory");
+}
+// streaming (evict-first) forms: output that no CTA of this launch reads again
+__device__ __forceinline__ void stg_cs_v8(void *p, const uint4 &a, const uint4 &b)
+{
+  asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+               "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void stg_cs_v4(void *p, const uint4 &a)
+{
+  asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w) : "memory");
+}
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *m)
 {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
