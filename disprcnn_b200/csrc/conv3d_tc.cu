@@ -353,21 +353,6 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
               ptx::tma_load_4d(stage_addr0 + s * C::STAGE_BYTES, &xmap, full_bar(s), (tw * TW - halo) * 8, th * TH - halo, z, n * p.in_blk_stride + p.in_blk_off);
             }
-            if constexpr (C::DTR) {
-              // The epilogue adds a residual tensor of the output's size; its loads were the layer's critical path (DRAM latency in a
-              // dependent chain per output plane).  The producer runs two to four steps ahead of the epilogue: it asks L2 for the
-              // residual boxes of the two output planes (2z, 2z+1) this input plane completes / opens -- one tiled TMA prefetch per
-              // plane and precision word (16 KB each), so the epilogue's loads are L2 hits.  (Per-row bulk prefetches, 512 per step,
-              // made the layer 2x SLOWER: the TMA unit is bound by operation count.)
-              if (p.res_map && lead && !(p.dbg & 256)) {
-                const int cblk_out = p.Cout / 8, out_blocks = p.x2 ? 2 * cblk_out : cblk_out;
-                for (int i = 0; i < (p.x2 ? 4 : 2); ++i) {
-                  const int qo = 2 * z + (i & 1), blk = n * out_blocks + nh * 2 + (i >> 1) * cblk_out;
-                  if (p.residual_is_split) ptx::tma_prefetch_5d(&rmap, tw * TW * 8, th * TH, qo >> 1, (qo & 1) * 4, blk);
-                  else ptx::tma_prefetch_4d(&rmap, 2 * tw * TW * 8, 2 * th * TH, qo, blk);
-                }
-              }
-            }
             ++q;
           }
         }
@@ -575,6 +560,21 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           const uint64_t a0 = desc_add(a_desc0, s * C::STAGE_BYTES);
           int ncol = col, nz = z + 1;
           if (nz == Din) { nz = 0; ncol += ncta; }
+          // The epilogue adds a residual tensor of the output's size; its loads are the layer's critical path.  Ask L2 for the
+          // residual boxes of output planes 2z and 2z+1 now -- one tiled TMA prefetch per plane and precision word (16 KB each) --
+          // one MMA step (plus the epilogue's lag) before the epilogue reads them.  Measured: issued from the producer warp (2-4
+          // steps = 12-25 us earlier) the lines were evicted again before their use (the layer streams ~5 TB/s through the 126 MB
+          // L2: DRAM reads rose from 3.5 to 5.8 GB, no speed-up); per-row bulk prefetches (512 per step) made the layer 2x slower.
+          if (p.res_map && lead && !(p.dbg & 256)) {
+            const int tw = col % p.tiles_w, th = (col / p.tiles_w) % p.tiles_h, n = col / (p.tiles_w * p.tiles_h);
+            const int cblk_out = p.Cout / 8, out_blocks = p.x2 ? 2 * cblk_out : cblk_out;
+            for (int i = 0; i < (p.x2 ? 4 : 2); ++i) {
+              const int qo = 2 * z + (i & 1), blk = n * out_blocks + nh * 2 + (i >> 1) * cblk_out;
+              if (p.residual_is_split) ptx::tma_prefetch_5d(&rmap, tw * TW * 8, th * TH, qo >> 1, (qo & 1) * 4, blk);
+              else ptx::tma_prefetch_4d(&rmap, 2 * tw * TW * 8, 2 * th * TH, qo, blk);
+            }
+          }
+          __syncwarp();
 #pragma unroll
           for (int ks = 0; ks < C::KSM; ++ks) {
             if (ks == C::KSM / 2) waits(ncol, q + 1);
@@ -1186,7 +1186,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         for (int z = 0; z < Din; ++z, ++tq) {
           const uint32_t t = tq % NSLOT;
           const uint32_t tb0 = tmem_base + lane_addr + t * C::DTR_STRIDE + ci0 * 3 * NT, tb1 = tmem_base + lane_addr + t * C::DTR_STRIDE + ci1 * 3 * NT;
-          Res r;
+          Res r, r2;
           if (live && has_res && z >= 1) rload(r, 2 * z - 1);
           ptx::mbar_wait(accf_bar(t), (tq / NSLOT) & 1);
           ptx::tc_fence_after();
@@ -1194,6 +1194,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             uint32_t a0[16], a1[16];
             ptx::tmem_ld_32x16(tb0, a0);
             ptx::tmem_ld_32x16(tb1, a1);
+            if (live && has_res) rload(r2, 2 * z);   // (in flight during the per-voxel work of plane 2z-1)
             ptx::tmem_ld_wait();
             if (live && z >= 1) {
               float v0[16], v1[16];
@@ -1202,7 +1203,6 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               emit(2 * z - 1, v0, v1, r);
             }
           }
-          if (live && has_res) rload(r, 2 * z);
           {
             uint32_t b0[16], b1[16], c0[16], c1[16];
             ptx::tmem_ld_32x16(tb0 + NT, b0);
@@ -1219,7 +1219,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               float v0[16], v1[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) { v0[i] = __uint_as_float(b0[i]); v1[i] = __uint_as_float(b1[i]); }
-              emit(2 * z, v0, v1, r);
+              emit(2 * z, v0, v1, r2);
             }
           }
           if (z == Din - 1 && live) {  // no step z+1: plane 2z+1 is complete with its kd = 2 contribution
