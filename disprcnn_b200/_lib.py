@@ -98,6 +98,8 @@ PROTOTYPES = {
     'idisp_plan_range_exceeded': (_i, [_vp, ctypes.POINTER(ctypes.c_int), _vp]),
     'idisp_plan_forward': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp, _vp]),
     'idisp_plan_forward_host': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    'idisp_plan_forward_host_async': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, ctypes.POINTER(ctypes.c_ulonglong)]),
+    'idisp_plan_host_wait': (_i, [_vp, ctypes.c_ulonglong]),
     'idisp_plan_get_logits': (_i, [_vp, _vp, _vp]),
     'idisp_plan_launches_per_forward': (_i, [_vp]),
     'idisp_plan_graph_stats': (_i, [_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),

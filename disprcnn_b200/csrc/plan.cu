@@ -104,6 +104,12 @@ struct idisp_plan {
   // host-buffer entry point staging
   void *stage = nullptr;
   size_t stage_bytes = 0;
+  // pipelined host-buffer entry point (idisp_plan_forward_host_async): copy streams, per-slot events, double-buffered staging
+  void *pstage = nullptr;
+  size_t pstage_bytes = 0;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  unsigned long long n_async = 0, async_base = 0;   // calls issued; first call that used the current staging allocation
   // optional per-launch CUDA-event timing (bench.py's roofline leg)
   int *range_flag = nullptr;  // device int: an fp16-mode forward saw a value outside the IEEE-half range
   bool timing = false;
@@ -157,6 +163,14 @@ extern "C" void idisp_plan_destroy(idisp_plan_t *p)
   if (p->blob) cudaFree(p->blob);
   if (p->range_flag) cudaFree(p->range_flag);
   if (p->stage) cudaFree(p->stage);
+  if (p->pstage) cudaFree(p->pstage);
+  if (p->s_in) cudaStreamDestroy(p->s_in);
+  if (p->s_out) cudaStreamDestroy(p->s_out);
+  for (int i = 0; i < 2; ++i) {
+    if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
+    if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]);
+    if (p->ev_out[i]) cudaEventDestroy(p->ev_out[i]);
+  }
   delete p;
 }
 
@@ -562,6 +576,76 @@ extern "C" int idisp_plan_forward_host(idisp_plan_t *p, const float *left_host, 
   int rc = idisp_plan_forward(p, dl, dr, B, Hf, Wf, H, W, wsp, ws, dout, stream);
   if (rc) return rc;
   IDISP_CUDA(cudaMemcpyAsync(out_host, dout, outb, cudaMemcpyDeviceToHost, s));
+  return IDISP_OK;
+}
+
+// Pipelined host-buffer call for a STREAM of batches (the reference's data loader hands DispRCNN3D one batch after another,
+// engine/inference.py:24-50).  Call i uses staging slot i & 1:
+//   copy-in stream : wait "kernels of call i-2 done"  -> H2D left/right -> record in[slot]
+//   caller's stream: wait in[slot], wait "result copy of call i-2 done" -> forward -> record done[slot]
+//   copy-out stream: wait done[slot] -> D2H result -> record out[slot]
+// so the H2D of call i overlaps the kernels of call i-1 and the D2H of call i overlaps the kernels of call i+1; the kernels
+// themselves stay serialised on the caller's stream (one workspace).  Nothing blocks the host here.
+extern "C" int idisp_plan_forward_host_async(idisp_plan_t *p, const float *left_host, const float *right_host, int B, int Hf, int Wf,
+                                             int H, int W, float *out_host, void *stream, unsigned long long *ticket)
+{
+  IDISP_REQUIRE(p != nullptr && ticket != nullptr, "plan_forward_host_async: NULL plan / ticket");
+  IDISP_REQUIRE(left_host && right_host && out_host && B > 0 && Hf > 0 && Wf > 0 && H > 0 && W > 0, "plan_forward_host_async: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!p->s_in) {
+    IDISP_CUDA(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+    IDISP_CUDA(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      IDISP_CUDA(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
+      IDISP_CUDA(cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming));
+      IDISP_CUDA(cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
+    }
+  }
+  const size_t fea = (size_t)B * p->C * Hf * Wf * sizeof(float), outb = (size_t)B * H * W * sizeof(float);
+  const size_t ws = idisp_plan_workspace_bytes(p, B, Hf, Wf);
+  auto up = [](size_t x) { return (x + 1023) / 1024 * 1024; };
+  const size_t slot_bytes = 2 * up(fea) + up(outb), total = 2 * slot_bytes + ws;
+  if (total > p->pstage_bytes) {  // (re)allocation: drain everything that may still use the old staging
+    IDISP_CUDA(cudaStreamSynchronize(p->s_in));
+    IDISP_CUDA(cudaStreamSynchronize(s));
+    IDISP_CUDA(cudaStreamSynchronize(p->s_out));
+    if (p->pstage) cudaFree(p->pstage);
+    p->pstage = nullptr; p->pstage_bytes = 0;
+    IDISP_CUDA(cudaMalloc(&p->pstage, total));
+    p->pstage_bytes = total;
+    p->async_base = p->n_async;   // no earlier call owns a slot of the new buffer
+  }
+  const unsigned long long i = p->n_async;
+  const int slot = (int)(i & 1);
+  char *base = (char *)p->pstage + (size_t)slot * slot_bytes;
+  float *dl = (float *)base, *dr = (float *)(base + up(fea)), *dout = (float *)(base + 2 * up(fea));
+  void *wsp = (char *)p->pstage + 2 * slot_bytes;
+  const bool reuse = i - p->async_base >= 2;   // the slot's previous owner (call i-2) may still be in flight
+  if (reuse) IDISP_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_done[slot], 0));
+  IDISP_CUDA(cudaMemcpyAsync(dl, left_host, fea, cudaMemcpyHostToDevice, p->s_in));
+  IDISP_CUDA(cudaMemcpyAsync(dr, right_host, fea, cudaMemcpyHostToDevice, p->s_in));
+  IDISP_CUDA(cudaEventRecord(p->ev_in[slot], p->s_in));
+  IDISP_CUDA(cudaStreamWaitEvent(s, p->ev_in[slot], 0));
+  if (reuse) IDISP_CUDA(cudaStreamWaitEvent(s, p->ev_out[slot], 0));
+  const int rc = idisp_plan_forward(p, dl, dr, B, Hf, Wf, H, W, wsp, ws, dout, stream);
+  if (rc) return rc;
+  IDISP_CUDA(cudaEventRecord(p->ev_done[slot], s));
+  IDISP_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_done[slot], 0));
+  IDISP_CUDA(cudaMemcpyAsync(out_host, dout, outb, cudaMemcpyDeviceToHost, p->s_out));
+  IDISP_CUDA(cudaEventRecord(p->ev_out[slot], p->s_out));
+  *ticket = i;
+  p->n_async = i + 1;
+  return IDISP_OK;
+}
+
+// Blocks the host until the result of the call that returned `ticket` has landed in its out_host buffer.
+extern "C" int idisp_plan_host_wait(idisp_plan_t *p, unsigned long long ticket)
+{
+  IDISP_REQUIRE(p != nullptr, "plan_host_wait: NULL plan");
+  IDISP_REQUIRE(ticket < p->n_async, "plan_host_wait: ticket %llu was never issued by this plan", ticket);
+  // (the slot's event may already have been re-recorded by call ticket+2: the copy-out stream is in order, so that later
+  //  record completing implies this call's copy has completed)
+  IDISP_CUDA(cudaEventSynchronize(p->ev_out[ticket & 1]));
   return IDISP_OK;
 }
 

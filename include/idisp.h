@@ -163,6 +163,16 @@ int idisp_plan_range_exceeded(idisp_plan_t *plan, int *exceeded, void *stream);
  * all enqueued on `stream`; the plan owns and grows the device staging + workspace. */
 int idisp_plan_forward_host(idisp_plan_t *plan, const float *left_host, const float *right_host,
                             int B, int Hf, int Wf, int H, int W, float *out_host, void *stream);
+/* Pipelined form for a stream of batches (the reference's loader feeds DispRCNN3D batch after batch, engine/inference.py:24-50):
+ * the host->device copy of this call's inputs runs on a plan-owned copy stream and overlaps the kernels of the previous call
+ * still running on `stream`; the device->host copy of the result runs on a second copy stream and overlaps the next call's
+ * kernels.  Device staging is double-buffered (slot = call parity); the kernels of successive calls stay ordered on `stream`.
+ * Never blocks the host.  *ticket identifies the call: out_host (and left_host / right_host for reuse) belong to the library
+ * until idisp_plan_host_wait(plan, ticket) has returned. */
+int idisp_plan_forward_host_async(idisp_plan_t *plan, const float *left_host, const float *right_host, int B, int Hf,
+                                  int Wf, int H, int W, float *out_host, void *stream, unsigned long long *ticket);
+/* Blocks the calling host thread until the result of the call that returned `ticket` is in its out_host buffer. */
+int idisp_plan_host_wait(idisp_plan_t *plan, unsigned long long ticket);
 /* Debug/test hook: copy the low-resolution logits cost3 [B,D,Hf,Wf] f32 of the last
  * idisp_plan_forward on this plan into a device buffer. */
 int idisp_plan_get_logits(idisp_plan_t *plan, float *logits, void *stream);

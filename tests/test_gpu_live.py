@@ -112,6 +112,36 @@ def test_host_buffer_entry_point_parity(lib, name, prec):
     assert e < TOL
 
 
+def test_pipelined_host_entry_point_matches_one_batch_at_a_time(lib):
+    """idisp_plan_forward_host_async / idisp_plan_host_wait (the call bench.py's e2e number goes through): five batches in
+    flight back to back -- two staging slots, so slots are reused while earlier copies may still be running -- each result
+    bit-identical to the device-pointer entry on the same inputs, whatever order the host waits in."""
+    import ctypes
+    from disprcnn_b200 import _lib
+    case, g, sd, L, R = load_case('live')
+    m = make_psmnet(case, sd, 'fp16x2')
+    B, Hf, Wf = case['B'], case['Hf'], case['Wf']
+    scales = [1.0, 0.5, 2.0, 0.25, 1.5]
+    ins = [((L * a).contiguous().pin_memory(), (R * a).contiguous().pin_memory()) for a in scales]
+    with torch.no_grad():
+        want = [m.forward_features(a.cuda(), b.cuda()).cpu() for a, b in ins]
+    outs = [torch.full((B, 4 * Hf, 4 * Wf), float('nan')).pin_memory() for _ in scales]
+    tickets = []
+    for (a, b), o in zip(ins, outs):
+        t = ctypes.c_ulonglong()
+        _lib.check(lib.idisp_plan_forward_host_async(m._plan, _lib.ptr(a), _lib.ptr(b), B, Hf, Wf, 4 * Hf, 4 * Wf, _lib.ptr(o),
+                                                     _lib.stream_ptr(), ctypes.byref(t)))
+        tickets.append(t.value)
+    assert tickets == list(range(tickets[0], tickets[0] + len(scales)))
+    for k in (2, 0, 4, 1, 3):
+        _lib.check(lib.idisp_plan_host_wait(m._plan, tickets[k]))
+        assert torch.equal(outs[k], want[k]), f'batch {k}'
+    assert np.abs(outs[0].numpy() - g['pred_up']).max() < TOL
+    with pytest.raises(RuntimeError):
+        _lib.check(lib.idisp_plan_host_wait(m._plan, tickets[-1] + 1))   # never issued
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize('name', ['raw_tiny', 'raw_live'])
 def test_default_initialised_weights(lib, name):
     """Raw default initialisation (stackhourglass.py:90-104): logits of std ~15, where the reference's OWN fp32 forward is
