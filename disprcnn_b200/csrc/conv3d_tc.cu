@@ -192,9 +192,11 @@ struct Params {
   int x2;                         // final pass: y / residual / y_split carry 2*Cout/8 blocks per sample (hi | lo)
   int *range_flag;                // optional device int: set to 1 when a value to be stored as IEEE half exceeds its range
   int in_blk_stride, in_blk_off;  // channel blocks per input sample in memory, and which block this launch's channels start at
+  int in_lo_off;                  // != 0: the lo group of this launch's channels starts that many blocks after its hi group (two TMA boxes per stage)
   int B, Din, Dout, Ho, Wo, Hr, Wr, Cout, relu;  // (Hr,Wr): row grid the 8x16 tiles cover
   int tiles_h, tiles_w, nh;
   int cv_shift0;                  // mindisp/4: plane k <-> right-view shift i = k + cv_shift0
+  int cv_view;                    // CV == 2: which view this launch reads (0 left, 1 right)
   int dbg;                        // timing experiments only (IDISP_TC_DBG): 1 no MMAs, 2 no TMA loads, 4 no global stores, 8 no tcgen05.ld, 16 no tcgen05.st, 32 TRI epilogue = handshake only, 64 TRI epilogue without the per-voxel work, 128 TRI epilogue without TMEM reads, 256 DTR without the residual L2 prefetch, 512 DTR without residual loads
 };
 
@@ -230,10 +232,10 @@ __device__ __forceinline__ F8 unpack8(const uint4 &a)
 // TMA box lands [left: hi, lo][right: hi, lo], so the logical block order (left, right) is permuted.
 template <int XP, int KS> __host__ __device__ constexpr int xp_a_word(int kk) { return XP == 0 ? 0 : (XP == 1 ? ((kk >= KS && kk < 2 * KS) ? 1 : 0) : kk / KS); }
 template <int XP, int KS> __host__ __device__ constexpr int xp_b_step(int kk) { return XP == 0 ? kk : (XP == 1 ? (kk < KS ? kk : kk - KS) : kk % KS); }
-template <int XP, int KS, bool CV, int PLANE> __host__ __device__ constexpr uint32_t xp_a_off(int kk)
+template <int XP, int KS, int CV, int PLANE> __host__ __device__ constexpr uint32_t xp_a_off(int kk)
 {
   const int word = xp_a_word<XP, KS>(kk), blk = 2 * (kk % KS), cblk = 2 * KS, h = cblk / 2;
-  const int phys = (CV && XP) ? ((blk < h ? blk : blk + h) + word * h) : word * cblk + blk;
+  const int phys = (CV == 1 && XP) ? ((blk < h ? blk : blk + h) + word * h) : word * cblk + blk;
   return (uint32_t)(phys * PLANE);
 }
 
@@ -243,10 +245,12 @@ struct XPre { float4 p0, p1; uint4 rh, rl; };
 __device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t byte_off) { return d + (uint64_t)(byte_off >> 4); }
 
 // FMT: 0 bf16, 1 IEEE half, 2 IEEE half split-precision pass (plain K), 3 / 4 the same with in-launch K concatenation XP = 1 / 2
-template <int CIN, int MODE, int OCC, bool CV, int NT, int FMT>
+// CV: 0 plain input tensor; 1 fused cost volume, both views (Cin = 2C); 2 fused cost volume, ONE view (Cin = C: the box lands
+//     that view's [hi blocks | lo blocks], i.e. the plain stage layout -- Params::cv_view selects left / right)
+template <int CIN, int MODE, int OCC, int CV, int NT, int FMT>
 __global__ void __launch_bounds__((Cfg<CIN, MODE, OCC, NT, (FMT < 2 ? 0 : (FMT == 2 ? 3 : FMT - 2))>::NTHREADS), OCC)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap rmap,
-                 const __grid_constant__ CvMaps<CV> lmaps, const Params p)
+                 const __grid_constant__ CvMaps<(CV != 0)> lmaps, const Params p)
 {
   constexpr int XM = FMT < 2 ? 0 : (FMT == 2 ? 3 : FMT - 2);
   using C = Cfg<CIN, MODE, OCC, NT, XM>;
@@ -326,9 +330,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               if (lead && (p.dbg & 2)) ptx::mbar_arrive(full_bar(s));
               else if (lead) {
                 ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
-                for (int pw = 0; pw < 2; ++pw)
+                for (int pw = 0; pw < 2; ++pw) {
                   ptx::tma_load_5d(stage_addr0 + s * C::STAGE_BYTES + pw * C::SUB_BYTES, &xmap, full_bar(s), (tw * TW - 1) * 8,
                                    th * TH - 1, z >> 1, (z & 1) * 4 + ph * 2 + pw, n * p.in_blk_stride + p.in_blk_off);
+                  if (XP != 0 && p.in_lo_off)   // channel subset of a wider tensor: its lo blocks are not adjacent to its hi blocks
+                    ptx::tma_load_5d(stage_addr0 + s * C::STAGE_BYTES + pw * C::SUB_BYTES + C::CBLK * C::PLANE_BYTES, &xmap, full_bar(s), (tw * TW - 1) * 8,
+                                     th * TH - 1, z >> 1, (z & 1) * 4 + ph * 2 + pw, n * p.in_blk_stride + p.in_blk_off + p.in_lo_off);
+                }
               }
             }
           } else {
@@ -345,13 +353,16 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               const int i = z + p.cv_shift0;
               const bool dead = i >= p.Wo || -i >= p.Wo;  // fully masked plane: read far out of range (all zero fill)
               ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
-              if constexpr (CV)
+              if constexpr (CV != 0)
                 ptx::tma_load_4d(stage_addr0 + s * C::STAGE_BYTES, &lmaps.m[z], full_bar(s), dead ? -(1 << 20) : (tw * TW - 1 - (i > 0 ? i : 0)) * 8,
-                                 th * TH - 1, n * p.in_blk_stride + p.in_blk_off, 0);
+                                 th * TH - 1, n * p.in_blk_stride + p.in_blk_off, CV == 2 ? p.cv_view : 0);
               }
             } else if (lead) {
               ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
               ptx::tma_load_4d(stage_addr0 + s * C::STAGE_BYTES, &xmap, full_bar(s), (tw * TW - halo) * 8, th * TH - halo, z, n * p.in_blk_stride + p.in_blk_off);
+              if (XP != 0 && p.in_lo_off)   // channel subset of a wider tensor: its lo blocks are not adjacent to its hi blocks
+                ptx::tma_load_4d(stage_addr0 + s * C::STAGE_BYTES + C::CBLK * C::PLANE_BYTES, &xmap, full_bar(s), (tw * TW - halo) * 8, th * TH - halo, z,
+                                 n * p.in_blk_stride + p.in_blk_off + p.in_lo_off);
             }
             ++q;
           }
@@ -1745,7 +1756,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
 {
   using C = tc::Cfg<CIN, MODE, OCC, NT>;
   const int aw = opts.xp ? 2 : 1;  // activation words one TMA box fetches (hi|lo block groups are adjacent in memory)
-  const int blk_stride = opts.in_blk_stride > 0 ? opts.in_blk_stride : (cv ? C::CBLK / 2 : C::CBLK);  // blocks per input sample
+  const int blk_stride = opts.in_blk_stride > 0 ? opts.in_blk_stride : (cv && cv->view < 0 ? C::CBLK / 2 : C::CBLK);  // blocks per input sample (and view)
   using MC = tc::ModeCfg<MODE>;
   tc::EncodeTiledFn enc = tc::get_encode();
   if (!enc) { set_error("tc_conv3d: cuTensorMapEncodeTiled not available from the driver"); return IDISP_ERR_CUDA; }
@@ -1770,17 +1781,18 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
     const int D2 = D / 2, H2 = H / 2, W2 = W / 2;
     const cuuint64_t dims[5] = {(cuuint64_t)W2 * 8, (cuuint64_t)H2, (cuuint64_t)D2, 8, (cuuint64_t)B * blk_stride};
     const cuuint64_t strides[4] = {(cuuint64_t)W2 * 16, (cuuint64_t)H2 * W2 * 16, (cuuint64_t)D2 * H2 * W2 * 16, (cuuint64_t)8 * D2 * H2 * W2 * 16};
-    const cuuint32_t box[5] = {8 * MC::SUB_W, (cuuint32_t)sub_h, 1, 1, (cuuint32_t)(aw * C::CBLK)};
+    const cuuint32_t box[5] = {8 * MC::SUB_W, (cuuint32_t)sub_h, 1, 1, (cuuint32_t)((opts.in_lo_off ? 1 : aw) * C::CBLK)};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else if (cv) {
     // fused cost volume: x is unused; one 4-D map per plane over {left, right} x [B*C/8] x [Hf] x [(Wf-|i|)*8]
-    const int halfblk = C::CBLK / 2;
+    const bool one_view = cv->view >= 0;
+    const int halfblk = one_view ? C::CBLK : C::CBLK / 2;   // channel blocks of one view (per precision word)
     if (D > tc::CV_MAX_PLANES) { set_error("tc_conv3d: fused cost volume supports at most %d planes", tc::CV_MAX_PLANES); return IDISP_ERR_INVALID; }
     const int64_t lr_bytes = (const char *)cv->right - (const char *)cv->left;
     if (lr_bytes <= 0 || lr_bytes % 16) { set_error("tc_conv3d: right features must follow the left ones in memory (16 B aligned)"); return IDISP_ERR_INVALID; }
-    const cuuint32_t box[4] = {8 * MC::SUB_W, MC::SUB_H, (cuuint32_t)(aw * halfblk), 2};
+    const cuuint32_t box[4] = {8 * MC::SUB_W, MC::SUB_H, (cuuint32_t)(aw * halfblk), one_view ? 1u : 2u};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     r = CUDA_SUCCESS;
     for (int k = 0; r == CUDA_SUCCESS && k < D; ++k) {
@@ -1798,7 +1810,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
     // (8 ch, W) are contiguous in the blocked layout -> ONE tensor dimension of 8*W elements: a box row is SUB_W voxels x 16 B
     const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B * blk_stride};
     const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
-    const cuuint32_t box[4] = {8 * MC::SUB_W, MC::SUB_H, 1, (cuuint32_t)(aw * C::CBLK)};
+    const cuuint32_t box[4] = {8 * MC::SUB_W, MC::SUB_H, 1, (cuuint32_t)((opts.in_lo_off ? 1 : aw) * C::CBLK)};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1807,8 +1819,8 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   tc::Params p;
   p.w = (const __nv_bfloat16 *)w.dev; p.bias = bias; p.residual = residual; p.y = y; p.res1 = res1; p.y1 = y1; p.y_split = y_split; p.residual_is_split = (x_is_split >> 1) & 1; p.skip_y = (x_is_split >> 2) & 1;
   p.B = B; p.Din = D; p.Cout = Cout; p.relu = relu; p.y1_cols = w.ncat ? 2 : 1;
-  p.cv_shift0 = cv ? cv->shift0 : 0;
-  p.part_in = opts.part_in; p.part_out = opts.part_out; p.x2 = opts.x2; p.in_blk_stride = blk_stride; p.in_blk_off = opts.in_blk_off;
+  p.cv_shift0 = cv ? cv->shift0 : 0; p.cv_view = cv && cv->view > 0 ? 1 : 0;
+  p.part_in = opts.part_in; p.part_out = opts.part_out; p.x2 = opts.x2; p.in_blk_stride = blk_stride; p.in_blk_off = opts.in_blk_off; p.in_lo_off = opts.in_lo_off;
   p.range_flag = opts.range_flag;
   if (!cv) rmap = map;
   p.res_map = 0;
@@ -1851,12 +1863,14 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   const int grid = per_slice * p.nh;
   auto go = [&](auto fmt_c, auto cv_c) -> int {
     constexpr int FMT = decltype(fmt_c)::value;
-    constexpr bool CVK = decltype(cv_c)::value;
+    constexpr int CVK = decltype(cv_c)::value;
     constexpr int XP = FMT == 3 ? 1 : (FMT == 4 ? 2 : 0);
     // in-launch K concatenation exists where its shared-memory budget closes (see Cfg)
     constexpr bool ok = (XP == 0 && (MODE != tc::M_DEC || NT == 32)) || (XP == 1 && CIN == 32 && OCC == 1 && NT <= 32 && MODE != tc::M_DEC) ||
                         (XP == 1 && MODE == tc::M_DEC && NT == 16) || (XP == 2 && (CIN == 64 || NT == 16) && OCC == 1 && MODE != tc::M_S2);
-    if constexpr (!ok) {
+    // (the one-view cost-volume loader exists for the launches that use it: the two halves of the K-split first layer)
+    constexpr bool ok1 = CVK != 2 || (CIN == 32 && FMT == 3 && NT == 32 && OCC == 1 && MODE == tc::M_S1);
+    if constexpr (!ok || !ok1) {
       set_error("tc_conv3d: K-concatenation mode %d not built for Cin=%d mode=%d", XP, CIN, MODE);
       return IDISP_ERR_UNSUPPORTED;
     } else {
@@ -1867,7 +1881,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
         IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CX::SMEM));
         smem_opt_in[dev] = true;
       }
-      if constexpr (CVK) kern<<<grid, CX::NTHREADS, CX::SMEM, s>>>(map, rmap, cvmaps, p);
+      if constexpr (CVK != 0) kern<<<grid, CX::NTHREADS, CX::SMEM, s>>>(map, rmap, cvmaps, p);
       else kern<<<grid, CX::NTHREADS, CX::SMEM, s>>>(map, rmap, tc::CvMaps<false>{}, p);
       return IDISP_OK;
     }
@@ -1885,9 +1899,9 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   int lrc = IDISP_OK;
   bool launched = false;
   if constexpr (MODE == tc::M_S1) {
-    if (cv) { lrc = by_fmt(std::true_type{}); launched = true; }
+    if (cv) { lrc = cv->view >= 0 ? by_fmt(std::integral_constant<int, 2>{}) : by_fmt(std::integral_constant<int, 1>{}); launched = true; }
   }
-  if (!launched) lrc = by_fmt(std::false_type{});
+  if (!launched) lrc = by_fmt(std::integral_constant<int, 0>{});
   if (lrc) return lrc;
   IDISP_LAUNCH_CHECK();
   return IDISP_OK;
@@ -1899,6 +1913,7 @@ int tc_conv3d(const TcWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D,
 {
   const TcOpts opts = optsp ? *optsp : TcOpts();
   if (cv && (kind != IDISP_CONV_S1 || !cv->left || !cv->right)) { set_error("tc_conv3d: bad fused cost-volume arguments"); return IDISP_ERR_INVALID; }
+  if (opts.in_lo_off && (kind == IDISP_DECONV_S2 || cv || !opts.xp)) { set_error("tc_conv3d: a separate lo-group offset exists for (strided) convolution K-concatenation launches only"); return IDISP_ERR_INVALID; }
   if (opts.xp < 0 || opts.xp > 2 || w.words != (opts.xp == 1 ? 2 : 1) || (opts.xp && !w.f16)) { set_error("tc_conv3d: weights do not match K-concatenation mode %d", opts.xp); return IDISP_ERR_INVALID; }
   if (!tc_supported(kind, Cin, Cout, D, H, W) || !w.dev || w.cin != Cin || w.cout != Cout || w.kind != kind) {
     set_error("tc_conv3d: layer (kind=%d, %d->%d) not prepared for the tensor-core path", kind, Cin, Cout);
@@ -1945,7 +1960,24 @@ static int split_launches(int kind, int cin)
   return 3;
 }
 
-void tc_split_weights_free(TcSplitWeights &w) { tc_weights_free(w.hi); tc_weights_free(w.lo); tc_weights_free(w.both); }
+void tc_split_weights_free(TcSplitWeights &w) { tc_weights_free(w.hi); tc_weights_free(w.lo); tc_weights_free(w.both); tc_weights_free(w.k0); tc_weights_free(w.k1); }
+
+// Stride-1 Cin = 64 layers, K split (default; IDISP_NO_KSPLIT=1 restores the term split).  Both weight words of all 64 input channels
+// do not fit in shared memory (2 x 110 KB), so the layer was two launches split by TERM: x_hi*w_lo -> fp32 partial, then
+// (x_hi, x_lo)*w_hi + partial (168 port cycles per tap and 16 input channels, two- or three-deep input ring).  Split by INPUT CHANNELS
+// instead, each launch is a complete 32 -> Cout split-precision convolution of one channel half (both words resident, the merged
+// x_hi*[w_hi | w_lo] MMA of Cfg::MRG: 152 port cycles, five-deep ring), chained through the same fp32 partial.
+static bool ksplit_enabled()
+{
+  static const int off = tc::env_flag("IDISP_NO_KSPLIT");
+  return !off;
+}
+static bool ksplit_layer(int kind, int cin, int cout)
+{
+  if (!IDISP_TRI || !ksplit_enabled() || cin != 64 || cout % 32) return false;
+  // stride 2 (64 -> 64 at the hourglass bottom, three term-split launches before): two launches of the stride-2 32 -> 64 form (Cfg::S2T)
+  return (kind == IDISP_CONV_S1 && IDISP_MRG) || (kind == IDISP_CONV_S2 && IDISP_S2T && cout == 64);
+}
 
 int tc_split_weights_prepare(const float *w_tap, int kind, int cin, int cout, TcSplitWeights &out, cudaStream_t s)
 {
@@ -1956,6 +1988,15 @@ int tc_split_weights_prepare(const float *w_tap, int kind, int cin, int cout, Tc
   int rc;
   if ((rc = tc_weights_prepare(w_tap, kind, cin, cout, 1, out.hi, s))) return rc;
   if ((rc = tc_weights_prepare(lo.data(), kind, cin, cout, 1, out.lo, s))) return rc;
+  if (ksplit_layer(kind, cin, cout)) {
+    std::vector<float> half((size_t)27 * 32 * cout);
+    for (int h = 0; h < 2; ++h) {
+      for (int t = 0; t < 27; ++t)
+        for (int c = 0; c < 32; ++c)
+          memcpy(&half[((size_t)t * 32 + c) * cout], &w_tap[((size_t)t * cin + 32 * h + c) * cout], sizeof(float) * cout);
+      if ((rc = tc_weights_prepare(half.data(), kind, 32, cout, 1, h ? out.k1 : out.k0, s, 2, kind == IDISP_CONV_S2 ? 32 : 0))) return rc;
+    }
+  }
   if (cout == 1 && split_launches(kind, cin) == 1) {
     // 1-channel head: w_lo rides in the (otherwise zero) output column 1, so x_hi feeds both weight words in ONE MMA
     if ((rc = tc_weights_prepare(w_tap, kind, cin, cout, 1, out.both, s, 1, 0, 1))) return rc;
@@ -1996,6 +2037,24 @@ int tc_conv3d_split(const TcSplitWeights &w, const __nv_bfloat16 *x, int B, int 
     return tc_conv3d(w.lo, x, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, y1, y1, scratch, flags & 1, nullptr, cv, s, &o);
   }
   if (!part) { set_error("tc_conv3d_split: this layer needs the fp32 partial buffer"); return IDISP_ERR_INVALID; }
+  if (cv && w.k0.dev && w.k1.dev && ksplit_layer(kind, Cin, Cout)) {
+    // fused cost volume: the two channel halves ARE the two views (left features masked, right features shifted)
+    if (launches) *launches = 2;
+    TcCostVolume half = *cv;
+    o.xp = 1; o.part_out = part;
+    half.view = 0;
+    if ((rc = tc_conv3d(w.k0, x, B, 32, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, nullptr, nullptr, scratch, flags & 1, nullptr, &half, s, &o))) return rc;
+    half.view = 1;
+    o.part_in = part; o.part_out = nullptr; o.x2 = 1;
+    return tc_conv3d(w.k1, x, B, 32, D, H, W, Cout, kind, bias, residual, relu, y, nullptr, nullptr, scratch, flags, y_split, &half, s, &o);
+  }
+  if (!cv && w.k0.dev && w.k1.dev && ksplit_layer(kind, Cin, Cout)) {
+    if (launches) *launches = 2;
+    o.xp = 1; o.in_lo_off = per_view; o.part_out = part;
+    if ((rc = tc_conv3d(w.k0, x, B, 32, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, nullptr, nullptr, scratch, flags & 1, nullptr, nullptr, s, &o))) return rc;
+    o.in_blk_off = 4; o.part_in = part; o.part_out = nullptr; o.x2 = 1;
+    return tc_conv3d(w.k1, x, B, 32, D, H, W, Cout, kind, bias, residual, relu, y, nullptr, nullptr, scratch, flags, y_split, nullptr, s, &o);
+  }
   static const int heavy_first = tc::env_flag("IDISP_X2_HEAVY_FIRST");  // A/B switch: the order before this scheduling
   if (nl == 2 && !heavy_first) {
     // light launch first: x_hi*w_lo (one term, its epilogue only stores the fp32 partial); then the two-term launch, whose

@@ -25,6 +25,8 @@ void tc_weights_free(TcWeights &w);
 struct TcCostVolume {
   const __nv_bfloat16 *left = nullptr, *right = nullptr;
   int shift0 = 0;  // mindisp / 4
+  int view = -1;   // -1: both views (the layer's Cin = 2C channels); 0 / 1: only the left / right half of the volume (Cin = C channels:
+                   // one launch of the K-split form of the first layer, see tc_conv3d_split)
 };
 
 // Split-precision ("x2") pass options.  Activations are then stored as 2*C/8 channel blocks per sample (hi words, then lo
@@ -35,6 +37,8 @@ struct TcOpts {
   int x2 = 0;                      // final pass: y / residual / y_split hold hi|lo block groups
   int in_blk_stride = 0;           // channel blocks per input sample in memory (0: Cin/8)
   int in_blk_off = 0;              // first channel block this launch reads
+  int in_lo_off = 0;               // xp launches over a channel SUBSET: block distance from the launch's hi group to its lo group
+                                   // (0: adjacent, i.e. Cin/8) -- the stage is then filled by two TMA boxes
   int *range_flag = nullptr;       // device int set to 1 if an activation leaves the IEEE-half range (fp16 modes)
   int xp = 0;                      // K concatenation inside the launch: 1 = (x_hi,w_hi)+(x_lo,w_hi)+(x_hi,w_lo) with two-word
                                    // weights (Cin 32), 2 = (x_hi,w_hi)+(x_lo,w_hi) with one-word weights (Cin 64)
@@ -44,6 +48,7 @@ struct TcOpts {
 struct TcSplitWeights {
   TcWeights hi, lo;  // one-word packings of half(w) and half(w - half(w))
   TcWeights both;    // two-word packing (Cin = 32 layers), empty otherwise
+  TcWeights k0, k1;  // stride-1 Cin = 64 layers, K split: two-word packings of input channels [0,32) and [32,64) (see tc_conv3d_split)
 };
 int tc_split_weights_prepare(const float *w_tap, int kind, int cin, int cout, TcSplitWeights &out, cudaStream_t s);
 void tc_split_weights_free(TcSplitWeights &w);
