@@ -331,11 +331,15 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               else if (lead) {
                 ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
                 for (int pw = 0; pw < 2; ++pw) {
-                  ptx::tma_load_5d(stage_addr0 + s * C::STAGE_BYTES + pw * C::SUB_BYTES, &xmap, full_bar(s), (tw * TW - 1) * 8,
-                                   th * TH - 1, z >> 1, (z & 1) * 4 + ph * 2 + pw, n * p.in_blk_stride + p.in_blk_off);
-                  if (XP != 0 && p.in_lo_off)   // channel subset of a wider tensor: its lo blocks are not adjacent to its hi blocks
-                    ptx::tma_load_5d(stage_addr0 + s * C::STAGE_BYTES + pw * C::SUB_BYTES + C::CBLK * C::PLANE_BYTES, &xmap, full_bar(s), (tw * TW - 1) * 8,
-                                     th * TH - 1, z >> 1, (z & 1) * 4 + ph * 2 + pw, n * p.in_blk_stride + p.in_blk_off + p.in_lo_off);
+                  if (XP != 0 && p.in_lo_off)
+                    // channel subset of a wider tensor (its lo blocks are not adjacent to its hi blocks; half a sub-tile would not be a
+                    // 128-byte-aligned TMA destination): the map merges (class, depth) into one dimension and splits the blocks into
+                    // (block of the group, group = sample x word), so ONE box still lands [hi blocks | lo blocks]
+                    ptx::tma_load_5d(stage_addr0 + s * C::STAGE_BYTES + pw * C::SUB_BYTES, &xmap, full_bar(s), (tw * TW - 1) * 8, th * TH - 1,
+                                     ((z & 1) * 4 + ph * 2 + pw) * (Din >> 1) + (z >> 1), 0, n * 2);
+                  else
+                    ptx::tma_load_5d(stage_addr0 + s * C::STAGE_BYTES + pw * C::SUB_BYTES, &xmap, full_bar(s), (tw * TW - 1) * 8,
+                                     th * TH - 1, z >> 1, (z & 1) * 4 + ph * 2 + pw, n * p.in_blk_stride + p.in_blk_off);
                 }
               }
             }
@@ -1781,8 +1785,19 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
     const int D2 = D / 2, H2 = H / 2, W2 = W / 2;
     const cuuint64_t dims[5] = {(cuuint64_t)W2 * 8, (cuuint64_t)H2, (cuuint64_t)D2, 8, (cuuint64_t)B * blk_stride};
     const cuuint64_t strides[4] = {(cuuint64_t)W2 * 16, (cuuint64_t)H2 * W2 * 16, (cuuint64_t)D2 * H2 * W2 * 16, (cuuint64_t)8 * D2 * H2 * W2 * 16};
-    const cuuint32_t box[5] = {8 * MC::SUB_W, (cuuint32_t)sub_h, 1, 1, (cuuint32_t)((opts.in_lo_off ? 1 : aw) * C::CBLK)};
+    const cuuint32_t box[5] = {8 * MC::SUB_W, (cuuint32_t)sub_h, 1, 1, (cuuint32_t)(aw * C::CBLK)};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (opts.in_lo_off) {
+      // K-split launch (channels [in_blk_off*8, +32) of a 64-channel tensor, hi group and lo group in_lo_off blocks apart): dimensions
+      // (8ch*W2, H2, class*D2 + depth, block of the group, sample*2 + word); the channel half is the base pointer
+      if (blk_stride != 2 * opts.in_lo_off) { set_error("tc_conv3d: K-split stride-2 input must be [hi blocks | lo blocks] per sample"); return IDISP_ERR_INVALID; }
+      const cuuint64_t sub16 = (cuuint64_t)D2 * H2 * W2 * 16;
+      const cuuint64_t kdims[5] = {(cuuint64_t)W2 * 8, (cuuint64_t)H2, (cuuint64_t)8 * D2, (cuuint64_t)C::CBLK, (cuuint64_t)B * 2};
+      const cuuint64_t kstrides[4] = {(cuuint64_t)W2 * 16, (cuuint64_t)H2 * W2 * 16, 8 * sub16, (cuuint64_t)opts.in_lo_off * 8 * sub16};
+      const cuuint32_t kbox[5] = {8 * MC::SUB_W, (cuuint32_t)sub_h, 1, (cuuint32_t)C::CBLK, 2};
+      r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (char *)const_cast<void *>(src) + (size_t)opts.in_blk_off * 8 * sub16, kdims, kstrides, kbox, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else
     r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else if (cv) {

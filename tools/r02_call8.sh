@@ -1,9 +1,9 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02h_pytest.log 2>&1; echo "pytest rc=$?"
-tail -5 gpurun_out/r02h_pytest.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02j_pytest.log 2>&1; echo "pytest rc=$?"
+tail -5 gpurun_out/r02j_pytest.log
 export IDISP_BENCH_SKIP_REFGPU=1
 export IDISP_BENCH_SKIP_LIVE=1
-timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02h_bench.json 2> gpurun_out/r02h_bench.err; echo "bench rc=$?"
-IDISP_NO_KSPLIT=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02h_noksplit.json 2> gpurun_out/r02h_noksplit.err
-python tools/show_bench.py gpurun_out/r02h_bench.json gpurun_out/r02h_noksplit.json
+timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02j_bench.json 2> gpurun_out/r02j_bench.err; echo "bench rc=$?"
+IDISP_NO_KSPLIT=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02j_noksplit.json 2> gpurun_out/r02j_noksplit.err
+python tools/show_bench.py gpurun_out/r02j_bench.json gpurun_out/r02j_noksplit.json
