@@ -184,6 +184,10 @@ struct Params {
   __nv_bfloat16 *y_split;         // optional second copy of y in the 8-parity-sub-volume layout a stride-2 consumer reads
   int residual_is_split;          // transposed conv only: `residual` is stored in that parity layout (of the OUTPUT grid)
   int skip_y;                     // write only y_split (the natural copy has no reader)
+  __nv_bfloat16 *x_split;         // per-step-triple 32 -> 32 kernel: the epilogue warps copy every input plane tile from its shared-memory stage
+                                  // into the parity layout here (the stage is released by the MMA commit AND the epilogue warps' arrivals).
+                                  // Why: the transposed conv that produces this tensor is memory-bound and wrote both layouts (natural for
+                                  // this launch, parity for the next hourglass's stride-2 conv); this launch is MMA-bound with DRAM at 30 %.
   int res_map;                    // Cfg::DTR: the second tensor map covers `residual` (boxes of one output plane tile x 2 channel blocks)
   // split-precision ("x2") passes: a product of (hi+lo) operands is three launches whose accumulators are chained through an
   // fp32 partial; the last pass applies the epilogue and stores the result as two 16-bit words (hi blocks, then lo blocks)
@@ -287,7 +291,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&xmap);
     ptx::prefetch_tensormap(&rmap);
-    for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), (C::MRG && p.x_split) ? 1 + 4 * C::EGROUPS : 1); }
     for (int r = 0; r < NSLOT; ++r) { ptx::mbar_init(accf_bar(r), 1); ptx::mbar_init(acce_bar(r), (C::TRI || C::S2T || C::DTR) ? 4 * C::EGROUPS : 4); }
     ptx::fence_barrier_init();
   }
@@ -924,6 +928,24 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(acce_bar(t));
             continue;
+          }
+          if constexpr (C::MRG) {
+            if (p.x_split) {  // parity-layout copy of input plane z, read back from its stage (resident: this group has not released it yet)
+              const uint32_t sq = tq % C::STAGES;
+              ptx::mbar_wait(full_bar(sq), (tq / C::STAGES) & 1);   // (completed long ago; makes the TMA's writes visible to these loads)
+              if (valid) {
+                const uint32_t src = stage_addr0 + sq * C::STAGE_BYTES + ((hl + 1) * MC::SUB_W + (wl + 1)) * 16 + egroup * NCBG * C::PLANE_BYTES;
+                const int64_t dst = spl_of(z);
+#pragma unroll
+                for (int i = 0; i < NCBG; ++i) {
+                  const uint4 vh = ptx::lds_v4(src + i * C::PLANE_BYTES), vl = ptx::lds_v4(src + (C::CBLK + i) * C::PLANE_BYTES);
+                  ptx::stg_cs_v4(p.x_split + dst + (int64_t)i * blk_elems, vh);
+                  ptx::stg_cs_v4(p.x_split + dst + (int64_t)i * blk_elems + lo_off, vl);
+                }
+              }
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(empty_bar(sq));
+            }
           }
           const uint32_t tb = tmem_base + lane_addr + t * C::TRI_STRIDE + egroup * CPG;
           if (p.dbg & 128) {  // timing experiment: no TMEM reads, the arithmetic and the stores run on whatever the registers hold
@@ -1838,6 +1860,15 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   p.part_in = opts.part_in; p.part_out = opts.part_out; p.x2 = opts.x2; p.in_blk_stride = blk_stride; p.in_blk_off = opts.in_blk_off; p.in_lo_off = opts.in_lo_off;
   p.range_flag = opts.range_flag;
   if (!cv) rmap = map;
+  p.x_split = nullptr;
+  if (opts.x_copy_split) {
+    if (!(MODE == tc::M_S1 && CIN == 32 && NT == 32 && OCC == 1 && fmt == 3 && IDISP_MRG && IDISP_TRI && Cout == 32 && !cv && opts.x2 && !opts.in_lo_off && blk_stride == 8)) {
+      set_error("tc_conv3d: the input side copy exists in the stride-1 32 -> 32 split-precision kernel only");
+      return IDISP_ERR_INVALID;
+    }
+    if (D % 2 || H % 2 || W % 2) { set_error("tc_conv3d: parity-split copy needs even dims"); return IDISP_ERR_INVALID; }
+    p.x_split = opts.x_copy_split;
+  }
   p.res_map = 0;
   if (MODE == tc::M_DEC && NT == 16 && fmt == 3 && IDISP_DTR && residual) {
     // Cfg::DTR: a second map over the residual tensor (output-sized, 2 * Cout/8 blocks per sample) for the producer's L2 prefetches:
@@ -2026,7 +2057,7 @@ int tc_split_weights_prepare(const float *w_tap, int kind, int cin, int cout, Tc
 int tc_conv3d_split(const TcSplitWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D, int H, int W, int Cout, int kind,
                     const float *bias, const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1,
                     void *scratch, int flags, __nv_bfloat16 *y_split, const TcCostVolume *cv, float *part, cudaStream_t s, int *launches,
-                    int *range_flag)
+                    int *range_flag, __nv_bfloat16 *x_copy_split)
 {
   const int per_view = cv ? Cin / 16 : Cin / 8;  // channel blocks of one precision word (per view for the fused cost volume)
   const int nl = split_launches(kind, Cin);
@@ -2039,8 +2070,10 @@ int tc_conv3d_split(const TcSplitWeights &w, const __nv_bfloat16 *x, int B, int 
     o.xp = w.both.ncat ? 2 : 1;
     if (y1) return tc_conv3d(w.both, x, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, res1, y1, scratch, flags & 1, nullptr, cv, s, &o);
     o.x2 = 1;
+    o.x_copy_split = x_copy_split;
     return tc_conv3d(w.both, x, B, Cin, D, H, W, Cout, kind, bias, residual, relu, y, nullptr, nullptr, scratch, flags, y_split, cv, s, &o);
   }
+  if (x_copy_split) { set_error("tc_conv3d_split: the input side copy needs a single-launch layer"); return IDISP_ERR_INVALID; }
   if (y1) {  // 1-channel head: the passes accumulate straight into the f32 logits
     if (nl == 2) o.xp = 2;
     if ((rc = tc_conv3d(w.hi, x, B, Cin, D, H, W, Cout, kind, nullptr, nullptr, 0, nullptr, res1, y1, scratch, flags & 1, nullptr, cv, s, &o))) return rc;

@@ -40,6 +40,8 @@ struct TcOpts {
   int in_lo_off = 0;               // xp launches over a channel SUBSET: block distance from the launch's hi group to its lo group
                                    // (0: adjacent, i.e. Cin/8) -- the stage is then filled by two TMA boxes
   int *range_flag = nullptr;       // device int set to 1 if an activation leaves the IEEE-half range (fp16 modes)
+  __nv_bfloat16 *x_copy_split = nullptr;  // stride-1 32 -> 32 split-precision launch only: ALSO write this launch's INPUT tensor, as it passes through
+                                   // shared memory, in the 8-parity-sub-volume layout a stride-2 consumer reads (see Params::x_split)
   int xp = 0;                      // K concatenation inside the launch: 1 = (x_hi,w_hi)+(x_lo,w_hi)+(x_hi,w_lo) with two-word
                                    // weights (Cin 32), 2 = (x_hi,w_hi)+(x_lo,w_hi) with one-word weights (Cin 64)
 };
@@ -57,7 +59,7 @@ void tc_split_weights_free(TcSplitWeights &w);
 int tc_conv3d_split(const TcSplitWeights &w, const __nv_bfloat16 *x, int B, int Cin, int D, int H, int W, int Cout, int kind,
                     const float *bias, const __nv_bfloat16 *residual, int relu, __nv_bfloat16 *y, const float *res1, float *y1,
                     void *scratch, int flags, __nv_bfloat16 *y_split, const TcCostVolume *cv, float *part, cudaStream_t s,
-                    int *launches = nullptr, int *range_flag = nullptr);
+                    int *launches = nullptr, int *range_flag = nullptr, __nv_bfloat16 *x_copy_split = nullptr);
 
 // The 32 -> 1 classifier convolutions as "all 27 taps in N" GEMM + shifted sum (head_tc.cu); f16 / x2 as above.
 struct TcHeadWeights {

@@ -115,6 +115,12 @@ __device__ __forceinline__ void stg_cs_v4(void *p, const uint4 &a)
 {
   asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w) : "memory");
 }
+__device__ __forceinline__ uint4 lds_v4(uint32_t smem_addr)
+{
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_addr) : "memory");
+  return r;
+}
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *m)
 {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

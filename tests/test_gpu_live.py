@@ -232,6 +232,22 @@ def test_cuda_graph_replay_is_bit_identical_to_eager_launches(lib, monkeypatch):
         assert torch.equal(e, eager.forward_features(Lc, Rc)) and not torch.equal(e, want2)
 
 
+@pytest.mark.parametrize('name', ['live', 'tiny'])
+def test_input_side_copy_is_bit_identical_to_the_producer_written_parity_copy(lib, monkeypatch, name):
+    """The parity-layout copy of out_k that the next hourglass's stride-2 conv reads: written by classif{k}.0 from its shared-memory
+    input stages (default) vs by conv6's own epilogue (IDISP_NO_SIDE_COPY=1, read when a plan is created).  Pure data movement, so
+    the disparity must be bit-identical -- and within the parity tolerance of the reference."""
+    case, g, sd, L, R = load_case(name)
+    Lc, Rc = L.cuda(), R.cuda()
+    with torch.no_grad():
+        base = make_psmnet(case, sd, 'fp16x2').forward_features(Lc, Rc)
+        monkeypatch.setenv('IDISP_NO_SIDE_COPY', '1')
+        a = make_psmnet(case, sd, 'fp16x2').forward_features(Lc, Rc)
+        monkeypatch.delenv('IDISP_NO_SIDE_COPY')
+    assert torch.equal(a, base)
+    assert np.abs(base.cpu().numpy() - g['pred_up']).max() < TOL
+
+
 def test_module_survives_deepcopy_and_pickle_after_a_forward(lib, tmp_path):
     import copy
     case, g, sd, L, R = load_case('tiny')
