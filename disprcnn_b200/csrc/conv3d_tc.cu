@@ -231,6 +231,32 @@ __device__ __forceinline__ F8 unpack8(const uint4 &a)
   return r;
 }
 
+// Work items of the per-step-triple kernels.  A CTA takes items cta, cta + ncta, ...  The rounds every CTA takes part in are whole
+// columns; the columns of the last, PARTIAL round (3 136 full-resolution columns over 148 CTAs = 21.2 rounds: 28 CTAs would walk
+// 48 planes while 120 idle) are split in depth into `split` chunks so that all CTAs share them.  A chunk of output planes [e0, e1)
+// streams the input planes [e0-1, e1+1) -- one extra step per cut -- and emits only its own planes.
+struct Items { int nfull, split, total; };
+__device__ __forceinline__ Items make_items(int ncols, int ncta, int D, bool enable)
+{
+  Items it;
+  it.nfull = enable ? (ncols / ncta) * ncta : ncols;
+  const int tail = ncols - it.nfull;
+  int sp = tail > 0 ? ncta / tail : 1;
+  if (sp > D / 6) sp = D / 6;   // chunks of at least six planes (two extra steps per chunk)
+  if (sp < 1) sp = 1;
+  it.split = sp;
+  it.total = it.nfull + tail * sp;
+  return it;
+}
+__device__ __forceinline__ void get_item(const Items &it, int i, int D, int &col, int &e0, int &e1)
+{
+  if (i < it.nfull) { col = i; e0 = 0; e1 = D; return; }
+  const int j = i - it.nfull, c = j % it.split;
+  col = it.nfull + j / it.split;
+  e0 = c * D / it.split;
+  e1 = (c + 1) * D / it.split;
+}
+
 // K-concatenation modes (Cfg::XP): MMA k-step kk of a tap -> activation word / weight k-step / byte offset (inside a
 // sub-tile) of the first of its two channel blocks.  A stage holds [hi blocks | lo blocks]; with the fused cost volume the
 // TMA box lands [left: hi, lo][right: hi, lo], so the logical block order (left, right) is permuted.
@@ -323,9 +349,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     {
       const bool lead = ptx::elect_one();
       uint32_t q = 0;
-      for (int col = cta; col < ncols; col += ncta) {
+      const Items items = make_items(ncols, ncta, Din, C::MRG && !(p.dbg & 2048));
+      for (int item = cta; item < items.total; item += ncta) {
+        int col, e0, e1;
+        get_item(items, item, Din, col, e0, e1);
+        const int zb = e0 > 0 ? e0 - 1 : 0, ze = e1 < Din ? e1 + 1 : Din;
         const int tw = col % p.tiles_w, th = (col / p.tiles_w) % p.tiles_h, n = col / (p.tiles_w * p.tiles_h);
-        for (int z = 0; z < Din; ++z) {
+        for (int z = zb; z < ze; ++z) {
           if (MODE == M_S2) {
             // two pipeline steps per input plane: even-row (ph=0) and odd-row (ph=1) sub-grids, each {pw=0, pw=1}
             for (int ph = 0; ph < 2; ++ph, ++q) {
@@ -392,14 +422,22 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       uint32_t q = 0, g0 = 0;
       if constexpr (C::TRI) {
         // one stage and one accumulator triple per step; the waits of step q+1 are issued in the middle of step q's stream
-        auto waits = [&](int col_, uint32_t q_) {
-          if (col_ >= ncols) return;
+        auto waits = [&](bool more, uint32_t q_) {
+          if (!more) return;
           ptx::mbar_wait(acce_bar(q_ % NSLOT), ((q_ / NSLOT) & 1) ^ 1);
           ptx::mbar_wait(full_bar(q_ % C::STAGES), (q_ / C::STAGES) & 1);
         };
-        int col = cta, z = 0;
-        waits(col, 0);
-        while (col < ncols) {
+        // (col, z) walk the work items (see Items): whole columns, or depth chunks of the last round's columns
+        const Items items = make_items(ncols, ncta, Din, C::MRG && !(p.dbg & 2048));
+        auto bounds = [&](int item_, int &zb_, int &ze_) {
+          int c_, e0_, e1_;
+          get_item(items, item_, Din, c_, e0_, e1_);
+          zb_ = e0_ > 0 ? e0_ - 1 : 0; ze_ = e1_ < Din ? e1_ + 1 : Din;
+        };
+        int col = cta, z = 0, zend = Din;   // `col` counts items here
+        if (col < items.total) bounds(col, z, zend);
+        waits(col < items.total, 0);
+        while (col < items.total) {
           ptx::tc_fence_after();
           const uint32_t s = q % C::STAGES, t = q % NSLOT;
           const int plo = z > 0 ? z - 1 : 0, phi = z + 1 < Dout ? z + 1 : Dout - 1;  // output planes this input plane feeds
@@ -407,15 +445,15 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           const uint32_t dm = tmem_base + t * C::TRI_STRIDE + j0 * NT, ds = dm + C::TRI_SMALL;
           const uint32_t id1 = ptx::make_idesc_h<F16>(128, NT * nblk);
           const uint64_t a0 = desc_add(a_desc0, s * C::STAGE_BYTES);
-          int ncol = col, nz = z + 1;
-          if (nz == Din) { nz = 0; ncol += ncta; }
+          int ncol = col, nz = z + 1, nzend = zend;
+          if (nz == zend) { ncol += ncta; if (ncol < items.total) bounds(ncol, nz, nzend); }
           if constexpr (C::MRG) {
             // B chunk of (tap, k-step): [2 kcores][hi: 3 x NT rows | lo: 3 x NT rows][8]
             const uint32_t id2 = ptx::make_idesc_h<F16>(128, 2 * 3 * NT);
             const uint64_t bm = ptx::make_smem_desc(w_addr, 6 * NT * 16, 128);
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-              if (tap == 5) waits(ncol, q + 1);
+              if (tap == 5) waits(ncol < items.total, q + 1);
 #pragma unroll
               for (int ks = 0; ks < C::KS; ++ks) {
                 const uint32_t a_tap = ((tap / 3) * MC::SUB_W + (tap % 3)) * 16;
@@ -429,7 +467,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           const uint64_t b1 = ptx::make_smem_desc(w_addr + j0 * NT * 16, 3 * NT * 16, 128);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            if (tap == 5) waits(ncol, q + 1);
+            if (tap == 5) waits(ncol < items.total, q + 1);
 #pragma unroll
             for (int ks = 0; ks < C::KSM; ++ks) {
               const uint32_t aoff = ((tap / 3) * MC::SUB_W + (tap % 3)) * 16 + A_KOFF(ks);
@@ -441,7 +479,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           }
           commit(empty_bar(s));
           commit(accf_bar(t));
-          col = ncol; z = nz; ++q;
+          col = ncol; z = nz; zend = nzend; ++q;
         }
       } else if (MODE == M_S1) {
         // Software-pipelined: the mbarrier waits of step q+1 (TMA data landed, fresh accumulator slot drained) are
@@ -707,7 +745,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
     for (int i = 0; i < 32; ++i) zero[i] = 0u;
     uint32_t g0 = 0, tq = 0;  // tq: step counter of the TRI mode (one accumulator triple per input plane)
-    for (int col = cta; col < ncols; col += ncta, g0 += Dout) {
+    const Items items = make_items(ncols, ncta, Dout, C::MRG && !(p.dbg & 2048));   // (Cfg::MRG: Dout == Din)
+    for (int item = cta; item < items.total; item += ncta, g0 += Dout) {
+      int col, e0, e1;   // this item's column and the output planes [e0, e1) it emits
+      get_item(items, item, Dout, col, e0, e1);
       const int tw = col % p.tiles_w, th = (col / p.tiles_w) % p.tiles_h, n = col / (p.tiles_w * p.tiles_h);
       const int hr = th * TH + hl, wr = tw * TW + wl;
       const bool valid = hr < p.Hr && wr < p.Wr;
@@ -917,10 +958,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             }
           }
         } else
-        for (int z = 0; z < Dout; ++z, ++tq) {
+        for (int z = (e0 > 0 ? e0 - 1 : 0); z < (e1 < Dout ? e1 + 1 : Dout); ++z, ++tq) {
           const uint32_t t = tq % NSLOT;
           XPre xq[NCBG];
-          if (valid && z >= 1) xload2(xq, z - 1);      // operands of the plane this step completes: requested before the wait
+          const bool mine = z - 1 >= e0;   // plane z-1 belongs to this item (a chunk's first two steps only build up its first plane)
+          if (valid && mine) xload2(xq, z - 1);      // operands of the plane this step completes: requested before the wait
           ptx::mbar_wait(accf_bar(t), (tq / NSLOT) & 1);
           ptx::tc_fence_after();
           if (p.dbg & 32) {  // timing experiment: handshake only (no TMEM traffic, no arithmetic, no global memory)
@@ -952,7 +994,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(acce_bar(t));
-            if (z >= 1 && valid) emit(z - 1, P0, xq);
+            if (mine && valid) emit(z - 1, P0, xq);
             continue;
           }
           // plane z-1 = P0 + block 0 (complete);  plane z: P1 + block 1;  plane z+1: block 2 (first contribution).
@@ -997,7 +1039,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(acce_bar(t));   // the MMA warp may overwrite this buffer (first MMA of a step: accumulate = 0)
-          if (z >= 1 && valid && !(p.dbg & 64)) emit(z - 1, P0, xq);   // (64: timing experiment without the per-voxel work)
+          if (mine && valid && !(p.dbg & 64)) emit(z - 1, P0, xq);   // (64: timing experiment without the per-voxel work)
 #pragma unroll
           for (int i = 0; i < CPG; ++i) P0[i] = N0[i];
           if (z == Dout - 1) {  // no step z+1: plane z is complete as well

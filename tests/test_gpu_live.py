@@ -248,6 +248,23 @@ def test_input_side_copy_is_bit_identical_to_the_producer_written_parity_copy(li
     assert np.abs(base.cpu().numpy() - g['pred_up']).max() < TOL
 
 
+def test_depth_split_tail_columns_match_whole_columns_bit_for_bit(lib):
+    """With more tile columns than CTAs and a partial last round, the per-step-triple kernels split the last round's columns in
+    depth (conv3d_tc.cu, Items): six ROI pairs at the KITTI shape = 168 columns over 148 CTAs -> 20 tail columns in 4 chunks.  A chunk
+    accumulates each of its planes from the same three input planes in the same order, so every ROI must equal its single-ROI
+    run (28 columns, no split) bit for bit."""
+    case, g, sd, L, R = load_case('live')
+    m = make_psmnet(case, sd, 'fp16x2')
+    L6 = torch.cat([L, L.flip(-1) * 0.5, R * 1.5], 0).cuda()
+    R6 = torch.cat([R, R.flip(-1) * 0.5, L * 1.5], 0).cuda()
+    assert L6.shape[0] == 6
+    with torch.no_grad():
+        full = m.forward_features(L6, R6)
+        for i in range(6):
+            assert torch.equal(m.forward_features(L6[i:i + 1], R6[i:i + 1]), full[i:i + 1]), i
+    assert np.abs(full[:2].cpu().numpy() - g['pred_up']).max() < TOL
+
+
 def test_module_survives_deepcopy_and_pickle_after_a_forward(lib, tmp_path):
     import copy
     case, g, sd, L, R = load_case('tiny')
