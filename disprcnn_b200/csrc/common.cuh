@@ -151,7 +151,8 @@ int launch_conv3d_to1(const T *x, int B, int Cin, int D, int H, int W, const flo
 int launch_conv3d_to1_x2(const __nv_bfloat16 *x, int B, int Cin, int D, int H, int W, const float *w_tap, const float *residual,
                          float *y, cudaStream_t s);
 
+// cellmax_scratch: optional B*Hf*Wf floats of device scratch (enables the one-pass form, see softargmin.cu)
 int launch_softargmin(const float *logits, int B, int D, int Hf, int Wf, int mindisp, int maxdisp, int H,
-                      int W, float *out, cudaStream_t s);
+                      int W, float *out, cudaStream_t s, float *cellmax_scratch = nullptr);
 
 }  // namespace idisp

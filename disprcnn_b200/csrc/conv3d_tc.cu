@@ -349,11 +349,14 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     {
       const bool lead = ptx::elect_one();
       uint32_t q = 0;
-      const Items items = make_items(ncols, ncta, Din, C::MRG && !(p.dbg & 2048));
+      // (items count OUTPUT planes: Dout = Din for the stride-1 kernels; the stride-2 form (S2T) walks a chunk [e0, e1) as the steps
+      //  [e0-1, e1) -- the extra first step only produces the odd input plane's carry into plane e0 -- i.e. input planes [2(e0-1), 2 e1))
+      const Items items = make_items(ncols, ncta, Dout, (C::MRG || C::S2T) && !(p.dbg & 2048));
       for (int item = cta; item < items.total; item += ncta) {
         int col, e0, e1;
-        get_item(items, item, Din, col, e0, e1);
-        const int zb = e0 > 0 ? e0 - 1 : 0, ze = e1 < Din ? e1 + 1 : Din;
+        get_item(items, item, Dout, col, e0, e1);
+        const int zb = C::S2T ? 2 * (e0 > 0 ? e0 - 1 : 0) : ((C::MRG && e0 > 0) ? e0 - 1 : 0);
+        const int ze = C::S2T ? 2 * e1 : ((C::MRG && e1 < Din) ? e1 + 1 : Din);
         const int tw = col % p.tiles_w, th = (col / p.tiles_w) % p.tiles_h, n = col / (p.tiles_w * p.tiles_h);
         for (int z = zb; z < ze; ++z) {
           if (MODE == M_S2) {
@@ -545,8 +548,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         uint32_t sq = 0;  // stage counter (two stages per input plane), tq: step counter
         uint32_t tq2 = 0;
         bool first_wait = true;
-        for (int col = cta; col < ncols; col += ncta) {
-          for (int pz = 0; pz < Dout; ++pz, ++tq2) {
+        const Items items = make_items(ncols, ncta, Dout, !(p.dbg & 2048));
+        for (int item = cta; item < items.total; item += ncta) {
+          int col_, e0, e1;
+          get_item(items, item, Dout, col_, e0, e1);
+          for (int pz = (e0 > 0 ? e0 - 1 : 0); pz < e1; ++pz, ++tq2) {
             const uint32_t t = tq2 % NSLOT;
             const uint32_t dbase = tmem_base + t * C::S2T_STRIDE;   // [C0 | M0 | M1 | C1 | X0 | X1]
             ptx::mbar_wait(acce_bar(t), ((tq2 / NSLOT) & 1) ^ 1);
@@ -568,7 +574,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                   const uint32_t aoff0 = sub_t * C::SUB_BYTES + (rh * MC::SUB_W + rw) * 16;
                   if (tt == (ph == 0 ? 1 : 3)) {   // the next stage's TMA data: waited for in the middle of this stage's stream
                     const uint32_t ns = (sq + 1) % C::STAGES;
-                    const bool more = !(odd == 1 && ph == 1 && pz == Dout - 1 && col + ncta >= ncols);
+                    const bool more = !(odd == 1 && ph == 1 && pz == e1 - 1 && item + ncta >= items.total);
                     if (more) ptx::mbar_wait(full_bar(ns), ((sq + 1) / C::STAGES) & 1);
                   }
 #pragma unroll
@@ -745,7 +751,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
     for (int i = 0; i < 32; ++i) zero[i] = 0u;
     uint32_t g0 = 0, tq = 0;  // tq: step counter of the TRI mode (one accumulator triple per input plane)
-    const Items items = make_items(ncols, ncta, Dout, C::MRG && !(p.dbg & 2048));   // (Cfg::MRG: Dout == Din)
+    const Items items = make_items(ncols, ncta, Dout, (C::MRG || C::S2T) && !(p.dbg & 2048));   // (Cfg::MRG: Dout == Din)
     for (int item = cta; item < items.total; item += ncta, g0 += Dout) {
       int col, e0, e1;   // this item's column and the output planes [e0, e1) it emits
       get_item(items, item, Dout, col, e0, e1);
@@ -923,10 +929,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           float CAR[CPG];   // block 1 of the previous step: what input plane 2p-1 (kd = 0) contributed to output plane p
 #pragma unroll
           for (int i = 0; i < CPG; ++i) CAR[i] = 0.f;
-          for (int pz = 0; pz < Dout; ++pz, ++tq) {
+          for (int pz = (e0 > 0 ? e0 - 1 : 0); pz < e1; ++pz, ++tq) {   // (a chunk's first step only builds the carry into plane e0)
             const uint32_t t = tq % NSLOT;
             XPre xq[NCBG];
-            if (valid) xload2(xq, pz);
+            if (valid && pz >= e0) xload2(xq, pz);
             ptx::mbar_wait(accf_bar(t), (tq / NSLOT) & 1);
             ptx::tc_fence_after();
             const uint32_t tb = tmem_base + lane_addr + t * C::S2T_STRIDE + egroup * CPG;   // [C0 | M0 | M1 | C1 | X0 | X1]
@@ -951,7 +957,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(acce_bar(t));
-            if (valid && !(p.dbg & 4)) emit(pz, P0, xq);
+            if (valid && pz >= e0 && !(p.dbg & 4)) emit(pz, P0, xq);
             if (pz == Dout - 1) {
 #pragma unroll
               for (int i = 0; i < CPG; ++i) CAR[i] = 0.f;

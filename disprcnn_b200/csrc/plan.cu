@@ -524,7 +524,9 @@ static int forward_impl(idisp_plan *p, const float *left, const float *right, in
   }
   // upsample + softmax + regression (:169-174)
   mark(-2);
-  RUN(launch_softargmin(b.costX, B, D, Hf, Wf, p->mindisp, p->maxdisp, H, W, out, s)); ++launches;
+  // (b.part -- the fp32 partial of the multi-launch layers, >= B*32*V floats -- is free here: scratch for the per-cell maxima)
+  RUN(launch_softargmin(b.costX, B, D, Hf, Wf, p->mindisp, p->maxdisp, H, W, out, s, (float *)b.part)); ++launches;
+  if (p->maxdisp - p->mindisp == 4 * D && (D == 24 || D == 48) && !getenv("IDISP_SOFTARGMIN_GENERIC") && !getenv("IDISP_SOFTARGMIN_NO_CELLMAX")) ++launches;  // + cell_max_kernel
   mark(-99);  // closing event
 #undef RUN
   p->last_logits = b.costX; p->last_B = B; p->last_Hf = Hf; p->last_Wf = Wf;

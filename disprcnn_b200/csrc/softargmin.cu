@@ -153,9 +153,24 @@ __device__ __noinline__ float softargmin_exact(SampleCtx sample, int mindisp)
 // through a rolling window of TWO samples and accumulates the exponentials (with an exact-maximum fallback, see below).  Keeping all D samples in registers instead (the
 // first version) cost 168 registers = 3 warps per scheduler, and the kernel ran at a third of its issue rate; re-sampling is
 // 48 x 11 instructions per pixel against 192 x 6 for the exponentials.
-template <int D>
+// per low-resolution cell: maximum of its D logits (one thread per cell, coalesced over x)
+__global__ void __launch_bounds__(256) cell_max_kernel(const float *__restrict__ logits, int64_t cells, int D, int plane, float *__restrict__ cm)
+{
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x) {
+    const float *p = logits + (i / plane) * (int64_t)D * plane + i % plane;
+    float m = __ldg(p);
+    for (int k = 1; k < D; ++k) m = fmaxf(m, __ldg(p + (int64_t)k * plane));
+    cm[i] = m;
+  }
+}
+
+// PRE: the softmax stabiliser comes from `cellmax` (maximum over depth of each low-resolution cell, computed once by cell_max_kernel):
+// the maximum over a pixel's four corner cells bounds every interpolated logit from above, like the maximum of the D blended plane
+// samples did, but costs 4 loads instead of a first sampling pass (48 x 11 of the ~2 300 instructions per pixel).
+template <int D, bool PRE>
 __global__ void __launch_bounds__(256, 3)  // <= 85 registers: the unrolled loops must not hoist all 4*D*... loads at once
-softargmin_x4_kernel(const float *__restrict__ logits, int B, int Hf, int Wf, int mindisp, int H, int W, float *__restrict__ out)
+softargmin_x4_kernel(const float *__restrict__ logits, int B, int Hf, int Wf, int mindisp, int H, int W, float *__restrict__ out,
+                     const float *__restrict__ cellmax)
 {
   constexpr int Dfull = 4 * D;
   constexpr float sd = (float)(D - 1) / (float)(Dfull - 1);
@@ -179,10 +194,16 @@ softargmin_x4_kernel(const float *__restrict__ logits, int B, int Hf, int Wf, in
     // independent sample per plane.  It is NOT safe on its own: with sharply peaked logits every exp(v - M) can underflow
     // (sum = 0 -> 0/0), so a vanishing sum falls back to softargmin_exact, as F.softmax on the upsampled volume
     // (stackhourglass.py:169-172) would behave.
-    float M = sample(0);
+    float M;
+    if constexpr (PRE) {
+      const float *c = cellmax + (int64_t)b * plane + y0 * Wf + x0;
+      M = fmaxf(fmaxf(__ldg(c), __ldg(c + d01)), fmaxf(__ldg(c + d10), __ldg(c + d10 + d01)));
+    } else {
+      M = sample(0);
 #pragma unroll
-    for (int k = 1; k < D; ++k) M = fmaxf(M, sample(k));
-    asm volatile("" : "+l"(sample.p00));  // the accumulation RE-samples (L1 hits): keeping the D samples alive would cost the occupancy
+      for (int k = 1; k < D; ++k) M = fmaxf(M, sample(k));
+      asm volatile("" : "+l"(sample.p00));  // the accumulation RE-samples (L1 hits): keeping the D samples alive would cost the occupancy
+    }
     float s, t;
     softargmin_accumulate<D>(sample, -M * 1.4426950408889634f, mindisp, s, t);
     out[idx] = (s >= 1e-30f) ? t / s : softargmin_exact<D>(sample, mindisp);
@@ -190,15 +211,21 @@ softargmin_x4_kernel(const float *__restrict__ logits, int B, int Hf, int Wf, in
 }
 
 int launch_softargmin(const float *logits, int B, int D, int Hf, int Wf, int mindisp, int maxdisp, int H, int W,
-                      float *out, cudaStream_t s)
+                      float *out, cudaStream_t s, float *cellmax_scratch)
 {
   const int64_t total = (int64_t)B * H * W;
   if (total == 0) return IDISP_OK;
-  if (maxdisp - mindisp == 4 * D && (D == 24 || D == 48) && !getenv("IDISP_SOFTARGMIN_GENERIC")) {
+  static const bool generic = getenv("IDISP_SOFTARGMIN_GENERIC") != nullptr, no_pre = getenv("IDISP_SOFTARGMIN_NO_CELLMAX") != nullptr;
+  if (maxdisp - mindisp == 4 * D && (D == 24 || D == 48) && !generic) {
     const int64_t want256 = ceil_div64(total, 256);
     const int grid = (int)(want256 < 148 * 64 ? want256 : 148 * 64);
-    if (D == 24) softargmin_x4_kernel<24><<<grid, 256, 0, s>>>(logits, B, Hf, Wf, mindisp, H, W, out);
-    else softargmin_x4_kernel<48><<<grid, 256, 0, s>>>(logits, B, Hf, Wf, mindisp, H, W, out);
+    if (cellmax_scratch && !no_pre) {   // (B * Hf * Wf floats of caller scratch)
+      const int64_t cells = (int64_t)B * Hf * Wf;
+      cell_max_kernel<<<(int)ceil_div64(cells, 256), 256, 0, s>>>(logits, cells, D, Hf * Wf, cellmax_scratch);
+      if (D == 24) softargmin_x4_kernel<24, true><<<grid, 256, 0, s>>>(logits, B, Hf, Wf, mindisp, H, W, out, cellmax_scratch);
+      else softargmin_x4_kernel<48, true><<<grid, 256, 0, s>>>(logits, B, Hf, Wf, mindisp, H, W, out, cellmax_scratch);
+    } else if (D == 24) softargmin_x4_kernel<24, false><<<grid, 256, 0, s>>>(logits, B, Hf, Wf, mindisp, H, W, out, nullptr);
+    else softargmin_x4_kernel<48, false><<<grid, 256, 0, s>>>(logits, B, Hf, Wf, mindisp, H, W, out, nullptr);
     IDISP_LAUNCH_CHECK();
     return IDISP_OK;
   }

@@ -249,19 +249,20 @@ def test_input_side_copy_is_bit_identical_to_the_producer_written_parity_copy(li
 
 
 def test_depth_split_tail_columns_match_whole_columns_bit_for_bit(lib):
-    """With more tile columns than CTAs and a partial last round, the per-step-triple kernels split the last round's columns in
-    depth (conv3d_tc.cu, Items): six ROI pairs at the KITTI shape = 168 columns over 148 CTAs -> 20 tail columns in 4 chunks.  A chunk
-    accumulates each of its planes from the same three input planes in the same order, so every ROI must equal its single-ROI
-    run (28 columns, no split) bit for bit."""
+    """With more tile columns than CTAs and a partial last round, the per-step kernels split the last round's columns in depth
+    (conv3d_tc.cu, Items).  Eleven ROI pairs at the KITTI shape: 308 full-resolution columns over 148 CTAs -> 12 tail columns in 4
+    chunks (stride-1 kernels); 88 half-resolution columns over 74 CTAs per channel slice -> 14 tail columns in 2 chunks (the stride-2
+    32->64 conv and the K-split 64->64 convs).  A chunk accumulates each of its planes from the same input planes in the same order,
+    so every ROI must equal its single-ROI run (no split) bit for bit."""
     case, g, sd, L, R = load_case('live')
     m = make_psmnet(case, sd, 'fp16x2')
-    L6 = torch.cat([L, L.flip(-1) * 0.5, R * 1.5], 0).cuda()
-    R6 = torch.cat([R, R.flip(-1) * 0.5, L * 1.5], 0).cuda()
-    assert L6.shape[0] == 6
+    Ls, Rs = [L, L.flip(-1) * 0.5, R * 1.5, L.flip(-2), R.flip(-2) * 0.75, L[:1] * 1.25], [R, R.flip(-1) * 0.5, L * 1.5, R.flip(-2), L.flip(-2) * 0.75, R[:1] * 1.25]
+    LB, RB = torch.cat(Ls, 0).cuda(), torch.cat(Rs, 0).cuda()
+    assert LB.shape[0] == 11
     with torch.no_grad():
-        full = m.forward_features(L6, R6)
-        for i in range(6):
-            assert torch.equal(m.forward_features(L6[i:i + 1], R6[i:i + 1]), full[i:i + 1]), i
+        full = m.forward_features(LB, RB)
+        for i in range(11):
+            assert torch.equal(m.forward_features(LB[i:i + 1], RB[i:i + 1]), full[i:i + 1]), i
     assert np.abs(full[:2].cpu().numpy() - g['pred_up']).max() < TOL
 
 
