@@ -188,6 +188,9 @@ struct Params {
                                   // into the parity layout here (the stage is released by the MMA commit AND the epilogue warps' arrivals).
                                   // Why: the transposed conv that produces this tensor is memory-bound and wrote both layouts (natural for
                                   // this launch, parity for the next hourglass's stride-2 conv); this launch is MMA-bound with DRAM at 30 %.
+  int cluster;                    // Cfg::S2T: CTAs (2k, 2k+1) -- the two output-channel slices of one column walk -- are a cluster of two and fetch
+                                  // each input stage ONCE between them: CTA r loads sub-tile pw = r with a multicast TMA that lands in both
+                                  // CTAs' shared memory; a stage is free when BOTH CTAs' MMAs have released it (multicast commit)
   int res_map;                    // Cfg::DTR: the second tensor map covers `residual` (boxes of one output plane tile x 2 channel blocks)
   // split-precision ("x2") passes: a product of (hi+lo) operands is three launches whose accumulators are chained through an
   // fp32 partial; the last pass applies the epilogue and stores the result as two 16-bit words (hi blocks, then lo blocks)
@@ -317,7 +320,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&xmap);
     ptx::prefetch_tensormap(&rmap);
-    for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), (C::MRG && p.x_split) ? 1 + 4 * C::EGROUPS : 1); }
+    for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), (C::MRG && p.x_split) ? 1 + 4 * C::EGROUPS : ((C::S2T && p.cluster) ? 2 : 1)); }
     for (int r = 0; r < NSLOT; ++r) { ptx::mbar_init(accf_bar(r), 1); ptx::mbar_init(acce_bar(r), (C::TRI || C::S2T || C::DTR) ? 4 * C::EGROUPS : 4); }
     ptx::fence_barrier_init();
   }
@@ -343,6 +346,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  const bool paired = C::S2T && p.cluster != 0;
+  const uint32_t crank = paired ? ptx::cluster_ctarank() : 0u;
+  if (paired) ptx::cluster_sync();   // the peer's barriers are initialised before anything of ours can reach them
 
   if (warp == 0) {
     // ================= TMA producer (whole warp converged; one elected lane issues) =================
@@ -365,7 +371,15 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
               const uint32_t s = q % C::STAGES;
               ptx::mbar_wait(empty_bar(s), ((q / C::STAGES) & 1) ^ 1);
               if (lead && (p.dbg & 2)) ptx::mbar_arrive(full_bar(s));
-              else if (lead) {
+              else if (lead && paired) {
+                // this CTA fetches sub-tile pw = its cluster rank for both CTAs of the pair; the peer's box completes the stage
+                ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
+                const int pw = (int)crank, cls = (z & 1) * 4 + ph * 2 + pw;
+                const bool merged = XP != 0 && p.in_lo_off;
+                ptx::tma_load_5d_multicast(stage_addr0 + s * C::STAGE_BYTES + pw * C::SUB_BYTES, &xmap, full_bar(s), (tw * TW - 1) * 8, th * TH - 1,
+                                           merged ? cls * (Din >> 1) + (z >> 1) : (z >> 1), merged ? 0 : cls,
+                                           merged ? n * 2 : n * p.in_blk_stride + p.in_blk_off, (uint16_t)3);
+              } else if (lead) {
                 ptx::mbar_arrive_expect_tx(full_bar(s), C::STAGE_BYTES);
                 for (int pw = 0; pw < 2; ++pw) {
                   if (XP != 0 && p.in_lo_off)
@@ -597,7 +611,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
                     }
                   }
                 }
-                commit(empty_bar(s));
+                if (paired) { if (lead) ptx::umma_commit_multicast(empty_bar(s), (uint16_t)3); }   // frees the stage in BOTH CTAs
+                else commit(empty_bar(s));
               }
             }
             commit(accf_bar(t));
@@ -1627,6 +1642,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   // ---- teardown ----
   ptx::tc_fence_before();
   __syncthreads();
+  if (C::S2T && p.cluster) ptx::cluster_sync();   // (a CTA must not exit while its peer's commits / boxes may still be addressed to it)
   if (warp == 2) ptx::tmem_dealloc<C::TCOLS>(tmem_base);
 }
 
@@ -1908,6 +1924,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   p.part_in = opts.part_in; p.part_out = opts.part_out; p.x2 = opts.x2; p.in_blk_stride = blk_stride; p.in_blk_off = opts.in_blk_off; p.in_lo_off = opts.in_lo_off;
   p.range_flag = opts.range_flag;
   if (!cv) rmap = map;
+  p.cluster = 0;
   p.x_split = nullptr;
   if (opts.x_copy_split) {
     if (!(MODE == tc::M_S1 && CIN == 32 && NT == 32 && OCC == 1 && fmt == 3 && IDISP_MRG && IDISP_TRI && Cout == 32 && !cv && opts.x2 && !opts.in_lo_off && blk_stride == 8)) {
@@ -1976,6 +1993,20 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
         smem_opt_in[dev] = true;
       }
       if constexpr (CVK != 0) kern<<<grid, CX::NTHREADS, CX::SMEM, s>>>(map, rmap, cvmaps, p);
+      else if constexpr (CX::S2T) {
+        static const int no_cluster = tc::env_flag("IDISP_NO_CLUSTER");   // A/B switch
+        if (p.nh == 2 && grid % 2 == 0 && !no_cluster) {
+          tc::Params pc = p;
+          pc.cluster = 1;
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3(grid); cfg.blockDim = dim3(CX::NTHREADS); cfg.dynamicSmemBytes = CX::SMEM; cfg.stream = s;
+          cudaLaunchAttribute at[1];
+          at[0].id = cudaLaunchAttributeClusterDimension;
+          at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+          cfg.attrs = at; cfg.numAttrs = 1;
+          IDISP_CUDA(cudaLaunchKernelEx(&cfg, kern, map, rmap, tc::CvMaps<false>{}, pc));
+        } else kern<<<grid, CX::NTHREADS, CX::SMEM, s>>>(map, rmap, tc::CvMaps<false>{}, p);
+      }
       else kern<<<grid, CX::NTHREADS, CX::SMEM, s>>>(map, rmap, tc::CvMaps<false>{}, p);
       return IDISP_OK;
     }

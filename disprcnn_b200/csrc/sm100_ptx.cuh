@@ -135,6 +135,29 @@ __device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const CUtensorMap
 }
 
 // A tensor map that lives in GLOBAL memory (not a kernel parameter) must be acquired by the tensormap proxy before use.
+// ---------------- thread-block clusters: rank, barrier, multicast forms ----------------
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// every thread of every CTA of the cluster (whole warps, converged)
+__device__ __forceinline__ void cluster_sync()
+{
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// The box lands at the SAME shared-memory offset in every CTA of `cta_mask`, and each of those CTAs' mbarrier at offset `bar`
+// receives the complete_tx for the box's bytes.
+__device__ __forceinline__ void tma_load_5d_multicast(uint32_t smem_dst, const CUtensorMap *m, uint32_t bar, int c0, int c1, int c2,
+                                                      int c3, int c4, uint16_t cta_mask)
+{
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tensormap_acquire(const CUtensorMap *m)
 {
   asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -215,6 +238,13 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, u
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// the same arrive on the mbarrier at offset `bar` of every CTA in `cta_mask`
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask)
+{
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask)
+               : "memory");
 }
 
 // ---------------- tcgen05: TMEM -> registers ----------------
