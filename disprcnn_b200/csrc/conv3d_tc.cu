@@ -1971,7 +1971,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
   const int sms = sm_count[dev] > 0 ? sm_count[dev] : 148;
   int per_slice = sms * OCC / p.nh;
   if (per_slice > ncols) per_slice = ncols;
-  const int grid = per_slice * p.nh;
+  const int grid_cols = per_slice * p.nh;
   auto go = [&](auto fmt_c, auto cv_c) -> int {
     constexpr int FMT = decltype(fmt_c)::value;
     constexpr int CVK = decltype(cv_c)::value;
@@ -1992,6 +1992,10 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
         IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CX::SMEM));
         smem_opt_in[dev] = true;
       }
+      // Kernels that walk work items (Items) get one CTA per SM even when there are fewer columns than that: the columns are then
+      // split in depth so that a small batch (the live call: 28 columns per ROI pair) still fills the machine.
+      static const int no_fill = tc::env_flag("IDISP_NO_DEPTH_FILL");   // A/B switch
+      const int grid = ((CX::MRG || CX::S2T) && !no_fill && !(p.dbg & 2048)) ? (sms * OCC / p.nh) * p.nh : grid_cols;
       if constexpr (CVK != 0) kern<<<grid, CX::NTHREADS, CX::SMEM, s>>>(map, rmap, cvmaps, p);
       else if constexpr (CX::S2T) {
         static const int no_cluster = tc::env_flag("IDISP_NO_CLUSTER");   // A/B switch
