@@ -325,13 +325,20 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<C::TCOLS>(ptx::smem_u32(tmem_ptr_smem));
-  {  // this slice's weights -> shared memory (generic proxy), then visible to the async proxy (tensor core)
-    const uint4 *src = reinterpret_cast<const uint4 *>(p.w) + (size_t)nh * (C::WBYTES / 16);
-    uint4 *dst = reinterpret_cast<uint4 *>(smem);
-    for (int i = threadIdx.x; i < C::WBYTES / 16; i += NTHREADS) dst[i] = __ldg(src + i);
-    if (threadIdx.x < NT) bias_s[threadIdx.x] = (p.bias && nh * NT + (int)threadIdx.x < p.Cout) ? p.bias[nh * NT + threadIdx.x] : 0.f;
-    ptx::fence_proxy_async_smem();
+  // This slice's weights (28-110 KB) -> shared memory with bulk TMA copies tracked by their own mbarrier; only the MMA warp waits for
+  // it, right before its first MMA, so the copy overlaps the rest of the prologue (TMEM allocation, accumulator clearing, the first
+  // input stages).  (A loop of 16-byte loads and stores by all threads took ~10 us per launch: 18 dependent round trips to L2 -- a
+  // quarter of a launch at the live shape, where a forward is ~50 launches of 20-30 us.)
+  const uint32_t wbar = bar0 + 8u * (2 * C::STAGES + 2 * NSLOT) + 8u;   // (second half of the 16-byte slot that holds the TMEM pointer)
+  if (warp == 0 && lane == 0) {
+    ptx::mbar_init(wbar, 1);
+    ptx::fence_barrier_init();
+    ptx::mbar_arrive_expect_tx(wbar, C::WBYTES);
+    const char *src = reinterpret_cast<const char *>(p.w) + (size_t)nh * C::WBYTES;
+    for (uint32_t off = 0; off < (uint32_t)C::WBYTES; off += 16384u)
+      ptx::bulk_g2s(w_addr + off, src + off, (uint32_t)C::WBYTES - off < 16384u ? (uint32_t)C::WBYTES - off : 16384u, wbar);
   }
+  if (threadIdx.x < NT) bias_s[threadIdx.x] = (p.bias && nh * NT + (int)threadIdx.x < p.Cout) ? p.bias[nh * NT + threadIdx.x] : 0.f;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -432,6 +439,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
     {
       const bool lead = ptx::elect_one();
       const bool do_mma = lead && !(p.dbg & 1);
+      ptx::mbar_wait(wbar, 0);   // the weights have landed (async proxy -> visible to the MMAs issued after this wait)
       auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc = 1u) { if (do_mma) ptx::umma_bf16_ss(d, a, b, id, acc); };
       auto commit = [&](uint32_t bar) { if (lead) ptx::umma_commit(bar); };
       const uint64_t a_desc0 = ptx::make_smem_desc(stage_addr0, C::PLANE_BYTES, C::ROW_BYTES);
