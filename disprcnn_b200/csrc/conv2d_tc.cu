@@ -85,11 +85,15 @@ __global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<512>(ptx::smem_u32(tmem_ptr_smem));
-  {
-    const uint4 *src = reinterpret_cast<const uint4 *>(p.w) + (size_t)nh * (p.w_slice_bytes / 16);
-    uint4 *dst = reinterpret_cast<uint4 *>(smem);
-    for (uint32_t i = threadIdx.x; i < wbytes / 16; i += 256) dst[i] = __ldg(src + i);
-    ptx::fence_proxy_async_smem();
+  // weights (36 KB per 32-channel chunk) -> shared memory as bulk TMA copies on their own mbarrier; only the MMA warp waits for it
+  // (the copy loop by all threads cost ~10 us of dependent L2 round trips per launch -- most of a launch at the live shape)
+  const uint32_t wbar = bar0 + 8u * (2 * S + 4) + 8u;   // (second half of the 16-byte slot that holds the TMEM pointer)
+  if (warp == 0 && lane == 0) {
+    ptx::mbar_init(wbar, 1);
+    ptx::fence_barrier_init();
+    ptx::mbar_arrive_expect_tx(wbar, wbytes);
+    const char *src = reinterpret_cast<const char *>(p.w) + (size_t)nh * p.w_slice_bytes;
+    for (uint32_t off = 0; off < wbytes; off += 16384u) ptx::bulk_g2s(w_addr + off, src + off, wbytes - off < 16384u ? wbytes - off : 16384u, wbar);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -121,6 +125,7 @@ __global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant
     const uint32_t id64 = ptx::make_idesc_h<true>(128, 64), id32 = ptx::make_idesc_h<true>(128, 32);
     const uint32_t nbuf = (uint32_t)p.nbuf, bufcols = (uint32_t)p.nchunks * 96;
     uint32_t q = 0, it = 0;
+    ptx::mbar_wait(wbar, 0);   // the weights have landed
     for (int tile = cta; tile < ntiles; tile += ncta, ++it) {
       const uint32_t t = it % nbuf;
       ptx::mbar_wait(acce_bar(t), ((it / nbuf) & 1) ^ 1);
