@@ -35,6 +35,13 @@
 //   ring (MMA <-> epilogue); the layer's weights (55/110 KB) stay resident in shared memory.
 // Roofline: tensor (dense bf16/fp16); algorithmic FLOPs = 2*27*Cin*Cout per output voxel (stride 1).
 //
+// Scheduling forms added on top of that (each documented at its Cfg flag / Params field): per-step accumulators with merged
+// x_hi * [w_hi | w_lo] MMAs (Cfg::TRI / MRG, stride 1), per-step pairs (Cfg::S2T, stride 2 32 -> 64) and class-major kd-stacked
+// buffers (Cfg::DTR, transposed); Cin = 64 layers split by input channels into two such launches (tc_conv3d_split); work items that
+// split the last round's columns -- or, for small batches, all columns -- in depth (Items); CTA pairs that fetch their common input
+// once with multicast TMA (Params::cluster); the parity-layout copy of a launch's input written by its two idle warps
+// (Params::x_split); residual boxes prefetched to L2 by the MMA warp (Params::res_map); weights loaded by bulk TMA copies.
+//
 // Storage formats (template parameter FMT): bf16 or IEEE-half words (one word per value), or SPLIT PRECISION -- every activation
 // and weight is two IEEE-half words (hi + lo, block groups [hi | lo] per sample), a product is x_hi*w_hi + x_lo*w_hi + x_hi*w_lo
 // accumulated in fp32: the tensor-core mode that meets the 1e-3 px parity bar (Cfg::XP: the three terms as extra k-steps of ONE
@@ -184,8 +191,8 @@ struct Params {
   __nv_bfloat16 *y_split;         // optional second copy of y in the 8-parity-sub-volume layout a stride-2 consumer reads
   int residual_is_split;          // transposed conv only: `residual` is stored in that parity layout (of the OUTPUT grid)
   int skip_y;                     // write only y_split (the natural copy has no reader)
-  __nv_bfloat16 *x_split;         // per-step-triple 32 -> 32 kernel: the epilogue warps copy every input plane tile from its shared-memory stage
-                                  // into the parity layout here (the stage is released by the MMA commit AND the epilogue warps' arrivals).
+  __nv_bfloat16 *x_split;         // per-step-triple 32 -> 32 kernel: warps 2 and 3 (otherwise idle) copy every input plane tile from its shared-memory
+                                  // stage into the parity layout here (the stage is released by the MMA commit AND these two warps' arrivals).
                                   // Why: the transposed conv that produces this tensor is memory-bound and wrote both layouts (natural for
                                   // this launch, parity for the next hourglass's stride-2 conv); this launch is MMA-bound with DRAM at 30 %.
   int cluster;                    // Cfg::S2T: CTAs (2k, 2k+1) -- the two output-channel slices of one column walk -- are a cluster of two and fetch
@@ -320,7 +327,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&xmap);
     ptx::prefetch_tensormap(&rmap);
-    for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), (C::MRG && p.x_split) ? 1 + 4 * C::EGROUPS : ((C::S2T && p.cluster) ? 2 : 1)); }
+    for (int s = 0; s < C::STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), (C::MRG && p.x_split) ? 3 : ((C::S2T && p.cluster) ? 2 : 1)); }
     for (int r = 0; r < NSLOT; ++r) { ptx::mbar_init(accf_bar(r), 1); ptx::mbar_init(acce_bar(r), (C::TRI || C::S2T || C::DTR) ? 4 * C::EGROUPS : 4); }
     ptx::fence_barrier_init();
   }
@@ -758,6 +765,41 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         }
       }
     }
+  } else if (warp == 2 || warp == 3) {
+    // ================= input side copy (Params::x_split; the two otherwise idle warps) =================
+    // Every input plane tile that passes through a stage is also written to global memory in the parity layout: consumers of the
+    // stage are then the MMA warp (commit) AND these two warps (one arrival each).  64 threads move the 128 voxels x 8 channel
+    // blocks (hi 4 | lo 4) of a tile, 16 x 16 B each; a chunked item's halo planes are written twice (same bytes).
+    if constexpr (C::MRG) {
+      if (p.x_split) {
+        const int ct = (warp - 2) * 32 + lane;
+        const int64_t Vo = (int64_t)Dout * p.Ho * p.Wo, sub = Vo / 8, plane_spl = (int64_t)(p.Ho / 2) * (p.Wo / 2) * 8;
+        const Items items = make_items(ncols, ncta, Dout, !(p.dbg & 2048));
+        uint32_t q = 0;
+        for (int item = cta; item < items.total; item += ncta) {
+          int col, e0, e1;
+          get_item(items, item, Dout, col, e0, e1);
+          const int tw = col % p.tiles_w, th = (col / p.tiles_w) % p.tiles_h, n = col / (p.tiles_w * p.tiles_h);
+          for (int z = (e0 > 0 ? e0 - 1 : 0); z < (e1 < Din ? e1 + 1 : Din); ++z, ++q) {
+            const uint32_t sq = q % C::STAGES;
+            ptx::mbar_wait(full_bar(sq), (q / C::STAGES) & 1);
+#pragma unroll 4
+            for (int j = 0; j < 16; ++j) {
+              const int u = ct + 64 * j, v = u & 127, b8 = u >> 7;        // voxel of the tile, block of [hi 4 | lo 4]
+              const int hl = v >> 3, wl = v & 7, hr = th * TH + hl, wr = tw * TW + wl;
+              if (hr < p.Hr && wr < p.Wr) {
+                const uint4 val = ptx::lds_v4(stage_addr0 + sq * C::STAGE_BYTES + b8 * C::PLANE_BYTES + ((hl + 1) * MC::SUB_W + (wl + 1)) * 16);
+                const int64_t off = ((int64_t)n * 8 + b8) * Vo * 8 +
+                                    ((int64_t)((z & 1) * 4 + (hr & 1) * 2 + (wr & 1)) * sub + (int64_t)(hr >> 1) * (p.Wo / 2) + (wr >> 1)) * 8 + (int64_t)(z >> 1) * plane_spl;
+                ptx::stg_cs_v4(p.x_split + off, val);
+              }
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(empty_bar(sq));
+          }
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ================= epilogue (4 warps = 128 TMEM lanes) =================
     const int quarter = warp & 3;
@@ -999,24 +1041,6 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(acce_bar(t));
             continue;
-          }
-          if constexpr (C::MRG) {
-            if (p.x_split) {  // parity-layout copy of input plane z, read back from its stage (resident: this group has not released it yet)
-              const uint32_t sq = tq % C::STAGES;
-              ptx::mbar_wait(full_bar(sq), (tq / C::STAGES) & 1);   // (completed long ago; makes the TMA's writes visible to these loads)
-              if (valid) {
-                const uint32_t src = stage_addr0 + sq * C::STAGE_BYTES + ((hl + 1) * MC::SUB_W + (wl + 1)) * 16 + egroup * NCBG * C::PLANE_BYTES;
-                const int64_t dst = spl_of(z);
-#pragma unroll
-                for (int i = 0; i < NCBG; ++i) {
-                  const uint4 vh = ptx::lds_v4(src + i * C::PLANE_BYTES), vl = ptx::lds_v4(src + (C::CBLK + i) * C::PLANE_BYTES);
-                  ptx::stg_cs_v4(p.x_split + dst + (int64_t)i * blk_elems, vh);
-                  ptx::stg_cs_v4(p.x_split + dst + (int64_t)i * blk_elems + lo_off, vl);
-                }
-              }
-              __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(empty_bar(sq));
-            }
           }
           const uint32_t tb = tmem_base + lane_addr + t * C::TRI_STRIDE + egroup * CPG;
           if (p.dbg & 128) {  // timing experiment: no TMEM reads, the arithmetic and the stores run on whatever the registers hold
