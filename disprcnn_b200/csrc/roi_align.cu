@@ -27,10 +27,17 @@ roi_align_fwd_kernel(const float *__restrict__ in, const float *__restrict__ roi
   const int64_t total = (int64_t)R * cgroups * ph_n * pw_n;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    const int pw = (int)(idx % pw_n);
-    const int ph = (int)((idx / pw_n) % ph_n);
-    const int cg = (int)((idx / ((int64_t)pw_n * ph_n)) % cgroups);
-    const int n = (int)(idx / ((int64_t)pw_n * ph_n * cgroups));
+    int pw, ph, cg, n;
+    if (total < (1ll << 31)) {  // (32-bit index arithmetic: the 64-bit divisions were a third of this kernel's instructions)
+      const uint32_t i = (uint32_t)idx, a = i / (uint32_t)pw_n, b2 = a / (uint32_t)ph_n;
+      pw = (int)(i - a * (uint32_t)pw_n); ph = (int)(a - b2 * (uint32_t)ph_n);
+      n = (int)(b2 / (uint32_t)cgroups); cg = (int)(b2 - (uint32_t)n * (uint32_t)cgroups);
+    } else {
+      pw = (int)(idx % pw_n);
+      ph = (int)((idx / pw_n) % ph_n);
+      cg = (int)((idx / ((int64_t)pw_n * ph_n)) % cgroups);
+      n = (int)(idx / ((int64_t)pw_n * ph_n * cgroups));
+    }
     const float *roi = rois + (int64_t)n * 5;
     const int b = (int)roi[0];
     const float rsw = __fmul_rn(roi[1], scale), rsh = __fmul_rn(roi[2], scale);
@@ -52,14 +59,15 @@ roi_align_fwd_kernel(const float *__restrict__ in, const float *__restrict__ roi
     const float ybase = __fadd_rn(rsh, __fmul_rn((float)ph, bin_h));
     const float xbase = __fadd_rn(rsw, __fmul_rn((float)pw, bin_w));
     for (int iy = 0; iy < gh; ++iy) {
-      float y = __fadd_rn(ybase, __fdiv_rn(__fmul_rn((float)iy + .5f, bin_h), (float)gh));
+      // (x / 1.0f == x exactly in IEEE arithmetic: the one-sample-per-bin case -- ROIs up to the crop size -- skips those divisions)
+      float y = __fadd_rn(ybase, gh == 1 ? __fmul_rn((float)iy + .5f, bin_h) : __fdiv_rn(__fmul_rn((float)iy + .5f, bin_h), (float)gh));
       const bool y_oob = (y < -1.0f) || (y > (float)H);
       if (y <= 0) y = 0;
       int y_low = (int)y, y_high;
       if (y_low >= H - 1) { y_high = y_low = H - 1; y = (float)y_low; } else y_high = y_low + 1;
       const float ly = __fsub_rn(y, (float)y_low), hy = __fsub_rn(1.f, ly);
       for (int ix = 0; ix < gw; ++ix) {
-        float x = __fadd_rn(xbase, __fdiv_rn(__fmul_rn((float)ix + .5f, bin_w), (float)gw));
+        float x = __fadd_rn(xbase, gw == 1 ? __fmul_rn((float)ix + .5f, bin_w) : __fdiv_rn(__fmul_rn((float)ix + .5f, bin_w), (float)gw));
         if (y_oob || x < -1.0f || x > (float)W) continue;  // contributes exactly 0
         if (x <= 0) x = 0;
         int x_low = (int)x, x_high;
@@ -82,7 +90,7 @@ roi_align_fwd_kernel(const float *__restrict__ in, const float *__restrict__ roi
 #pragma unroll
     for (int c = 0; c < ROI_CG; ++c) {
       if (c < nc) {
-        float v = __fdiv_rn(acc[c], count);
+        float v = count == 1.f ? acc[c] : __fdiv_rn(acc[c], count);
         if (mean != nullptr) v = __fdiv_rn(__fsub_rn(v, mean[c0 + c]), stdv[c0 + c]);
         out[(((int64_t)n * C + c0 + c) * ph_n + ph) * pw_n + pw] = v;
       }
