@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256, 2) conv2d_kernel(const ConvParams p)
     __syncthreads();
     // input patch (zero outside the image = conv padding; zero for the channels beyond Cin): one warp per (channel, row),
     // lanes along the row -- coalesced, and no integer division per element
-    for (int rowi = tid >> 5; rowi < CI * PH; rowi += 8) {
+    for (int rowi = tid >> 5; rowi < nci * PH; rowi += 8) {   // (only the channels that exist: firstconv.0 has 3 of the 16)
       const int ci = rowi / PH, yy = rowi - ci * PH;
       const int gy = iy0 + yy;
       const bool rok = ci < nci && gy >= 0 && gy < p.H;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256, 2) conv2d_kernel(const ConvParams p)
         dst[xx] = (rok && gx >= 0 && gx < p.W) ? __ldg(src + gx) : 0.f;
       }
     }
-    for (int i = tid; i < CI * K * K * COB; i += 256) {
+    for (int i = tid; i < nci * K * K * COB; i += 256) {
       const int co = i % COB, t = (i / COB) % (K * K), ci = i / (COB * K * K);
       float v = 0.f;
       if (ci < nci && cb + co < p.Cout) v = __ldg(p.w + ((long long)(c0 + ci) * K * K + t) * p.Cout + cb + co);
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256, 2) conv2d_kernel(const ConvParams p)
     }
     __syncthreads();
 #pragma unroll 1
-    for (int ci = 0; ci < CI; ++ci) {
+    for (int ci = 0; ci < nci; ++ci) {
 #pragma unroll
       for (int kh = 0; kh < K; ++kh) {
         const float *row = s_in + (ci * PH + py * p.stride + kh * p.dil) * PWp + px0 * p.stride;
@@ -145,19 +145,64 @@ __global__ void avgpool_kernel(const float *__restrict__ x, long long xbs, int C
   }
 }
 
+// 1x1 conv (any stride) + bias (+ residual) (+ ReLU) straight from global memory: one thread per output pixel and group of 16 output
+// channels, x read once per input channel (coalesced along the row; stride 2 uses every other element of its sectors), the 16 weights
+// of a step are one address for the whole warp.  The tiled kernel above stages the full-resolution patch of a stride-2 1x1 conv in
+// shared memory (four times the pixels it uses): 138 us for the 0.2 GFLOP of layer2.0.downsample at 16 images, this one ~15 us.
+__global__ void __launch_bounds__(256) pointwise_kernel(const float *__restrict__ x, long long xbs, const float *__restrict__ w, const float *__restrict__ bias,
+                                                          const float *__restrict__ res, long long rbs, float *__restrict__ y, long long ybs, int Cin, int Cout,
+                                                          int H, int W, int Ho, int Wo, int stride, int relu)
+{
+  const int n = blockIdx.z, g = blockIdx.y;   // image, group of 16 output channels
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= Ho * Wo) return;
+  const int oy = pix / Wo, ox = pix - oy * Wo;
+  const float *xp = x + (long long)n * xbs + (long long)(oy * stride) * W + ox * stride;
+  const float4 *wp = reinterpret_cast<const float4 *>(w + g * 16);
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+#pragma unroll 4
+  for (int ci = 0; ci < Cin; ++ci) {
+    const float xv = __ldg(xp + (long long)ci * H * W);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 wv = __ldg(wp + (long long)ci * (Cout / 4) + q);
+      acc[q * 4 + 0] = fmaf(xv, wv.x, acc[q * 4 + 0]); acc[q * 4 + 1] = fmaf(xv, wv.y, acc[q * 4 + 1]);
+      acc[q * 4 + 2] = fmaf(xv, wv.z, acc[q * 4 + 2]); acc[q * 4 + 3] = fmaf(xv, wv.w, acc[q * 4 + 3]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const int co = g * 16 + c;
+    const long long o = ((long long)co * Ho + oy) * Wo + ox;
+    float v = acc[c] + (bias ? __ldg(bias + co) : 0.f);
+    if (res) v += __ldg(res + (long long)n * rbs + o);
+    if (relu) v = fmaxf(v, 0.f);
+    y[(long long)n * ybs + o] = v;
+  }
+}
+
 // 1x1 conv + bias (+ ReLU) on a handful of pixels (the SPP branches: 128 -> 32 channels on 1 .. 49 pixels per image): one thread
 // per output element, weights [Cin][Cout] read coalesced across the output channels
 __global__ void pointwise_small_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias, int Cin, int Cout,
                                        int HW, int relu, float *__restrict__ y)
 {
-  const int n = blockIdx.y;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Cout * HW; i += gridDim.x * blockDim.x) {
+  // one WARP per output element, the lanes split the input channels (a serial 128-long chain of dependent loads per thread took
+  // 47 us for a few hundred outputs), shuffle reduction
+  const int n = blockIdx.y, lane = threadIdx.x & 31;
+  const int nwarp = gridDim.x * (blockDim.x >> 5);
+  for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < Cout * HW; i += nwarp) {
     const int co = i % Cout, pos = i / Cout;
     const float *xp = x + (long long)n * Cin * HW + pos;
     float a = 0.f;
-    for (int ci = 0; ci < Cin; ++ci) a = fmaf(__ldg(xp + (long long)ci * HW), __ldg(w + (long long)ci * Cout + co), a);
-    a += bias ? __ldg(bias + co) : 0.f;
-    y[((long long)n * Cout + co) * HW + pos] = relu ? fmaxf(a, 0.f) : a;
+    for (int ci = lane; ci < Cin; ci += 32) a = fmaf(__ldg(xp + (long long)ci * HW), __ldg(w + (long long)ci * Cout + co), a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) {
+      a += bias ? __ldg(bias + co) : 0.f;
+      y[((long long)n * Cout + co) * HW + pos] = relu ? fmaxf(a, 0.f) : a;
+    }
   }
 }
 
@@ -434,6 +479,12 @@ static int f2d_conv(idisp_extractor *e, const std::string &prefix, const float *
   };
   static bool o0[64], o1[64], o2[64], o3[64];
   ++e->launches;
+  if (L.k == 1 && L.cout % 16 == 0) {
+    f2d::pointwise_kernel<<<dim3(ceil_div(p.Ho * p.Wo, 256), L.cout / 16, B), 256, 0, s>>>(x, xbs, L.w, L.bias, res, p.rbs, y, p.ybs, L.cin, L.cout, H, W, p.Ho, p.Wo,
+                                                                                            L.stride, relu);
+    IDISP_LAUNCH_CHECK();
+    return IDISP_OK;
+  }
   if (L.k == 3) return cob == 64 ? go(f2d::conv2d_kernel<3, 64>, o0) : go(f2d::conv2d_kernel<3, 32>, o1);
   return cob == 64 ? go(f2d::conv2d_kernel<1, 64>, o2) : go(f2d::conv2d_kernel<1, 32>, o3);
 }
@@ -443,7 +494,7 @@ static int f2d_pointwise_small(idisp_extractor *e, const std::string &prefix, co
   auto it = e->index.find(prefix);
   if (it == e->index.end()) { set_error("extractor: unknown layer '%s'", prefix.c_str()); return IDISP_ERR_INVALID; }
   const F2dLayer &L = e->layers[it->second];
-  f2d::pointwise_small_kernel<<<dim3(ceil_div(L.cout * HW, 128), B), 128, 0, s>>>(x, L.w, L.bias, L.cin, L.cout, HW, relu, y);
+  f2d::pointwise_small_kernel<<<dim3(ceil_div(L.cout * HW, 8), B), 256, 0, s>>>(x, L.w, L.bias, L.cin, L.cout, HW, relu, y);   // 8 warps = 8 outputs per CTA
   IDISP_LAUNCH_CHECK();
   ++e->launches;
   return IDISP_OK;
