@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant
   auto acce_bar = [&](uint32_t t) { return bar0 + 8u * (2 * S + 2 + t); };
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + wbytes + (size_t)p.stages * G::STAGE + (2 * S + 4) * 8);
 
+  ptx::pdl_launch_dependents();
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int nh = blockIdx.x % p.nslices;                 // this CTA's 32-wide output-channel slice (its weights stay resident)
   const int cta = blockIdx.x / p.nslices, ncta = gridDim.x / p.nslices;
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(256, 1) conv2d_tc_kernel(const __grid_constant
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  ptx::pdl_wait();   // (programmatic dependent launch: the prologue above overlapped the previous kernel's tail)
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -440,16 +442,17 @@ int c2d_conv(const C2dWeights &w, int dil, const C2dTensor &x, int chunk0, int n
   if (per_slice > ntiles) per_slice = ntiles;
   const int grid = per_slice * p.nslices;
   const int smem = wbytes + stages * stage + (2 * stages + 4) * 8 + 16;
+  const bool pdl = (long long)ntiles * p.nslices <= 2ll * sm_count[dev];   // small launches only (see launch_ex)
   static bool o0[64], o1[64], o2[64];
   if (dil == 0) {
     if (!o0[dev]) { IDISP_CUDA(cudaFuncSetAttribute(c2d::conv2d_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)); o0[dev] = true; }
-    c2d::conv2d_tc_kernel<0><<<grid, 256, smem, s>>>(map, p);
+    IDISP_CUDA(launch_ex(c2d::conv2d_tc_kernel<0>, grid, 256, (size_t)smem, s, false, pdl, map, p));
   } else if (dil == 1) {
     if (!o1[dev]) { IDISP_CUDA(cudaFuncSetAttribute(c2d::conv2d_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)); o1[dev] = true; }
-    c2d::conv2d_tc_kernel<1><<<grid, 256, smem, s>>>(map, p);
+    IDISP_CUDA(launch_ex(c2d::conv2d_tc_kernel<1>, grid, 256, (size_t)smem, s, false, pdl, map, p));
   } else {
     if (!o2[dev]) { IDISP_CUDA(cudaFuncSetAttribute(c2d::conv2d_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)); o2[dev] = true; }
-    c2d::conv2d_tc_kernel<2><<<grid, 256, smem, s>>>(map, p);
+    IDISP_CUDA(launch_ex(c2d::conv2d_tc_kernel<2>, grid, 256, (size_t)smem, s, false, pdl, map, p));
   }
   IDISP_LAUNCH_CHECK();
   return IDISP_OK;

@@ -318,6 +318,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   // warp index made PROVABLY warp-uniform (shfl from lane 0) so the role branches are uniform branches and the
   // producer / MMA warps can keep their addresses and descriptors in uniform registers
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  ptx::pdl_launch_dependents();       // (the next kernel's CTAs may take this SM as soon as this CTA is gone: their prologue overlaps our tail)
   const int nh = blockIdx.x % p.nh;  // this CTA's fixed 32-wide output-channel slice
   const int cta = blockIdx.x / p.nh, ncta = gridDim.x / p.nh;
   const int ncols = p.B * p.tiles_h * p.tiles_w;
@@ -363,6 +364,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
   const bool paired = C::S2T && p.cluster != 0;
   const uint32_t crank = paired ? ptx::cluster_ctarank() : 0u;
   if (paired) ptx::cluster_sync();   // the peer's barriers are initialised before anything of ours can reach them
+  // Programmatic dependent launch: everything above (barriers, TMEM, weight copies, bias) touches nothing the previous kernel in the
+  // stream produces, so it ran while that kernel drained; from here on its activations are read.
+  ptx::pdl_wait();
 
   if (warp == 0) {
     // ================= TMA producer (whole warp converged; one elected lane issues) =================
@@ -2028,22 +2032,15 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
       // split in depth so that a small batch (the live call: 28 columns per ROI pair) still fills the machine.
       static const int no_fill = tc::env_flag("IDISP_NO_DEPTH_FILL");   // A/B switch
       const int grid = ((CX::MRG || CX::S2T) && !no_fill && !(p.dbg & 2048)) ? (sms * OCC / p.nh) * p.nh : grid_cols;
-      if constexpr (CVK != 0) kern<<<grid, CX::NTHREADS, CX::SMEM, s>>>(map, rmap, cvmaps, p);
+      const bool pdl = (long long)ncols * p.nh <= 2ll * sms;   // small launches only (see launch_ex)
+      if constexpr (CVK != 0) IDISP_CUDA(launch_ex(kern, grid, CX::NTHREADS, CX::SMEM, s, false, pdl, map, rmap, cvmaps, p));
       else if constexpr (CX::S2T) {
         static const int no_cluster = tc::env_flag("IDISP_NO_CLUSTER");   // A/B switch
-        if (p.nh == 2 && grid % 2 == 0 && !no_cluster) {
-          tc::Params pc = p;
-          pc.cluster = 1;
-          cudaLaunchConfig_t cfg = {};
-          cfg.gridDim = dim3(grid); cfg.blockDim = dim3(CX::NTHREADS); cfg.dynamicSmemBytes = CX::SMEM; cfg.stream = s;
-          cudaLaunchAttribute at[1];
-          at[0].id = cudaLaunchAttributeClusterDimension;
-          at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-          cfg.attrs = at; cfg.numAttrs = 1;
-          IDISP_CUDA(cudaLaunchKernelEx(&cfg, kern, map, rmap, tc::CvMaps<false>{}, pc));
-        } else kern<<<grid, CX::NTHREADS, CX::SMEM, s>>>(map, rmap, tc::CvMaps<false>{}, p);
+        tc::Params pc = p;
+        pc.cluster = (p.nh == 2 && grid % 2 == 0 && !no_cluster) ? 1 : 0;
+        IDISP_CUDA(launch_ex(kern, grid, CX::NTHREADS, CX::SMEM, s, pc.cluster != 0, pdl, map, rmap, tc::CvMaps<false>{}, pc));
       }
-      else kern<<<grid, CX::NTHREADS, CX::SMEM, s>>>(map, rmap, tc::CvMaps<false>{}, p);
+      else IDISP_CUDA(launch_ex(kern, grid, CX::NTHREADS, CX::SMEM, s, false, pdl, map, rmap, tc::CvMaps<false>{}, p));
       return IDISP_OK;
     }
   };

@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(384, OCC) head_tc_kernel(const __grid_constant
   auto acce_bar = [&](uint32_t t) { return bar0 + 8u * (2 * C::STAGES + 2 + t); };
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + C::BAR_OFF + (2 * C::STAGES + 4) * 8);
 
+  ptx::pdl_launch_dependents();
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int ncols = p.B * p.tiles_h * p.tiles_w, D = p.D;
 
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(384, OCC) head_tc_kernel(const __grid_constant
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  ptx::pdl_wait();   // (programmatic dependent launch: the prologue above overlapped the previous kernel's tail)
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -331,8 +333,7 @@ int tc_head_conv(const TcHeadWeights &w, const __nv_bfloat16 *x, int B, int D, i
       IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
       opted[dev] = true;
     }
-    kern<<<grid, 384, smem_bytes, s>>>(map, p);
-    IDISP_LAUNCH_CHECK();
+    IDISP_CUDA(launch_ex(kern, grid, 384, (size_t)smem_bytes, s, false, ncols <= 2 * sm_count[dev], map, p));
     return IDISP_OK;
   };
   static bool o0[64], o1[64], o2[64], o3[64], o4[64], o5[64];

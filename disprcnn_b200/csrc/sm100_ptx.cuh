@@ -135,6 +135,13 @@ __device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const CUtensorMap
 }
 
 // A tensor map that lives in GLOBAL memory (not a kernel parameter) must be acquired by the tensormap proxy before use.
+// ---------------- programmatic dependent launch ----------------
+// launch_dependents: the next kernel in the stream (launched with the programmatic-serialization attribute) may start its CTAs as soon
+// as every CTA of this grid has executed this (or exited) and an SM has room; wait: blocks until the PREVIOUS grid has completed and
+// its memory is visible.  Everything a kernel does before its wait must not touch what its predecessor produces.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------- thread-block clusters: rank, barrier, multicast forms ----------------
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
