@@ -139,6 +139,17 @@ def test_pipelined_host_entry_point_matches_one_batch_at_a_time(lib):
     assert np.abs(outs[0].numpy() - g['pred_up']).max() < TOL
     with pytest.raises(RuntimeError):
         _lib.check(lib.idisp_plan_host_wait(m._plan, tickets[-1] + 1))   # never issued
+    # a larger batch re-allocates the double-buffered staging (drains what is in flight first); tickets keep counting
+    L2, R2 = torch.cat([L, L * 0.5], 0).contiguous().pin_memory(), torch.cat([R, R * 0.5], 0).contiguous().pin_memory()
+    with torch.no_grad():
+        want2 = m.forward_features(L2.cuda(), R2.cuda()).cpu()
+    out2 = torch.full((2 * B, 4 * Hf, 4 * Wf), float('nan')).pin_memory()
+    t = ctypes.c_ulonglong()
+    _lib.check(lib.idisp_plan_forward_host_async(m._plan, _lib.ptr(L2), _lib.ptr(R2), 2 * B, Hf, Wf, 4 * Hf, 4 * Wf, _lib.ptr(out2),
+                                                 _lib.stream_ptr(), ctypes.byref(t)))
+    assert t.value == tickets[-1] + 1
+    _lib.check(lib.idisp_plan_host_wait(m._plan, t.value))
+    assert torch.equal(out2, want2)
     torch.cuda.synchronize()
 
 
