@@ -211,7 +211,7 @@ struct Params {
   int tiles_h, tiles_w, nh;
   int cv_shift0;                  // mindisp/4: plane k <-> right-view shift i = k + cv_shift0
   int cv_view;                    // CV == 2: which view this launch reads (0 left, 1 right)
-  int dbg;                        // timing experiments only (IDISP_TC_DBG): 1 no MMAs, 2 no TMA loads, 4 no global stores, 8 no tcgen05.ld, 16 no tcgen05.st, 32 TRI epilogue = handshake only, 64 TRI epilogue without the per-voxel work, 128 TRI epilogue without TMEM reads, 256 DTR without the residual L2 prefetch, 512 DTR without residual loads
+  int dbg;                        // timing experiments only (IDISP_TC_DBG): 1 no MMAs, 2 no TMA loads, 4 no global stores, 8 no tcgen05.ld, 16 no tcgen05.st, 32 TRI epilogue = handshake only, 64 TRI epilogue without the per-voxel work, 128 TRI epilogue without TMEM reads, 256 DTR without the residual L2 prefetch, 512 DTR without residual loads, 1024 DTR plain instead of streaming stores, 2048 no depth-split work items, 4096 DTR prefetch one step further ahead
 };
 
 // DECONV stacking table: per kd, five MMAs (entries) that share an input shift
@@ -665,11 +665,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           if (p.res_map && lead && !(p.dbg & 256)) {
             const int tw = col % p.tiles_w, th = (col / p.tiles_w) % p.tiles_h, n = col / (p.tiles_w * p.tiles_h);
             const int cblk_out = p.Cout / 8, out_blocks = p.x2 ? 2 * cblk_out : cblk_out;
-            for (int i = 0; i < (p.x2 ? 4 : 2); ++i) {
-              const int qo = 2 * z + (i & 1), blk = n * out_blocks + nh * 2 + (i >> 1) * cblk_out;
-              if (p.residual_is_split) ptx::tma_prefetch_5d(&rmap, tw * TW * 8, th * TH, qo >> 1, (qo & 1) * 4, blk);
-              else ptx::tma_prefetch_4d(&rmap, 2 * tw * TW * 8, 2 * th * TH, qo, blk);
-            }
+            const int ahead = (p.dbg & 4096) ? 1 : 0;   // (timing experiment: one more step of lead -- measured WORSE, conv6 1.30 -> 1.51 ms)
+            for (int zz = (z == 0 ? 0 : z + ahead); zz <= z + ahead && zz < Din; ++zz)
+              for (int i = 0; i < (p.x2 ? 4 : 2); ++i) {
+                const int qo = 2 * zz + (i & 1), blk = n * out_blocks + nh * 2 + (i >> 1) * cblk_out;
+                if (p.residual_is_split) ptx::tma_prefetch_5d(&rmap, tw * TW * 8, th * TH, qo >> 1, (qo & 1) * 4, blk);
+                else ptx::tma_prefetch_4d(&rmap, 2 * tw * TW * 8, 2 * th * TH, qo, blk);
+              }
           }
           __syncwarp();
 #pragma unroll
