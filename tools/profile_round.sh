@@ -1,3 +1,5 @@
+# One round-end capture on a GPU box (gpurun): GPU tests, smoke, the driver-style bench line, launch lists (stack + live) and an
+# ncu --set full capture of one configs[1] forward, everything written to gpurun_out/r02_final_* (copy to profiles/ afterwards).
 set -x
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r02_final_pytest.log 2>&1; echo "pytest rc=$?"
