@@ -442,7 +442,8 @@ int c2d_conv(const C2dWeights &w, int dil, const C2dTensor &x, int chunk0, int n
   if (per_slice > ntiles) per_slice = ntiles;
   const int grid = per_slice * p.nslices;
   const int smem = wbytes + stages * stage + (2 * stages + 4) * 8 + 16;
-  const bool pdl = (long long)ntiles * p.nslices <= 2ll * sm_count[dev];   // small launches only (see launch_ex)
+  // short launches only (see launch_ex): rounds x chunks <= 64 is below ~100 us -- every extractor launch of the live call (R <= 15)
+  const bool pdl = (long long)ntiles * p.nslices * p.nchunks <= 64ll * sm_count[dev];
   static bool o0[64], o1[64], o2[64];
   if (dil == 0) {
     if (!o0[dev]) { IDISP_CUDA(cudaFuncSetAttribute(c2d::conv2d_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)); o0[dev] = true; }

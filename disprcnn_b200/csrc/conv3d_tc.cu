@@ -2034,7 +2034,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
       // split in depth so that a small batch (the live call: 28 columns per ROI pair) still fills the machine.
       static const int no_fill = tc::env_flag("IDISP_NO_DEPTH_FILL");   // A/B switch
       const int grid = ((CX::MRG || CX::S2T) && !no_fill && !(p.dbg & 2048)) ? (sms * OCC / p.nh) * p.nh : grid_cols;
-      const bool pdl = (long long)ncols * p.nh <= 2ll * sms;   // small launches only (see launch_ex)
+      const bool pdl = (long long)ncols * p.nh <= 4ll * sms;   // short launches only (see launch_ex): at most four rounds of columns
       if constexpr (CVK != 0) IDISP_CUDA(launch_ex(kern, grid, CX::NTHREADS, CX::SMEM, s, false, pdl, map, rmap, cvmaps, p));
       else if constexpr (CX::S2T) {
         static const int no_cluster = tc::env_flag("IDISP_NO_CLUSTER");   // A/B switch

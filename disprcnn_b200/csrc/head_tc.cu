@@ -333,7 +333,7 @@ int tc_head_conv(const TcHeadWeights &w, const __nv_bfloat16 *x, int B, int D, i
       IDISP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
       opted[dev] = true;
     }
-    IDISP_CUDA(launch_ex(kern, grid, 384, (size_t)smem_bytes, s, false, ncols <= 2 * sm_count[dev], map, p));
+    IDISP_CUDA(launch_ex(kern, grid, 384, (size_t)smem_bytes, s, false, ncols <= 4 * sm_count[dev], map, p));
     return IDISP_OK;
   };
   static bool o0[64], o1[64], o2[64], o3[64], o4[64], o5[64];
