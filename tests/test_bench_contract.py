@@ -16,7 +16,8 @@ def _line(name):
     return json.loads(open(path).read().strip().splitlines()[-1])
 
 
-@pytest.mark.parametrize('name', ['r01_bench_fp16x2_final.json', 'r01_bench_fp16x2_2gpu.json'])
+@pytest.mark.parametrize('name', ['r01_bench_fp16x2_final.json', 'r01_bench_fp16x2_2gpu.json', 'r02_final_bench.json', 'r02_final_bench_first.json',
+                                  'r02o_bench_2gpu.json', 'r02z_bench_4gpu.json'])
 def test_recorded_bench_lines_carry_the_contract(name):
     d = _line(name)
     for k in REQUIRED:
