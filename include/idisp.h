@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define IDISP_VERSION 1
+#define IDISP_VERSION 2  /* 2: + idisp_extractor_*, idisp_roi_*_paste, idisp_stereo_rois, idisp_plan_forward_host_async / host_wait */
 
 enum {
   IDISP_OK = 0,

@@ -24,7 +24,7 @@ def test_header_symbols_are_exported(built_lib):
     for n in names:
         assert hasattr(built_lib, n), f'{n} declared in include/idisp.h but not exported by libidisp.so'
     assert sorted(_lib.PROTOTYPES) == names  # the ctypes table binds exactly the header
-    assert built_lib.idisp_version() == 1
+    assert built_lib.idisp_version() == 2
 
 
 def test_argument_validation_without_gpu(built_lib):
