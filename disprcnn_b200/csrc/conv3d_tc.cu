@@ -375,12 +375,15 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
       uint32_t q = 0;
       // (items count OUTPUT planes: Dout = Din for the stride-1 kernels; the stride-2 form (S2T) walks a chunk [e0, e1) as the steps
       //  [e0-1, e1) -- the extra first step only produces the odd input plane's carry into plane e0 -- i.e. input planes [2(e0-1), 2 e1))
-      const Items items = make_items(ncols, ncta, Dout, (C::MRG || C::S2T) && !(p.dbg & 2048));
+      //  the transposed form (DTR) counts INPUT planes: a chunk [e0, e1) runs the steps [e0-1, e1), the extra first step only producing
+      //  the carry into output plane 2*e0-1)
+      const int DI = C::DTR ? Din : Dout;
+      const Items items = make_items(ncols, ncta, DI, (C::MRG || C::S2T || C::DTR) && !(p.dbg & 2048));
       for (int item = cta; item < items.total; item += ncta) {
         int col, e0, e1;
-        get_item(items, item, Dout, col, e0, e1);
-        const int zb = C::S2T ? 2 * (e0 > 0 ? e0 - 1 : 0) : ((C::MRG && e0 > 0) ? e0 - 1 : 0);
-        const int ze = C::S2T ? 2 * e1 : ((C::MRG && e1 < Din) ? e1 + 1 : Din);
+        get_item(items, item, DI, col, e0, e1);
+        const int zb = C::S2T ? 2 * (e0 > 0 ? e0 - 1 : 0) : (((C::MRG || C::DTR) && e0 > 0) ? e0 - 1 : 0);
+        const int ze = C::S2T ? 2 * e1 : (C::DTR ? e1 : ((C::MRG && e1 < Din) ? e1 + 1 : Din));
         const int tw = col % p.tiles_w, th = (col / p.tiles_w) % p.tiles_h, n = col / (p.tiles_w * p.tiles_h);
         for (int z = zb; z < ze; ++z) {
           if (MODE == M_S2) {
@@ -643,20 +646,28 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         constexpr uint32_t KCH = 2 * 27 * NT * 16;   // bytes of one weight k-step
         const uint64_t b0 = ptx::make_smem_desc(w_addr, 27 * NT * 16, 128);
         const uint32_t id12 = ptx::make_idesc_h<F16>(128, 12 * NT), id6 = ptx::make_idesc_h<F16>(128, 6 * NT), id3 = ptx::make_idesc_h<F16>(128, 3 * NT);
-        auto waits = [&](int col_, uint32_t q_) {
-          if (col_ >= ncols) return;
+        auto waits = [&](bool more, uint32_t q_) {
+          if (!more) return;
           ptx::mbar_wait(acce_bar(q_ % NSLOT), ((q_ / NSLOT) & 1) ^ 1);
           ptx::mbar_wait(full_bar(q_ % C::STAGES), (q_ / C::STAGES) & 1);
         };
-        int col = cta, z = 0;
-        waits(col, 0);
-        while (col < ncols) {
+        // work items (see Items), here in INPUT planes: a chunk [e0, e1) runs the steps [e0-1, e1)
+        const Items items = make_items(ncols, ncta, Din, !(p.dbg & 2048));
+        int it = cta, col = 0, z = 0, zend = Din;
+        auto bounds = [&](int item_, int &col_, int &zb_, int &ze_) {
+          int e0_, e1_;
+          get_item(items, item_, Din, col_, e0_, e1_);
+          zb_ = e0_ > 0 ? e0_ - 1 : 0; ze_ = e1_;
+        };
+        if (it < items.total) bounds(it, col, z, zend);
+        waits(it < items.total, 0);
+        while (it < items.total) {
           ptx::tc_fence_after();
           const uint32_t s = q % C::STAGES, t = q % NSLOT;
           const uint32_t d = tmem_base + t * C::DTR_STRIDE;   // [c00 | c10 | c11 | c01] x [2z-1 | 2z | 2z+1] x NT
           const uint64_t a0 = desc_add(a_desc0, s * C::STAGE_BYTES);
-          int ncol = col, nz = z + 1;
-          if (nz == Din) { nz = 0; ncol += ncta; }
+          int nit = it, ncol = col, nz = z + 1, nzend = zend;
+          if (nz == zend) { nit += ncta; if (nit < items.total) bounds(nit, ncol, nz, nzend); }
           // The epilogue adds a residual tensor of the output's size; its loads are the layer's critical path.  Ask L2 for the
           // residual boxes of output planes 2z and 2z+1 now -- one tiled TMA prefetch per plane and precision word (16 KB each) --
           // one MMA step (plus the epilogue's lag) before the epilogue reads them.  Measured: issued from the producer warp (2-4
@@ -676,7 +687,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           __syncwarp();
 #pragma unroll
           for (int ks = 0; ks < C::KSM; ++ks) {
-            if (ks == C::KSM / 2) waits(ncol, q + 1);
+            if (ks == C::KSM / 2) waits(nit < items.total, q + 1);
             const uint32_t ak = A_KOFF(ks), bk = B_KS(ks) * KCH;
             // (the step's buffer is fresh: the first MMA, which covers all of it, overwrites)
             mma(d, desc_add(a0, ak), desc_add(b0, bk), id12, ks ? 1u : 0u);                                                  // shift (0,0)
@@ -686,7 +697,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
           }
           commit(empty_bar(s));
           commit(accf_bar(t));
-          col = ncol; z = nz; ++q;
+          it = nit; col = ncol; z = nz; zend = nzend; ++q;
         }
       }
       for (int col = cta; MODE != M_S1 && !C::TRI && !C::S2T && !C::DTR && col < ncols; col += ncta, g0 += Dout) {
@@ -822,10 +833,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
 #pragma unroll
     for (int i = 0; i < 32; ++i) zero[i] = 0u;
     uint32_t g0 = 0, tq = 0;  // tq: step counter of the TRI mode (one accumulator triple per input plane)
-    const Items items = make_items(ncols, ncta, Dout, (C::MRG || C::S2T) && !(p.dbg & 2048));   // (Cfg::MRG: Dout == Din)
+    const int DIe = C::DTR ? Din : Dout;   // (Cfg::DTR counts input planes, the others output planes; Cfg::MRG: Dout == Din)
+    const Items items = make_items(ncols, ncta, DIe, (C::MRG || C::S2T || C::DTR) && !(p.dbg & 2048));
     for (int item = cta; item < items.total; item += ncta, g0 += Dout) {
-      int col, e0, e1;   // this item's column and the output planes [e0, e1) it emits
-      get_item(items, item, Dout, col, e0, e1);
+      int col, e0, e1;   // this item's column and the planes [e0, e1) it owns
+      get_item(items, item, DIe, col, e0, e1);
       const int tw = col % p.tiles_w, th = (col / p.tiles_w) % p.tiles_h, n = col / (p.tiles_w * p.tiles_h);
       const int hr = th * TH + hl, wr = tw * TW + wl;
       const bool valid = hr < p.Hr && wr < p.Wr;
@@ -1215,7 +1227,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         // The residual words of a plane are requested before its TMEM read (the producer warp prefetched them into L2 earlier).
         const int ph = egroup;
         const int ci0 = ph == 0 ? 0 : 1, ci1 = ph == 0 ? 3 : 2;   // column groups of (ph, pw=0), (ph, pw=1): [c00 | c10 | c11 | c01]
-        const bool live = valid && !(p.dbg & 4);
+        const bool live_col = valid && !(p.dbg & 4);
         const int64_t blk_elems = Vo * 8, lo_off = (int64_t)cblk_out * blk_elems;
         const int64_t col_blk = ((int64_t)n * out_blocks + nh * 2) * blk_elems;
         const int64_t plane_nat = (int64_t)p.Ho * p.Wo * 8, plane_spl = (int64_t)(p.Ho / 2) * (p.Wo / 2) * 8;
@@ -1321,9 +1333,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant
         float CAR0[16], CAR1[16];   // block 2 of the previous step: what input plane z-1 (kd = 2) contributed to output plane 2z-1
 #pragma unroll
         for (int i = 0; i < 16; ++i) { CAR0[i] = 0.f; CAR1[i] = 0.f; }
-        for (int z = 0; z < Din; ++z, ++tq) {
+        for (int z = (e0 > 0 ? e0 - 1 : 0); z < e1; ++z, ++tq) {
           const uint32_t t = tq % NSLOT;
           const uint32_t tb0 = tmem_base + lane_addr + t * C::DTR_STRIDE + ci0 * 3 * NT, tb1 = tmem_base + lane_addr + t * C::DTR_STRIDE + ci1 * 3 * NT;
+          const bool live = live_col && z >= e0;   // (a chunk's extra first step only produces the carry into plane 2*e0-1)
           Res r, r2;
           if (live && has_res && z >= 1) rload(r, 2 * z - 1);
           ptx::mbar_wait(accf_bar(t), (tq / NSLOT) & 1);
@@ -2033,7 +2046,7 @@ static int tc_launch(const TcWeights &w, const __nv_bfloat16 *x, int B, int D, i
       // Kernels that walk work items (Items) get one CTA per SM even when there are fewer columns than that: the columns are then
       // split in depth so that a small batch (the live call: 28 columns per ROI pair) still fills the machine.
       static const int no_fill = tc::env_flag("IDISP_NO_DEPTH_FILL");   // A/B switch
-      const int grid = ((CX::MRG || CX::S2T) && !no_fill && !(p.dbg & 2048)) ? (sms * OCC / p.nh) * p.nh : grid_cols;
+      const int grid = ((CX::MRG || CX::S2T || CX::DTR) && !no_fill && !(p.dbg & 2048)) ? (sms * OCC / p.nh) * p.nh : grid_cols;
       const bool pdl = (long long)ncols * p.nh <= 4ll * sms;   // short launches only (see launch_ex): at most four rounds of columns
       if constexpr (CVK != 0) IDISP_CUDA(launch_ex(kern, grid, CX::NTHREADS, CX::SMEM, s, false, pdl, map, rmap, cvmaps, p));
       else if constexpr (CX::S2T) {
