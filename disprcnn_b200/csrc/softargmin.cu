@@ -89,32 +89,53 @@ struct SampleCtx {  // bilinear sampling of one low-resolution plane at this thr
   }
 };
 
-// sum and disparity-weighted sum of exp(v(d) - m) over the 4D interpolated logits; rolling window of two plane samples
-template <int D>
-__device__ __forceinline__ void softargmin_accumulate(const SampleCtx &sample, float mneg, int mindisp, float &s_out, float &t_out)
+// sum and disparity-weighted sum of exp(v(d) - m) over the 4D interpolated logits; rolling window of two plane samples.
+// RECUR: between two planes the interpolated logit is linear in d, so its exponentials form a geometric progression -- the first one
+// of a segment and the ratio g = 2^(sd * (P[k+1] - P[k]) * log2 e) cost two MUFU.EX2, the other three or four are one multiply each
+// (96 instead of 192 exponentials and 3 instead of 6 instructions per output disparity).  The progression starts from the segment's
+// first term; if that one underflows while a later one would not (logits more than ~44 apart between adjacent planes) the terms in
+// between are lost, so such a pixel reports `steep` and the caller redoes it with one exponential per disparity (RECUR = false).
+template <int D, bool RECUR>
+__device__ __forceinline__ bool softargmin_accumulate(const SampleCtx &sample, float mneg, int mindisp, float &s_out, float &t_out)
 {
   constexpr int Dfull = 4 * D;
   constexpr float sd = (float)(D - 1) / (float)(Dfull - 1);
+  constexpr float LOG2E = 1.4426950408889634f;
   // four independent (sum, weighted-sum) chains: with one chain the add latency of 2 x 192 dependent accumulations sets the pace
   float s4[4] = {0.f, 0.f, 0.f, 0.f}, t4[4] = {0.f, 0.f, 0.f, 0.f};
   float Pk = sample(0), Pk1 = sample(D > 1 ? 1 : 0);
+  float e = 0.f, g = 1.f;
+  bool steep = false;
 #pragma unroll
   for (int d = 0; d < Dfull; ++d) {
     const float fd = sd * (float)d;      // compile-time per unrolled iteration
     const int d0 = (int)fd;
-    if (d > 0 && d0 != (int)(sd * (float)(d - 1))) {  // (compile-time) the window advances by one plane
+    const bool first = d == 0 || d0 != (int)(sd * (float)(d - 1));   // (compile-time) first output disparity of a segment
+    if (d > 0 && first) {  // the window advances by one plane
       Pk = Pk1;
       Pk1 = sample(d0 + (d0 < D - 1 ? 1 : 0));
     }
     const float l1 = fd - (float)d0, l0 = 1.f - l1;
-    const float v = l0 * Pk + l1 * Pk1;
-    float e;  // one MUFU.EX2 (arguments are <= 0; flushing the far tail to zero is what softmax does to it anyway)
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v, 1.4426950408889634f, mneg)));
+    if (RECUR) {
+      if (first) {
+        const float delta2 = (Pk1 - Pk) * LOG2E;
+        steep |= fabsf(delta2) > 64.f;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(sd * delta2));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(l1, delta2, fmaf(Pk, LOG2E, mneg))));
+      } else {
+        e *= g;
+      }
+    } else {
+      const float v = l0 * Pk + l1 * Pk1;
+      // one MUFU.EX2 (arguments are <= 0; flushing the far tail to zero is what softmax does to it anyway)
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v, LOG2E, mneg)));
+    }
     s4[d & 3] += e;
     t4[d & 3] = fmaf(e, (float)(mindisp + d), t4[d & 3]);
   }
   s_out = (s4[0] + s4[1]) + (s4[2] + s4[3]);
   t_out = (t4[0] + t4[1]) + (t4[2] + t4[3]);
+  return steep;
 }
 
 // rare path (kept out of line so that it does not weigh on the fast path's registers): exact maximum of the interpolated
@@ -143,7 +164,7 @@ __device__ __noinline__ float softargmin_exact(SampleCtx sample, int mindisp)
   }
   asm volatile("" : "+l"(sample.p00));
   float s, t;
-  softargmin_accumulate<D>(sample, -m * 1.4426950408889634f, mindisp, s, t);
+  softargmin_accumulate<D, false>(sample, -m * 1.4426950408889634f, mindisp, s, t);
   return t / s;
 }
 
@@ -205,8 +226,8 @@ softargmin_x4_kernel(const float *__restrict__ logits, int B, int Hf, int Wf, in
       asm volatile("" : "+l"(sample.p00));  // the accumulation RE-samples (L1 hits): keeping the D samples alive would cost the occupancy
     }
     float s, t;
-    softargmin_accumulate<D>(sample, -M * 1.4426950408889634f, mindisp, s, t);
-    out[idx] = (s >= 1e-30f) ? t / s : softargmin_exact<D>(sample, mindisp);
+    const bool steep = softargmin_accumulate<D, true>(sample, -M * 1.4426950408889634f, mindisp, s, t);
+    out[idx] = (s >= 1e-30f && !steep) ? t / s : softargmin_exact<D>(sample, mindisp);
   }
 }
 
